@@ -1,0 +1,271 @@
+"""
+ctypes binding of libchbin_b200.so (include/chbin_b200.h).  No torch, no numpy types cross the ABI: only raw
+pointers and sizes.  The library is hand-written sm_100a CUDA; there is NO CPU fallback -- `load()` raises if the
+shared object is missing and `Context()` raises if no B200-class device is usable.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from . import build as _build
+
+CHB_OK, CHB_EINVAL, CHB_ENODEV, CHB_ECUDA, CHB_ENOMEM, CHB_ENOTIMPL, CHB_EUNASSIGNED = range(7)
+METRICS = {"convex": 0, "affine-qp": 1}
+UNOWNED = -(2**31)
+
+EXPORTED_SYMBOLS = [
+    "chb_abi_version", "chb_create", "chb_destroy", "chb_last_error", "chb_set_stream", "chb_synchronize",
+    "chb_get_timers", "chb_reset_timers", "chb_enable_timers", "chb_set_features", "chb_set_features_dev",
+    "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
+    "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
+    "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
+]
+
+
+class Timers(ctypes.Structure):
+    _fields_ = [
+        ("ms_distance", ctypes.c_double), ("ms_knn", ctypes.c_double), ("ms_qp", ctypes.c_double),
+        ("ms_commit", ctypes.c_double),
+        ("launches_distance", ctypes.c_int64), ("launches_knn", ctypes.c_int64), ("launches_qp", ctypes.c_int64),
+        ("launches_commit", ctypes.c_int64), ("launches_other", ctypes.c_int64),
+        ("qps_solved", ctypes.c_int64), ("qps_reference", ctypes.c_int64), ("rounds", ctypes.c_int64),
+        ("rows_scanned", ctypes.c_int64),
+    ]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
+_lib: Optional[ctypes.CDLL] = None
+_vp, _i64, _i32, _dbl = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_double
+
+
+def library_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(build_if_missing: bool = True) -> ctypes.CDLL:
+    """dlopen libchbin_b200.so (building it with nvcc first if the in-tree .so is missing or stale)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if build_if_missing and (not os.path.exists(path) or (_build.is_stale() and _nvcc_available())):
+        _build.build_library()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            f"{path} not found: the CUDA extension of chbin_b200 is not built and there is no CPU fallback. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'`."
+        )
+    L = ctypes.CDLL(path)
+    L.chb_abi_version.restype = ctypes.c_int
+    L.chb_last_error.restype = ctypes.c_char_p
+    L.chb_last_error.argtypes = [_vp]
+    L.chb_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_int]
+    L.chb_destroy.argtypes = [_vp]
+    L.chb_set_stream.argtypes = [_vp, _vp]
+    L.chb_synchronize.argtypes = [_vp]
+    L.chb_get_timers.argtypes = [_vp, ctypes.POINTER(Timers)]
+    L.chb_reset_timers.argtypes = [_vp]
+    L.chb_enable_timers.argtypes = [_vp, ctypes.c_int]
+    L.chb_set_features.argtypes = [_vp, _vp, _i64, _i32]
+    L.chb_set_features_dev.argtypes = [_vp, _vp, _i64, _i32]
+    L.chb_set_labels.argtypes = [_vp, _vp, _i64, _i32, _i64, _i64]
+    L.chb_set_params.argtypes = [_vp, _i32, _i32]
+    L.chb_build_distance_matrix.argtypes = [_vp, ctypes.c_int]
+    L.chb_get_distance_rows.argtypes = [_vp, _i64, _i64, _vp]
+    L.chb_knn_per_bin.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
+    L.chb_hull_distance_batch.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
+    L.chb_fit_iteration.argtypes = [_vp, _vp, _i64, _vp, ctypes.POINTER(_i64)]
+    L.chb_fit.argtypes = [_vp, _vp, _i64, _i32, _vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32), _vp]
+    L.chb_get_labels.argtypes = [_vp, _vp]
+    L.chb_iteration_begin.argtypes = [_vp, _vp, _i64]
+    L.chb_round_run.argtypes = [_vp, _i64, _i64, _vp]
+    L.chb_round_commit.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_i64)]
+    L.chb_iteration_end.argtypes = [_vp, ctypes.POINTER(_i64)]
+    L.chb_set_window.argtypes = [_vp, _i64]
+    L.chb_get_window.argtypes = [_vp]
+    L.chb_get_window.restype = _i64
+    for name in EXPORTED_SYMBOLS:
+        fn = getattr(L, name)
+        if name not in ("chb_last_error", "chb_get_window"):
+            fn.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def _nvcc_available() -> bool:
+    try:
+        _build.find_nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data
+
+
+class Context:
+    """One libchbin_b200 context = one GPU.  Error codes become the exceptions the reference raises."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        self._h = _vp()
+        rc = self._lib.chb_create(ctypes.byref(self._h), int(device))
+        if rc != CHB_OK:
+            msg = self._lib.chb_last_error(None).decode()
+            self._h = None
+            raise RuntimeError(f"chb_create failed ({rc}): {msg}")
+        self.device = int(device)
+
+    # -- plumbing
+    def _check(self, rc: int):
+        if rc == CHB_OK:
+            return
+        msg = self._lib.chb_last_error(self._h).decode()
+        if rc in (CHB_EINVAL, CHB_EUNASSIGNED):
+            raise ValueError(msg)
+        if rc == CHB_ENOTIMPL:
+            raise NotImplementedError(msg)
+        if rc == CHB_ENOMEM:
+            raise MemoryError(msg)
+        raise RuntimeError(f"libchbin_b200 error {rc}: {msg}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.chb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.chb_set_stream(self._h, _vp(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self._check(self._lib.chb_synchronize(self._h))
+
+    def timers(self) -> dict:
+        t = Timers()
+        self._check(self._lib.chb_get_timers(self._h, ctypes.byref(t)))
+        return t.as_dict()
+
+    def reset_timers(self):
+        self._check(self._lib.chb_reset_timers(self._h))
+
+    def enable_timers(self, on: bool):
+        self._check(self._lib.chb_enable_timers(self._h, int(bool(on))))
+
+    # -- set-up
+    def set_features(self, samples: np.ndarray):
+        x = np.ascontiguousarray(samples, dtype=np.float64)  # DataFrame.values arrives F-ordered
+        if x.ndim != 2:
+            raise ValueError("samples must be a 2-D array")
+        self.n, self.d = x.shape
+        self._check(self._lib.chb_set_features(self._h, _ptr(x), x.shape[0], x.shape[1]))
+
+    def set_features_dev(self, dev_ptr: int, n: int, d: int):
+        self.n, self.d = int(n), int(d)
+        self._check(self._lib.chb_set_features_dev(self._h, _vp(dev_ptr), n, d))
+
+    def set_labels(self, initial_bins: np.ndarray, num_clusters: int, slot_begin: int = 0, slot_end: int = -1):
+        b = np.ascontiguousarray(initial_bins, dtype=np.int64)
+        self.C = int(num_clusters)
+        self.U = int(np.sum(b == -1))
+        self._check(self._lib.chb_set_labels(self._h, _ptr(b), len(b), int(num_clusters), int(slot_begin), int(slot_end)))
+
+    def set_params(self, num_neighbors: int, metric: str = "convex"):
+        if metric not in METRICS:
+            raise NotImplementedError(f"Metric {metric} not implemented")
+        self.k = int(num_neighbors)
+        self._check(self._lib.chb_set_params(self._h, int(num_neighbors), METRICS[metric]))
+
+    def build_distance_matrix(self, materialise: bool = True):
+        self._check(self._lib.chb_build_distance_matrix(self._h, int(bool(materialise))))
+
+    def get_distance_rows(self, slot0: int, nrows: int) -> np.ndarray:
+        out = np.empty((nrows, self.n))
+        self._check(self._lib.chb_get_distance_rows(self._h, slot0, nrows, _ptr(out)))
+        return out
+
+    # -- building blocks
+    def knn_per_bin(self, labels: np.ndarray, queries: np.ndarray):
+        labels = np.ascontiguousarray(labels, dtype=np.int64)
+        queries = np.ascontiguousarray(queries, dtype=np.int64)
+        nq = len(queries)
+        idx = np.empty((nq, self.C, self.k), dtype=np.int64)
+        m = np.empty((nq, self.C), dtype=np.int32)
+        self._check(self._lib.chb_knn_per_bin(self._h, _ptr(labels), _ptr(queries), nq, _ptr(idx), _ptr(m)))
+        return idx, m
+
+    def hull_distance_batch(self, queries: np.ndarray, idx: np.ndarray, m: np.ndarray, want_alpha: bool = False):
+        queries = np.ascontiguousarray(queries, dtype=np.int64)
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        m = np.ascontiguousarray(m, dtype=np.int32)
+        nq = len(queries)
+        dist = np.empty((nq, self.C))
+        status = np.empty((nq, self.C), dtype=np.int32)
+        alpha = np.empty((nq, self.C, self.k)) if want_alpha else None
+        self._check(self._lib.chb_hull_distance_batch(self._h, _ptr(queries), nq, _ptr(idx), _ptr(m), _ptr(dist),
+                                                      _ptr(status), _ptr(alpha)))
+        return (dist, status, alpha) if want_alpha else (dist, status)
+
+    # -- assignment loop
+    def set_window(self, window: int):
+        self._check(self._lib.chb_set_window(self._h, int(window)))
+
+    def get_window(self) -> int:
+        return int(self._lib.chb_get_window(self._h))
+
+    def fit_iteration(self, perm: np.ndarray, want_labels: bool = True):
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        labels = np.empty(self.n, dtype=np.int64) if want_labels else None
+        nch = _i64(0)
+        self._check(self._lib.chb_fit_iteration(self._h, _ptr(perm), len(perm), _ptr(labels), ctypes.byref(nch)))
+        return labels, int(nch.value)
+
+    def fit(self, perms: np.ndarray, max_iterations: int):
+        perms = np.ascontiguousarray(perms, dtype=np.int64)
+        U = perms.shape[1] if perms.ndim == 2 else 0
+        labels = np.empty(self.n, dtype=np.int64)
+        iters, conv = _i32(0), _i32(0)
+        changed = np.zeros(max(int(max_iterations), 1), dtype=np.int64)
+        self._check(self._lib.chb_fit(self._h, _ptr(perms), U, int(max_iterations), _ptr(labels), ctypes.byref(iters),
+                                      ctypes.byref(conv), _ptr(changed)))
+        return labels, int(iters.value), bool(conv.value), changed[: iters.value].copy()
+
+    def get_labels(self) -> np.ndarray:
+        labels = np.empty(self.n, dtype=np.int64)
+        self._check(self._lib.chb_get_labels(self._h, _ptr(labels)))
+        return labels
+
+    def iteration_begin(self, perm: np.ndarray):
+        perm = np.ascontiguousarray(perm, dtype=np.int64)
+        self._check(self._lib.chb_iteration_begin(self._h, _ptr(perm), len(perm)))
+
+    def round_run(self, lo: int, hi: int, tent_dev_ptr: int):
+        self._check(self._lib.chb_round_run(self._h, lo, hi, _vp(tent_dev_ptr)))
+
+    def round_commit(self, lo: int, hi: int, tent_dev_ptr: int) -> int:
+        first = _i64(-1)
+        self._check(self._lib.chb_round_commit(self._h, lo, hi, _vp(tent_dev_ptr), ctypes.byref(first)))
+        return int(first.value)
+
+    def iteration_end(self) -> int:
+        nch = _i64(0)
+        self._check(self._lib.chb_iteration_end(self._h, ctypes.byref(nch)))
+        return int(nch.value)

@@ -1,0 +1,300 @@
+"""
+Host-side mirror of the reference's clustering interface for the B200 path.
+
+    fit_cluster(...)           <- /root/reference/ch_bin/core/clustering/algorithm.py:12-76   (same names, same
+                                  argument meaning, same RNG draws, same log lines, same return value)
+    perform_clustering(...)    <- /root/reference/ch_bin/cli/clustering.py:19-99 steps 01-04 (CSV in, CSV out)
+    install(ref_module)        <- adds the `AlgoQpSolver = b200` branch to the reference's own
+                                  ch_bin.cli.clustering module
+
+All arithmetic of the hot path (distance rows, per-bin kNN, hull-distance QPs, ordered assignment) runs in
+libchbin_b200.so (hand-written sm_100a CUDA) behind the C-ABI of include/chbin_b200.h.  This module only owns
+what the reference keeps in Python: the permutation draws on numpy's global legacy RNG, the early-stop rule,
+logging, and -- when torch.distributed is initialised with more than one rank -- the per-round label exchange.
+There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import logging
+from pathlib import Path
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import capi
+
+logger = logging.getLogger(__name__)
+
+B200_SOLVER = "b200"
+
+
+# ----------------------------------------------------------------------------------------------------------
+# round driver (shared by the single- and multi-GPU paths; engine-agnostic so the host logic is testable)
+# ----------------------------------------------------------------------------------------------------------
+def owned_slots(U: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slice of query slots (= points_to_assign in ascending order) a rank owns."""
+    return (U * rank) // world, (U * (rank + 1)) // world
+
+
+def run_iteration(engine, perm: np.ndarray, comm=None) -> Tuple[int, int]:
+    """One iteration of algorithm.py:43-72 as speculate/repair rounds (csrc/api.cu header).
+
+    engine: iteration_begin(perm), round_run(lo, hi) -> tent, round_commit(lo, hi, tent) -> first_changed (-1 = none),
+            iteration_end() -> n_changed, window() -> int.
+    comm:   None, or an object with all_reduce_max(tent) -> tent merging the ranks' tentative labels.
+    Returns (n_changed, rounds)."""
+    U = len(perm)
+    engine.iteration_begin(perm)
+    W = engine.window() or U
+    lo, rounds = 0, 0
+    while lo < U:
+        hi = min(U, lo + W)
+        tent = engine.round_run(lo, hi)
+        if comm is not None:
+            tent = comm.all_reduce_max(tent)
+        first = engine.round_commit(lo, hi, tent)
+        lo = hi if first < 0 else first + 1
+        rounds += 1
+    return engine.iteration_end(), rounds
+
+
+class GpuEngine:
+    """Engine over one libchbin_b200 context; tentative labels live in a torch int32 device tensor so that
+    torch.distributed (NCCL) can all-reduce them in place between chb_round_run and chb_round_commit."""
+
+    def __init__(self, ctx: capi.Context, device_index: int):
+        import torch
+
+        self.ctx = ctx
+        self.torch = torch
+        self.device = torch.device("cuda", device_index)
+        self._tent = None
+        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def window(self) -> int:
+        return self.ctx.get_window()
+
+    def iteration_begin(self, perm):
+        self.ctx.iteration_begin(perm)
+
+    def round_run(self, lo, hi):
+        n = hi - lo
+        if self._tent is None or self._tent.numel() < n:
+            self._tent = self.torch.empty(max(n, self.ctx.get_window()), dtype=self.torch.int32, device=self.device)
+        t = self._tent[:n]
+        self.ctx.round_run(lo, hi, t.data_ptr())
+        return t
+
+    def round_commit(self, lo, hi, tent):
+        return self.ctx.round_commit(lo, hi, tent.data_ptr())
+
+    def iteration_end(self):
+        return self.ctx.iteration_end()
+
+
+class TorchComm:
+    """Label exchange between ranks: one all-reduce(MAX) of a window of int32 labels per round (un-owned
+    positions hold INT32_MIN).  NCCL over NVLink on the GPU box, gloo in the CPU tests."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+
+    def all_reduce_max(self, tent):
+        self.dist.all_reduce(tent, op=self.dist.ReduceOp.MAX, group=self.group)
+        return tent
+
+
+def _dist_state():
+    try:
+        import torch.distributed as dist
+    except Exception:  # torch missing: single process
+        return None, 0, 1
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def _draw_permutation(points_to_assign: np.ndarray, dist_mod, device_index: int) -> np.ndarray:
+    """algorithm.py:45.  Every rank draws from its own global RNG (so the stream advances exactly as in the
+    reference); rank 0's draw is authoritative and broadcast so that differently-seeded ranks cannot diverge."""
+    perm = np.random.permutation(points_to_assign).astype(np.int64)
+    if dist_mod is not None and dist_mod.get_world_size() > 1:
+        import torch
+
+        dev = torch.device("cuda", device_index) if dist_mod.get_backend() == "nccl" else torch.device("cpu")
+        t = torch.from_numpy(perm).to(dev)
+        dist_mod.broadcast(t, src=0)
+        perm = t.cpu().numpy()
+    return perm
+
+
+# ----------------------------------------------------------------------------------------------------------
+# fit_cluster
+# ----------------------------------------------------------------------------------------------------------
+def fit_cluster(
+    samples: np.ndarray,
+    num_clusters: int,
+    initial_bins: np.ndarray,
+    distance_matrix: Optional[np.ndarray] = None,
+    num_neighbors: int = 15,
+    max_iterations: int = 10,
+    metric: str = "convex",
+    qp_solver: str = B200_SOLVER,
+    in_mem_dist_matrix: bool = True,
+    device: Optional[int] = None,
+    window: int = 0,
+    return_info: bool = False,
+):
+    """
+    Cevikalp et al. 2019 convex-hull binning specialised for metagenomic binning, on B200.
+
+    Drop-in for algorithm.py:12-21 (`fit_cluster`).  `distance_matrix` is accepted for signature compatibility
+    and ignored: distances are the same doubles (scipy-cdist recipe, bit-exact), produced on the device --
+    materialised in HBM when `in_mem_dist_matrix` (InMemDistMatrix=yes) and recomputed on demand otherwise.
+    `qp_solver` must be "b200": quadprog / cvxopt belong to the reference's CPU path (solve_qp.py:125-132).
+
+    :param samples: Dataset points (n, d) float64.
+    :param num_clusters: Number of clusters.
+    :param initial_bins: Initial bin vector. Use -1 for un-binned.
+    :param num_neighbors: Number of neighbors to consider for polytope.
+    :param max_iterations: Number of maximum iterations to perform.
+    :param metric: Polytope distance metric (convex/affine-qp).
+    :return: Final binning result (int64, n).
+    """
+    if qp_solver != B200_SOLVER:
+        raise NotImplementedError(f"Unknown solver {qp_solver}")  # solve_qp.py:132
+    if metric not in capi.METRICS:
+        raise NotImplementedError(f"Metric {metric} not implemented")  # hull_distance.py:108
+
+    dist_mod, rank, world = _dist_state()
+    if device is None:
+        device = 0
+        if world > 1:
+            import torch
+
+            device = torch.cuda.current_device()
+
+    initial_bins = np.asarray(initial_bins)
+    curr = initial_bins.astype(np.int64, copy=True)  # algorithm.py:37 -- inputs are never mutated
+    points_to_assign = np.where(curr == -1)[0]  # algorithm.py:38
+    num_points_to_assign = len(points_to_assign)
+    logger.debug("Assigning %s points.", num_points_to_assign)
+
+    ctx = capi.Context(device)
+    try:
+        ctx.set_features(samples)
+        u0, u1 = owned_slots(num_points_to_assign, rank, world)
+        ctx.set_labels(curr, int(num_clusters), u0, u1)
+        ctx.set_params(int(num_neighbors), metric)
+        ctx.set_window(int(window))
+        ctx.build_distance_matrix(bool(in_mem_dist_matrix))
+        engine = comm = None
+        if world > 1:
+            engine = GpuEngine(ctx, device)
+            comm = TorchComm()
+
+        iterations, converged, rounds_total, changed = 0, False, 0, []
+        for i_iter in range(max_iterations):
+            sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
+            if world > 1:
+                change_count, rounds = run_iteration(engine, sample_perm, comm)
+            else:
+                _, change_count = ctx.fit_iteration(sample_perm, want_labels=False)
+                rounds = 0
+            rounds_total += rounds
+            iterations += 1
+            changed.append(change_count)
+            # If the assignments did not change, break  (algorithm.py:63-66)
+            if change_count == 0:
+                logger.info("Iteration %s: No changes with previous iteration... Stopping...", i_iter + 1)
+                converged = True
+                break
+            change_avg = change_count / len(curr)
+            logger.info("Iteration %s: Points changed clusters. avg=%s, count=%s", i_iter + 1, change_avg, change_count)
+        else:
+            logger.info("Exit due to max iteration limit.")
+        labels = ctx.get_labels()
+        info = dict(iterations=iterations, converged=converged, changed=changed, timers=ctx.timers(), rank=rank,
+                    world=world, owned_slots=(u0, u1))
+    finally:
+        ctx.close()
+    if return_info:
+        return labels, info
+    return labels
+
+
+# ----------------------------------------------------------------------------------------------------------
+# perform_clustering (steps 01-04 of cli/clustering.py) and the plug-in hook
+# ----------------------------------------------------------------------------------------------------------
+def perform_clustering(
+    contig_fasta: Optional[Path],
+    features_csv: Path,
+    operating_dir: Path,
+    num_neighbors: int = 15,
+    max_iterations: int = 10,
+    metric: str = "convex",
+    qp_solver: str = B200_SOLVER,
+    in_mem_dist_matrix: bool = True,
+) -> Path:
+    """cli/clustering.py:19-99 with steps 02-03 on the GPU.  Step 05 (FASTA dump, needs Biopython) is the
+    reference's own `dump_bins` and is only invoked when this function is installed into the reference."""
+    import pandas as pd
+
+    operating_dir = Path(operating_dir)
+    dist_bin_csv = operating_dir / "binning-assignment.csv"
+    operating_dir.mkdir(parents=True, exist_ok=True)
+
+    logger.info(">> Reading feature CSV...")
+    df_features = pd.read_csv(features_csv)
+    num_clusters = int(df_features.CLUSTER.max() + 1)
+    initial_bins = df_features.CLUSTER.values.copy()
+    samples = df_features.drop(["CONTIG_NAME", "PARENT_NAME", "CLUSTER"], axis=1).values
+
+    logger.info(">> Performing binning using %s solver...", qp_solver)
+    convex_labels = fit_cluster(
+        samples=samples, num_clusters=num_clusters, initial_bins=initial_bins, num_neighbors=num_neighbors,
+        max_iterations=max_iterations, metric=metric, qp_solver=qp_solver, in_mem_dist_matrix=in_mem_dist_matrix,
+    )
+    if np.any(convex_labels < 0):
+        raise ValueError("There were some un-clustered points left... Aborting.")  # cli/clustering.py:79-80
+
+    logger.info(">> Assigning bins...")
+    df_samples = df_features.drop("CLUSTER", axis=1)
+    df_combined = pd.concat([df_samples, pd.DataFrame({"BIN": convex_labels})], axis=1)
+    parent_groups = df_combined[["PARENT_NAME", "BIN"]].groupby("PARENT_NAME")
+    df_dist_bin = parent_groups.BIN.apply(lambda x: np.bincount(x).argmax()).reset_index()
+    df_dist_bin.rename(columns={"PARENT_NAME": "CONTIG_NAME"}, inplace=True)
+    df_dist_bin.to_csv(dist_bin_csv, index=False)
+    logger.info("Dumped binning assignment CSV at %s...", dist_bin_csv)
+    return dist_bin_csv
+
+
+def install(ref_cli_clustering_module) -> None:
+    """Adds the `AlgoQpSolver = b200` branch to the reference's own `ch_bin.cli.clustering` module, in place:
+    `perform_clustering(..., qp_solver="b200")` then runs steps 01-04 here (distance structure + fit_cluster on
+    the GPU) and hands step 05 (FASTA dump) back to the reference's `dump_bins`; any other solver value goes
+    to the untouched original.  `run_perform_clustering` (cli/clustering.py:102-127) needs no change: it looks
+    `perform_clustering` up in the module at call time."""
+    mod = ref_cli_clustering_module
+    orig_perform = mod.perform_clustering
+
+    def perform_dispatch(contig_fasta, features_csv, operating_dir, num_neighbors=15, max_iterations=10,
+                         metric="convex", qp_solver="quadprog", in_mem_dist_matrix=True):
+        if qp_solver != B200_SOLVER:
+            return orig_perform(contig_fasta, features_csv, operating_dir, num_neighbors, max_iterations, metric,
+                                qp_solver, in_mem_dist_matrix)
+        import pandas as pd
+
+        csv = perform_clustering(contig_fasta, features_csv, operating_dir, num_neighbors, max_iterations, metric,
+                                 qp_solver, in_mem_dist_matrix)
+        bin_dump_dir = Path(operating_dir) / "bins"
+        bin_dump_dir.mkdir(parents=True, exist_ok=True)
+        logger.info(">> Writing binned FASTA files...")
+        mod.dump_bins(pd.read_csv(csv), contig_fasta, bin_dump_dir)  # cli/clustering.py:94-97
+        return csv
+
+    perform_dispatch.__wrapped__ = orig_perform
+    mod.perform_clustering = perform_dispatch

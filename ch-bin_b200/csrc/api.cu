@@ -1,0 +1,750 @@
+// api.cu -- host side of libchbin_b200's C-ABI (include/chbin_b200.h) plus the small ordering kernels.
+//
+// The assignment loop of the reference (/root/reference/ch_bin/core/clustering/algorithm.py:43-72) is a
+// Gauss-Seidel sweep: the point at permutation position p sees the new labels of positions < p and last
+// iteration's labels of positions > p.  It is reproduced EXACTLY by iterating a speculative map to its unique
+// fixed point ("speculate + repair"):
+//     T[p] = assign(p | new labels T[q] for q < p, old labels for q > p)          for every p in a window
+// Round r recomputes T from the previous round's T.  All positions up to and including the first position whose
+// T changed are final after the round (their inputs did not change), so the frontier strictly advances and the
+// fixed point -- the sequential result, by induction over p -- is reached in at most `window` rounds; on
+// binnable data it takes 2-4.  Per round only (query, bin) pairs whose neighbour list changed are re-solved.
+#include <algorithm>
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+thread_local std::string g_chb_create_error;
+
+int chb_fail(chb_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_chb_create_error = buf;
+    return code;
+}
+
+void chb_resolve_timers(chb_ctx *c)
+{
+    for (auto &p : c->ev_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.e0, p.e1) == cudaSuccess) {
+            switch (p.stage) {
+            case CHB_ST_DISTANCE: c->tm.ms_distance += ms; break;
+            case CHB_ST_KNN: c->tm.ms_knn += ms; break;
+            case CHB_ST_QP: c->tm.ms_qp += ms; break;
+            case CHB_ST_COMMIT: c->tm.ms_commit += ms; break;
+            default: break;
+            }
+        } else {
+            (void)cudaGetLastError();
+        }
+        c->ev_free.emplace_back(p.e0, p.e1);
+    }
+    c->ev_pending.clear();
+}
+
+namespace {
+
+template <typename T>
+int dev_alloc(chb_ctx *ctx, T **p, int64_t count)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count <= 0) return CHB_OK;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void **>(p), sizeof(T) * (size_t)count);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *p = nullptr;
+        return chb_fail(ctx, CHB_ENOMEM, "cudaMalloc of %lld bytes failed: %s", (long long)(sizeof(T) * (size_t)count),
+                        cudaGetErrorString(e));
+    }
+    return CHB_OK;
+}
+template <typename T>
+void dev_free(T **p)
+{
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+}
+
+#define CHB_TRY(expr)                  \
+    do {                               \
+        int _rc = (expr);              \
+        if (_rc != CHB_OK) return _rc; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+__global__ void set_pos_kernel(const int32_t *__restrict__ perm_pt, int64_t U, int32_t *__restrict__ pos)
+{
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < U) pos[perm_pt[p]] = (int32_t)p;
+}
+
+__global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
+                                   int32_t *__restrict__ rows)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) rows[i] = perm_pt[own_pos[i]];
+}
+
+// algorithm.py:47-48,57-58,60: strict '<' so the lowest bin wins ties and NaN never wins; when no bin wins the
+// point keeps the label it had (min_cluster initialised to curr_bins[i_sample]).
+__global__ void argmin_kernel(const int32_t *__restrict__ own_pos, int64_t cnt, const int32_t *__restrict__ perm_pt,
+                              const int32_t *__restrict__ qslot, int64_t u0, const double *__restrict__ pair_dist, int32_t C,
+                              const int32_t *__restrict__ old_label, int64_t lo, int32_t *__restrict__ tent)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= cnt) return;
+    const int p = own_pos[w];
+    const int j = perm_pt[p];
+    const double *dr = pair_dist + ((int64_t)qslot[j] - u0) * C;
+    double best = INFINITY;
+    int bc = INT32_MAX;
+    for (int c = lane; c < C; c += 32) {
+        const double v = dr[c];
+        if (v < best) { best = v; bc = c; } // ascending c per lane: first minimum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(CHB_FULL, best, o);
+        const int oc = __shfl_xor_sync(CHB_FULL, bc, o);
+        if (ov < best || (ov == best && oc < bc)) { best = ov; bc = oc; }
+    }
+    if (lane == 0) tent[p - lo] = (best < INFINITY) ? bc : old_label[j];
+}
+
+__global__ void commit_kernel(const int32_t *__restrict__ tent, int64_t lo, int64_t hi, const int32_t *__restrict__ perm_pt,
+                              int32_t *__restrict__ tent_pt, int32_t *__restrict__ counters)
+{
+    const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= hi) return;
+    const int32_t v = tent[p - lo];
+    const int j = perm_pt[p];
+    if (v != tent_pt[j]) {
+        tent_pt[j] = v;
+        atomicMin(&counters[1], (int32_t)p);
+    }
+}
+
+__global__ void count_changed_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t n,
+                                     int32_t *__restrict__ counters)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ch = (i < n) && (a[i] != b[i]);
+    const unsigned m = __ballot_sync(CHB_FULL, ch);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], __popc(m));
+}
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+int ensure_caches(chb_ctx *c)
+{
+    const int64_t nown = c->u1 - c->u0;
+    if (c->cache_nown == nown && c->cache_C == c->C && c->cache_k == c->k && c->knn_idx) return CHB_OK;
+    CHB_TRY(dev_alloc(c, &c->knn_idx, nown * c->C * c->k));
+    CHB_TRY(dev_alloc(c, &c->knn_cnt, nown * c->C));
+    CHB_TRY(dev_alloc(c, &c->pair_dist, nown * c->C));
+    CHB_TRY(dev_alloc(c, &c->pair_status, nown * c->C));
+    c->cache_nown = nown;
+    c->cache_C = c->C;
+    c->cache_k = c->k;
+    if (nown * c->C > 0) {
+        fill_i32_kernel<<<nblk(nown * c->C, 256), 256, 0, c->stream>>>(c->knn_cnt, nown * c->C, -1);
+        CHB_CUDA(c, cudaGetLastError());
+        ++c->tm.launches_other;
+    }
+    return CHB_OK;
+}
+
+int ensure_work(chb_ctx *c, int64_t items)
+{
+    const int64_t need = std::max<int64_t>(items * c->C, 1);
+    if (need > c->work_cap) {
+        CHB_TRY(dev_alloc(c, &c->work, need));
+        c->work_cap = need;
+    }
+    return CHB_OK;
+}
+
+int sync_stream(chb_ctx *c)
+{
+    CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    chb_resolve_timers(c);
+    return CHB_OK;
+}
+
+} // namespace
+
+// =========================================================================================================
+extern "C" {
+
+int chb_abi_version(void) { return CHB_ABI_VERSION; }
+
+const char *chb_last_error(const chb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_chb_create_error.c_str(); }
+
+int chb_create(chb_ctx **out, int device_id)
+{
+    if (!out) return chb_fail(nullptr, CHB_EINVAL, "chb_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        (void)cudaGetLastError();
+        return chb_fail(nullptr, CHB_ENODEV, "no CUDA device available (%s); libchbin_b200 has no CPU fallback",
+                        e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device_id < 0 || device_id >= ndev)
+        return chb_fail(nullptr, CHB_EINVAL, "device_id %d out of range [0,%d)", device_id, ndev);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device_id) != cudaSuccess)
+        return chb_fail(nullptr, CHB_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return chb_fail(nullptr, CHB_ENODEV, "device %d is sm_%d%d; libchbin_b200 is built for sm_100a only", device_id,
+                        prop.major, prop.minor);
+    if (cudaSetDevice(device_id) != cudaSuccess) return chb_fail(nullptr, CHB_ECUDA, "cudaSetDevice failed");
+    chb_ctx *c = new chb_ctx();
+    c->device = device_id;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return chb_fail(nullptr, CHB_ECUDA, "cudaStreamCreate failed");
+    }
+    c->stream = c->own_stream;
+    if (cudaMalloc(&c->counters, sizeof(int32_t) * 8) != cudaSuccess ||
+        cudaMallocHost(&c->counters_host, sizeof(int32_t) * 8) != cudaSuccess) {
+        delete c;
+        return chb_fail(nullptr, CHB_ENOMEM, "counter allocation failed");
+    }
+    cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * 8, c->stream);
+    *out = c;
+    return CHB_OK;
+}
+
+int chb_destroy(chb_ctx *c)
+{
+    if (!c) return CHB_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    chb_resolve_timers(c);
+    for (auto &p : c->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    dev_free(&c->X); dev_free(&c->old_label); dev_free(&c->tent_pt); dev_free(&c->pos); dev_free(&c->qslot);
+    dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
+    dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
+    dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win);
+    if (c->counters_host) cudaFreeHost(c->counters_host);
+    delete[] c->own_pos_host;
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return CHB_OK;
+}
+
+int chb_set_stream(chb_ctx *c, void *cuda_stream)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_TRY(sync_stream(c));
+    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return CHB_OK;
+}
+
+int chb_synchronize(chb_ctx *c)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    return sync_stream(c);
+}
+
+int chb_get_timers(chb_ctx *c, chb_timers *out)
+{
+    CHB_CHECK(c, c && out, CHB_EINVAL, "NULL argument");
+    CHB_TRY(sync_stream(c));
+    *out = c->tm;
+    return CHB_OK;
+}
+
+int chb_reset_timers(chb_ctx *c)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_TRY(sync_stream(c));
+    c->tm = chb_timers{};
+    return CHB_OK;
+}
+
+int chb_enable_timers(chb_ctx *c, int enable)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    c->timers_on = enable != 0;
+    return CHB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, src && n > 0 && d > 0, CHB_EINVAL, "samples must be a non-empty (n, d) float64 array");
+    CHB_CHECK(c, n < INT32_MAX, CHB_EINVAL, "n = %lld exceeds the 32-bit point index range", (long long)n);
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    c->n = n;
+    c->d = d;
+    c->ldx = (d + 1) & ~1; // 16-byte row pitch
+    CHB_TRY(dev_alloc(c, &c->X, n * c->ldx));
+    CHB_CUDA(c, cudaMemsetAsync(c->X, 0, sizeof(double) * (size_t)n * c->ldx, c->stream));
+    CHB_CUDA(c, cudaMemcpy2DAsync(c->X, sizeof(double) * c->ldx, src, sizeof(double) * d, sizeof(double) * d, (size_t)n,
+                                  kind, c->stream));
+    CHB_TRY(sync_stream(c));
+    c->dist_ready = false;
+    c->labels_set = false;
+    dev_free(&c->Dq);
+    return CHB_OK;
+}
+
+int chb_set_features(chb_ctx *c, const double *x, int64_t n, int32_t d)
+{
+    return set_features_common(c, x, n, d, cudaMemcpyHostToDevice);
+}
+int chb_set_features_dev(chb_ctx *c, const double *x_dev, int64_t n, int32_t d)
+{
+    return set_features_common(c, x_dev, n, d, cudaMemcpyDeviceToDevice);
+}
+
+int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_t slot_begin, int64_t slot_end)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, c->X && n == c->n, CHB_EINVAL, "set_labels: call chb_set_features first with the same n");
+    CHB_CHECK(c, bins && C >= 1, CHB_EINVAL, "initial_bins is NULL or num_clusters < 1");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    std::vector<int32_t> lab((size_t)n), qs((size_t)n), qp;
+    qp.reserve((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t b = bins[i];
+        CHB_CHECK(c, b >= -1 && b < C, CHB_EINVAL, "initial_bins[%lld] = %lld outside [-1, %d)", (long long)i, (long long)b, C);
+        lab[(size_t)i] = (int32_t)b;
+        if (b == -1) {
+            qs[(size_t)i] = (int32_t)qp.size();
+            qp.push_back((int32_t)i);
+        } else {
+            qs[(size_t)i] = -1;
+        }
+    }
+    const int64_t U = (int64_t)qp.size();
+    if (slot_end < 0) slot_end = U;
+    CHB_CHECK(c, 0 <= slot_begin && slot_begin <= slot_end && slot_end <= U, CHB_EINVAL, "owned slot range [%lld,%lld) invalid for U=%lld",
+              (long long)slot_begin, (long long)slot_end, (long long)U);
+    c->C = C;
+    c->U = U;
+    c->u0 = slot_begin;
+    c->u1 = slot_end;
+    CHB_TRY(dev_alloc(c, &c->old_label, n));
+    CHB_TRY(dev_alloc(c, &c->tent_pt, n));
+    CHB_TRY(dev_alloc(c, &c->pos, n));
+    CHB_TRY(dev_alloc(c, &c->qslot, n));
+    CHB_TRY(dev_alloc(c, &c->qpoint, std::max<int64_t>(U, 1)));
+    CHB_TRY(dev_alloc(c, &c->perm_pt, std::max<int64_t>(U, 1)));
+    CHB_TRY(dev_alloc(c, &c->own_pos, std::max<int64_t>(slot_end - slot_begin, 1)));
+    delete[] c->own_pos_host;
+    c->own_pos_host = new int64_t[(size_t)std::max<int64_t>(slot_end - slot_begin, 1)];
+    CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (U) CHB_CUDA(c, cudaMemcpyAsync(c->qpoint, qp.data(), sizeof(int32_t) * (size_t)U, cudaMemcpyHostToDevice, c->stream));
+    fill_i32_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->pos, n, -1);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    CHB_TRY(sync_stream(c));
+    c->labels_set = true;
+    c->in_iteration = false;
+    c->dist_ready = false;
+    dev_free(&c->Dq);
+    c->cache_nown = -1; // force cache re-initialisation
+    return CHB_OK;
+}
+
+int chb_set_params(chb_ctx *c, int32_t k, int32_t metric)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, k >= 1 && k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d], got %d", CHB_KMAX, k);
+    CHB_CHECK(c, metric == CHB_METRIC_CONVEX || metric == CHB_METRIC_AFFINE_QP, CHB_ENOTIMPL, "Metric %d not implemented",
+              metric);
+    if (k != c->k || metric != c->metric) c->cache_nown = -1;
+    c->k = k;
+    c->metric = metric;
+    return CHB_OK;
+}
+
+int chb_build_distance_matrix(chb_ctx *c, int materialise)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, c->labels_set, CHB_EINVAL, "build_distance_matrix: call chb_set_features and chb_set_labels first");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int64_t nown = c->u1 - c->u0;
+    dev_free(&c->Dq);
+    dev_free(&c->Dscratch);
+    c->materialise = materialise != 0;
+    if (c->materialise) {
+        CHB_TRY(dev_alloc(c, &c->Dq, nown * c->n));
+        const int64_t step = 65535LL * 64;
+        for (int64_t r0 = 0; r0 < nown; r0 += step)
+            CHB_TRY(chb_launch_distance_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Dq + r0 * c->n));
+        CHB_TRY(sync_stream(c));
+    } else {
+        // scratch for recomputed rows: ~1 GiB, at least 64 rows
+        int64_t rows = (1LL << 30) / (8 * c->n);
+        rows = std::max<int64_t>(64, std::min<int64_t>(rows, std::max<int64_t>(nown, 64)));
+        CHB_TRY(dev_alloc(c, &c->Dscratch, rows * c->n));
+        c->scratch_rows = rows;
+    }
+    c->dist_ready = true;
+    return CHB_OK;
+}
+
+int chb_get_distance_rows(chb_ctx *c, int64_t slot0, int64_t nrows, double *out)
+{
+    CHB_CHECK(c, c && out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->dist_ready, CHB_EINVAL, "distance matrix not built");
+    CHB_CHECK(c, slot0 >= c->u0 && nrows >= 0 && slot0 + nrows <= c->u1, CHB_EINVAL, "slots [%lld,%lld) not owned",
+              (long long)slot0, (long long)(slot0 + nrows));
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    if (c->materialise) {
+        CHB_CUDA(c, cudaMemcpyAsync(out, c->Dq + (slot0 - c->u0) * c->n, sizeof(double) * (size_t)nrows * c->n,
+                                    cudaMemcpyDeviceToHost, c->stream));
+        return sync_stream(c);
+    }
+    for (int64_t r0 = 0; r0 < nrows; r0 += c->scratch_rows) {
+        const int64_t cnt = std::min(c->scratch_rows, nrows - r0);
+        CHB_TRY(chb_launch_distance_rows(c, c->qpoint + slot0 + r0, cnt, c->Dscratch));
+        CHB_CUDA(c, cudaMemcpyAsync(out + r0 * c->n, c->Dscratch, sizeof(double) * (size_t)cnt * c->n, cudaMemcpyDeviceToHost,
+                                    c->stream));
+        CHB_TRY(sync_stream(c));
+    }
+    return CHB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, int64_t nq, int64_t *idx_out, int32_t *m_out)
+{
+    CHB_CHECK(c, c && labels && queries && idx_out && m_out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->X && c->C > 0, CHB_EINVAL, "knn_per_bin: set features and labels first");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int64_t n = c->n;
+    const int32_t C = c->C, k = c->k;
+    std::vector<int32_t> lab((size_t)n);
+    for (int64_t i = 0; i < n; ++i) lab[(size_t)i] = (int32_t)labels[i];
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nq, std::max<int64_t>(1, (1LL << 29) / (8 * n))));
+    int32_t *d_lab = nullptr, *d_q = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
+    double *d_rows = nullptr;
+    int rc = CHB_OK;
+    std::vector<int32_t> q32((size_t)chunk), idx32((size_t)chunk * C * k);
+    do {
+        if ((rc = dev_alloc(c, &d_lab, n)) || (rc = dev_alloc(c, &d_q, chunk)) || (rc = dev_alloc(c, &d_idx, chunk * C * k)) ||
+            (rc = dev_alloc(c, &d_cnt, chunk * C)) || (rc = dev_alloc(c, &d_rows, chunk * n)))
+            break;
+        cudaMemcpyAsync(d_lab, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
+        for (int64_t q0 = 0; q0 < nq && rc == CHB_OK; q0 += chunk) {
+            const int64_t cnt = std::min(chunk, nq - q0);
+            for (int64_t i = 0; i < cnt; ++i) {
+                const int64_t q = queries[q0 + i];
+                if (q < 0 || q >= n) { rc = chb_fail(c, CHB_EINVAL, "query index %lld out of range", (long long)q); break; }
+                q32[(size_t)i] = (int32_t)q;
+            }
+            if (rc) break;
+            cudaMemcpyAsync(d_q, q32.data(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, c->stream);
+            if ((rc = chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
+            chb_knn_args a{};
+            a.rows = d_rows; a.row_stride = n; a.row_is_item = 1; a.items = d_q; a.n_items = cnt; a.mode = 1;
+            a.old_label = d_lab; a.n = n; a.C = C; a.k = k; a.u0 = 0; a.knn_idx = d_idx; a.knn_cnt = d_cnt;
+            if ((rc = chb_launch_knn_scan(c, a))) break;
+            cudaMemcpyAsync(idx32.data(), d_idx, sizeof(int32_t) * (size_t)cnt * C * k, cudaMemcpyDeviceToHost, c->stream);
+            cudaMemcpyAsync(m_out + q0 * C, d_cnt, sizeof(int32_t) * (size_t)cnt * C, cudaMemcpyDeviceToHost, c->stream);
+            if ((rc = sync_stream(c))) break;
+            for (int64_t i = 0; i < cnt * C * k; ++i) idx_out[q0 * C * k + i] = idx32[(size_t)i];
+        }
+    } while (0);
+    dev_free(&d_lab); dev_free(&d_q); dev_free(&d_idx); dev_free(&d_cnt); dev_free(&d_rows);
+    return rc;
+}
+
+int chb_hull_distance_batch(chb_ctx *c, const int64_t *queries, int64_t nq, const int64_t *idx, const int32_t *m,
+                            double *dist_out, int32_t *status_out, double *alpha_out)
+{
+    CHB_CHECK(c, c && queries && idx && m && dist_out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->X && c->C > 0, CHB_EINVAL, "hull_distance_batch: set features and labels first");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int32_t C = c->C, k = c->k;
+    const int64_t np = nq * C;
+    if (np == 0) return CHB_OK;
+    std::vector<int32_t> q32((size_t)nq), idx32((size_t)np * k);
+    std::vector<int2> work((size_t)np);
+    for (int64_t i = 0; i < nq; ++i) {
+        CHB_CHECK(c, queries[i] >= 0 && queries[i] < c->n, CHB_EINVAL, "query index out of range");
+        q32[(size_t)i] = (int32_t)queries[i];
+    }
+    for (int64_t i = 0; i < np; ++i) {
+        CHB_CHECK(c, m[i] >= 0 && m[i] <= k, CHB_EINVAL, "m[%lld] = %d outside [0, k=%d]", (long long)i, m[i], k);
+        for (int32_t s = 0; s < k; ++s) {
+            const int64_t v = idx[i * k + s];
+            CHB_CHECK(c, s >= m[i] || (v >= 0 && v < c->n), CHB_EINVAL, "neighbour index out of range");
+            idx32[(size_t)(i * k + s)] = (int32_t)v;
+        }
+        work[(size_t)i] = make_int2((int)(i / C), (int)(i % C));
+    }
+    int32_t *d_q = nullptr, *d_idx = nullptr, *d_m = nullptr, *d_st = nullptr;
+    int2 *d_work = nullptr;
+    double *d_dist = nullptr, *d_alpha = nullptr;
+    int rc = CHB_OK;
+    do {
+        if ((rc = dev_alloc(c, &d_q, nq)) || (rc = dev_alloc(c, &d_idx, np * k)) || (rc = dev_alloc(c, &d_m, np)) ||
+            (rc = dev_alloc(c, &d_st, np)) || (rc = dev_alloc(c, &d_work, np)) || (rc = dev_alloc(c, &d_dist, np)))
+            break;
+        if (alpha_out && (rc = dev_alloc(c, &d_alpha, np * k))) break;
+        cudaMemcpyAsync(d_q, q32.data(), sizeof(int32_t) * (size_t)nq, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_idx, idx32.data(), sizeof(int32_t) * (size_t)np * k, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_m, m, sizeof(int32_t) * (size_t)np, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(d_work, work.data(), sizeof(int2) * (size_t)np, cudaMemcpyHostToDevice, c->stream);
+        chb_qp_args a{};
+        a.X = c->X; a.ldx = c->ldx; a.d = c->d; a.work = d_work; a.work_count = nullptr; a.n_work = np; a.row_point = d_q;
+        a.knn_idx = d_idx; a.knn_cnt = d_m; a.C = C; a.k = k; a.metric = c->metric; a.dist = d_dist; a.status = d_st;
+        a.alpha = d_alpha;
+        if ((rc = chb_launch_qp(c, a))) break;
+        c->tm.qps_solved += np;
+        cudaMemcpyAsync(dist_out, d_dist, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, c->stream);
+        if (status_out) cudaMemcpyAsync(status_out, d_st, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream);
+        if (alpha_out) cudaMemcpyAsync(alpha_out, d_alpha, sizeof(double) * (size_t)np * k, cudaMemcpyDeviceToHost, c->stream);
+        rc = sync_stream(c);
+    } while (0);
+    dev_free(&d_q); dev_free(&d_idx); dev_free(&d_m); dev_free(&d_st); dev_free(&d_work); dev_free(&d_dist); dev_free(&d_alpha);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+int chb_set_window(chb_ctx *c, int64_t window)
+{
+    CHB_CHECK(c, c && window >= 0, CHB_EINVAL, "bad window");
+    c->window = window;
+    return CHB_OK;
+}
+int64_t chb_get_window(chb_ctx *c) { return c ? (c->window > 0 ? c->window : c->U) : 0; }
+
+int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
+{
+    CHB_CHECK(c, c && (perm || U == 0), CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->labels_set && c->dist_ready, CHB_EINVAL, "iteration_begin: labels / distance matrix not set up");
+    CHB_CHECK(c, U == c->U, CHB_EINVAL, "permutation length %lld != number of points to assign %lld", (long long)U,
+              (long long)c->U);
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_TRY(ensure_caches(c));
+    std::vector<int32_t> p32((size_t)std::max<int64_t>(U, 1));
+    // positions this context owns, ascending (a context owns the queries of slots [u0, u1))
+    std::vector<int32_t> qs_host; // slot of point: recomputed from qpoint ordering (slots are ascending point order)
+    std::vector<int32_t> own32;
+    own32.reserve((size_t)(c->u1 - c->u0));
+    {
+        // qpoint is ascending, so slot(point) = rank of point among query points: build a lookup once per call
+        std::vector<int32_t> qp((size_t)std::max<int64_t>(U, 1));
+        if (U) CHB_CUDA(c, cudaMemcpyAsync(qp.data(), c->qpoint, sizeof(int32_t) * (size_t)U, cudaMemcpyDeviceToHost, c->stream));
+        CHB_TRY(sync_stream(c));
+        const int32_t lo_pt = (c->u1 > c->u0) ? qp[(size_t)c->u0] : 0;
+        const int32_t hi_pt = (c->u1 > c->u0) ? qp[(size_t)(c->u1 - 1)] : -1;
+        int64_t cnt = 0;
+        std::vector<char> seen((size_t)std::max<int64_t>(U, 1), 0);
+        for (int64_t p = 0; p < U; ++p) {
+            const int64_t pt = perm[p];
+            CHB_CHECK(c, pt >= 0 && pt < c->n, CHB_EINVAL, "permutation entry %lld out of range", (long long)pt);
+            const auto it = std::lower_bound(qp.begin(), qp.begin() + U, (int32_t)pt);
+            CHB_CHECK(c, it != qp.begin() + U && *it == (int32_t)pt, CHB_EINVAL,
+                      "permutation entry %lld is not an un-assigned point", (long long)pt);
+            const int64_t slot = it - qp.begin();
+            CHB_CHECK(c, !seen[(size_t)slot], CHB_EINVAL, "permutation repeats point %lld", (long long)pt);
+            seen[(size_t)slot] = 1;
+            p32[(size_t)p] = (int32_t)pt;
+            if (pt >= lo_pt && pt <= hi_pt) {
+                own32.push_back((int32_t)p);
+                c->own_pos_host[cnt++] = p;
+            }
+        }
+        c->n_own_pos = cnt;
+    }
+    if (U) {
+        CHB_CUDA(c, cudaMemcpyAsync(c->perm_pt, p32.data(), sizeof(int32_t) * (size_t)U, cudaMemcpyHostToDevice, c->stream));
+        if (!own32.empty())
+            CHB_CUDA(c, cudaMemcpyAsync(c->own_pos, own32.data(), sizeof(int32_t) * own32.size(), cudaMemcpyHostToDevice, c->stream));
+        set_pos_kernel<<<nblk(U, 256), 256, 0, c->stream>>>(c->perm_pt, U, c->pos);
+        CHB_CUDA(c, cudaGetLastError());
+        ++c->tm.launches_other;
+    }
+    CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    CHB_TRY(sync_stream(c)); // p32 / own32 are stack-owned
+    c->in_iteration = true;
+    c->tm.qps_reference += (c->u1 - c->u0) * c->C;
+    return CHB_OK;
+}
+
+int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
+{
+    CHB_CHECK(c, c && tent_dev, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->in_iteration, CHB_EINVAL, "round_run outside chb_iteration_begin/end");
+    CHB_CHECK(c, 0 <= lo && lo < hi && hi <= c->U, CHB_EINVAL, "round window [%lld,%lld) invalid", (long long)lo, (long long)hi);
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int64_t *ob = c->own_pos_host, *oe = c->own_pos_host + c->n_own_pos;
+    const int64_t b = std::lower_bound(ob, oe, lo) - ob, e = std::lower_bound(ob, oe, hi) - ob;
+    const int64_t cnt = e - b;
+    fill_i32_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, hi - lo, CHB_UNOWNED);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    ++c->tm.rounds;
+    if (cnt == 0) return CHB_OK;
+    CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));
+    const int64_t step = c->materialise ? cnt : c->scratch_rows;
+    int32_t *rows_tmp = nullptr;
+    if (!c->materialise) CHB_TRY(dev_alloc(c, &rows_tmp, step));
+    int rc = CHB_OK;
+    for (int64_t s0 = 0; s0 < cnt && rc == CHB_OK; s0 += step) {
+        const int64_t sc = std::min(step, cnt - s0);
+        cudaMemsetAsync(c->counters, 0, sizeof(int32_t), c->stream);
+        chb_knn_args a{};
+        a.row_stride = c->n; a.items = c->own_pos + b + s0; a.n_items = sc; a.mode = 0; a.perm_pt = c->perm_pt;
+        a.qslot = c->qslot; a.pos = c->pos; a.tent_pt = c->tent_pt; a.old_label = c->old_label; a.n = c->n; a.C = c->C;
+        a.k = c->k; a.u0 = c->u0; a.knn_idx = c->knn_idx; a.knn_cnt = c->knn_cnt; a.work = c->work;
+        a.work_count = c->counters;
+        if (c->materialise) {
+            a.rows = c->Dq;
+            a.row_is_item = 0;
+        } else {
+            gather_rows_kernel<<<nblk(sc, 256), 256, 0, c->stream>>>(c->own_pos + b + s0, c->perm_pt, sc, rows_tmp);
+            ++c->tm.launches_other;
+            if ((rc = chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch))) break;
+            a.rows = c->Dscratch;
+            a.row_is_item = 1;
+        }
+        if ((rc = chb_launch_knn_scan(c, a))) break;
+        chb_qp_args q{};
+        q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = sc * c->C;
+        q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
+        q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
+        if ((rc = chb_launch_qp(c, q))) break;
+        // bookkeeping of solved QPs (read back lazily together with the commit counters)
+        cudaMemcpyAsync(&c->counters_host[4], c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        if (!c->materialise || s0 + step < cnt) {
+            if ((rc = sync_stream(c))) break;
+            c->tm.qps_solved += c->counters_host[4];
+            c->counters_host[4] = 0;
+        }
+    }
+    if (rows_tmp) { cudaStreamSynchronize(c->stream); cudaFree(rows_tmp); }
+    if (rc) return rc;
+    {
+        chb_stage_timer t(c, CHB_ST_COMMIT);
+        argmin_kernel<<<nblk(cnt * 32, 256), 256, 0, c->stream>>>(c->own_pos + b, cnt, c->perm_pt, c->qslot, c->u0, c->pair_dist,
+                                                                  c->C, c->old_label, lo, tent_dev);
+    }
+    CHB_CUDA(c, cudaGetLastError());
+    return CHB_OK;
+}
+
+int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed)
+{
+    CHB_CHECK(c, c && tent_dev && first_changed, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->in_iteration, CHB_EINVAL, "round_commit outside chb_iteration_begin/end");
+    CHB_CHECK(c, 0 <= lo && lo < hi && hi <= c->U, CHB_EINVAL, "round window [%lld,%lld) invalid", (long long)lo, (long long)hi);
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_CUDA(c, cudaMemsetAsync(&c->counters[1], 0x7f, sizeof(int32_t), c->stream)); // 0x7f7f7f7f: above any position
+    {
+        chb_stage_timer t(c, CHB_ST_COMMIT);
+        commit_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters);
+    }
+    CHB_CUDA(c, cudaGetLastError());
+    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[1], &c->counters[1], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CHB_TRY(sync_stream(c));
+    c->tm.qps_solved += c->counters_host[4];
+    c->counters_host[4] = 0;
+    *first_changed = (c->counters_host[1] == 0x7f7f7f7f) ? -1 : (int64_t)c->counters_host[1];
+    return CHB_OK;
+}
+
+int chb_iteration_end(chb_ctx *c, int64_t *n_changed)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, c->in_iteration, CHB_EINVAL, "iteration_end without iteration_begin");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_CUDA(c, cudaMemsetAsync(&c->counters[2], 0, sizeof(int32_t), c->stream));
+    count_changed_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->old_label, c->tent_pt, c->n, c->counters);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[2], &c->counters[2], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->old_label, c->tent_pt, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    CHB_TRY(sync_stream(c));
+    if (n_changed) *n_changed = c->counters_host[2];
+    c->in_iteration = false;
+    return CHB_OK;
+}
+
+int chb_get_labels(chb_ctx *c, int64_t *labels_out)
+{
+    CHB_CHECK(c, c && labels_out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->labels_set, CHB_EINVAL, "labels not set");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    std::vector<int32_t> lab((size_t)c->n);
+    CHB_CUDA(c, cudaMemcpyAsync(lab.data(), c->in_iteration ? c->tent_pt : c->old_label, sizeof(int32_t) * (size_t)c->n,
+                                cudaMemcpyDeviceToHost, c->stream));
+    CHB_TRY(sync_stream(c));
+    for (int64_t i = 0; i < c->n; ++i) labels_out[i] = lab[(size_t)i];
+    return CHB_OK;
+}
+
+int chb_fit_iteration(chb_ctx *c, const int64_t *perm, int64_t U, int64_t *labels_out, int64_t *n_changed)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, c->u0 == 0 && c->u1 == c->U, CHB_EINVAL,
+              "chb_fit_iteration needs a context that owns every query slot; use the chb_round_* calls when sharded");
+    CHB_TRY(chb_iteration_begin(c, perm, U));
+    const int64_t W = chb_get_window(c);
+    if (U > 0) {
+        if (c->tent_win_cap < W) {
+            CHB_TRY(dev_alloc(c, &c->tent_win, W));
+            c->tent_win_cap = W;
+        }
+        int64_t lo = 0;
+        while (lo < U) {
+            const int64_t hi = std::min(U, lo + W);
+            CHB_TRY(chb_round_run(c, lo, hi, c->tent_win));
+            int64_t first = -1;
+            CHB_TRY(chb_round_commit(c, lo, hi, c->tent_win, &first));
+            lo = (first < 0) ? hi : first + 1;
+        }
+    }
+    CHB_TRY(chb_iteration_end(c, n_changed));
+    if (labels_out) CHB_TRY(chb_get_labels(c, labels_out));
+    return CHB_OK;
+}
+
+int chb_fit(chb_ctx *c, const int64_t *perms, int64_t U, int32_t max_iterations, int64_t *labels_out, int32_t *iterations_run,
+            int32_t *converged, int64_t *changed_per_iter)
+{
+    CHB_CHECK(c, c && (perms || U == 0 || max_iterations == 0), CHB_EINVAL, "NULL argument");
+    int32_t it = 0, conv = 0;
+    for (; it < max_iterations; ++it) {
+        int64_t nch = 0;
+        CHB_TRY(chb_fit_iteration(c, perms + (int64_t)it * U, U, nullptr, &nch));
+        if (changed_per_iter) changed_per_iter[it] = nch;
+        if (nch == 0) { conv = 1; ++it; break; } // algorithm.py:63-66
+    }
+    if (iterations_run) *iterations_run = it;
+    if (converged) *converged = conv;
+    if (labels_out) CHB_TRY(chb_get_labels(c, labels_out));
+    return CHB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,170 @@
+// common.cuh -- context, error handling and launch helpers shared by the sm_100a kernels of libchbin_b200.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "chbin_b200.h"
+
+#define CHB_WARP 32
+#define CHB_FULL 0xffffffffu
+#define CHB_KMAX 32          // largest AlgoNumNeighbors supported (one warp lane per neighbour slot)
+#define CHB_UNOWNED INT32_MIN // tentative-label sentinel for positions another rank owns
+
+struct chb_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    cudaStream_t own_stream = nullptr;
+    std::string err;
+
+    // ---- features: n x ldx float64, row pitch padded to 16 bytes, pad columns are zero
+    int64_t n = 0;
+    int32_t d = 0, ldx = 0;
+    double *X = nullptr;
+
+    // ---- labels / slots
+    int32_t C = 0;
+    int64_t U = 0, u0 = 0, u1 = 0; // all query slots, owned slice [u0,u1)
+    int32_t *old_label = nullptr;  // n : label at the start of the running iteration (seeds: fixed)
+    int32_t *tent_pt = nullptr;    // n : tentative label of this iteration, by point
+    int32_t *pos = nullptr;        // n : position in this iteration's permutation; -1 for seeds
+    int32_t *qslot = nullptr;      // n : query slot of the point or -1
+    int32_t *qpoint = nullptr;     // U : point of a slot
+    int32_t *perm_pt = nullptr;    // U : this iteration's permutation (point indices)
+    int32_t *own_pos = nullptr;    // n_own: ascending positions whose query this context owns
+    int64_t n_own_pos = 0;
+    int64_t *own_pos_host = nullptr;
+    bool labels_set = false, in_iteration = false;
+
+    // ---- parameters
+    int32_t k = 5, metric = CHB_METRIC_CONVEX;
+    bool params_dirty = true;
+
+    // ---- distances
+    bool dist_ready = false, materialise = false;
+    double *Dq = nullptr;       // (u1-u0) x n when materialised
+    double *Dscratch = nullptr; // scratch_rows x n otherwise
+    int64_t scratch_rows = 0;
+
+    // ---- per (owned slot, bin) caches
+    int32_t *knn_idx = nullptr;  // nown x C x k   canonical (distance, index) order
+    int32_t *knn_cnt = nullptr;  // nown x C       -1 = never computed
+    double *pair_dist = nullptr; // nown x C
+    int32_t *pair_status = nullptr;
+    int64_t cache_nown = 0;
+    int32_t cache_C = 0, cache_k = 0;
+
+    // ---- work list of dirty (slot_local, bin) pairs
+    int2 *work = nullptr;
+    int64_t work_cap = 0;
+    int32_t *counters = nullptr;      // [0] work count, [1] first changed position, [2] n_changed, [3] scratch
+    int32_t *counters_host = nullptr; // pinned mirror
+
+    int64_t window = 0;
+    int32_t *tent_win = nullptr; // window-sized tentative buffer for the single-context driver
+    int64_t tent_win_cap = 0;
+
+    // ---- timers: event pairs are recorded around launches and resolved lazily after a stream sync
+    bool timers_on = true;
+    chb_timers tm{};
+    struct pending_ev { cudaEvent_t e0, e1; int stage; };
+    std::vector<pending_ev> ev_pending;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_free;
+};
+
+void chb_resolve_timers(chb_ctx *ctx); // call only when the stream is known to be idle
+
+extern thread_local std::string g_chb_create_error;
+
+int chb_fail(chb_ctx *ctx, int code, const char *fmt, ...);
+
+#define CHB_CUDA(ctx, expr)                                                                             \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            return chb_fail(ctx, _e == cudaErrorMemoryAllocation ? CHB_ENOMEM : CHB_ECUDA, "%s: %s (%s:%d)", #expr, \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                               \
+    } while (0)
+
+#define CHB_CHECK(ctx, cond, code, ...)                     \
+    do {                                                    \
+        if (!(cond)) return chb_fail(ctx, code, __VA_ARGS__); \
+    } while (0)
+
+enum chb_stage { CHB_ST_DISTANCE = 0, CHB_ST_KNN = 1, CHB_ST_QP = 2, CHB_ST_COMMIT = 3, CHB_ST_OTHER = 4 };
+
+// Brackets one kernel launch with events when timers are on; resolved by chb_resolve_timers.
+struct chb_stage_timer {
+    chb_ctx *c;
+    chb_stage st;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    chb_stage_timer(chb_ctx *ctx, chb_stage s) : c(ctx), st(s)
+    {
+        if (!c->timers_on || st == CHB_ST_OTHER) return;
+        if (c->ev_free.empty()) {
+            cudaEventCreate(&e0);
+            cudaEventCreate(&e1);
+        } else {
+            e0 = c->ev_free.back().first;
+            e1 = c->ev_free.back().second;
+            c->ev_free.pop_back();
+        }
+        cudaEventRecord(e0, c->stream);
+    }
+    ~chb_stage_timer()
+    {
+        int64_t *cnt = st == CHB_ST_DISTANCE ? &c->tm.launches_distance
+                     : st == CHB_ST_KNN      ? &c->tm.launches_knn
+                     : st == CHB_ST_QP       ? &c->tm.launches_qp
+                     : st == CHB_ST_COMMIT   ? &c->tm.launches_commit
+                                             : &c->tm.launches_other;
+        ++*cnt;
+        if (e0) {
+            cudaEventRecord(e1, c->stream);
+            c->ev_pending.push_back({e0, e1, (int)st});
+        }
+    }
+};
+
+// ---- kernel launchers (each defined in its own .cu) ------------------------------------------------------
+// distance.cu : out[r*n + i] = cdist(X[rows[r]], X[i]) with the exact scipy recipe
+int chb_launch_distance_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, double *out_dev);
+
+// knn.cu
+struct chb_knn_args {
+    const double *rows;        // distance rows
+    int64_t row_stride;        // n
+    int row_is_item;           // 0: row index = owned slot of the query; 1: row index = item (scratch rows)
+    const int32_t *items;      // per CTA: position p (mode 0) or query point (mode 1)
+    int64_t n_items;
+    int mode;                  // 0 = round (effective labels from pos/tent/old), 1 = snapshot labels (old_label only)
+    const int32_t *perm_pt, *qslot, *pos, *tent_pt, *old_label;
+    int64_t n;
+    int32_t C, k;
+    int64_t u0;
+    int32_t *knn_idx, *knn_cnt; // caches (mode 0) or plain outputs indexed by item (mode 1)
+    int2 *work;
+    int32_t *work_count;
+};
+int chb_launch_knn_scan(chb_ctx *ctx, const chb_knn_args &a);
+
+// qp.cu
+struct chb_qp_args {
+    const double *X;
+    int32_t ldx, d;
+    const int2 *work;           // (row, c) pairs; row indexes knn/dist arrays
+    const int32_t *work_count;  // device count (may be nullptr -> n_work)
+    int64_t n_work;             // upper bound / exact count
+    const int32_t *row_point;   // point index of row (query)
+    const int32_t *knn_idx, *knn_cnt;
+    int32_t C, k, metric;
+    double *dist;
+    int32_t *status;
+    double *alpha; // optional rows x C x k
+};
+int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a);

@@ -1,0 +1,305 @@
+// qp.cu -- batched point-to-hull distance QPs, one warp per (query, bin) pair (sm_100a).
+//
+// Replaces, per pair, the whole chain
+//   calculate_distance -> convex_hull_distance   /root/reference/ch_bin/core/clustering/hull_distance.py:90-108, 7-35
+//   solve_qp -> _quadprog_solve_qp               /root/reference/ch_bin/core/clustering/solve_qp.py:96-132, 18-51
+//   nearest_positive_definite                    /root/reference/ch_bin/core/clustering/positive_def.py:25-48
+//   quadprog.solve_qp (third party, Goldfarb-Idnani)
+// i.e.   minimise || x - V' alpha ||^2   s.t.  alpha >= 0, sum(alpha) = 1,   return || alpha V - x ||_2
+// (the distance is recomputed from alpha in d dimensions exactly as hull_distance.py:34-35 does).
+//
+// Method.  With W = V - 1 x' the objective is alpha' G alpha, G = W W' (m x m, PSD): the minimum-norm point of
+// the hull of the rows of W.  Phase 1 forms G in FP64 (lane i accumulates row i from a shared-memory tile of W);
+// phase 2 runs Wolfe's finite active-set method on G -- lane i owns vertex i; the affine minimiser on the
+// current corral S solves (G_SS + s 11') y = 1 by Gauss-Jordan with rows distributed over lanes; affinely
+// dependent vertices (duplicate contigs) show up as a vanishing pivot and are banned, which leaves the distance
+// unchanged; phase 3 evaluates the residual norm in d dimensions from global memory.
+// The QP is strictly convex on the affine hull, so its distance is unique: any exact solver agrees with
+// quadprog to rounding; the parity bar is 1e-6 relative, this kernel is good to ~1e-12.
+//
+// Roofline: k neighbour rows (8kd bytes) per pair from L2/HBM against k(k+1)d + 4kd + 3d + 2k^3 FP64 flops.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int QP_WARPS = 4;
+constexpr int TC = 32;        // feature columns per staged tile
+constexpr int LDW = TC + 2;   // padded tile pitch (doubles), keeps double2 alignment
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(CHB_FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(CHB_FULL, v, o));
+    return v;
+}
+// minimum with the lowest lane winning ties
+__device__ __forceinline__ void warp_argmin(double &v, int &idx)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(CHB_FULL, v, o);
+        const int oi = __shfl_xor_sync(CHB_FULL, idx, o);
+        if (ov < v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+    }
+}
+
+// Solve (G_SS + s 11') y = 1 on the vertices in smask; rows over lanes, Gauss-Jordan without pivoting (SPD).
+// Returns the lane index of a vanishing pivot (affinely dependent vertex) or -1.  y is 0 outside S.
+template <int KMAX>
+__device__ __forceinline__ int affine_solve(const double *sG, double *sRow, unsigned smask, int m, double shift, int lane,
+                                            double &y)
+{
+    const bool in = (lane < m) && ((smask >> lane) & 1u);
+    double A[KMAX];
+    double rhs = in ? 1.0 : 0.0;
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c) {
+        const bool cin = (c < m) && ((smask >> c) & 1u);
+        A[c] = (in && cin) ? sG[lane * LDW + c] + shift : ((c == lane) ? 1.0 : 0.0);
+    }
+    int bad = -1;
+#pragma unroll
+    for (int j = 0; j < KMAX; ++j) {
+        if (j >= m || !((smask >> j) & 1u)) continue; // warp-uniform
+        if (lane == j) {
+#pragma unroll
+            for (int c = 0; c < KMAX; ++c) sRow[c] = A[c];
+            sRow[KMAX] = rhs;
+        }
+        __syncwarp();
+        const double piv = sRow[j];
+        const double ref = sG[j * LDW + j] + shift;
+        if (!(piv > 1e-11 * ref)) { bad = j; __syncwarp(); break; }
+        if (lane != j) {
+            const double f = A[j] / piv;
+#pragma unroll
+            for (int c = 0; c < KMAX; ++c)
+                if (c >= j) A[c] -= f * sRow[c];
+            rhs -= f * sRow[KMAX];
+        }
+        __syncwarp();
+    }
+    double diag = 1.0;
+#pragma unroll
+    for (int c = 0; c < KMAX; ++c)
+        if (c == lane) diag = A[c];
+    y = in ? rhs / diag : 0.0;
+    return bad;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
+{
+    __shared__ __align__(16) double sWall[QP_WARPS][KMAX * LDW];
+    __shared__ __align__(16) double sRowAll[QP_WARPS][KMAX + 2];
+    __shared__ __align__(16) double sAlphaAll[QP_WARPS][KMAX];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *sW = sWall[warp];
+    double *sRow = sRowAll[warp];
+    double *sAlpha = sAlphaAll[warp];
+    const int64_t n_work = a.work_count ? (int64_t)*a.work_count : a.n_work;
+    const int d = a.d, ldx = a.ldx, k = a.k, C = a.C;
+
+    for (int64_t item = (int64_t)blockIdx.x * QP_WARPS + warp; item < n_work; item += (int64_t)gridDim.x * QP_WARPS) {
+        const int2 wk = a.work[item];
+        const int64_t pair = (int64_t)wk.x * C + wk.y;
+        const int m = a.knn_cnt[pair];
+        if (m <= 0) {
+            if (lane == 0) {
+                a.dist[pair] = INFINITY;
+                if (a.status) a.status[pair] = CHB_QP_EMPTY_BIN;
+            }
+            continue;
+        }
+        const int jq = a.row_point[wk.x];
+        const int myidx = lane < m ? a.knn_idx[pair * k + lane] : 0;
+        const double *__restrict__ xq = a.X + (int64_t)jq * ldx;
+
+        // ---------------- phase 1: G = W W', lane i accumulates row i
+        double G[KMAX];
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) G[c] = 0.0;
+        for (int t0 = 0; t0 < d; t0 += TC) {
+            const int t = t0 + lane;
+            const bool tin = t < d;
+            const double xv = tin ? xq[t] : 0.0;
+#pragma unroll
+            for (int r = 0; r < KMAX; ++r) {
+                if (r < m) {
+                    const int ir = __shfl_sync(CHB_FULL, myidx, r);
+                    const double v = tin ? a.X[(int64_t)ir * ldx + t] : 0.0;
+                    sW[r * LDW + lane] = v - xv;
+                }
+            }
+            __syncwarp();
+            if (lane < m) {
+#pragma unroll 4
+                for (int tt = 0; tt < TC; tt += 2) {
+                    const double2 own = *reinterpret_cast<const double2 *>(&sW[lane * LDW + tt]);
+#pragma unroll
+                    for (int c = 0; c < KMAX; ++c) {
+                        if (c < m) {
+                            const double2 wc = *reinterpret_cast<const double2 *>(&sW[c * LDW + tt]);
+                            G[c] = fma(own.x, wc.x, G[c]);
+                            G[c] = fma(own.y, wc.y, G[c]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        // G to shared memory (the tile buffer is free now): sG[i][c] at sW[i*LDW + c]
+        double gii = 0.0;
+        if (lane < m) {
+#pragma unroll
+            for (int c = 0; c < KMAX; ++c) {
+                if (c < m) sW[lane * LDW + c] = G[c];
+                if (c == lane) gii = G[c];
+            }
+        }
+        __syncwarp();
+        const double *sG = sW;
+
+        // ---------------- phase 2: active set
+        const double scale = warp_max(lane < m ? gii : 0.0);
+        double alpha = 0.0;
+        int status = CHB_QP_OK;
+        if (!(scale > 0.0)) {
+            alpha = (lane == 0) ? 1.0 : 0.0; // every neighbour coincides with the query
+        } else if (a.metric == CHB_METRIC_AFFINE_QP) {
+            unsigned smask = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
+            for (int guard = 0; guard < m; ++guard) {
+                double y;
+                const int bad = affine_solve<KMAX>(sG, sRow, smask, m, scale, lane, y);
+                if (bad < 0) {
+                    const double sy = warp_sum(y);
+                    alpha = y / sy;
+                    break;
+                }
+                smask &= ~(1u << bad); // dependent vertex: same affine hull without it
+                status = CHB_QP_DEGENERATE;
+            }
+        } else {
+            const double tol = 1e-14 * scale;
+            double key = lane < m ? gii : DBL_MAX;
+            int start = lane;
+            warp_argmin(key, start);
+            alpha = (lane == start) ? 1.0 : 0.0;
+            unsigned smask = 1u << start, banned = 0u;
+            const int itmax = 3 * m + 8;
+            int it = 0;
+            for (; it < itmax; ++it) {
+                if (lane < KMAX) sAlpha[lane] = alpha;
+                __syncwarp();
+                double g = 0.0;
+                if (lane < m) {
+#pragma unroll
+                    for (int c = 0; c < KMAX; ++c)
+                        if (c < m) g = fma(sG[lane * LDW + c], sAlpha[c], g);
+                }
+                const double f = warp_sum(alpha * g);
+                const bool cand = (lane < m) && !((smask >> lane) & 1u) && !((banned >> lane) & 1u) && (g < f - tol);
+                double gk = cand ? g : DBL_MAX;
+                int jn = lane;
+                warp_argmin(gk, jn);
+                if (gk == DBL_MAX) break; // optimal
+                smask |= 1u << jn;
+                for (int minor = 0; minor <= m; ++minor) {
+                    double y;
+                    const int bad = affine_solve<KMAX>(sG, sRow, smask, m, scale, lane, y);
+                    if (bad >= 0) {
+                        smask &= ~(1u << jn);
+                        banned |= 1u << jn;
+                        status = CHB_QP_DEGENERATE;
+                        break;
+                    }
+                    const double beta = y / warp_sum(y);
+                    const bool in = (smask >> lane) & 1u;
+                    const bool neg = in && !(beta > 0.0);
+                    const unsigned negm = __ballot_sync(CHB_FULL, neg);
+                    if (!negm) {
+                        alpha = in ? beta : 0.0;
+                        break;
+                    }
+                    double th = DBL_MAX;
+                    if (neg) th = (alpha > 0.0) ? alpha / (alpha - beta) : 0.0;
+                    int lt = lane;
+                    warp_argmin(th, lt);
+                    th = fmin(fmax(th, 0.0), 1.0);
+                    alpha = in ? alpha + th * (beta - alpha) : 0.0;
+                    const bool drop = in && (lane == lt || !(alpha > 0.0));
+                    const unsigned dropm = __ballot_sync(CHB_FULL, drop);
+                    smask &= ~dropm;
+                    if (drop) alpha = 0.0;
+                    if ((dropm >> jn) & 1u) banned |= 1u << jn; // the entering vertex bounced straight out
+                    const double sa = warp_sum(alpha);
+                    alpha = alpha / sa;
+                    if (!((smask >> jn) & 1u)) break;
+                }
+            }
+            if (it >= itmax) status = CHB_QP_ITER_CAP;
+        }
+
+        // ---------------- phase 3: || alpha V - x ||  in d dimensions (hull_distance.py:34-35)
+        double ss = 0.0;
+        for (int t0 = 0; t0 < d; t0 += TC) {
+            const int t = t0 + lane;
+            const bool tin = t < d;
+            double pr = 0.0;
+#pragma unroll
+            for (int r = 0; r < KMAX; ++r) {
+                if (r < m) {
+                    const int ir = __shfl_sync(CHB_FULL, myidx, r);
+                    const double ar = __shfl_sync(CHB_FULL, alpha, r);
+                    const double v = tin ? a.X[(int64_t)ir * ldx + t] : 0.0;
+                    pr = fma(ar, v, pr);
+                }
+            }
+            const double df = tin ? pr - xq[t] : 0.0;
+            ss = fma(df, df, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) {
+            a.dist[pair] = sqrt(ss);
+            if (a.status) a.status[pair] = status;
+        }
+        if (a.alpha && lane < k) a.alpha[pair * k + lane] = lane < m ? alpha : 0.0;
+        __syncwarp();
+    }
+}
+
+template <int KMAX>
+int launch(chb_ctx *ctx, const chb_qp_args &a)
+{
+    int64_t blocks = (a.n_work + QP_WARPS - 1) / QP_WARPS;
+    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    {
+        chb_stage_timer t(ctx, CHB_ST_QP);
+        qp_kernel<KMAX><<<(unsigned)blocks, QP_WARPS * 32, 0, ctx->stream>>>(a);
+    }
+    CHB_CUDA(ctx, cudaGetLastError());
+    return CHB_OK;
+}
+
+} // namespace
+
+int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
+{
+    if (a.n_work <= 0) return CHB_OK;
+    CHB_CHECK(ctx, a.k >= 1 && a.k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d]", CHB_KMAX);
+    CHB_CHECK(ctx, a.metric == CHB_METRIC_CONVEX || a.metric == CHB_METRIC_AFFINE_QP, CHB_ENOTIMPL,
+              "Metric %d not implemented", a.metric);
+    if (a.k <= 8) return launch<8>(ctx, a);
+    if (a.k <= 16) return launch<16>(ctx, a);
+    return launch<32>(ctx, a);
+}

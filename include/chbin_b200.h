@@ -1,0 +1,144 @@
+/*
+ * chbin_b200.h -- C-ABI of libchbin_b200.so: the B200-native replacement for CH-Bin's clustering hot path.
+ *
+ * Every entry point below names the reference interface it replaces (paths relative to the reference tree,
+ * kdsuneraavinash/CH-Bin).  Plain C: pointers + sizes, no torch / numpy types.  Pointers are HOST memory
+ * unless the parameter name ends in `_dev`.  The context owns all device memory; the caller owns every
+ * buffer it passes; no pointer is retained after the call returns (except the stream handle).
+ * All functions return CHB_OK (0) or a CHB_E* code; chb_last_error() gives the message.
+ * One context = one CUDA device = one host thread at a time (the reference is single-threaded,
+ * ch_bin/core/clustering/algorithm.py:43-60).  Multi-GPU = one process and one context per GPU; the label
+ * exchange between ranks happens above this ABI (torch.distributed / NCCL on the *_dev buffers).
+ *
+ * There is no CPU fallback: chb_create fails with CHB_ENODEV when no sm_100 device is usable.
+ */
+#ifndef CHBIN_B200_H
+#define CHBIN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHB_ABI_VERSION 1
+
+enum {
+    CHB_OK = 0,
+    CHB_EINVAL = 1,    /* bad argument / call order          -> Python ValueError            */
+    CHB_ENODEV = 2,    /* no usable CUDA device              -> Python RuntimeError          */
+    CHB_ECUDA = 3,     /* CUDA runtime fault                 -> Python RuntimeError          */
+    CHB_ENOMEM = 4,    /* device allocation failed           -> Python MemoryError           */
+    CHB_ENOTIMPL = 5,  /* unsupported metric / solver        -> Python NotImplementedError   */
+                       /*   (hull_distance.py:108, solve_qp.py:132)                          */
+    CHB_EUNASSIGNED = 6 /* un-clustered points left           -> ValueError (cli/clustering.py:79-80) */
+};
+
+/* AlgoDistanceMetric (config/default.ini:18 -> hull_distance.py:90-108) */
+enum { CHB_METRIC_CONVEX = 0, CHB_METRIC_AFFINE_QP = 1 };
+
+/* per-QP status written by chb_hull_distance_batch (SURVEY.md 8(b) "Errors") */
+enum {
+    CHB_QP_OK = 0,
+    CHB_QP_DEGENERATE = 1, /* an affinely dependent neighbour set was met and handled          */
+    CHB_QP_ITER_CAP = 2,   /* active-set iteration cap hit; alpha feasible, near-optimal       */
+    CHB_QP_EMPTY_BIN = 3   /* m == 0: distance = +inf, never selected (algorithm.py:57 never fires) */
+};
+
+typedef struct chb_ctx chb_ctx;
+
+typedef struct chb_timers {
+    /* accumulated device time in milliseconds (CUDA events on the context's stream) and launch counts
+     * since chb_create / chb_reset_timers */
+    double ms_distance;  /* exact FP64 distance-row kernel (scipy cdist, distance_matrix.py:26,41)     */
+    double ms_knn;       /* label-segmented top-k scan (find_nearest_from_cluster, distance_matrix.py:47-62) */
+    double ms_qp;        /* batched hull-distance QP kernel (hull_distance.py:7-35 + solve_qp.py:18-51)  */
+    double ms_commit;    /* argmin over bins + ordered-commit check (algorithm.py:47-60)               */
+    int64_t launches_distance, launches_knn, launches_qp, launches_commit, launches_other;
+    int64_t qps_solved;     /* QPs actually solved on the device (includes speculative re-solves)  */
+    int64_t qps_reference;  /* QPs the reference would have solved: sum over iterations of U*C     */
+    int64_t rounds;         /* speculate/repair rounds executed                                    */
+    int64_t rows_scanned;   /* distance rows streamed by the kNN kernel                            */
+} chb_timers;
+
+/* ---- lifetime ---------------------------------------------------------------------------------------- */
+int chb_abi_version(void);
+/* device_id: CUDA ordinal.  Replaces nothing in the reference (it has no device); called by the
+ * AlgoQpSolver=b200 branch added at cli/clustering.py:56. */
+int chb_create(chb_ctx **out, int device_id);
+int chb_destroy(chb_ctx *ctx);
+const char *chb_last_error(const chb_ctx *ctx); /* ctx may be NULL: error of the last failed chb_create */
+/* Run every kernel on this cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int chb_set_stream(chb_ctx *ctx, void *cuda_stream);
+int chb_synchronize(chb_ctx *ctx);
+int chb_get_timers(chb_ctx *ctx, chb_timers *out);
+int chb_reset_timers(chb_ctx *ctx);
+/* enable=1: bracket every kernel with CUDA events (adds two event records per launch). Default 1. */
+int chb_enable_timers(chb_ctx *ctx, int enable);
+
+/* ---- problem set-up ---------------------------------------------------------------------------------- */
+/* `samples` of fit_cluster (algorithm.py:13): n x d float64, ROW-major (the Python wrapper converts the
+ * F-ordered DataFrame.values of cli/clustering.py:53).  Copied to the device in a 16-byte-pitched layout. */
+int chb_set_features(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
+int chb_set_features_dev(chb_ctx *ctx, const double *x_rowmajor_dev, int64_t n, int32_t d);
+/* `initial_bins` + `num_clusters` of fit_cluster (algorithm.py:14-15): int64, -1 = to be assigned.
+ * Defines points_to_assign = where(initial_bins == -1) (algorithm.py:38), ascending: "query slot" u is the
+ * u-th such point.  [slot_begin, slot_end) is the slice of query slots THIS context owns (multi-GPU query
+ * sharding); pass 0, -1 for all. */
+int chb_set_labels(chb_ctx *ctx, const int64_t *initial_bins, int64_t n, int32_t num_clusters, int64_t slot_begin,
+                   int64_t slot_end);
+/* num_neighbors / metric of fit_cluster (algorithm.py:17,19). */
+int chb_set_params(chb_ctx *ctx, int32_t num_neighbors, int32_t metric);
+/* create_in_mem_distance_matrix / create_distance_matrix (distance_matrix.py:12-44) for the owned query
+ * rows.  materialise=1: rows are computed once (exact cdist recipe) and kept in HBM (InMemDistMatrix=yes,
+ * cli/clustering.py:57-59); fails with CHB_ENOMEM if they do not fit.  materialise=0: nothing is stored,
+ * distances are recomputed bit-identically inside the kNN scan whenever consulted (stands in for the
+ * on-disk memmap of cli/clustering.py:61-63). */
+int chb_build_distance_matrix(chb_ctx *ctx, int materialise);
+/* Copy distance rows of query slots [slot0, slot0+nrows) (must be owned) to the host: nrows x n float64. */
+int chb_get_distance_rows(chb_ctx *ctx, int64_t slot0, int64_t nrows, double *out);
+
+/* ---- building blocks (parity-testable stages) -------------------------------------------------------- */
+/* find_nearest_from_cluster (distance_matrix.py:47-62) for every bin at once, against an explicit label
+ * vector `labels` (int64, n; the query itself is always excluded, algorithm.py:50).  queries: point indices
+ * that are owned query slots' points.  idx_out: nq*C*k int64, padded with -1, each list in canonical
+ * (distance, index) order; m_out: nq*C int32 = min(k, |bin|). */
+int chb_knn_per_bin(chb_ctx *ctx, const int64_t *labels, const int64_t *queries, int64_t nq, int64_t *idx_out,
+                    int32_t *m_out);
+/* calculate_distance / convex_hull_distance (hull_distance.py:7-35,90-108) for nq*C (query, bin) pairs with
+ * given neighbour lists (layout as chb_knn_per_bin's output).  dist_out: nq*C float64 (+inf where m == 0);
+ * status_out: nq*C int32 (may be NULL); alpha_out: nq*C*k float64 (may be NULL). */
+int chb_hull_distance_batch(chb_ctx *ctx, const int64_t *queries, int64_t nq, const int64_t *idx, const int32_t *m,
+                            double *dist_out, int32_t *status_out, double *alpha_out);
+
+/* ---- the assignment loop (algorithm.py:43-72) --------------------------------------------------------- */
+/* One iteration of fit_cluster's outer loop for the permutation `perm` (U int64 point indices = this
+ * iteration's np.random.permutation(points_to_assign), algorithm.py:45).  Single-context form: runs the
+ * speculate/repair rounds to the exact sequential fixed point, commits, and reports n_changed =
+ * sum(initial_bins != curr_bins) (algorithm.py:63,68).  labels_out (n int64) may be NULL. */
+int chb_fit_iteration(chb_ctx *ctx, const int64_t *perm, int64_t U, int64_t *labels_out, int64_t *n_changed);
+/* Whole fit_cluster (algorithm.py:12-76): perms = max_iterations x U.  iterations_run / converged mirror the
+ * loop's break (algorithm.py:64-66) and for-else (algorithm.py:74-75); changed_per_iter: max_iterations. */
+int chb_fit(chb_ctx *ctx, const int64_t *perms, int64_t U, int32_t max_iterations, int64_t *labels_out,
+            int32_t *iterations_run, int32_t *converged, int64_t *changed_per_iter);
+int chb_get_labels(chb_ctx *ctx, int64_t *labels_out);
+
+/* Multi-context (one per GPU) form of one iteration; the caller merges `tent_dev` across ranks between
+ * chb_round_run and chb_round_commit (all-reduce MAX over int32; un-owned entries hold INT32_MIN).
+ *   chb_iteration_begin(perm)                 once per iteration
+ *   repeat: chb_round_run(lo, hi, tent_dev)   tentative labels of the owned positions in [lo, hi)
+ *           <all-reduce MAX tent_dev[0 .. hi-lo)>
+ *           chb_round_commit(lo, hi, tent_dev, &first_changed)   -> next lo = first_changed+1, or hi if -1
+ *   chb_iteration_end(&n_changed)
+ * window: suggested hi-lo (chb_get_window). */
+int chb_iteration_begin(chb_ctx *ctx, const int64_t *perm, int64_t U);
+int chb_round_run(chb_ctx *ctx, int64_t lo, int64_t hi, int32_t *tent_dev);
+int chb_round_commit(chb_ctx *ctx, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed);
+int chb_iteration_end(chb_ctx *ctx, int64_t *n_changed);
+int chb_set_window(chb_ctx *ctx, int64_t window); /* 0 = whole iteration */
+int64_t chb_get_window(chb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHBIN_B200_H */

@@ -1,0 +1,178 @@
+"""
+GPU parity tests proper: every check goes through the C-ABI (chbin_b200.capi.Context -> libchbin_b200.so) and is
+compared with the CPU oracle (oracle/*.c) on the same seeded inputs.  Bars: bit-exact for distances, kNN index
+sets and labels; |d_gpu - d_ref| <= 1e-6*d_ref + 1e-12*||x|| for hull distances.
+"""
+import numpy as np
+import pytest
+
+import chbin_b200
+import oracle
+from chbin_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _ctx(X, bins, C, k, metric="convex", materialise=True, slots=(0, -1)):
+    ctx = capi.Context(0)
+    ctx.set_features(X)
+    ctx.set_labels(bins, C, *slots)
+    ctx.set_params(k, metric)
+    ctx.build_distance_matrix(materialise)
+    return ctx
+
+
+@pytest.mark.parametrize("n,d_extra", [(300, 1), (1000, 10), (257, 3)])
+def test_distance_rows_bit_exact(n, d_extra):
+    X, bins, _ = synth.make_contig_features(n, 4, d_extra, 10, seed=3)
+    D = oracle.create_in_mem_distance_matrix(X)
+    pts = np.where(bins == -1)[0]
+    for mat in (True, False):
+        with _ctx(X, bins, 4, 5, materialise=mat) as ctx:
+            rows = ctx.get_distance_rows(0, len(pts))
+        assert rows.shape == (len(pts), n)
+        assert np.array_equal(rows, D[pts]), "distance rows differ from the scipy-cdist recipe"
+
+
+@pytest.mark.parametrize("k", [1, 3, 5, 10, 32])
+def test_knn_per_bin_exact(k):
+    n, C = 1500, 7
+    X, bins, truth = synth.make_contig_features(n, C, 1, 12, seed=5)
+    rng = np.random.default_rng(k)
+    labels = truth.copy()
+    labels[rng.random(n) < 0.3] = -1            # a mix of assigned / unassigned
+    labels[truth == 6] = -1
+    labels[np.where(truth == 6)[0][:2]] = 6     # a bin smaller than k
+    D = oracle.create_in_mem_distance_matrix(X)
+    queries = rng.choice(n, 64, replace=False)
+    with _ctx(X, bins, C, k) as ctx:
+        idx, m = ctx.knn_per_bin(labels, queries)
+    for qi, q in enumerate(queries):
+        lab = labels.copy()
+        lab[q] = -1                              # algorithm.py:50
+        for c in range(C):
+            ref = oracle.find_nearest_from_cluster(c, lab, D[q], k)
+            got = idx[qi, c, : m[qi, c]]
+            assert m[qi, c] == len(ref)
+            assert np.array_equal(np.sort(got), np.sort(ref)), (q, c)
+            assert np.all(idx[qi, c, m[qi, c]:] == -1)
+
+
+def _hull_case(X, rng, k, nq, C):
+    n = len(X)
+    queries = rng.choice(n, nq, replace=False)
+    idx = np.full((nq, C, k), -1, dtype=np.int64)
+    m = np.zeros((nq, C), dtype=np.int32)
+    for qi in range(nq):
+        for c in range(C):
+            mm = int(rng.integers(0, k + 1)) if c == 0 else k
+            m[qi, c] = mm
+            cand = np.setdiff1d(np.arange(n), [queries[qi]])
+            idx[qi, c, :mm] = rng.choice(cand, mm, replace=False)
+    return queries, idx, m
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 5, 8, 10, 16, 32])
+def test_hull_distance_vs_oracle(k):
+    n, C = 800, 6
+    X, bins, _ = synth.make_contig_features(n, C, 1 if k <= 5 else 10, 20, seed=11)
+    rng = np.random.default_rng(100 + k)
+    queries, idx, m = _hull_case(X, rng, k, 48, C)
+    with _ctx(X, bins, C, k) as ctx:
+        dist, status, alpha = ctx.hull_distance_batch(queries, idx, m, want_alpha=True)
+    for qi, q in enumerate(queries):
+        for c in range(C):
+            mm = m[qi, c]
+            if mm == 0:
+                assert np.isinf(dist[qi, c]) and status[qi, c] == 3
+                continue
+            ref = oracle.convex_hull_distance(X[q], X[idx[qi, c, :mm]])
+            tol = 1e-6 * ref + 1e-12 * np.linalg.norm(X[q])
+            assert abs(dist[qi, c] - ref) <= tol, (q, c, mm, dist[qi, c], ref)
+            a = alpha[qi, c, :mm]
+            assert abs(a.sum() - 1) < 1e-10 and a.min() >= 0.0
+
+
+def test_hull_distance_degenerate_duplicates():
+    # duplicated neighbour rows and a query identical to a neighbour (hard part 3)
+    n, C, k = 400, 3, 5
+    X, bins, _ = synth.make_contig_features(n, C, 1, 10, seed=2)
+    X[10] = X[11]
+    X[12] = X[11]
+    X[50] = X[51]
+    queries = np.array([0, 51], dtype=np.int64)
+    idx = np.full((2, C, k), -1, dtype=np.int64)
+    m = np.zeros((2, C), dtype=np.int32)
+    idx[0, 0] = [10, 11, 12, 13, 14]; m[0, 0] = 5
+    idx[0, 1, :3] = [10, 11, 12]; m[0, 1] = 3
+    idx[0, 2, :2] = [20, 21]; m[0, 2] = 2
+    idx[1, 0] = [50, 60, 61, 62, 63]; m[1, 0] = 5
+    idx[1, 1, :1] = [50]; m[1, 1] = 1
+    idx[1, 2, :4] = [10, 11, 70, 71]; m[1, 2] = 4
+    with _ctx(X, bins, C, k) as ctx:
+        dist, status = ctx.hull_distance_batch(queries, idx, m)
+    for qi, q in enumerate(queries):
+        for c in range(C):
+            ref = oracle.convex_hull_distance(X[q], X[idx[qi, c, : m[qi, c]]])
+            scale = np.linalg.norm(X[idx[qi, c, 0]] - X[q]) + 1e-300
+            assert abs(dist[qi, c] - ref) <= 1e-6 * ref + 1e-7 * scale, (qi, c, dist[qi, c], ref)
+    assert dist[1, 0] <= 1e-9 and dist[1, 1] <= 1e-12
+
+
+def test_affine_qp_metric():
+    n, C, k = 500, 4, 6
+    X, bins, _ = synth.make_contig_features(n, C, 3, 15, seed=4)
+    rng = np.random.default_rng(9)
+    queries, idx, m = _hull_case(X, rng, k, 24, C)
+    m[m == 0] = 1
+    for qi in range(len(queries)):
+        for c in range(C):
+            if idx[qi, c, 0] < 0:
+                idx[qi, c, 0] = (queries[qi] + 1) % n
+    with _ctx(X, bins, C, k, metric="affine-qp") as ctx:
+        dist, status = ctx.hull_distance_batch(queries, idx, m)
+    for qi, q in enumerate(queries):
+        for c in range(C):
+            ref = oracle.affine_hull_distance_qp(X[q], X[idx[qi, c, : m[qi, c]]])
+            assert abs(dist[qi, c] - ref) <= 1e-6 * ref + 1e-12, (qi, c)
+
+
+FIT_CASES = [
+    # n, C, S, n_seed, k, concentration, window, materialise
+    (600, 5, 1, 40, 5, 4000.0, 0, True),
+    (1500, 8, 1, 30, 5, 60.0, 0, True),      # hard, overlapping genomes: many repair rounds, 10 iterations
+    (1500, 8, 1, 30, 5, 60.0, 97, True),     # same with a small window
+    (1200, 6, 10, 25, 10, 300.0, 0, False),  # k = 10, rows recomputed on demand (InMemDistMatrix = no)
+    (900, 4, 3, 3, 7, 500.0, 0, True),       # bins smaller than k at the start
+]
+
+
+@pytest.mark.parametrize("n,C,S,n_seed,k,conc,window,mat", FIT_CASES)
+def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat):
+    X, bins, _ = synth.make_contig_features(n, C, S, n_seed, seed=7, concentration=conc)
+    perms = oracle.draw_permutations(bins, 10, seed=0)
+    ref, info = oracle.fit_cluster(X, C, bins, None, k, 10, perms=perms, return_info=True, threads=4)
+    np.random.seed(0)
+    bins_before = bins.copy()
+    got, ginfo = chbin_b200.fit_cluster(X, C, bins, None, k, 10, "convex", "b200", in_mem_dist_matrix=mat,
+                                        window=window, return_info=True)
+    assert np.array_equal(bins, bins_before), "inputs must not be mutated (algorithm.py:37)"
+    assert got.dtype == np.int64
+    assert ginfo["iterations"] == info["iterations"] and ginfo["converged"] == info["converged"]
+    assert list(ginfo["changed"]) == list(info["changed"])
+    assert np.array_equal(got, ref)
+
+
+def test_fit_cluster_fortran_order_and_errors():
+    X, bins, _ = synth.make_contig_features(400, 3, 1, 20, seed=1)
+    perms = oracle.draw_permutations(bins, 10, seed=0)
+    ref = oracle.fit_cluster(X, 3, bins, None, 5, 10, perms=perms)
+    np.random.seed(0)
+    got = chbin_b200.fit_cluster(np.asfortranarray(X), np.int64(3), bins, None, 5, 10)  # DataFrame.values is F-ordered
+    assert np.array_equal(got, ref)
+    with pytest.raises(NotImplementedError):
+        chbin_b200.fit_cluster(X, 3, bins, None, 5, 10, metric="cosine")
+    with pytest.raises(NotImplementedError):
+        chbin_b200.fit_cluster(X, 3, bins, None, 5, 10, qp_solver="quadprog")
+    with pytest.raises(ValueError):
+        chbin_b200.fit_cluster(X, 3, bins, None, 64, 10)
