@@ -114,7 +114,7 @@ def test_hull_distance_degenerate_duplicates():
     for qi, q in enumerate(queries):
         for c in range(C):
             ref = oracle.convex_hull_distance(X[q], X[idx[qi, c, : m[qi, c]]])
-            scale = np.linalg.norm(X[idx[qi, c, 0]] - X[q]) + 1e-300
+            scale = np.linalg.norm(X[idx[qi, c, : m[qi, c]]] - X[q], axis=1).max() + np.linalg.norm(X[q])
             assert abs(dist[qi, c] - ref) <= 1e-6 * ref + 1e-7 * scale, (qi, c, dist[qi, c], ref)
     assert dist[1, 0] <= 1e-9 and dist[1, 1] <= 1e-12
 
