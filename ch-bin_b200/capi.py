@@ -23,6 +23,7 @@ EXPORTED_SYMBOLS = [
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
+    "chb_measure_fp64_tflops",
 ]
 
 
@@ -90,6 +91,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_window.argtypes = [_vp, _i64]
     L.chb_get_window.argtypes = [_vp]
     L.chb_get_window.restype = _i64
+    L.chb_measure_fp64_tflops.argtypes = [_vp, ctypes.POINTER(_dbl)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("chb_last_error", "chb_get_window"):
@@ -264,6 +266,11 @@ class Context:
         first = _i64(-1)
         self._check(self._lib.chb_round_commit(self._h, lo, hi, _vp(tent_dev_ptr), ctypes.byref(first)))
         return int(first.value)
+
+    def measure_fp64_tflops(self) -> float:
+        v = _dbl(0.0)
+        self._check(self._lib.chb_measure_fp64_tflops(self._h, ctypes.byref(v)))
+        return float(v.value)
 
     def iteration_end(self) -> int:
         nch = _i64(0)

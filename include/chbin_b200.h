@@ -138,6 +138,10 @@ int chb_iteration_end(chb_ctx *ctx, int64_t *n_changed);
 int chb_set_window(chb_ctx *ctx, int64_t window); /* 0 = whole iteration */
 int64_t chb_get_window(chb_ctx *ctx);
 
+/* ---- measurement aid (bench.py only) ------------------------------------------------------------------ */
+/* DFMA-saturating microbenchmark: measured FP64 pipe peak of this device in TFLOP/s (FMA = 2 flop). */
+int chb_measure_fp64_tflops(chb_ctx *ctx, double *tflops);
+
 #ifdef __cplusplus
 }
 #endif
