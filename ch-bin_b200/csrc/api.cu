@@ -66,6 +66,16 @@ int dev_alloc(chb_ctx *ctx, T **p, int64_t count)
     }
     return CHB_OK;
 }
+// grow-only allocation: keeps the buffer when it is already large enough
+template <typename T>
+int dev_reserve(chb_ctx *ctx, T **p, int64_t *cap, int64_t count)
+{
+    if (*p && *cap >= count) return CHB_OK;
+    *cap = 0;
+    int rc = dev_alloc(ctx, p, count);
+    if (rc == CHB_OK) *cap = count;
+    return rc;
+}
 template <typename T>
 void dev_free(T **p)
 {
@@ -156,10 +166,13 @@ int ensure_caches(chb_ctx *c)
 {
     const int64_t nown = c->u1 - c->u0;
     if (c->cache_nown == nown && c->cache_C == c->C && c->cache_k == c->k && c->knn_idx) return CHB_OK;
-    CHB_TRY(dev_alloc(c, &c->knn_idx, nown * c->C * c->k));
-    CHB_TRY(dev_alloc(c, &c->knn_cnt, nown * c->C));
-    CHB_TRY(dev_alloc(c, &c->pair_dist, nown * c->C));
-    CHB_TRY(dev_alloc(c, &c->pair_status, nown * c->C));
+    CHB_TRY(dev_reserve(c, &c->knn_idx, &c->cap_knn, nown * c->C * c->k));
+    if (c->cap_pairs < nown * c->C) {
+        CHB_TRY(dev_alloc(c, &c->knn_cnt, nown * c->C));
+        CHB_TRY(dev_alloc(c, &c->pair_dist, nown * c->C));
+        CHB_TRY(dev_alloc(c, &c->pair_status, nown * c->C));
+        c->cap_pairs = nown * c->C;
+    }
     c->cache_nown = nown;
     c->cache_C = c->C;
     c->cache_k = c->k;
@@ -245,7 +258,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->X); dev_free(&c->old_label); dev_free(&c->tent_pt); dev_free(&c->pos); dev_free(&c->qslot);
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
-    dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win);
+    dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -308,7 +321,6 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     CHB_TRY(sync_stream(c));
     c->dist_ready = false;
     c->labels_set = false;
-    dev_free(&c->Dq);
     return CHB_OK;
 }
 
@@ -348,15 +360,24 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     c->U = U;
     c->u0 = slot_begin;
     c->u1 = slot_end;
-    CHB_TRY(dev_alloc(c, &c->old_label, n));
-    CHB_TRY(dev_alloc(c, &c->tent_pt, n));
-    CHB_TRY(dev_alloc(c, &c->pos, n));
-    CHB_TRY(dev_alloc(c, &c->qslot, n));
-    CHB_TRY(dev_alloc(c, &c->qpoint, std::max<int64_t>(U, 1)));
-    CHB_TRY(dev_alloc(c, &c->perm_pt, std::max<int64_t>(U, 1)));
-    CHB_TRY(dev_alloc(c, &c->own_pos, std::max<int64_t>(slot_end - slot_begin, 1)));
-    delete[] c->own_pos_host;
-    c->own_pos_host = new int64_t[(size_t)std::max<int64_t>(slot_end - slot_begin, 1)];
+    if (c->cap_n < n) {
+        CHB_TRY(dev_alloc(c, &c->old_label, n));
+        CHB_TRY(dev_alloc(c, &c->tent_pt, n));
+        CHB_TRY(dev_alloc(c, &c->pos, n));
+        CHB_TRY(dev_alloc(c, &c->qslot, n));
+        c->cap_n = n;
+    }
+    if (c->cap_U < std::max<int64_t>(U, 1)) {
+        CHB_TRY(dev_alloc(c, &c->qpoint, std::max<int64_t>(U, 1)));
+        CHB_TRY(dev_alloc(c, &c->perm_pt, std::max<int64_t>(U, 1)));
+        c->cap_U = std::max<int64_t>(U, 1);
+    }
+    if (c->cap_own < std::max<int64_t>(slot_end - slot_begin, 1)) {
+        CHB_TRY(dev_alloc(c, &c->own_pos, std::max<int64_t>(slot_end - slot_begin, 1)));
+        delete[] c->own_pos_host;
+        c->own_pos_host = new int64_t[(size_t)std::max<int64_t>(slot_end - slot_begin, 1)];
+        c->cap_own = std::max<int64_t>(slot_end - slot_begin, 1);
+    }
     CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -368,7 +389,6 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     c->labels_set = true;
     c->in_iteration = false;
     c->dist_ready = false;
-    dev_free(&c->Dq);
     c->cache_nown = -1; // force cache re-initialisation
     return CHB_OK;
 }
@@ -391,11 +411,11 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
     CHB_CHECK(c, c->labels_set, CHB_EINVAL, "build_distance_matrix: call chb_set_features and chb_set_labels first");
     CHB_CUDA(c, cudaSetDevice(c->device));
     const int64_t nown = c->u1 - c->u0;
-    dev_free(&c->Dq);
-    dev_free(&c->Dscratch);
     c->materialise = materialise != 0;
     if (c->materialise) {
-        CHB_TRY(dev_alloc(c, &c->Dq, nown * c->n));
+        dev_free(&c->Dscratch);
+        c->cap_scratch = 0;
+        CHB_TRY(dev_reserve(c, &c->Dq, &c->cap_Dq, nown * c->n));
         const int64_t step = 65535LL * 64;
         for (int64_t r0 = 0; r0 < nown; r0 += step)
             CHB_TRY(chb_launch_distance_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Dq + r0 * c->n));
@@ -404,7 +424,9 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
         // scratch for recomputed rows: ~1 GiB, at least 64 rows
         int64_t rows = (1LL << 30) / (8 * c->n);
         rows = std::max<int64_t>(64, std::min<int64_t>(rows, std::max<int64_t>(nown, 64)));
-        CHB_TRY(dev_alloc(c, &c->Dscratch, rows * c->n));
+        dev_free(&c->Dq);
+        c->cap_Dq = 0;
+        CHB_TRY(dev_reserve(c, &c->Dscratch, &c->cap_scratch, rows * c->n));
         c->scratch_rows = rows;
     }
     c->dist_ready = true;

@@ -65,6 +65,12 @@ struct chb_ctx {
     int32_t *counters = nullptr;      // [0] work count, [1] first changed position, [2] n_changed, [3] scratch
     int32_t *counters_host = nullptr; // pinned mirror
 
+    // capacities (elements) of the re-usable allocations above, so that repeated set-ups do not re-malloc
+    int64_t cap_n = 0, cap_U = 0, cap_own = 0, cap_Dq = 0, cap_scratch = 0, cap_pairs = 0, cap_knn = 0;
+
+    int2 *fallback = nullptr; // pairs the small-k QP kernel hands to the general one
+    int64_t fallback_cap = 0;
+
     int64_t window = 0;
     int32_t *tent_win = nullptr; // window-sized tentative buffer for the single-context driver
     int64_t tent_win_cap = 0;
@@ -168,3 +174,5 @@ struct chb_qp_args {
     double *alpha; // optional rows x C x k
 };
 int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a);
+// qp_small.cu : k <= 5 fast path; ill-conditioned pairs are appended to `fallback`
+int chb_launch_qp_small(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count);

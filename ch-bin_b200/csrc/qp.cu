@@ -277,10 +277,10 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
 }
 
 template <int KMAX>
-int launch(chb_ctx *ctx, const chb_qp_args &a)
+int launch(chb_ctx *ctx, const chb_qp_args &a, int blocks_per_sm = 16)
 {
     int64_t blocks = (a.n_work + QP_WARPS - 1) / QP_WARPS;
-    const int64_t cap = (int64_t)ctx->sm_count * 16;
+    const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     {
@@ -299,6 +299,27 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
     CHB_CHECK(ctx, a.k >= 1 && a.k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d]", CHB_KMAX);
     CHB_CHECK(ctx, a.metric == CHB_METRIC_CONVEX || a.metric == CHB_METRIC_AFFINE_QP, CHB_ENOTIMPL,
               "Metric %d not implemented", a.metric);
+    if (a.k <= 5 && a.metric == CHB_METRIC_CONVEX) {
+        // fast path; pairs whose a'Ga is too small to trust go through the general kernel afterwards
+        if (ctx->fallback_cap < a.n_work) {
+            if (ctx->fallback) cudaFree(ctx->fallback);
+            ctx->fallback = nullptr;
+            cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->fallback), sizeof(int2) * (size_t)a.n_work);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                ctx->fallback_cap = 0;
+                return chb_fail(ctx, CHB_ENOMEM, "cudaMalloc of the QP fallback list failed: %s", cudaGetErrorString(e));
+            }
+            ctx->fallback_cap = a.n_work;
+        }
+        CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[3], 0, sizeof(int32_t), ctx->stream));
+        int rc = chb_launch_qp_small(ctx, a, ctx->fallback, &ctx->counters[3]);
+        if (rc != CHB_OK) return rc;
+        chb_qp_args b = a;
+        b.work = ctx->fallback;
+        b.work_count = &ctx->counters[3];
+        return launch<8>(ctx, b, 1);
+    }
     if (a.k <= 8) return launch<8>(ctx, a);
     if (a.k <= 16) return launch<16>(ctx, a);
     return launch<32>(ctx, a);
