@@ -23,7 +23,7 @@ EXPORTED_SYMBOLS = [
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
-    "chb_measure_fp64_tflops",
+    "chb_measure_fp64_tflops", "chb_set_distance_mode",
 ]
 
 
@@ -78,6 +78,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_labels.argtypes = [_vp, _vp, _i64, _i32, _i64, _i64]
     L.chb_set_params.argtypes = [_vp, _i32, _i32]
     L.chb_build_distance_matrix.argtypes = [_vp, ctypes.c_int]
+    L.chb_set_distance_mode.argtypes = [_vp, ctypes.c_int]
     L.chb_get_distance_rows.argtypes = [_vp, _i64, _i64, _vp]
     L.chb_knn_per_bin.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
     L.chb_hull_distance_batch.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
@@ -195,6 +196,10 @@ class Context:
             raise NotImplementedError(f"Metric {metric} not implemented")
         self.k = int(num_neighbors)
         self._check(self._lib.chb_set_params(self._h, int(num_neighbors), METRICS[metric]))
+
+    def set_distance_mode(self, mode: int):
+        """1 = FP32 candidate filter + exact FP64 re-rank (default), 0 = exact FP64 rows."""
+        self._check(self._lib.chb_set_distance_mode(self._h, int(mode)))
 
     def build_distance_matrix(self, materialise: bool = True):
         self._check(self._lib.chb_build_distance_matrix(self._h, int(bool(materialise))))

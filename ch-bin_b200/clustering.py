@@ -147,6 +147,7 @@ def fit_cluster(
     device: Optional[int] = None,
     window: int = 0,
     return_info: bool = False,
+    distance_mode: int = 1,
 ):
     """
     Cevikalp et al. 2019 convex-hull binning specialised for metagenomic binning, on B200.
@@ -190,6 +191,7 @@ def fit_cluster(
         ctx.set_labels(curr, int(num_clusters), u0, u1)
         ctx.set_params(int(num_neighbors), metric)
         ctx.set_window(int(window))
+        ctx.set_distance_mode(int(distance_mode))
         ctx.build_distance_matrix(bool(in_mem_dist_matrix))
         engine = comm = None
         if world > 1:

@@ -167,6 +167,7 @@ int ensure_caches(chb_ctx *c)
     const int64_t nown = c->u1 - c->u0;
     if (c->cache_nown == nown && c->cache_C == c->C && c->cache_k == c->k && c->knn_idx) return CHB_OK;
     CHB_TRY(dev_reserve(c, &c->knn_idx, &c->cap_knn, nown * c->C * c->k));
+    CHB_TRY(dev_reserve(c, &c->knn_dist, &c->cap_knn_dist, nown * c->C * c->k));
     if (c->cap_pairs < nown * c->C) {
         CHB_TRY(dev_alloc(c, &c->knn_cnt, nown * c->C));
         CHB_TRY(dev_alloc(c, &c->pair_dist, nown * c->C));
@@ -259,6 +260,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -318,9 +320,29 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     CHB_CUDA(c, cudaMemsetAsync(c->X, 0, sizeof(double) * (size_t)n * c->ldx, c->stream));
     CHB_CUDA(c, cudaMemcpy2DAsync(c->X, sizeof(double) * c->ldx, src, sizeof(double) * d, sizeof(double) * d, (size_t)n,
                                   kind, c->stream));
+    c->ldf = (d + 3) & ~3;
+    CHB_TRY(dev_alloc(c, &c->Xf, n * c->ldf));
+    CHB_TRY(dev_alloc(c, &c->nrm, n));
+    CHB_TRY(chb_launch_prep_f32(c));
+    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[5], &c->counters[5], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CHB_TRY(sync_stream(c));
+    {
+        float nmax;
+        memcpy(&nmax, &c->counters_host[5], sizeof(float));
+        // the FP32 filter's error bound needs |x|^2 far from FP32 overflow / underflow; otherwise use exact rows
+        c->filter_ok = (nmax > 1e-30f) && (nmax < 1e30f);
+    }
     c->dist_ready = false;
     c->labels_set = false;
+    return CHB_OK;
+}
+
+int chb_set_distance_mode(chb_ctx *c, int mode)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, mode == 0 || mode == 1, CHB_EINVAL, "distance mode must be 0 (exact rows) or 1 (FP32 filter + exact re-rank)");
+    if (mode != c->dist_mode) { c->dist_ready = false; c->cache_nown = -1; }
+    c->dist_mode = mode;
     return CHB_OK;
 }
 
@@ -405,6 +427,8 @@ int chb_set_params(chb_ctx *c, int32_t k, int32_t metric)
     return CHB_OK;
 }
 
+static inline bool use_filter(const chb_ctx *c) { return c->dist_mode == 1 && c->filter_ok; }
+
 int chb_build_distance_matrix(chb_ctx *c, int materialise)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
@@ -412,23 +436,39 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
     CHB_CUDA(c, cudaSetDevice(c->device));
     const int64_t nown = c->u1 - c->u0;
     c->materialise = materialise != 0;
-    if (c->materialise) {
-        dev_free(&c->Dscratch);
-        c->cap_scratch = 0;
-        CHB_TRY(dev_reserve(c, &c->Dq, &c->cap_Dq, nown * c->n));
-        const int64_t step = 65535LL * 64;
-        for (int64_t r0 = 0; r0 < nown; r0 += step)
-            CHB_TRY(chb_launch_distance_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Dq + r0 * c->n));
-        CHB_TRY(sync_stream(c));
+    const bool filt = use_filter(c);
+    const int64_t step = 65535LL * 64;
+    // scratch for recomputed rows: ~1 GiB, at least 64 rows
+    int64_t srows = (1LL << 30) / ((filt ? 4 : 8) * c->n);
+    srows = std::max<int64_t>(64, std::min<int64_t>(srows, std::max<int64_t>(nown, 64)));
+    if (filt) {
+        dev_free(&c->Dq); c->cap_Dq = 0;
+        dev_free(&c->Dscratch); c->cap_scratch = 0;
+        if (c->materialise) {
+            dev_free(&c->Ascratch); c->cap_Ascratch = 0;
+            CHB_TRY(dev_reserve(c, &c->Aq, &c->cap_Aq, nown * c->n));
+            for (int64_t r0 = 0; r0 < nown; r0 += step)
+                CHB_TRY(chb_launch_approx_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Aq + r0 * c->n));
+        } else {
+            dev_free(&c->Aq); c->cap_Aq = 0;
+            CHB_TRY(dev_reserve(c, &c->Ascratch, &c->cap_Ascratch, srows * c->n));
+            c->scratch_rows = srows;
+        }
     } else {
-        // scratch for recomputed rows: ~1 GiB, at least 64 rows
-        int64_t rows = (1LL << 30) / (8 * c->n);
-        rows = std::max<int64_t>(64, std::min<int64_t>(rows, std::max<int64_t>(nown, 64)));
-        dev_free(&c->Dq);
-        c->cap_Dq = 0;
-        CHB_TRY(dev_reserve(c, &c->Dscratch, &c->cap_scratch, rows * c->n));
-        c->scratch_rows = rows;
+        dev_free(&c->Aq); c->cap_Aq = 0;
+        dev_free(&c->Ascratch); c->cap_Ascratch = 0;
+        if (c->materialise) {
+            dev_free(&c->Dscratch); c->cap_scratch = 0;
+            CHB_TRY(dev_reserve(c, &c->Dq, &c->cap_Dq, nown * c->n));
+            for (int64_t r0 = 0; r0 < nown; r0 += step)
+                CHB_TRY(chb_launch_distance_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Dq + r0 * c->n));
+        } else {
+            dev_free(&c->Dq); c->cap_Dq = 0;
+            CHB_TRY(dev_reserve(c, &c->Dscratch, &c->cap_scratch, srows * c->n));
+            c->scratch_rows = srows;
+        }
     }
+    CHB_TRY(sync_stream(c));
     c->dist_ready = true;
     return CHB_OK;
 }
@@ -440,19 +480,35 @@ int chb_get_distance_rows(chb_ctx *c, int64_t slot0, int64_t nrows, double *out)
     CHB_CHECK(c, slot0 >= c->u0 && nrows >= 0 && slot0 + nrows <= c->u1, CHB_EINVAL, "slots [%lld,%lld) not owned",
               (long long)slot0, (long long)(slot0 + nrows));
     CHB_CUDA(c, cudaSetDevice(c->device));
-    if (c->materialise) {
+    if (c->materialise && !use_filter(c)) {
         CHB_CUDA(c, cudaMemcpyAsync(out, c->Dq + (slot0 - c->u0) * c->n, sizeof(double) * (size_t)nrows * c->n,
                                     cudaMemcpyDeviceToHost, c->stream));
         return sync_stream(c);
     }
-    for (int64_t r0 = 0; r0 < nrows; r0 += c->scratch_rows) {
-        const int64_t cnt = std::min(c->scratch_rows, nrows - r0);
-        CHB_TRY(chb_launch_distance_rows(c, c->qpoint + slot0 + r0, cnt, c->Dscratch));
-        CHB_CUDA(c, cudaMemcpyAsync(out + r0 * c->n, c->Dscratch, sizeof(double) * (size_t)cnt * c->n, cudaMemcpyDeviceToHost,
-                                    c->stream));
-        CHB_TRY(sync_stream(c));
+    // exact rows are not stored in this mode: recompute them (same kernel, same recipe) through a temporary
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(std::max<int64_t>(nrows, 1), (1LL << 28) / (8 * c->n) + 1));
+    double *tmp = nullptr;
+    CHB_TRY(dev_alloc(c, &tmp, chunk * c->n));
+    int rc = CHB_OK;
+    for (int64_t r0 = 0; r0 < nrows && rc == CHB_OK; r0 += chunk) {
+        const int64_t cnt = std::min(chunk, nrows - r0);
+        if ((rc = chb_launch_distance_rows(c, c->qpoint + slot0 + r0, cnt, tmp))) break;
+        cudaMemcpyAsync(out + r0 * c->n, tmp, sizeof(double) * (size_t)cnt * c->n, cudaMemcpyDeviceToHost, c->stream);
+        rc = sync_stream(c);
     }
-    return CHB_OK;
+    dev_free(&tmp);
+    return rc;
+}
+
+static void fill_filter_args(chb_ctx *c, chb_knn_args &a, bool filt)
+{
+    a.filter = filt ? 1 : 0;
+    a.nrm = c->nrm;
+    a.nrm_max_bits = reinterpret_cast<const unsigned int *>(&c->counters[5]);
+    a.eps_rel = (double)(c->d + 16) * 1.1920928955078125e-07; // (d + 16) * 2^-23, see approx.cu
+    a.X = c->X;
+    a.ldx = c->ldx;
+    a.d = c->d;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -468,12 +524,15 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
     const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(nq, std::max<int64_t>(1, (1LL << 29) / (8 * n))));
     int32_t *d_lab = nullptr, *d_q = nullptr, *d_idx = nullptr, *d_cnt = nullptr;
     double *d_rows = nullptr;
+    float *d_arows = nullptr;
+    const bool filt = use_filter(c);
     int rc = CHB_OK;
     std::vector<int32_t> q32((size_t)chunk), idx32((size_t)chunk * C * k);
     do {
         if ((rc = dev_alloc(c, &d_lab, n)) || (rc = dev_alloc(c, &d_q, chunk)) || (rc = dev_alloc(c, &d_idx, chunk * C * k)) ||
-            (rc = dev_alloc(c, &d_cnt, chunk * C)) || (rc = dev_alloc(c, &d_rows, chunk * n)))
+            (rc = dev_alloc(c, &d_cnt, chunk * C)))
             break;
+        if (filt ? (rc = dev_alloc(c, &d_arows, chunk * n)) : (rc = dev_alloc(c, &d_rows, chunk * n))) break;
         cudaMemcpyAsync(d_lab, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
         for (int64_t q0 = 0; q0 < nq && rc == CHB_OK; q0 += chunk) {
             const int64_t cnt = std::min(chunk, nq - q0);
@@ -484,8 +543,10 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
             }
             if (rc) break;
             cudaMemcpyAsync(d_q, q32.data(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, c->stream);
-            if ((rc = chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
+            if ((rc = filt ? chb_launch_approx_rows(c, d_q, cnt, d_arows) : chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
             chb_knn_args a{};
+            fill_filter_args(c, a, filt);
+            a.arows = d_arows;
             a.rows = d_rows; a.row_stride = n; a.row_is_item = 1; a.items = d_q; a.n_items = cnt; a.mode = 1;
             a.old_label = d_lab; a.n = n; a.C = C; a.k = k; a.u0 = 0; a.knn_idx = d_idx; a.knn_cnt = d_cnt;
             if ((rc = chb_launch_knn_scan(c, a))) break;
@@ -495,7 +556,7 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
             for (int64_t i = 0; i < cnt * C * k; ++i) idx_out[q0 * C * k + i] = idx32[(size_t)i];
         }
     } while (0);
-    dev_free(&d_lab); dev_free(&d_q); dev_free(&d_idx); dev_free(&d_cnt); dev_free(&d_rows);
+    dev_free(&d_lab); dev_free(&d_q); dev_free(&d_idx); dev_free(&d_cnt); dev_free(&d_rows); dev_free(&d_arows);
     return rc;
 }
 
@@ -628,6 +689,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     ++c->tm.launches_other;
     ++c->tm.rounds;
     if (cnt == 0) return CHB_OK;
+    const bool filt = use_filter(c);
     CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));
     const int64_t step = c->materialise ? cnt : c->scratch_rows;
     int32_t *rows_tmp = nullptr;
@@ -641,14 +703,19 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         a.qslot = c->qslot; a.pos = c->pos; a.tent_pt = c->tent_pt; a.old_label = c->old_label; a.n = c->n; a.C = c->C;
         a.k = c->k; a.u0 = c->u0; a.knn_idx = c->knn_idx; a.knn_cnt = c->knn_cnt; a.work = c->work;
         a.work_count = c->counters;
+        fill_filter_args(c, a, filt);
+        a.knn_dist = c->knn_dist;
         if (c->materialise) {
             a.rows = c->Dq;
+            a.arows = c->Aq;
             a.row_is_item = 0;
         } else {
             gather_rows_kernel<<<nblk(sc, 256), 256, 0, c->stream>>>(c->own_pos + b + s0, c->perm_pt, sc, rows_tmp);
             ++c->tm.launches_other;
-            if ((rc = chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch))) break;
+            if ((rc = filt ? chb_launch_approx_rows(c, rows_tmp, sc, c->Ascratch) : chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch)))
+                break;
             a.rows = c->Dscratch;
+            a.arows = c->Ascratch;
             a.row_is_item = 1;
         }
         if ((rc = chb_launch_knn_scan(c, a))) break;

@@ -26,6 +26,11 @@ struct chb_ctx {
     int64_t n = 0;
     int32_t d = 0, ldx = 0;
     double *X = nullptr;
+    float *Xf = nullptr;  // n x ldf FP32 copy of the features (candidate filter)
+    float *nrm = nullptr; // n : |x|^2 rounded up to FP32
+    int32_t ldf = 0;
+    int dist_mode = 1;    // 1: FP32 candidate filter + exact FP64 re-rank (default); 0: exact FP64 rows
+    bool filter_ok = true; // feature magnitudes inside the FP32 filter's validated range
 
     // ---- labels / slots
     int32_t C = 0;
@@ -47,8 +52,13 @@ struct chb_ctx {
 
     // ---- distances
     bool dist_ready = false, materialise = false;
-    double *Dq = nullptr;       // (u1-u0) x n when materialised
+    double *Dq = nullptr;       // (u1-u0) x n when materialised (dist_mode 0)
     double *Dscratch = nullptr; // scratch_rows x n otherwise
+    float *Aq = nullptr;        // (u1-u0) x n FP32 approximate squared distances when materialised (dist_mode 1)
+    float *Ascratch = nullptr;
+    int64_t cap_Aq = 0, cap_Ascratch = 0;
+    double *knn_dist = nullptr; // nown x C x k exact distances of the cached lists
+    int64_t cap_knn_dist = 0;
     int64_t scratch_rows = 0;
 
     // ---- per (owned slot, bin) caches
@@ -141,8 +151,20 @@ struct chb_stage_timer {
 // distance.cu : out[r*n + i] = cdist(X[rows[r]], X[i]) with the exact scipy recipe
 int chb_launch_distance_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, double *out_dev);
 
+// approx.cu : FP32 feature copy + norms; FP32 approximate squared distance rows
+int chb_launch_prep_f32(chb_ctx *ctx);
+int chb_launch_approx_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *out_dev);
+
 // knn.cu
 struct chb_knn_args {
+    int filter;                // 0: `rows` = exact FP64 distances; 1: `arows` = FP32 approximate squared distances
+    const float *arows;
+    const float *nrm;          // |x|^2 rounded up to FP32 (filter)
+    const unsigned int *nrm_max_bits;
+    double eps_rel;            // |arows - d^2| <= eps_rel * (nrm[query] + nrm_max)
+    const double *X;           // features, for the exact re-rank (filter)
+    int32_t ldx, d;
+    double *knn_dist;          // exact distances of the cached lists (filter, mode 0)
     const double *rows;        // distance rows
     int64_t row_stride;        // n
     int row_is_item;           // 0: row index = owned slot of the query; 1: row index = item (scratch rows)

@@ -89,6 +89,11 @@ int chb_set_labels(chb_ctx *ctx, const int64_t *initial_bins, int64_t n, int32_t
                    int64_t slot_end);
 /* num_neighbors / metric of fit_cluster (algorithm.py:17,19). */
 int chb_set_params(chb_ctx *ctx, int32_t num_neighbors, int32_t metric);
+/* How the distances behind find_nearest_from_cluster are produced.  mode 1 (default): an FP32 approximation of
+ * every squared distance (error-bounded) filters candidates and the exact scipy-cdist recipe is evaluated only
+ * for candidates -- the neighbour sets are bit-identical to ranking the exact rows; mode 0: every exact FP64
+ * distance is formed (3 non-fusable FP64 ops per feature).  Call before chb_build_distance_matrix. */
+int chb_set_distance_mode(chb_ctx *ctx, int mode);
 /* create_in_mem_distance_matrix / create_distance_matrix (distance_matrix.py:12-44) for the owned query
  * rows.  materialise=1: rows are computed once (exact cdist recipe) and kept in HBM (InMemDistMatrix=yes,
  * cli/clustering.py:57-59); fails with CHB_ENOMEM if they do not fit.  materialise=0: nothing is stored,

@@ -13,11 +13,12 @@ from chbin_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-def _ctx(X, bins, C, k, metric="convex", materialise=True, slots=(0, -1)):
+def _ctx(X, bins, C, k, metric="convex", materialise=True, slots=(0, -1), dist_mode=1):
     ctx = capi.Context(0)
     ctx.set_features(X)
     ctx.set_labels(bins, C, *slots)
     ctx.set_params(k, metric)
+    ctx.set_distance_mode(dist_mode)
     ctx.build_distance_matrix(materialise)
     return ctx
 
@@ -28,14 +29,16 @@ def test_distance_rows_bit_exact(n, d_extra):
     D = oracle.create_in_mem_distance_matrix(X)
     pts = np.where(bins == -1)[0]
     for mat in (True, False):
-        with _ctx(X, bins, 4, 5, materialise=mat) as ctx:
-            rows = ctx.get_distance_rows(0, len(pts))
-        assert rows.shape == (len(pts), n)
-        assert np.array_equal(rows, D[pts]), "distance rows differ from the scipy-cdist recipe"
+        for mode in (0, 1):
+            with _ctx(X, bins, 4, 5, materialise=mat, dist_mode=mode) as ctx:
+                rows = ctx.get_distance_rows(0, len(pts))
+            assert rows.shape == (len(pts), n)
+            assert np.array_equal(rows, D[pts]), "distance rows differ from the scipy-cdist recipe"
 
 
+@pytest.mark.parametrize("dist_mode", [0, 1])
 @pytest.mark.parametrize("k", [1, 3, 5, 10, 32])
-def test_knn_per_bin_exact(k):
+def test_knn_per_bin_exact(k, dist_mode):
     n, C = 1500, 7
     X, bins, truth = synth.make_contig_features(n, C, 1, 12, seed=5)
     rng = np.random.default_rng(k)
@@ -43,10 +46,14 @@ def test_knn_per_bin_exact(k):
     labels[rng.random(n) < 0.3] = -1            # a mix of assigned / unassigned
     labels[truth == 6] = -1
     labels[np.where(truth == 6)[0][:2]] = 6     # a bin smaller than k
-    D = oracle.create_in_mem_distance_matrix(X)
     queries = rng.choice(n, 64, replace=False)
-    with _ctx(X, bins, C, k) as ctx:
+    X[100] = X[101]                              # exact duplicates: ties broken by index
+    X[102] = X[101]
+    X[200:240] = X[200]                          # 40 identical contigs: more ties than the kept-set reserve
+    labels[200:240] = truth[200]
+    with _ctx(X, bins, C, k, dist_mode=dist_mode) as ctx:
         idx, m = ctx.knn_per_bin(labels, queries)
+    D = oracle.create_in_mem_distance_matrix(X)
     for qi, q in enumerate(queries):
         lab = labels.copy()
         lab[q] = -1                              # algorithm.py:50
@@ -138,24 +145,28 @@ def test_affine_qp_metric():
 
 
 FIT_CASES = [
-    # n, C, S, n_seed, k, concentration, window, materialise
-    (600, 5, 1, 40, 5, 4000.0, 0, True),
-    (1500, 8, 1, 30, 5, 60.0, 0, True),      # hard, overlapping genomes: many repair rounds, 10 iterations
-    (1500, 8, 1, 30, 5, 60.0, 97, True),     # same with a small window
-    (1200, 6, 10, 25, 10, 300.0, 0, False),  # k = 10, rows recomputed on demand (InMemDistMatrix = no)
-    (900, 4, 3, 3, 7, 500.0, 0, True),       # bins smaller than k at the start
+    # n, C, S, n_seed, k, concentration, window, materialise, distance_mode
+    (600, 5, 1, 40, 5, 4000.0, 0, True, 1),
+    (600, 5, 1, 40, 5, 4000.0, 0, True, 0),
+    (1500, 8, 1, 30, 5, 60.0, 0, True, 1),      # hard, overlapping genomes: many repair rounds, 10 iterations
+    (1500, 8, 1, 30, 5, 60.0, 0, True, 0),
+    (1500, 8, 1, 30, 5, 60.0, 97, True, 1),     # same with a small window
+    (1200, 6, 10, 25, 10, 300.0, 0, False, 1),  # k = 10, rows recomputed on demand (InMemDistMatrix = no)
+    (1200, 6, 10, 25, 10, 300.0, 0, False, 0),
+    (900, 4, 3, 3, 7, 500.0, 0, True, 1),       # bins smaller than k at the start
+    (5000, 20, 1, 20, 5, 1000.0, 0, True, 1),   # larger: several CTAs per SM, chunked queue
 ]
 
 
-@pytest.mark.parametrize("n,C,S,n_seed,k,conc,window,mat", FIT_CASES)
-def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat):
+@pytest.mark.parametrize("n,C,S,n_seed,k,conc,window,mat,dmode", FIT_CASES)
+def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat, dmode):
     X, bins, _ = synth.make_contig_features(n, C, S, n_seed, seed=7, concentration=conc)
     perms = oracle.draw_permutations(bins, 10, seed=0)
     ref, info = oracle.fit_cluster(X, C, bins, None, k, 10, perms=perms, return_info=True, threads=4)
     np.random.seed(0)
     bins_before = bins.copy()
     got, ginfo = chbin_b200.fit_cluster(X, C, bins, None, k, 10, "convex", "b200", in_mem_dist_matrix=mat,
-                                        window=window, return_info=True)
+                                        window=window, return_info=True, distance_mode=dmode)
     assert np.array_equal(bins, bins_before), "inputs must not be mutated (algorithm.py:37)"
     assert got.dtype == np.int64
     assert ginfo["iterations"] == info["iterations"] and ginfo["converged"] == info["converged"]
