@@ -104,6 +104,13 @@ __global__ void set_pos_kernel(const int32_t *__restrict__ perm_pt, int64_t U, i
     if (p < U) pos[perm_pt[p]] = (int32_t)p;
 }
 
+__global__ void pack_labels_kernel(const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
+                                   int64_t n, int2 *__restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = make_int2(pos[i], (int)(((unsigned)tent[i] << 16) | ((unsigned)old[i] & 0xffffu)));
+}
+
 __global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
                                    int32_t *__restrict__ rows)
 {
@@ -260,7 +267,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
-    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -387,6 +394,7 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
         CHB_TRY(dev_alloc(c, &c->tent_pt, n));
         CHB_TRY(dev_alloc(c, &c->pos, n));
         CHB_TRY(dev_alloc(c, &c->qslot, n));
+        CHB_TRY(dev_alloc(c, &c->packed, n + 4));
         c->cap_n = n;
     }
     if (c->cap_U < std::max<int64_t>(U, 1)) {
@@ -437,6 +445,7 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
     const int64_t nown = c->u1 - c->u0;
     c->materialise = materialise != 0;
     const bool filt = use_filter(c);
+    c->lda = (c->n + 3) & ~int64_t(3);
     const int64_t step = 65535LL * 64;
     // scratch for recomputed rows: ~1 GiB, at least 64 rows
     int64_t srows = (1LL << 30) / ((filt ? 4 : 8) * c->n);
@@ -446,12 +455,12 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
         dev_free(&c->Dscratch); c->cap_scratch = 0;
         if (c->materialise) {
             dev_free(&c->Ascratch); c->cap_Ascratch = 0;
-            CHB_TRY(dev_reserve(c, &c->Aq, &c->cap_Aq, nown * c->n));
+            CHB_TRY(dev_reserve(c, &c->Aq, &c->cap_Aq, nown * c->lda));
             for (int64_t r0 = 0; r0 < nown; r0 += step)
-                CHB_TRY(chb_launch_approx_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Aq + r0 * c->n));
+                CHB_TRY(chb_launch_approx_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Aq + r0 * c->lda, c->lda));
         } else {
             dev_free(&c->Aq); c->cap_Aq = 0;
-            CHB_TRY(dev_reserve(c, &c->Ascratch, &c->cap_Ascratch, srows * c->n));
+            CHB_TRY(dev_reserve(c, &c->Ascratch, &c->cap_Ascratch, srows * c->lda));
             c->scratch_rows = srows;
         }
     } else {
@@ -532,7 +541,8 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
         if ((rc = dev_alloc(c, &d_lab, n)) || (rc = dev_alloc(c, &d_q, chunk)) || (rc = dev_alloc(c, &d_idx, chunk * C * k)) ||
             (rc = dev_alloc(c, &d_cnt, chunk * C)))
             break;
-        if (filt ? (rc = dev_alloc(c, &d_arows, chunk * n)) : (rc = dev_alloc(c, &d_rows, chunk * n))) break;
+        const int64_t lda = (n + 3) & ~int64_t(3);
+        if (filt ? (rc = dev_alloc(c, &d_arows, chunk * lda)) : (rc = dev_alloc(c, &d_rows, chunk * n))) break;
         cudaMemcpyAsync(d_lab, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream);
         for (int64_t q0 = 0; q0 < nq && rc == CHB_OK; q0 += chunk) {
             const int64_t cnt = std::min(chunk, nq - q0);
@@ -543,11 +553,11 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
             }
             if (rc) break;
             cudaMemcpyAsync(d_q, q32.data(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, c->stream);
-            if ((rc = filt ? chb_launch_approx_rows(c, d_q, cnt, d_arows) : chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
+            if ((rc = filt ? chb_launch_approx_rows(c, d_q, cnt, d_arows, lda) : chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
             chb_knn_args a{};
             fill_filter_args(c, a, filt);
             a.arows = d_arows;
-            a.rows = d_rows; a.row_stride = n; a.row_is_item = 1; a.items = d_q; a.n_items = cnt; a.mode = 1;
+            a.rows = d_rows; a.row_stride = filt ? lda : n; a.row_is_item = 1; a.items = d_q; a.n_items = cnt; a.mode = 1;
             a.old_label = d_lab; a.n = n; a.C = C; a.k = k; a.u0 = 0; a.knn_idx = d_idx; a.knn_cnt = d_cnt;
             if ((rc = chb_launch_knn_scan(c, a))) break;
             cudaMemcpyAsync(idx32.data(), d_idx, sizeof(int32_t) * (size_t)cnt * C * k, cudaMemcpyDeviceToHost, c->stream);
@@ -689,6 +699,11 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     ++c->tm.launches_other;
     ++c->tm.rounds;
     if (cnt == 0) return CHB_OK;
+    if (use_filter(c) && c->C < 32768) {
+        pack_labels_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->pos, c->tent_pt, c->old_label, c->n, c->packed);
+        CHB_CUDA(c, cudaGetLastError());
+        ++c->tm.launches_other;
+    }
     const bool filt = use_filter(c);
     CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));
     const int64_t step = c->materialise ? cnt : c->scratch_rows;
@@ -699,12 +714,13 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         const int64_t sc = std::min(step, cnt - s0);
         cudaMemsetAsync(c->counters, 0, sizeof(int32_t), c->stream);
         chb_knn_args a{};
-        a.row_stride = c->n; a.items = c->own_pos + b + s0; a.n_items = sc; a.mode = 0; a.perm_pt = c->perm_pt;
+        a.row_stride = filt ? c->lda : c->n; a.items = c->own_pos + b + s0; a.n_items = sc; a.mode = 0; a.perm_pt = c->perm_pt;
         a.qslot = c->qslot; a.pos = c->pos; a.tent_pt = c->tent_pt; a.old_label = c->old_label; a.n = c->n; a.C = c->C;
         a.k = c->k; a.u0 = c->u0; a.knn_idx = c->knn_idx; a.knn_cnt = c->knn_cnt; a.work = c->work;
         a.work_count = c->counters;
         fill_filter_args(c, a, filt);
         a.knn_dist = c->knn_dist;
+        a.packed = (filt && c->C < 32768) ? c->packed : nullptr;
         if (c->materialise) {
             a.rows = c->Dq;
             a.arows = c->Aq;
@@ -712,7 +728,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         } else {
             gather_rows_kernel<<<nblk(sc, 256), 256, 0, c->stream>>>(c->own_pos + b + s0, c->perm_pt, sc, rows_tmp);
             ++c->tm.launches_other;
-            if ((rc = filt ? chb_launch_approx_rows(c, rows_tmp, sc, c->Ascratch) : chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch)))
+            if ((rc = filt ? chb_launch_approx_rows(c, rows_tmp, sc, c->Ascratch, c->lda) : chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch)))
                 break;
             a.rows = c->Dscratch;
             a.arows = c->Ascratch;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) prep_f32_kernel(const double *__restrict_
 
 __global__ void __launch_bounds__(256) approx_rows_kernel(const float *__restrict__ Xf, int32_t ldf, const float *__restrict__ nrm,
                                                             const int32_t *__restrict__ rows, int64_t nrows, int64_t n,
-                                                            float *__restrict__ out)
+                                                            float *__restrict__ out, int64_t ldo)
 {
     __shared__ __align__(16) float sA[BK][PADM];
     __shared__ __align__(16) float sB[BK][PADM];
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(256) approx_rows_kernel(const float *__restric
                 const float nc = c < n ? nrm[c] : 0.f;
                 v[j] = fmaf(-2.f, acc[i][h * 4 + j], nr + nc);
             }
-            float *o = out + gr * n + gc;
+            float *o = out + gr * ldo + gc;
             if (gc + 3 < n && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
                 *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
             } else {
@@ -132,14 +132,14 @@ int chb_launch_prep_f32(chb_ctx *ctx)
     return CHB_OK;
 }
 
-int chb_launch_approx_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *out_dev)
+int chb_launch_approx_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *out_dev, int64_t ldo)
 {
     if (nrows <= 0) return CHB_OK;
     dim3 grid((unsigned)((ctx->n + BN - 1) / BN), (unsigned)((nrows + BM - 1) / BM));
     CHB_CHECK(ctx, grid.y <= 65535u, CHB_EINVAL, "approx rows: too many rows per launch (%lld)", (long long)nrows);
     {
         chb_stage_timer t(ctx, CHB_ST_DISTANCE);
-        approx_rows_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Xf, ctx->ldf, ctx->nrm, rows_dev, nrows, ctx->n, out_dev);
+        approx_rows_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->Xf, ctx->ldf, ctx->nrm, rows_dev, nrows, ctx->n, out_dev, ldo);
     }
     CHB_CUDA(ctx, cudaGetLastError());
     return CHB_OK;

@@ -54,7 +54,9 @@ struct chb_ctx {
     bool dist_ready = false, materialise = false;
     double *Dq = nullptr;       // (u1-u0) x n when materialised (dist_mode 0)
     double *Dscratch = nullptr; // scratch_rows x n otherwise
-    float *Aq = nullptr;        // (u1-u0) x n FP32 approximate squared distances when materialised (dist_mode 1)
+    int2 *packed = nullptr;     // n : packed labels for the kNN scan, rebuilt before every round
+    int64_t lda = 0;            // row pitch (floats) of Aq / Ascratch: n rounded up to 4
+    float *Aq = nullptr;        // (u1-u0) x lda FP32 approximate squared distances when materialised (dist_mode 1)
     float *Ascratch = nullptr;
     int64_t cap_Aq = 0, cap_Ascratch = 0;
     double *knn_dist = nullptr; // nown x C x k exact distances of the cached lists
@@ -153,7 +155,7 @@ int chb_launch_distance_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrow
 
 // approx.cu : FP32 feature copy + norms; FP32 approximate squared distance rows
 int chb_launch_prep_f32(chb_ctx *ctx);
-int chb_launch_approx_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *out_dev);
+int chb_launch_approx_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *out_dev, int64_t ldo);
 
 // knn.cu
 struct chb_knn_args {
@@ -172,6 +174,7 @@ struct chb_knn_args {
     int64_t n_items;
     int mode;                  // 0 = round (effective labels from pos/tent/old), 1 = snapshot labels (old_label only)
     const int32_t *perm_pt, *qslot, *pos, *tent_pt, *old_label;
+    const int2 *packed;        // optional: {pos, (tent << 16) | (old & 0xffff)} per point (C < 32768), 16-byte aligned
     int64_t n;
     int32_t C, k;
     int64_t u0;
