@@ -193,10 +193,13 @@ def run_b200(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
         import torch.distributed as dist
 
+        import datetime
+
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
 
@@ -209,7 +212,8 @@ def run_b200(args):
 
     # ---------------- value arm: features resident in HBM, one context reused ----------------
     ctx = capi.Context(local_rank)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)  # the library's kernels, torch events and NCCL collectives all run on this stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     Xd = torch.from_numpy(X).to(dev)
     ctx.set_features_dev(Xd.data_ptr(), n, d)
@@ -226,14 +230,15 @@ def run_b200(args):
             labels, iters, conv, changed = ctx.fit(perms, MAX_ITERATIONS)
             return labels, iters
         if engine is None:
-            engine = clustering.GpuEngine(ctx, local_rank)
+            engine = clustering.GpuEngine(ctx, local_rank, stream)
             comm = clustering.TorchComm()
         iters = 0
-        for it in range(MAX_ITERATIONS):
-            nch, _ = clustering.run_iteration(engine, perms[it], comm)
-            iters += 1
-            if nch == 0:
-                break
+        with engine.stream_context():
+            for it in range(MAX_ITERATIONS):
+                nch, _ = clustering.run_iteration(engine, perms[it], comm)
+                iters += 1
+                if nch == 0:
+                    break
         return ctx.get_labels(), iters
 
     def barrier():

@@ -62,14 +62,20 @@ class GpuEngine:
     """Engine over one libchbin_b200 context; tentative labels live in a torch int32 device tensor so that
     torch.distributed (NCCL) can all-reduce them in place between chb_round_run and chb_round_commit."""
 
-    def __init__(self, ctx: capi.Context, device_index: int):
+    def __init__(self, ctx: capi.Context, device_index: int, stream=None):
         import torch
 
         self.ctx = ctx
         self.torch = torch
         self.device = torch.device("cuda", device_index)
         self._tent = None
-        ctx.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        # one dedicated stream shared by the library's kernels and torch.distributed's collectives: the all-reduce
+        # of the tentative labels must be ordered between chb_round_run and chb_round_commit
+        self.stream = stream if stream is not None else torch.cuda.Stream(self.device)
+        ctx.set_stream(self.stream.cuda_stream)
+
+    def stream_context(self):
+        return self.torch.cuda.stream(self.stream)
 
     def window(self) -> int:
         return self.ctx.get_window()
@@ -200,10 +206,12 @@ def fit_cluster(
 
         iterations, converged, rounds_total, changed = 0, False, 0, []
         for i_iter in range(max_iterations):
-            sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
             if world > 1:
-                change_count, rounds = run_iteration(engine, sample_perm, comm)
+                with engine.stream_context():
+                    sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
+                    change_count, rounds = run_iteration(engine, sample_perm, comm)
             else:
+                sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
                 _, change_count = ctx.fit_iteration(sample_perm, want_labels=False)
                 rounds = 0
             rounds_total += rounds

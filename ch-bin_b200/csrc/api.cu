@@ -280,7 +280,9 @@ int chb_set_stream(chb_ctx *c, void *cuda_stream)
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CUDA(c, cudaSetDevice(c->device));
     CHB_TRY(sync_stream(c));
-    c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    // (void*)-1 = back to the context's own stream; anything else (including NULL, the legacy default stream) is adopted
+    c->stream = (cuda_stream == reinterpret_cast<void *>(static_cast<intptr_t>(-1))) ? c->own_stream
+                                                                                     : reinterpret_cast<cudaStream_t>(cuda_stream);
     return CHB_OK;
 }
 

@@ -68,7 +68,10 @@ int chb_abi_version(void);
 int chb_create(chb_ctx **out, int device_id);
 int chb_destroy(chb_ctx *ctx);
 const char *chb_last_error(const chb_ctx *ctx); /* ctx may be NULL: error of the last failed chb_create */
-/* Run every kernel on this cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+/* Run every kernel on this cudaStream_t (e.g. a torch stream; NULL = the legacy default stream) instead of the
+ * context's own non-blocking stream; pass CHB_OWN_STREAM to go back.  Needed whenever another library (NCCL via
+ * torch.distributed) touches the *_dev buffers: both must be ordered on the same stream. */
+#define CHB_OWN_STREAM ((void *)(intptr_t)-1)
 int chb_set_stream(chb_ctx *ctx, void *cuda_stream);
 int chb_synchronize(chb_ctx *ctx);
 int chb_get_timers(chb_ctx *ctx, chb_timers *out);
