@@ -19,9 +19,10 @@ from .clustering import (  # noqa: F401
     owned_slots,
     perform_clustering,
     run_iteration,
+    shutdown,
 )
 
 __all__ = [
     "B200_SOLVER", "GpuEngine", "TorchComm", "fit_cluster", "install", "owned_slots", "perform_clustering",
-    "run_iteration", "build", "capi", "synth",
+    "run_iteration", "shutdown", "build", "capi", "synth",
 ]

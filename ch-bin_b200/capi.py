@@ -16,6 +16,7 @@ from . import build as _build
 CHB_OK, CHB_EINVAL, CHB_ENODEV, CHB_ECUDA, CHB_ENOMEM, CHB_ENOTIMPL, CHB_EUNASSIGNED = range(7)
 METRICS = {"convex": 0, "affine-qp": 1}
 UNOWNED = -(2**31)
+OWN_STREAM = 2**64 - 1  # CHB_OWN_STREAM: (void*)-1
 
 EXPORTED_SYMBOLS = [
     "chb_abi_version", "chb_create", "chb_destroy", "chb_last_error", "chb_set_stream", "chb_synchronize",
@@ -23,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
-    "chb_measure_fp64_tflops", "chb_set_distance_mode",
+    "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows",
 ]
 
 
@@ -79,6 +80,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_params.argtypes = [_vp, _i32, _i32]
     L.chb_build_distance_matrix.argtypes = [_vp, ctypes.c_int]
     L.chb_set_distance_mode.argtypes = [_vp, ctypes.c_int]
+    L.chb_set_gram_engine.argtypes = [_vp, ctypes.c_int]
+    L.chb_get_candidate_rows.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_dbl), _vp]
     L.chb_get_distance_rows.argtypes = [_vp, _i64, _i64, _vp]
     L.chb_knn_per_bin.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
     L.chb_hull_distance_batch.argtypes = [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]
@@ -200,6 +203,17 @@ class Context:
     def set_distance_mode(self, mode: int):
         """1 = FP32 candidate filter + exact FP64 re-rank (default), 0 = exact FP64 rows."""
         self._check(self._lib.chb_set_distance_mode(self._h, int(mode)))
+
+    def set_gram_engine(self, engine: int):
+        """1 = tcgen05 TF32x3 tensor-core Gram (default), 0 = FFMA Gram."""
+        self._check(self._lib.chb_set_gram_engine(self._h, int(engine)))
+
+    def get_candidate_rows(self, slot0: int, nrows: int):
+        out = np.empty((nrows, self.n), dtype=np.float32)
+        nrm = np.empty(self.n, dtype=np.float32)
+        eps = _dbl(0.0)
+        self._check(self._lib.chb_get_candidate_rows(self._h, slot0, nrows, _ptr(out), ctypes.byref(eps), _ptr(nrm)))
+        return out, float(eps.value), nrm
 
     def build_distance_matrix(self, materialise: bool = True):
         self._check(self._lib.chb_build_distance_matrix(self._h, int(bool(materialise))))

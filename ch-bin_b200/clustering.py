@@ -27,6 +27,27 @@ logger = logging.getLogger(__name__)
 
 B200_SOLVER = "b200"
 
+# One library context per device is kept alive between fit_cluster calls of a process (like a BLAS handle): creating
+# a context, its stream and its multi-GB device buffers costs ~10 ms, comparable to the whole 20k-contig stage.
+_CTX_CACHE = {}
+
+
+def _get_context(device: int, reuse: bool) -> "capi.Context":
+    if not reuse:
+        return capi.Context(device)
+    ctx = _CTX_CACHE.get(device)
+    if ctx is None or getattr(ctx, "_h", None) is None:
+        ctx = capi.Context(device)
+        _CTX_CACHE[device] = ctx
+    return ctx
+
+
+def shutdown() -> None:
+    """Destroys the cached per-device contexts (frees all device memory held by the library)."""
+    for ctx in list(_CTX_CACHE.values()):
+        ctx.close()
+    _CTX_CACHE.clear()
+
 
 # ----------------------------------------------------------------------------------------------------------
 # round driver (shared by the single- and multi-GPU paths; engine-agnostic so the host logic is testable)
@@ -154,6 +175,8 @@ def fit_cluster(
     window: int = 0,
     return_info: bool = False,
     distance_mode: int = 1,
+    reuse_context: bool = True,
+    gram_engine: int = 1,
 ):
     """
     Cevikalp et al. 2019 convex-hull binning specialised for metagenomic binning, on B200.
@@ -190,14 +213,17 @@ def fit_cluster(
     num_points_to_assign = len(points_to_assign)
     logger.debug("Assigning %s points.", num_points_to_assign)
 
-    ctx = capi.Context(device)
+    ctx = _get_context(device, reuse_context)
     try:
+        ctx.set_stream(capi.OWN_STREAM)
+        ctx.reset_timers()
         ctx.set_features(samples)
         u0, u1 = owned_slots(num_points_to_assign, rank, world)
         ctx.set_labels(curr, int(num_clusters), u0, u1)
         ctx.set_params(int(num_neighbors), metric)
         ctx.set_window(int(window))
         ctx.set_distance_mode(int(distance_mode))
+        ctx.set_gram_engine(int(gram_engine))
         ctx.build_distance_matrix(bool(in_mem_dist_matrix))
         engine = comm = None
         if world > 1:
@@ -229,8 +255,13 @@ def fit_cluster(
         labels = ctx.get_labels()
         info = dict(iterations=iterations, converged=converged, changed=changed, timers=ctx.timers(), rank=rank,
                     world=world, owned_slots=(u0, u1))
-    finally:
+    except BaseException:
+        _CTX_CACHE.pop(device, None)  # never reuse a context after a failure
         ctx.close()
+        raise
+    finally:
+        if not reuse_context:
+            ctx.close()
     if return_info:
         return labels, info
     return labels

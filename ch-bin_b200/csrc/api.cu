@@ -89,6 +89,8 @@ void dev_free(T **p)
         if (_rc != CHB_OK) return _rc; \
     } while (0)
 
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
 // ---------------------------------------------------------------------------------------------------------
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
@@ -109,6 +111,16 @@ __global__ void pack_labels_kernel(const int32_t *__restrict__ pos, const int32_
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = make_int2(pos[i], (int)(((unsigned)tent[i] << 16) | ((unsigned)old[i] & 0xffffu)));
+}
+
+// row-major n x d (contiguous) -> n x ldx (16-byte pitch, zero pad)
+__global__ void repack_features_kernel(const double *__restrict__ src, int64_t n, int32_t d, int32_t ldx, double *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ldx) return;
+    const int64_t r = i / ldx;
+    const int32_t t = (int32_t)(i - r * ldx);
+    dst[i] = t < d ? src[r * d + t] : 0.0;
 }
 
 __global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
@@ -167,7 +179,6 @@ __global__ void count_changed_kernel(const int32_t *__restrict__ a, const int32_
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], __popc(m));
 }
 
-inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 int ensure_caches(chb_ctx *c)
 {
@@ -267,7 +278,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
-    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -315,6 +326,34 @@ int chb_enable_timers(chb_ctx *c, int enable)
     return CHB_OK;
 }
 
+static inline bool use_filter(const chb_ctx *c) { return c->dist_mode == 1 && c->filter_ok; }
+
+// FP32 candidate rows for `nrows` query points (device list rows_dev), through the selected Gram engine
+static int candidate_rows(chb_ctx *c, const int32_t *rows_dev, int64_t nrows, float *out, int64_t ldo)
+{
+    if (c->gram_engine == 0) return chb_launch_approx_rows(c, rows_dev, nrows, out, ldo);
+    c->Kp = (3 * c->d + 31) & ~31;
+    if (!c->bsplit_ready) {
+        CHB_TRY(dev_reserve(c, &c->Bsplit, &c->cap_Bsplit, c->n * c->Kp));
+    }
+    CHB_TRY(dev_reserve(c, &c->Asplit, &c->cap_Asplit, nrows * c->Kp));
+    CHB_TRY(chb_gram_tc_prepare(c, rows_dev, nrows, c->Asplit, c->Bsplit, c->Kp, !c->bsplit_ready));
+    c->bsplit_ready = true;
+    return chb_launch_gram_tc(c, c->Asplit, c->Bsplit, c->Kp, rows_dev, nrows, out, ldo);
+}
+
+static void fill_filter_args(chb_ctx *c, chb_knn_args &a, bool filt)
+{
+    a.filter = filt ? 1 : 0;
+    a.nrm = c->nrm;
+    a.nrm_max_bits = reinterpret_cast<const unsigned int *>(&c->counters[5]);
+    a.eps_rel = c->gram_engine == 0 ? (double)(c->d + 16) * 1.1920928955078125e-07   // (d + 16) * 2^-23, approx.cu
+                                    : (double)(3 * c->d + 64) * 1.1920928955078125e-07; // (3d + 64) * 2^-23, gram_tc.cu
+    a.X = c->X;
+    a.ldx = c->ldx;
+    a.d = c->d;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind)
 {
@@ -325,13 +364,26 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     c->n = n;
     c->d = d;
     c->ldx = (d + 1) & ~1; // 16-byte row pitch
-    CHB_TRY(dev_alloc(c, &c->X, n * c->ldx));
-    CHB_CUDA(c, cudaMemsetAsync(c->X, 0, sizeof(double) * (size_t)n * c->ldx, c->stream));
-    CHB_CUDA(c, cudaMemcpy2DAsync(c->X, sizeof(double) * c->ldx, src, sizeof(double) * d, sizeof(double) * d, (size_t)n,
-                                  kind, c->stream));
     c->ldf = (d + 3) & ~3;
-    CHB_TRY(dev_alloc(c, &c->Xf, n * c->ldf));
-    CHB_TRY(dev_alloc(c, &c->nrm, n));
+    if (c->cap_X < n * c->ldx) { CHB_TRY(dev_alloc(c, &c->X, n * c->ldx)); c->cap_X = n * c->ldx; }
+    if (c->cap_Xf < n * c->ldf) { CHB_TRY(dev_alloc(c, &c->Xf, n * c->ldf)); c->cap_Xf = n * c->ldf; }
+    if (c->cap_nrm < n) { CHB_TRY(dev_alloc(c, &c->nrm, n)); c->cap_nrm = n; }
+    CHB_TRY(dev_alloc(c, &c->colsum, d));
+    {
+        // one contiguous copy (a strided 2-D copy from pageable host memory is several times slower), then repack
+        const double *dsrc = src;
+        double *stage = nullptr;
+        if (kind == cudaMemcpyHostToDevice) {
+            CHB_TRY(dev_alloc(c, &stage, n * (int64_t)d));
+            CHB_CUDA(c, cudaMemcpyAsync(stage, src, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
+            dsrc = stage;
+        }
+        repack_features_kernel<<<nblk(n * c->ldx, 256), 256, 0, c->stream>>>(dsrc, n, d, c->ldx, c->X);
+        ++c->tm.launches_other;
+        cudaError_t le = cudaGetLastError();
+        if (stage) { cudaStreamSynchronize(c->stream); cudaFree(stage); }
+        CHB_CUDA(c, le);
+    }
     CHB_TRY(chb_launch_prep_f32(c));
     CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[5], &c->counters[5], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CHB_TRY(sync_stream(c));
@@ -343,7 +395,35 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     }
     c->dist_ready = false;
     c->labels_set = false;
+    c->bsplit_ready = false;
     return CHB_OK;
+}
+
+int chb_set_gram_engine(chb_ctx *c, int engine)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, engine == 0 || engine == 1, CHB_EINVAL, "gram engine must be 0 (FFMA) or 1 (tcgen05 TF32x3)");
+    if (engine != c->gram_engine) { c->dist_ready = false; c->cache_nown = -1; }
+    c->gram_engine = engine;
+    return CHB_OK;
+}
+
+int chb_get_candidate_rows(chb_ctx *c, int64_t slot0, int64_t nrows, float *out, double *eps_rel, float *nrm_out)
+{
+    CHB_CHECK(c, c && out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->dist_ready && use_filter(c) && c->materialise, CHB_EINVAL,
+              "candidate rows exist only in distance mode 1 with a materialised matrix");
+    CHB_CHECK(c, slot0 >= c->u0 && nrows >= 0 && slot0 + nrows <= c->u1, CHB_EINVAL, "slots not owned");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_CUDA(c, cudaMemcpy2DAsync(out, sizeof(float) * c->n, c->Aq + (slot0 - c->u0) * c->lda, sizeof(float) * c->lda,
+                                  sizeof(float) * c->n, (size_t)nrows, cudaMemcpyDeviceToHost, c->stream));
+    if (nrm_out) CHB_CUDA(c, cudaMemcpyAsync(nrm_out, c->nrm, sizeof(float) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    if (eps_rel) {
+        chb_knn_args a{};
+        fill_filter_args(c, a, true);
+        *eps_rel = a.eps_rel;
+    }
+    return sync_stream(c);
 }
 
 int chb_set_distance_mode(chb_ctx *c, int mode)
@@ -437,8 +517,6 @@ int chb_set_params(chb_ctx *c, int32_t k, int32_t metric)
     return CHB_OK;
 }
 
-static inline bool use_filter(const chb_ctx *c) { return c->dist_mode == 1 && c->filter_ok; }
-
 int chb_build_distance_matrix(chb_ctx *c, int materialise)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
@@ -459,7 +537,7 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
             dev_free(&c->Ascratch); c->cap_Ascratch = 0;
             CHB_TRY(dev_reserve(c, &c->Aq, &c->cap_Aq, nown * c->lda));
             for (int64_t r0 = 0; r0 < nown; r0 += step)
-                CHB_TRY(chb_launch_approx_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Aq + r0 * c->lda, c->lda));
+                CHB_TRY(candidate_rows(c, c->qpoint + c->u0 + r0, std::min(step, nown - r0), c->Aq + r0 * c->lda, c->lda));
         } else {
             dev_free(&c->Aq); c->cap_Aq = 0;
             CHB_TRY(dev_reserve(c, &c->Ascratch, &c->cap_Ascratch, srows * c->lda));
@@ -511,17 +589,6 @@ int chb_get_distance_rows(chb_ctx *c, int64_t slot0, int64_t nrows, double *out)
     return rc;
 }
 
-static void fill_filter_args(chb_ctx *c, chb_knn_args &a, bool filt)
-{
-    a.filter = filt ? 1 : 0;
-    a.nrm = c->nrm;
-    a.nrm_max_bits = reinterpret_cast<const unsigned int *>(&c->counters[5]);
-    a.eps_rel = (double)(c->d + 16) * 1.1920928955078125e-07; // (d + 16) * 2^-23, see approx.cu
-    a.X = c->X;
-    a.ldx = c->ldx;
-    a.d = c->d;
-}
-
 // ---------------------------------------------------------------------------------------------------------
 int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, int64_t nq, int64_t *idx_out, int32_t *m_out)
 {
@@ -555,7 +622,7 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
             }
             if (rc) break;
             cudaMemcpyAsync(d_q, q32.data(), sizeof(int32_t) * (size_t)cnt, cudaMemcpyHostToDevice, c->stream);
-            if ((rc = filt ? chb_launch_approx_rows(c, d_q, cnt, d_arows, lda) : chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
+            if ((rc = filt ? candidate_rows(c, d_q, cnt, d_arows, lda) : chb_launch_distance_rows(c, d_q, cnt, d_rows))) break;
             chb_knn_args a{};
             fill_filter_args(c, a, filt);
             a.arows = d_arows;
@@ -730,7 +797,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         } else {
             gather_rows_kernel<<<nblk(sc, 256), 256, 0, c->stream>>>(c->own_pos + b + s0, c->perm_pt, sc, rows_tmp);
             ++c->tm.launches_other;
-            if ((rc = filt ? chb_launch_approx_rows(c, rows_tmp, sc, c->Ascratch, c->lda) : chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch)))
+            if ((rc = filt ? candidate_rows(c, rows_tmp, sc, c->Ascratch, c->lda) : chb_launch_distance_rows(c, rows_tmp, sc, c->Dscratch)))
                 break;
             a.rows = c->Dscratch;
             a.arows = c->Ascratch;

@@ -8,7 +8,8 @@
 //
 //     A[r][i] = fl32( nrm[r] + nrm[i] - 2 * sum_t xf[r][t] * xf[i][t] )          (Gram form, FFMA accumulation)
 //
-// with xf = fl32(x) and nrm = |x|^2 evaluated in FP64 and rounded UP to FP32.  Error bound used by the filter
+// with xf = fl32(x - mu) (mu = column means: distances are translation invariant and centring shrinks the bound)
+// and nrm = |xf|^2 evaluated in FP64 and rounded UP to FP32.  Error bound used by the filter
 // (standard gamma_d analysis, inputs rounded once, d FMAs, three final roundings):
 //     | A[r][i] - |x_r - x_i|^2 |  <=  (d + 16) * 2^-23 * (nrm[r] + nrm_max)
 // Valid while no intermediate overflows or flushes to zero: features must satisfy 1e-15 < |x|_max < 1e15, which
@@ -22,7 +23,23 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int PADM = BM + 4;
 
+// column sums of X (for the centring translation): block b adds rows [256 b, 256 b + 256) to colsum[]
+__global__ void __launch_bounds__(256) colsum_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, int64_t n,
+                                                       double *__restrict__ colsum)
+{
+    const int64_t r0 = (int64_t)blockIdx.x * 256;
+    const int64_t r1 = r0 + 256 < n ? r0 + 256 : n;
+    for (int t = threadIdx.x; t < d; t += 256) {
+        double s = 0.0;
+        for (int64_t r = r0; r < r1; ++r) s += X[r * ldx + t];
+        atomicAdd(&colsum[t], s);
+    }
+}
+
+// Xf = fl32(x - mu), nrm = |x - mu|^2 rounded up.  Distances are translation invariant, and centring the all-positive
+// k-mer profiles shrinks |x|^2 -- and with it the filter's error bound E ~ eps (nrm[r] + nrm_max) -- several times.
 __global__ void __launch_bounds__(256) prep_f32_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, int64_t n,
+                                                         const double *__restrict__ colsum, double inv_n,
                                                          float *__restrict__ Xf, int32_t ldf, float *__restrict__ nrm,
                                                          unsigned int *__restrict__ nrm_max_bits)
 {
@@ -32,9 +49,10 @@ __global__ void __launch_bounds__(256) prep_f32_kernel(const double *__restrict_
     if (i >= n) return;
     double s = 0.0;
     for (int t = lane; t < ldf; t += 32) {
-        const double v = t < d ? X[i * ldx + t] : 0.0;
-        Xf[i * ldf + t] = (float)v;
-        s = fma(v, v, s);
+        const double v = t < d ? X[i * ldx + t] - colsum[t] * inv_n : 0.0;
+        const float vf = (float)v;
+        Xf[i * ldf + t] = vf;
+        s = fma((double)vf, (double)vf, s); // the norm of the value the Gram kernels actually contract
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
@@ -125,10 +143,13 @@ int chb_launch_prep_f32(chb_ctx *ctx)
 {
     const int64_t n = ctx->n;
     CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[5], 0, sizeof(int32_t), ctx->stream));
+    CHB_CUDA(ctx, cudaMemsetAsync(ctx->colsum, 0, sizeof(double) * (size_t)ctx->d, ctx->stream));
+    colsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->X, ctx->ldx, ctx->d, n, ctx->colsum);
     prep_f32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-        ctx->X, ctx->ldx, ctx->d, n, ctx->Xf, ctx->ldf, ctx->nrm, reinterpret_cast<unsigned int *>(&ctx->counters[5]));
+        ctx->X, ctx->ldx, ctx->d, n, ctx->colsum, 1.0 / (double)n, ctx->Xf, ctx->ldf, ctx->nrm,
+        reinterpret_cast<unsigned int *>(&ctx->counters[5]));
     CHB_CUDA(ctx, cudaGetLastError());
-    ++ctx->tm.launches_other;
+    ctx->tm.launches_other += 2;
     return CHB_OK;
 }
 

@@ -27,9 +27,15 @@ struct chb_ctx {
     int32_t d = 0, ldx = 0;
     double *X = nullptr;
     float *Xf = nullptr;  // n x ldf FP32 copy of the features (candidate filter)
-    float *nrm = nullptr; // n : |x|^2 rounded up to FP32
+    float *nrm = nullptr; // n : |x - mu|^2 rounded up to FP32
+    double *colsum = nullptr; // d : column sums of X (mu = colsum / n)
     int32_t ldf = 0;
     int dist_mode = 1;    // 1: FP32 candidate filter + exact FP64 re-rank (default); 0: exact FP64 rows
+    int gram_engine = 1;  // filter mode: 1 = tcgen05 TF32x3 tensor-core Gram (gram_tc.cu), 0 = FFMA Gram (approx.cu)
+    float *Asplit = nullptr, *Bsplit = nullptr; // TF32 hi/lo split operands: rows x Kp (queries), n x Kp (points)
+    int64_t cap_Asplit = 0, cap_Bsplit = 0;
+    int32_t Kp = 0;
+    bool bsplit_ready = false;
     bool filter_ok = true; // feature magnitudes inside the FP32 filter's validated range
 
     // ---- labels / slots
@@ -78,6 +84,7 @@ struct chb_ctx {
     int32_t *counters_host = nullptr; // pinned mirror
 
     // capacities (elements) of the re-usable allocations above, so that repeated set-ups do not re-malloc
+    int64_t cap_X = 0, cap_Xf = 0, cap_nrm = 0;
     int64_t cap_n = 0, cap_U = 0, cap_own = 0, cap_Dq = 0, cap_scratch = 0, cap_pairs = 0, cap_knn = 0;
 
     int2 *fallback = nullptr; // pairs the small-k QP kernel hands to the general one
@@ -156,6 +163,12 @@ int chb_launch_distance_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrow
 // approx.cu : FP32 feature copy + norms; FP32 approximate squared distance rows
 int chb_launch_prep_f32(chb_ctx *ctx);
 int chb_launch_approx_rows(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *out_dev, int64_t ldo);
+
+// gram_tc.cu : tcgen05 / TMA / TMEM version of the candidate-distance Gram contraction
+int chb_gram_tc_prepare(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, float *a_split, float *b_split, int32_t Kp,
+                        bool do_b);
+int chb_launch_gram_tc(chb_ctx *ctx, const float *a_split, const float *b_split, int32_t Kp, const int32_t *rows_dev,
+                       int64_t nrows, float *out_dev, int64_t ldo);
 
 // knn.cu
 struct chb_knn_args {

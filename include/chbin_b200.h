@@ -97,6 +97,12 @@ int chb_set_params(chb_ctx *ctx, int32_t num_neighbors, int32_t metric);
  * for candidates -- the neighbour sets are bit-identical to ranking the exact rows; mode 0: every exact FP64
  * distance is formed (3 non-fusable FP64 ops per feature).  Call before chb_build_distance_matrix. */
 int chb_set_distance_mode(chb_ctx *ctx, int mode);
+/* Engine of the FP32 candidate values in distance mode 1: 1 (default) = tcgen05 tensor cores, TF32 with a 3-term
+ * hi/lo split, TMA-fed, TMEM accumulators (gram_tc.cu); 0 = FFMA on the CUDA cores (approx.cu). */
+int chb_set_gram_engine(chb_ctx *ctx, int engine);
+/* Test aid: the FP32 candidate values A (nrows x n) of owned slots, the relative bound eps_rel with
+ * |A - d^2| <= eps_rel * (nrm[query] + max nrm), and nrm (n floats, may be NULL).  Mode 1, materialised only. */
+int chb_get_candidate_rows(chb_ctx *ctx, int64_t slot0, int64_t nrows, float *out, double *eps_rel, float *nrm_out);
 /* create_in_mem_distance_matrix / create_distance_matrix (distance_matrix.py:12-44) for the owned query
  * rows.  materialise=1: rows are computed once (exact cdist recipe) and kept in HBM (InMemDistMatrix=yes,
  * cli/clustering.py:57-59); fails with CHB_ENOMEM if they do not fit.  materialise=0: nothing is stored,

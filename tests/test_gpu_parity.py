@@ -13,14 +13,34 @@ from chbin_b200 import capi, synth
 pytestmark = pytest.mark.gpu
 
 
-def _ctx(X, bins, C, k, metric="convex", materialise=True, slots=(0, -1), dist_mode=1):
+def _ctx(X, bins, C, k, metric="convex", materialise=True, slots=(0, -1), dist_mode=1, gram_engine=1):
     ctx = capi.Context(0)
     ctx.set_features(X)
     ctx.set_labels(bins, C, *slots)
     ctx.set_params(k, metric)
     ctx.set_distance_mode(dist_mode)
+    ctx.set_gram_engine(gram_engine)
     ctx.build_distance_matrix(materialise)
     return ctx
+
+
+@pytest.mark.parametrize("engine", [0, 1])
+@pytest.mark.parametrize("n,S", [(700, 1), (1111, 10), (300, 20)])
+def test_candidate_values_within_proven_bound(engine, n, S):
+    """|A - d^2| <= eps_rel * (nrm[query] + max nrm) for the FFMA (approx.cu) and tcgen05 (gram_tc.cu) engines."""
+    X, bins, _ = synth.make_contig_features(n, 4, S, 10, seed=13)
+    X[5] = X[6]
+    pts = np.where(bins == -1)[0]
+    D = oracle.create_in_mem_distance_matrix(X)[pts]
+    with _ctx(X, bins, 4, 5, gram_engine=engine) as ctx:
+        A, eps_rel, nrm = ctx.get_candidate_rows(0, len(pts))
+    Xc = (X - X.mean(axis=0)).astype(np.float32).astype(np.float64)   # the kernels contract fl32(x - mean)
+    nn = np.sum(Xc * Xc, axis=1)
+    assert np.all(nrm >= nn * (1 - 1e-6)) and np.all(nrm <= nn * (1 + 1e-5) + 1e-30)
+    bound = eps_rel * (nrm[pts].astype(np.float64)[:, None] + float(nrm.max()))
+    err = np.abs(A.astype(np.float64) - D * D)
+    assert np.all(err <= bound), f"bound violated by {np.max(err / bound):.3f}x"
+    assert np.max(err / bound) < 0.5, "the proven bound should hold with margin"
 
 
 @pytest.mark.parametrize("n,d_extra", [(300, 1), (1000, 10), (257, 3)])
@@ -155,18 +175,22 @@ FIT_CASES = [
     (1200, 6, 10, 25, 10, 300.0, 0, False, 0),
     (900, 4, 3, 3, 7, 500.0, 0, True, 1),       # bins smaller than k at the start
     (5000, 20, 1, 20, 5, 1000.0, 0, True, 1),   # larger: several CTAs per SM, chunked queue
+    (1500, 8, 1, 30, 5, 60.0, 0, True, 2),      # distance mode 1 with the FFMA Gram engine
+    (1200, 6, 10, 25, 10, 300.0, 0, False, 2),
 ]
 
 
 @pytest.mark.parametrize("n,C,S,n_seed,k,conc,window,mat,dmode", FIT_CASES)
 def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat, dmode):
+    engine = 0 if dmode == 2 else 1
+    dmode = 1 if dmode == 2 else dmode
     X, bins, _ = synth.make_contig_features(n, C, S, n_seed, seed=7, concentration=conc)
     perms = oracle.draw_permutations(bins, 10, seed=0)
     ref, info = oracle.fit_cluster(X, C, bins, None, k, 10, perms=perms, return_info=True, threads=4)
     np.random.seed(0)
     bins_before = bins.copy()
     got, ginfo = chbin_b200.fit_cluster(X, C, bins, None, k, 10, "convex", "b200", in_mem_dist_matrix=mat,
-                                        window=window, return_info=True, distance_mode=dmode)
+                                        window=window, return_info=True, distance_mode=dmode, gram_engine=engine)
     assert np.array_equal(bins, bins_before), "inputs must not be mutated (algorithm.py:37)"
     assert got.dtype == np.int64
     assert ginfo["iterations"] == info["iterations"] and ginfo["converged"] == info["converged"]
