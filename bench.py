@@ -315,9 +315,9 @@ def run_b200(args):
                 traffic = None
         nown = u1 - u0
         stages = {}
-        # kNN scan: one distance row (8n bytes) per (launch item)
+        # kNN scan: one row of FP32 candidate values (4n bytes) per (launch item)
         if ln["knn"]:
-            b = tm["rows_scanned"] * n * 8.0
+            b = tm["rows_scanned"] * n * 4.0
             stages["knn"] = {"bound": "hbm", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"]}
         if ln["qp"]:
@@ -328,15 +328,23 @@ def run_b200(args):
                             "qps_solved": tm["qps_solved"], "qps_per_s": tm["qps_solved"] / (ms["qp"] * 1e-3),
                             "fp64_tflops": f / (ms["qp"] * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak}
         if ln["distance"]:
-            ops = 3.0 * nown * n * d * args.steps
-            stages["distance"] = {"bound": "fp64", "achieved": ops / (ms["distance"] * 1e-3) / 1e12, "peak": fp64_peak / 2.0,
-                                  "unit": "Tinstr/s (non-FMA FP64: sub, mul, add per element)", "ms_total": ms["distance"],
-                                  "launches": ln["distance"]}
+            # candidate-distance Gram on tcgen05: TF32 with a 3-term split, K = 3d rounded up to 32
+            kp = (3 * d + 31) // 32 * 32
+            fl = 2.0 * nown * n * kp * args.steps
+            tf32_peak = None
+            try:
+                tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
+            except Exception:
+                tf32_peak = 1590.0 / 2.0
+            stages["distance"] = {"bound": "tensor", "achieved": fl / (ms["distance"] * 1e-3) / 1e12, "peak": tf32_peak,
+                                  "unit": "TFLOP/s (TF32; peak = half the measured cuBLAS bf16 burst figure)",
+                                  "ms_total": ms["distance"], "launches": ln["distance"],
+                                  "bytes_written_per_launch": nown * n * 4.0}
         for s in stages.values():
             s["frac"] = s["achieved"] / s["peak"] if s["peak"] else None
         roof = dict(stages[dom])
-        roof["kernel"] = {"knn": "knn_scan_kernel", "qp": "qp_kernel", "distance": "distance_rows_kernel"}[dom]
-        roof["peak_source"] = hbm_src if roof["bound"] == "hbm" else "own DFMA microbenchmark (chb_measure_fp64_tflops), halved for non-FMA ops"
+        roof["kernel"] = {"knn": "knn_scan_kernel", "qp": "qp_small_kernel" if k <= 5 else "qp_kernel", "distance": "gram_tc_kernel"}[dom]
+        roof["peak_source"] = hbm_src if roof["bound"] == "hbm" else "MEASURED_PEAKS.json bf16_tflops / 2"
         roof["traffic"] = traffic
         roof["share_of_step"] = ms[dom] / elapsed_ms
 
