@@ -34,3 +34,12 @@ for s in range(args.stages):
     print(f"stage {s}: iterations={iters} converged={conv} changed={list(changed)} acc={np.mean(labels == truth):.4f}")
     print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in t.items()})
 ctx.close()
+# steady-state probe: two more iterations after convergence (nothing changes): cost of a pure warm scan
+ctx = capi.Context(0)
+ctx.set_features(X); ctx.set_params(cfg["k"], "convex"); ctx.set_labels(bins, cfg["C"]); ctx.build_distance_matrix(True)
+for it in range(4):
+    ctx.reset_timers()
+    _, nch = ctx.fit_iteration(perms[it], want_labels=False)
+    t = ctx.timers()
+    print(f"iteration {it+1}: changed={nch} rounds={t['rounds']} knn_ms={t['ms_knn']:.3f} ({t['launches_knn']} launches) qp_ms={t['ms_qp']:.3f} qps_solved={t['qps_solved']}")
+ctx.close()
