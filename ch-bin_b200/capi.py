@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
-    "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows",
+    "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
 ]
 
 
@@ -81,6 +81,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_build_distance_matrix.argtypes = [_vp, ctypes.c_int]
     L.chb_set_distance_mode.argtypes = [_vp, ctypes.c_int]
     L.chb_set_gram_engine.argtypes = [_vp, ctypes.c_int]
+    L.chb_get_pair_cache.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp]
     L.chb_get_candidate_rows.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_dbl), _vp]
     L.chb_get_distance_rows.argtypes = [_vp, _i64, _i64, _vp]
     L.chb_knn_per_bin.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
@@ -214,6 +215,13 @@ class Context:
         eps = _dbl(0.0)
         self._check(self._lib.chb_get_candidate_rows(self._h, slot0, nrows, _ptr(out), ctypes.byref(eps), _ptr(nrm)))
         return out, float(eps.value), nrm
+
+    def get_pair_cache(self, slot0: int, nslots: int):
+        idx = np.empty((nslots, self.C, self.k), dtype=np.int32)
+        cnt = np.empty((nslots, self.C), dtype=np.int32)
+        dist = np.empty((nslots, self.C))
+        self._check(self._lib.chb_get_pair_cache(self._h, slot0, nslots, _ptr(idx), _ptr(cnt), _ptr(dist)))
+        return idx, cnt, dist
 
     def build_distance_matrix(self, materialise: bool = True):
         self._check(self._lib.chb_build_distance_matrix(self._h, int(bool(materialise))))

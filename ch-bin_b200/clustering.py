@@ -174,7 +174,7 @@ def fit_cluster(
     device: Optional[int] = None,
     window: int = 0,
     return_info: bool = False,
-    distance_mode: int = 1,
+    distance_mode: int = 2,
     reuse_context: bool = True,
     gram_engine: int = 1,
 ):

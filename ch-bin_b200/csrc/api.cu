@@ -123,6 +123,20 @@ __global__ void repack_features_kernel(const double *__restrict__ src, int64_t n
     dst[i] = t < d ? src[r * d + t] : 0.0;
 }
 
+// fused-mode fallback: owned slot -> permutation position and point; the row's cached lists are invalidated so that
+// the exact-path kNN kernel recomputes every bin of that query from scratch
+__global__ void fallback_prepare_kernel(const int32_t *__restrict__ fb_rows, int32_t cnt, const int32_t *__restrict__ qpoint_own,
+                                        const int32_t *__restrict__ pos, int32_t C, int32_t *__restrict__ items,
+                                        int32_t *__restrict__ points, int32_t *__restrict__ knn_cnt)
+{
+    const int i = blockIdx.x;
+    if (i >= cnt) return;
+    const int r = fb_rows[i];
+    const int pt = qpoint_own[r];
+    if (threadIdx.x == 0) { items[i] = pos[pt]; points[i] = pt; }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) knn_cnt[(int64_t)r * C + c] = -1;
+}
+
 __global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
                                    int32_t *__restrict__ rows)
 {
@@ -278,7 +292,8 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
-    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->f_fb_items);
+    chb_fused_free(c); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -326,7 +341,8 @@ int chb_enable_timers(chb_ctx *c, int enable)
     return CHB_OK;
 }
 
-static inline bool use_filter(const chb_ctx *c) { return c->dist_mode == 1 && c->filter_ok; }
+static inline bool use_filter(const chb_ctx *c) { return c->dist_mode >= 1 && c->filter_ok; }
+static inline bool use_fused(const chb_ctx *c) { return c->dist_mode == 2 && c->filter_ok && chb_fused_supported(c); }
 
 // FP32 candidate rows for `nrows` query points (device list rows_dev), through the selected Gram engine
 static int candidate_rows(chb_ctx *c, const int32_t *rows_dev, int64_t nrows, float *out, int64_t ldo)
@@ -396,6 +412,7 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     c->dist_ready = false;
     c->labels_set = false;
     c->bsplit_ready = false;
+    c->f_asplit_ready = false;
     return CHB_OK;
 }
 
@@ -411,7 +428,7 @@ int chb_set_gram_engine(chb_ctx *c, int engine)
 int chb_get_candidate_rows(chb_ctx *c, int64_t slot0, int64_t nrows, float *out, double *eps_rel, float *nrm_out)
 {
     CHB_CHECK(c, c && out, CHB_EINVAL, "NULL argument");
-    CHB_CHECK(c, c->dist_ready && use_filter(c) && c->materialise, CHB_EINVAL,
+    CHB_CHECK(c, c->dist_ready && use_filter(c) && !use_fused(c) && c->materialise, CHB_EINVAL,
               "candidate rows exist only in distance mode 1 with a materialised matrix");
     CHB_CHECK(c, slot0 >= c->u0 && nrows >= 0 && slot0 + nrows <= c->u1, CHB_EINVAL, "slots not owned");
     CHB_CUDA(c, cudaSetDevice(c->device));
@@ -426,10 +443,23 @@ int chb_get_candidate_rows(chb_ctx *c, int64_t slot0, int64_t nrows, float *out,
     return sync_stream(c);
 }
 
+int chb_get_pair_cache(chb_ctx *c, int64_t slot0, int64_t nslots, int32_t *idx_out, int32_t *cnt_out, double *dist_out)
+{
+    CHB_CHECK(c, c && idx_out && cnt_out && dist_out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->knn_idx && slot0 >= c->u0 && nslots >= 0 && slot0 + nslots <= c->u1, CHB_EINVAL, "slots not owned / no cache yet");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int64_t r0 = slot0 - c->u0, np = nslots * c->C;
+    CHB_CUDA(c, cudaMemcpyAsync(idx_out, c->knn_idx + r0 * c->C * c->k, sizeof(int32_t) * (size_t)np * c->k, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(cnt_out, c->knn_cnt + r0 * c->C, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(dist_out, c->pair_dist + r0 * c->C, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
+    return sync_stream(c);
+}
+
 int chb_set_distance_mode(chb_ctx *c, int mode)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
-    CHB_CHECK(c, mode == 0 || mode == 1, CHB_EINVAL, "distance mode must be 0 (exact rows) or 1 (FP32 filter + exact re-rank)");
+    CHB_CHECK(c, mode >= 0 && mode <= 2, CHB_EINVAL,
+              "distance mode must be 0 (exact rows), 1 (FP32 filter + exact re-rank) or 2 (fused tensor-core Gram + selection)");
     if (mode != c->dist_mode) { c->dist_ready = false; c->cache_nown = -1; }
     c->dist_mode = mode;
     return CHB_OK;
@@ -501,6 +531,7 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     c->labels_set = true;
     c->in_iteration = false;
     c->dist_ready = false;
+    c->f_asplit_ready = false;
     c->cache_nown = -1; // force cache re-initialisation
     return CHB_OK;
 }
@@ -530,7 +561,17 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
     // scratch for recomputed rows: ~1 GiB, at least 64 rows
     int64_t srows = (1LL << 30) / ((filt ? 4 : 8) * c->n);
     srows = std::max<int64_t>(64, std::min<int64_t>(srows, std::max<int64_t>(nown, 64)));
-    if (filt) {
+    if (use_fused(c)) {
+        // nothing is materialised: distances are regenerated on the tensor cores every round (fused.cu); a small
+        // scratch serves the rare exact-path fallback
+        dev_free(&c->Dq); c->cap_Dq = 0;
+        dev_free(&c->Dscratch); c->cap_scratch = 0;
+        dev_free(&c->Aq); c->cap_Aq = 0;
+        srows = std::min<int64_t>(srows, 256);
+        CHB_TRY(dev_reserve(c, &c->Ascratch, &c->cap_Ascratch, srows * c->lda));
+        c->scratch_rows = srows;
+        c->materialise = false;
+    } else if (filt) {
         dev_free(&c->Dq); c->cap_Dq = 0;
         dev_free(&c->Dscratch); c->cap_scratch = 0;
         if (c->materialise) {
@@ -768,12 +809,61 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     ++c->tm.launches_other;
     ++c->tm.rounds;
     if (cnt == 0) return CHB_OK;
-    if (use_filter(c) && c->C < 32768) {
+    if (use_filter(c) && !use_fused(c) && c->C < 32768) {
         pack_labels_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->pos, c->tent_pt, c->old_label, c->n, c->packed);
         CHB_CUDA(c, cudaGetLastError());
         ++c->tm.launches_other;
     }
     const bool filt = use_filter(c);
+    if (use_fused(c)) {
+        const int64_t nown = c->u1 - c->u0;
+        CHB_TRY(ensure_work(c, 2 * nown)); // a pair can be listed by the re-rank AND again by the exact-path fallback
+        CHB_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(int32_t), c->stream));
+        CHB_TRY(chb_round_fused(c));
+        // exact-path fallback for queries whose kept candidate list may be incomplete (duplicate contigs): rare
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_TRY(sync_stream(c));
+        const int64_t nfb = c->counters_host[6];
+        if (nfb > 0) {
+            if (c->f_cap_fb < 2 * nfb) {
+                CHB_TRY(dev_alloc(c, &c->f_fb_items, 2 * nfb));
+                c->f_cap_fb = 2 * nfb;
+            }
+            int32_t *items = c->f_fb_items, *points = c->f_fb_items + nfb;
+            fallback_prepare_kernel<<<(unsigned)nfb, 128, 0, c->stream>>>(c->f_fb_rows, (int32_t)nfb, c->qpoint + c->u0, c->pos, c->C,
+                                                                          items, points, c->knn_cnt);
+            ++c->tm.launches_other;
+            c->f_asplit_ready = false; // candidate_rows() re-uses the Asplit buffer for the fallback rows
+            for (int64_t s0 = 0; s0 < nfb; s0 += c->scratch_rows) {
+                const int64_t sc = std::min(c->scratch_rows, nfb - s0);
+                CHB_TRY(candidate_rows(c, points + s0, sc, c->Ascratch, c->lda));
+                chb_knn_args a{};
+                a.row_stride = c->lda; a.items = items + s0; a.n_items = sc; a.mode = 0; a.perm_pt = c->perm_pt;
+                a.qslot = c->qslot; a.pos = c->pos; a.tent_pt = c->tent_pt; a.old_label = c->old_label; a.n = c->n; a.C = c->C;
+                a.k = c->k; a.u0 = c->u0; a.knn_idx = c->knn_idx; a.knn_cnt = c->knn_cnt; a.work = c->work;
+                a.work_count = c->counters;
+                fill_filter_args(c, a, true);
+                a.knn_dist = c->knn_dist;
+                a.packed = nullptr;
+                a.arows = c->Ascratch;
+                a.row_is_item = 1;
+                CHB_TRY(chb_launch_knn_scan(c, a));
+            }
+        }
+        chb_qp_args q{};
+        q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = 2 * nown * c->C;
+        q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
+        q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
+        CHB_TRY(chb_launch_qp(c, q));
+        cudaMemcpyAsync(&c->counters_host[4], c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        {
+            chb_stage_timer t(c, CHB_ST_COMMIT);
+            argmin_kernel<<<nblk(cnt * 32, 256), 256, 0, c->stream>>>(c->own_pos + b, cnt, c->perm_pt, c->qslot, c->u0, c->pair_dist,
+                                                                      c->C, c->old_label, lo, tent_dev);
+        }
+        CHB_CUDA(c, cudaGetLastError());
+        return CHB_OK;
+    }
     CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));
     const int64_t step = c->materialise ? cnt : c->scratch_rows;
     int32_t *rows_tmp = nullptr;

@@ -30,7 +30,7 @@ struct chb_ctx {
     float *nrm = nullptr; // n : |x - mu|^2 rounded up to FP32
     double *colsum = nullptr; // d : column sums of X (mu = colsum / n)
     int32_t ldf = 0;
-    int dist_mode = 1;    // 1: FP32 candidate filter + exact FP64 re-rank (default); 0: exact FP64 rows
+    int dist_mode = 2;    // 2: fused tensor-core Gram + selection (default); 1: FP32 candidate matrix + scan; 0: exact FP64 rows
     int gram_engine = 1;  // filter mode: 1 = tcgen05 TF32x3 tensor-core Gram (gram_tc.cu), 0 = FFMA Gram (approx.cu)
     float *Asplit = nullptr, *Bsplit = nullptr; // TF32 hi/lo split operands: rows x Kp (queries), n x Kp (points)
     int64_t cap_Asplit = 0, cap_Bsplit = 0;
@@ -86,6 +86,16 @@ struct chb_ctx {
     // capacities (elements) of the re-usable allocations above, so that repeated set-ups do not re-malloc
     int64_t cap_X = 0, cap_Xf = 0, cap_nrm = 0;
     int64_t cap_n = 0, cap_U = 0, cap_own = 0, cap_Dq = 0, cap_scratch = 0, cap_pairs = 0, cap_knn = 0;
+
+    // ---- distance mode 2 (fused.cu): column entries, permuted operand, candidate lists
+    int32_t *f_bin_cnt = nullptr, *f_seg_off = nullptr, *f_cursor = nullptr, *f_tile_bin = nullptr, *f_ntiles = nullptr;
+    int32_t *f_col_pt = nullptr, *f_col_a = nullptr, *f_col_b = nullptr;
+    float *f_col_nrm = nullptr, *f_bperm = nullptr, *f_cand_key = nullptr;
+    int32_t *f_cand_idx = nullptr, *f_fb_rows = nullptr;
+    int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0;
+    bool f_asplit_ready = false;
+    int32_t *f_fb_items = nullptr; // positions of the fallback queries
+    int64_t f_cap_fb = 0;
 
     int2 *fallback = nullptr; // pairs the small-k QP kernel hands to the general one
     int64_t fallback_cap = 0;
@@ -169,6 +179,11 @@ int chb_gram_tc_prepare(chb_ctx *ctx, const int32_t *rows_dev, int64_t nrows, fl
                         bool do_b);
 int chb_launch_gram_tc(chb_ctx *ctx, const float *a_split, const float *b_split, int32_t Kp, const int32_t *rows_dev,
                        int64_t nrows, float *out_dev, int64_t ldo);
+
+// fused.cu : distance mode 2, Gram + per-bin selection in one tcgen05 kernel, then exact re-rank
+bool chb_fused_supported(const chb_ctx *c);
+int chb_round_fused(chb_ctx *c);
+void chb_fused_free(chb_ctx *c);
 
 // knn.cu
 struct chb_knn_args {

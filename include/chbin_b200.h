@@ -92,10 +92,15 @@ int chb_set_labels(chb_ctx *ctx, const int64_t *initial_bins, int64_t n, int32_t
                    int64_t slot_end);
 /* num_neighbors / metric of fit_cluster (algorithm.py:17,19). */
 int chb_set_params(chb_ctx *ctx, int32_t num_neighbors, int32_t metric);
-/* How the distances behind find_nearest_from_cluster are produced.  mode 1 (default): an FP32 approximation of
- * every squared distance (error-bounded) filters candidates and the exact scipy-cdist recipe is evaluated only
- * for candidates -- the neighbour sets are bit-identical to ranking the exact rows; mode 0: every exact FP64
- * distance is formed (3 non-fusable FP64 ops per feature).  Call before chb_build_distance_matrix. */
+/* How the distances behind find_nearest_from_cluster are produced.
+ *   mode 2 (default): nothing is stored; every round the tensor cores regenerate error-bounded FP32 candidate values
+ *           and the per-bin selection happens in the same kernel's epilogue (fused.cu); exact scipy-cdist values are
+ *           evaluated only where the FP32 bound cannot decide.  Needs num_neighbors <= 13, else mode 1 is used.
+ *   mode 1: the FP32 candidate matrix of the owned query rows is kept in HBM (InMemDistMatrix=yes) or recomputed per
+ *           round (no) and scanned by knn.cu; exact values for candidates only.
+ *   mode 0: every exact FP64 distance is formed (3 non-fusable FP64 ops per feature) and ranked directly.
+ * In all modes the neighbour sets are bit-identical to ranking scipy's exact rows.  Call before
+ * chb_build_distance_matrix. */
 int chb_set_distance_mode(chb_ctx *ctx, int mode);
 /* Engine of the FP32 candidate values in distance mode 1: 1 (default) = tcgen05 tensor cores, TF32 with a 3-term
  * hi/lo split, TMA-fed, TMEM accumulators (gram_tc.cu); 0 = FFMA on the CUDA cores (approx.cu). */
@@ -103,6 +108,9 @@ int chb_set_gram_engine(chb_ctx *ctx, int engine);
 /* Test aid: the FP32 candidate values A (nrows x n) of owned slots, the relative bound eps_rel with
  * |A - d^2| <= eps_rel * (nrm[query] + max nrm), and nrm (n floats, may be NULL).  Mode 1, materialised only. */
 int chb_get_candidate_rows(chb_ctx *ctx, int64_t slot0, int64_t nrows, float *out, double *eps_rel, float *nrm_out);
+/* Test aid: the per-(query, bin) state the assignment rounds keep for owned slots [slot0, slot0+nslots): neighbour
+ * lists (nslots*C*k int32, -1 padded, order unspecified), their lengths (nslots*C) and hull distances (nslots*C). */
+int chb_get_pair_cache(chb_ctx *ctx, int64_t slot0, int64_t nslots, int32_t *idx_out, int32_t *cnt_out, double *dist_out);
 /* create_in_mem_distance_matrix / create_distance_matrix (distance_matrix.py:12-44) for the owned query
  * rows.  materialise=1: rows are computed once (exact cdist recipe) and kept in HBM (InMemDistMatrix=yes,
  * cli/clustering.py:57-59); fails with CHB_ENOMEM if they do not fit.  materialise=0: nothing is stored,

@@ -165,25 +165,31 @@ def test_affine_qp_metric():
 
 
 FIT_CASES = [
-    # n, C, S, n_seed, k, concentration, window, materialise, distance_mode
-    (600, 5, 1, 40, 5, 4000.0, 0, True, 1),
-    (600, 5, 1, 40, 5, 4000.0, 0, True, 0),
-    (1500, 8, 1, 30, 5, 60.0, 0, True, 1),      # hard, overlapping genomes: many repair rounds, 10 iterations
-    (1500, 8, 1, 30, 5, 60.0, 0, True, 0),
-    (1500, 8, 1, 30, 5, 60.0, 97, True, 1),     # same with a small window
-    (1200, 6, 10, 25, 10, 300.0, 0, False, 1),  # k = 10, rows recomputed on demand (InMemDistMatrix = no)
-    (1200, 6, 10, 25, 10, 300.0, 0, False, 0),
-    (900, 4, 3, 3, 7, 500.0, 0, True, 1),       # bins smaller than k at the start
-    (5000, 20, 1, 20, 5, 1000.0, 0, True, 1),   # larger: several CTAs per SM, chunked queue
-    (1500, 8, 1, 30, 5, 60.0, 0, True, 2),      # distance mode 1 with the FFMA Gram engine
-    (1200, 6, 10, 25, 10, 300.0, 0, False, 2),
+    # n, C, S, n_seed, k, concentration, window, materialise, distance path
+    (600, 5, 1, 40, 5, 4000.0, 0, True, "filter"),
+    (600, 5, 1, 40, 5, 4000.0, 0, True, "exact"),
+    (600, 5, 1, 40, 5, 4000.0, 0, True, "fused"),
+    (1500, 8, 1, 30, 5, 60.0, 0, True, "filter"),      # hard, overlapping genomes: many repair rounds, 10 iterations
+    (1500, 8, 1, 30, 5, 60.0, 0, True, "exact"),
+    (1500, 8, 1, 30, 5, 60.0, 0, True, "fused"),
+    (1500, 8, 1, 30, 5, 60.0, 97, True, "filter"),     # same with a small window
+    (1500, 8, 1, 30, 5, 60.0, 97, True, "fused"),
+    (1200, 6, 10, 25, 10, 300.0, 0, False, "filter"),  # k = 10, rows recomputed on demand (InMemDistMatrix = no)
+    (1200, 6, 10, 25, 10, 300.0, 0, False, "exact"),
+    (1200, 6, 10, 25, 10, 300.0, 0, True, "fused"),
+    (900, 4, 3, 3, 7, 500.0, 0, True, "filter"),       # bins smaller than k at the start
+    (900, 4, 3, 3, 7, 500.0, 0, True, "fused"),
+    (5000, 20, 1, 20, 5, 1000.0, 0, True, "filter"),   # larger: several CTAs per SM, chunked queue
+    (5000, 20, 1, 20, 5, 1000.0, 0, True, "fused"),
+    (1500, 8, 1, 30, 5, 60.0, 0, True, "filter-ffma"), # distance mode 1 with the FFMA Gram engine
+    (1200, 6, 10, 25, 10, 300.0, 0, False, "filter-ffma"),
 ]
+_PATHS = {"exact": (0, 1), "filter": (1, 1), "filter-ffma": (1, 0), "fused": (2, 1)}
 
 
-@pytest.mark.parametrize("n,C,S,n_seed,k,conc,window,mat,dmode", FIT_CASES)
-def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat, dmode):
-    engine = 0 if dmode == 2 else 1
-    dmode = 1 if dmode == 2 else dmode
+@pytest.mark.parametrize("n,C,S,n_seed,k,conc,window,mat,path", FIT_CASES)
+def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat, path):
+    dmode, engine = _PATHS[path]
     X, bins, _ = synth.make_contig_features(n, C, S, n_seed, seed=7, concentration=conc)
     perms = oracle.draw_permutations(bins, 10, seed=0)
     ref, info = oracle.fit_cluster(X, C, bins, None, k, 10, perms=perms, return_info=True, threads=4)
@@ -196,6 +202,55 @@ def test_fit_cluster_labels_identical(n, C, S, n_seed, k, conc, window, mat, dmo
     assert ginfo["iterations"] == info["iterations"] and ginfo["converged"] == info["converged"]
     assert list(ginfo["changed"]) == list(info["changed"])
     assert np.array_equal(got, ref)
+
+
+def test_fit_cluster_fused_with_duplicate_contigs():
+    # many identical contigs: more candidates inside the filter slack than the kept list holds -> exact-path fallback
+    X, bins, _ = synth.make_contig_features(1200, 5, 1, 20, seed=17, concentration=300.0)
+    X[300:340] = X[300]
+    X[700:712] = X[700]
+    perms = oracle.draw_permutations(bins, 10, seed=0)
+    ref = oracle.fit_cluster(X, 5, bins, None, 5, 10, perms=perms, threads=4)
+    np.random.seed(0)
+    got = chbin_b200.fit_cluster(X, 5, bins, None, 5, 10, distance_mode=2)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("path", ["exact", "filter", "fused"])
+def test_cached_neighbour_sets_match_each_querys_view(path):
+    """After every iteration, the (query, bin) neighbour sets the rounds left in the cache must equal
+    find_nearest_from_cluster evaluated on the labels exactly as the reference's sequential loop showed them to
+    that query (earlier positions re-assigned, later positions not yet)."""
+    dmode, engine = _PATHS[path]
+    X, bins, _ = synth.make_contig_features(1000, 5, 1, 20, seed=17, concentration=300.0)
+    X[300:340] = X[300]          # duplicate contigs: ties, candidate-list overflow, exact-path fallback
+    X[700:712] = X[700]
+    perms = oracle.draw_permutations(bins, 3, seed=0)
+    D = oracle.create_in_mem_distance_matrix(X)
+    pts = np.where(bins == -1)[0]
+    ctx = capi.Context(0)
+    ctx.set_features(X); ctx.set_params(5, "convex"); ctx.set_distance_mode(dmode); ctx.set_gram_engine(engine)
+    ctx.set_labels(bins, 5); ctx.build_distance_matrix(True)
+    cur = bins.copy()
+    for it in range(3):
+        lab, _ = ctx.fit_iteration(perms[it])
+        ref = oracle.fit_cluster(X, 5, cur, None, 5, 1, perms=perms[it:it + 1], threads=4)
+        assert np.array_equal(lab, ref)
+        idx, cnt, dist = ctx.get_pair_cache(0, len(pts))
+        pos = np.full(len(X), -1)
+        pos[perms[it]] = np.arange(len(perms[it]))
+        for u, j in enumerate(pts[::7]):
+            u = u * 7
+            eff = np.where(pos < pos[j], lab, cur)
+            eff[j] = -1
+            for c in range(5):
+                want = np.sort(oracle.find_nearest_from_cluster(c, eff, D[j], 5))
+                got = np.sort(idx[u, c, : cnt[u, c]])
+                assert np.array_equal(want, got), (it, j, c)
+                dref = oracle.convex_hull_distance(X[j], X[want])
+                assert abs(dist[u, c] - dref) <= 1e-6 * dref + 1e-12
+        cur = ref
+    ctx.close()
 
 
 def test_fit_cluster_fortran_order_and_errors():

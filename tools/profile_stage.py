@@ -13,7 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--workload", default="20k")
 ap.add_argument("--n", type=int, default=None)
 ap.add_argument("--stages", type=int, default=1)
-ap.add_argument("--mode", type=int, default=1)
+ap.add_argument("--mode", type=int, default=2)
 ap.add_argument("--window", type=int, default=0)
 args = ap.parse_args()
 X, bins, truth, cfg = synth.make_config(args.workload, seed=0, n=args.n)
@@ -36,7 +36,7 @@ for s in range(args.stages):
 ctx.close()
 # steady-state probe: two more iterations after convergence (nothing changes): cost of a pure warm scan
 ctx = capi.Context(0)
-ctx.set_features(X); ctx.set_params(cfg["k"], "convex"); ctx.set_labels(bins, cfg["C"]); ctx.build_distance_matrix(True)
+ctx.set_features(X); ctx.set_params(cfg["k"], "convex"); ctx.set_distance_mode(args.mode); ctx.set_labels(bins, cfg["C"]); ctx.build_distance_matrix(True)
 for it in range(4):
     ctx.reset_timers()
     _, nch = ctx.fit_iteration(perms[it], want_labels=False)
