@@ -292,7 +292,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
-    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->f_fb_items);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->f_fb_items); dev_free(&c->stage_X);
     chb_fused_free(c); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
@@ -384,21 +384,19 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     if (c->cap_X < n * c->ldx) { CHB_TRY(dev_alloc(c, &c->X, n * c->ldx)); c->cap_X = n * c->ldx; }
     if (c->cap_Xf < n * c->ldf) { CHB_TRY(dev_alloc(c, &c->Xf, n * c->ldf)); c->cap_Xf = n * c->ldf; }
     if (c->cap_nrm < n) { CHB_TRY(dev_alloc(c, &c->nrm, n)); c->cap_nrm = n; }
-    CHB_TRY(dev_alloc(c, &c->colsum, d));
+    if (c->cap_colsum < d) { CHB_TRY(dev_alloc(c, &c->colsum, d)); c->cap_colsum = d; }
     {
-        // one contiguous copy (a strided 2-D copy from pageable host memory is several times slower), then repack
+        // one contiguous copy into a persistent staging buffer (a strided 2-D copy from pageable host memory is several
+        // times slower, and allocating / freeing the staging area per call costs more than the copy), then repack
         const double *dsrc = src;
-        double *stage = nullptr;
         if (kind == cudaMemcpyHostToDevice) {
-            CHB_TRY(dev_alloc(c, &stage, n * (int64_t)d));
-            CHB_CUDA(c, cudaMemcpyAsync(stage, src, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
-            dsrc = stage;
+            CHB_TRY(dev_reserve(c, &c->stage_X, &c->cap_stage_X, n * (int64_t)d));
+            CHB_CUDA(c, cudaMemcpyAsync(c->stage_X, src, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
+            dsrc = c->stage_X;
         }
         repack_features_kernel<<<nblk(n * c->ldx, 256), 256, 0, c->stream>>>(dsrc, n, d, c->ldx, c->X);
         ++c->tm.launches_other;
-        cudaError_t le = cudaGetLastError();
-        if (stage) { cudaStreamSynchronize(c->stream); cudaFree(stage); }
-        CHB_CUDA(c, le);
+        CHB_CUDA(c, cudaGetLastError());
     }
     CHB_TRY(chb_launch_prep_f32(c));
     CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[5], &c->counters[5], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -84,7 +84,9 @@ struct chb_ctx {
     int32_t *counters_host = nullptr; // pinned mirror
 
     // capacities (elements) of the re-usable allocations above, so that repeated set-ups do not re-malloc
-    int64_t cap_X = 0, cap_Xf = 0, cap_nrm = 0;
+    int64_t cap_X = 0, cap_Xf = 0, cap_nrm = 0, cap_colsum = 0;
+    double *stage_X = nullptr; // persistent staging area of chb_set_features
+    int64_t cap_stage_X = 0;
     int64_t cap_n = 0, cap_U = 0, cap_own = 0, cap_Dq = 0, cap_scratch = 0, cap_pairs = 0, cap_knn = 0;
 
     // ---- distance mode 2 (fused.cu): column entries, permuted operand, candidate lists
