@@ -231,3 +231,5 @@ struct chb_qp_args {
 int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a);
 // qp_small.cu : k <= 5 fast path; ill-conditioned pairs are appended to `fallback`
 int chb_launch_qp_small(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count);
+// qp_mid.cu : 6 <= k <= 10
+int chb_launch_qp_mid(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count);

@@ -320,6 +320,27 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
         b.work_count = &ctx->counters[3];
         return launch<8>(ctx, b, 1);
     }
+    if (a.k <= 10 && a.metric == CHB_METRIC_CONVEX) {
+        // 6..10 neighbours: 8-lane Gram + one-lane-per-pair active set (qp_mid.cu); ill-conditioned pairs come back here
+        if (ctx->fallback_cap < a.n_work) {
+            if (ctx->fallback) cudaFree(ctx->fallback);
+            ctx->fallback = nullptr;
+            cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->fallback), sizeof(int2) * (size_t)a.n_work);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                ctx->fallback_cap = 0;
+                return chb_fail(ctx, CHB_ENOMEM, "cudaMalloc of the QP fallback list failed: %s", cudaGetErrorString(e));
+            }
+            ctx->fallback_cap = a.n_work;
+        }
+        CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[3], 0, sizeof(int32_t), ctx->stream));
+        int rc = chb_launch_qp_mid(ctx, a, ctx->fallback, &ctx->counters[3]);
+        if (rc != CHB_OK) return rc;
+        chb_qp_args b = a;
+        b.work = ctx->fallback;
+        b.work_count = &ctx->counters[3];
+        return launch<16>(ctx, b, 1);
+    }
     if (a.k <= 8) return launch<8>(ctx, a);
     if (a.k <= 16) return launch<16>(ctx, a);
     return launch<32>(ctx, a);
