@@ -127,14 +127,17 @@ __global__ void repack_features_kernel(const double *__restrict__ src, int64_t n
 // the exact-path kNN kernel recomputes every bin of that query from scratch
 __global__ void fallback_prepare_kernel(const int32_t *__restrict__ fb_rows, int32_t cnt, const int32_t *__restrict__ qpoint_own,
                                         const int32_t *__restrict__ pos, int32_t C, int32_t *__restrict__ items,
-                                        int32_t *__restrict__ points, int32_t *__restrict__ knn_cnt)
+                                        int32_t *__restrict__ points, int32_t *__restrict__ knn_cnt, float *__restrict__ thr)
 {
     const int i = blockIdx.x;
     if (i >= cnt) return;
     const int r = fb_rows[i];
     const int pt = qpoint_own[r];
     if (threadIdx.x == 0) { items[i] = pos[pt]; points[i] = pt; }
-    for (int c = threadIdx.x; c < C; c += blockDim.x) knn_cnt[(int64_t)r * C + c] = -1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        knn_cnt[(int64_t)r * C + c] = -1;
+        thr[(int64_t)r * C + c] = INFINITY; // no admission threshold next round (fused.cu threshold_kernel)
+    }
 }
 
 __global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
@@ -478,7 +481,10 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     CHB_CHECK(c, c->X && n == c->n, CHB_EINVAL, "set_labels: call chb_set_features first with the same n");
     CHB_CHECK(c, bins && C >= 1, CHB_EINVAL, "initial_bins is NULL or num_clusters < 1");
     CHB_CUDA(c, cudaSetDevice(c->device));
-    std::vector<int32_t> lab((size_t)n), qs((size_t)n), qp;
+    std::vector<int32_t> &lab = c->h_lab, &qs = c->h_qslot, &qp = c->h_qpoint;
+    lab.resize((size_t)n);
+    qs.resize((size_t)n);
+    qp.clear();
     qp.reserve((size_t)n);
     for (int64_t i = 0; i < n; ++i) {
         const int64_t b = bins[i];
@@ -525,7 +531,6 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     fill_i32_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->pos, n, -1);
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
-    CHB_TRY(sync_stream(c));
     c->labels_set = true;
     c->in_iteration = false;
     c->dist_ready = false;
@@ -747,31 +752,25 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
               (long long)c->U);
     CHB_CUDA(c, cudaSetDevice(c->device));
     CHB_TRY(ensure_caches(c));
-    std::vector<int32_t> p32((size_t)std::max<int64_t>(U, 1));
-    // positions this context owns, ascending (a context owns the queries of slots [u0, u1))
-    std::vector<int32_t> qs_host; // slot of point: recomputed from qpoint ordering (slots are ascending point order)
-    std::vector<int32_t> own32;
-    own32.reserve((size_t)(c->u1 - c->u0));
+    // positions this context owns, ascending (a context owns the queries of slots [u0, u1)); host mirrors of
+    // qslot / the permutation scratch are kept in the context so that nothing is allocated or read back per iteration
+    std::vector<int32_t> &p32 = c->h_perm32;
+    std::vector<int32_t> &own32 = c->h_own32;
+    p32.resize((size_t)std::max<int64_t>(U, 1));
+    own32.clear();
     {
-        // qpoint is ascending, so slot(point) = rank of point among query points: build a lookup once per call
-        std::vector<int32_t> qp((size_t)std::max<int64_t>(U, 1));
-        if (U) CHB_CUDA(c, cudaMemcpyAsync(qp.data(), c->qpoint, sizeof(int32_t) * (size_t)U, cudaMemcpyDeviceToHost, c->stream));
-        CHB_TRY(sync_stream(c));
-        const int32_t lo_pt = (c->u1 > c->u0) ? qp[(size_t)c->u0] : 0;
-        const int32_t hi_pt = (c->u1 > c->u0) ? qp[(size_t)(c->u1 - 1)] : -1;
+        std::vector<uint8_t> &seen = c->h_seen;
+        seen.assign((size_t)std::max<int64_t>(U, 1), 0);
         int64_t cnt = 0;
-        std::vector<char> seen((size_t)std::max<int64_t>(U, 1), 0);
         for (int64_t p = 0; p < U; ++p) {
             const int64_t pt = perm[p];
             CHB_CHECK(c, pt >= 0 && pt < c->n, CHB_EINVAL, "permutation entry %lld out of range", (long long)pt);
-            const auto it = std::lower_bound(qp.begin(), qp.begin() + U, (int32_t)pt);
-            CHB_CHECK(c, it != qp.begin() + U && *it == (int32_t)pt, CHB_EINVAL,
-                      "permutation entry %lld is not an un-assigned point", (long long)pt);
-            const int64_t slot = it - qp.begin();
+            const int64_t slot = c->h_qslot[(size_t)pt];
+            CHB_CHECK(c, slot >= 0, CHB_EINVAL, "permutation entry %lld is not an un-assigned point", (long long)pt);
             CHB_CHECK(c, !seen[(size_t)slot], CHB_EINVAL, "permutation repeats point %lld", (long long)pt);
             seen[(size_t)slot] = 1;
             p32[(size_t)p] = (int32_t)pt;
-            if (pt >= lo_pt && pt <= hi_pt) {
+            if (slot >= c->u0 && slot < c->u1) {
                 own32.push_back((int32_t)p);
                 c->own_pos_host[cnt++] = p;
             }
@@ -787,7 +786,7 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
         ++c->tm.launches_other;
     }
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
-    CHB_TRY(sync_stream(c)); // p32 / own32 are stack-owned
+    // no sync: the host arrays are context-owned and pageable (the runtime stages them before returning)
     c->in_iteration = true;
     c->tm.qps_reference += (c->u1 - c->u0) * c->C;
     return CHB_OK;
@@ -829,9 +828,8 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
             }
             int32_t *items = c->f_fb_items, *points = c->f_fb_items + nfb;
             fallback_prepare_kernel<<<(unsigned)nfb, 128, 0, c->stream>>>(c->f_fb_rows, (int32_t)nfb, c->qpoint + c->u0, c->pos, c->C,
-                                                                          items, points, c->knn_cnt);
+                                                                          items, points, c->knn_cnt, c->f_thr);
             ++c->tm.launches_other;
-            c->f_asplit_ready = false; // candidate_rows() re-uses the Asplit buffer for the fallback rows
             for (int64_t s0 = 0; s0 < nfb; s0 += c->scratch_rows) {
                 const int64_t sc = std::min(c->scratch_rows, nfb - s0);
                 CHB_TRY(candidate_rows(c, points + s0, sc, c->Ascratch, c->lda));

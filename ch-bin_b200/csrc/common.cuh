@@ -51,6 +51,8 @@ struct chb_ctx {
     int64_t n_own_pos = 0;
     int64_t *own_pos_host = nullptr;
     bool labels_set = false, in_iteration = false;
+    std::vector<int32_t> h_lab, h_qslot, h_qpoint, h_perm32, h_own32; // host mirrors / per-iteration scratch
+    std::vector<uint8_t> h_seen;
 
     // ---- parameters
     int32_t k = 5, metric = CHB_METRIC_CONVEX;
@@ -94,7 +96,12 @@ struct chb_ctx {
     int32_t *f_col_pt = nullptr, *f_col_a = nullptr, *f_col_b = nullptr;
     float *f_col_nrm = nullptr, *f_bperm = nullptr, *f_cand_key = nullptr;
     int32_t *f_cand_idx = nullptr, *f_fb_rows = nullptr;
-    int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0;
+    int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0, f_cap_thr = 0;
+    float *f_thr = nullptr; // nown x C : largest FP32 key of the cached neighbour set (+inf: fewer than k members)
+    float *f_t0 = nullptr;  // C x f_ldt : this round's admission threshold per (bin, owned slot)
+    int64_t f_ldt = 0;
+    float *f_a2 = nullptr;  // nown x Kp2 : TF32 [hi | lo] operand rows of the owned queries
+    int64_t f_cap_a2 = 0, f_cap_bperm = 0;
     bool f_asplit_ready = false;
     int32_t *f_fb_items = nullptr; // positions of the fallback queries
     int64_t f_cap_fb = 0;

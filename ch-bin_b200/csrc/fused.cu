@@ -28,35 +28,46 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
 namespace {
 
 constexpr int BM = 128, BN = 128, BK = 32;
-constexpr int STAGES = 3;
 constexpr int UMMA_K = 8;
-constexpr uint32_t TILE_BYTES = BM * BK * 4;
+constexpr uint32_t TILE_BYTES = BM * BK * 4; // one 128-row x 32-float operand box (128-byte swizzle atom rows)
 constexpr int FUSED_THREADS = 320; // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quadrant)
 constexpr int EPI_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 256; // two 128-column accumulator buffers
+constexpr int MAX_BOX = 10;         // resident query operand: at most 10 boxes = 160 KB  (d <= 160)
+constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in shared memory per CTA
 
-struct ColMeta { // per-tile column metadata staged in shared memory
-    float nrm[BN];
-    int pt[BN];
-    int a[BN]; // visible to the query at position p iff p > a || p < b
-    int b[BN];
+// Operand layout (queries and columns alike): row = [hi(dp8) | lo(dp8) | 0...] floats, dp8 = d rounded up to 8, padded to
+// nbox boxes of 32 floats.  hi/lo are the TF32 halves of the centred FP32 feature (gram_tc.cu).  The contraction
+// hi.hi + hi.lo + lo.hi is issued as UMMA K=8 steps that pair step i of the RESIDENT query operand with step j of the
+// streamed column operand, so the query operand is read from L2 once per row block instead of once per tile.
+struct WarpMeta { // column metadata of one epilogue warp's 64 columns of the current tile (warp-private)
+    float nrm[64];
+    int a[64]; // visible to the query at position p iff p > a || p < b
+    int b[64];
 };
 
-struct SharedStorage {
-    alignas(1024) uint8_t a[STAGES][TILE_BYTES];
-    alignas(1024) uint8_t b[STAGES][TILE_BYTES];
-    alignas(16) ColMeta meta[2];
-    alignas(16) float stage_vals[2][32][BM]; // per column half: one 32-column batch of A values, [column][row]
-    alignas(8) uint64_t full_bar[STAGES];
-    alignas(8) uint64_t empty_bar[STAGES];
+constexpr int NC = 8; // per-thread candidate stack depth
+struct SmemTail {
+    alignas(16) WarpMeta meta[8];
+    // candidates that passed the screen wait here (thread-private stacks, [slot][thread]) until the warp drains them into
+    // the register lists: draining costs max-over-lanes insertions, so it pays to drain rarely
+    alignas(16) float cand_val[NC][EPI_THREADS];
+    uint8_t cand_col[NC][EPI_THREADS];
+    alignas(8) uint64_t full_bar[8];
+    alignas(8) uint64_t empty_bar[8];
     alignas(8) uint64_t tmem_full_bar[2];
     alignas(8) uint64_t tmem_empty_bar[2];
+    alignas(8) uint64_t a_full_bar;
+    alignas(8) uint64_t a_empty_bar;
+    alignas(8) uint2 prog[MAX_BOX * 8]; // per-tile MMA program: {query-operand descriptor (low word), column step offset}
+    int prog_start[MAX_BOX + 1];        // first program entry of each column box
     uint32_t tmem_base;
 };
 
@@ -114,11 +125,22 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ bool elect_one_sync()
+{
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P;\n"
+        "elect.sync _|P, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, P;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint64_t *bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------------------
 // column entries
@@ -189,21 +211,37 @@ __global__ void entries_fill_kernel(int64_t ncol, int32_t *__restrict__ col_pt, 
     col_b[e] = INT32_MIN;
 }
 
-// gathers the TF32-split operand rows and norms into column order; padding columns are zero
-__global__ void entries_gather_kernel(const int32_t *__restrict__ col_pt, const int32_t *__restrict__ ntiles, const float *__restrict__ bsplit,
-                                      const float *__restrict__ nrm, int32_t Kp, float *__restrict__ bperm, float *__restrict__ col_nrm)
+// Gathers rows of the centred FP32 features (Xf, prep_f32_kernel) through `idx` and writes them as TF32 operands in the
+// [hi(dp8) | lo(dp8) | 0] layout, Kp2 floats per row; idx < 0 (padding columns) gives a zero row.  `count_tiles`
+// (device, may be NULL) bounds the rows to *count_tiles * BN; otherwise nrows_max rows are written.
+__global__ void split2_gather_kernel(const int32_t *__restrict__ idx, const int32_t *__restrict__ count_tiles, int64_t nrows_max,
+                                     const float *__restrict__ Xf, int32_t ldf, int32_t d, int32_t dp8, int32_t Kp2,
+                                     const float *__restrict__ nrm, float *__restrict__ out, float *__restrict__ out_nrm)
 {
-    const int64_t ncol = (int64_t)(*ntiles) * BN;
-    const int64_t kq = Kp / 4; // float4 per row
+    const int64_t nr = count_tiles ? (int64_t)(*count_tiles) * BN : nrows_max;
+    const int64_t kq = Kp2 / 4; // float4 per row
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ncol * kq) return;
+    if (i >= nr * kq) return;
     const int64_t e = i / kq;
     const int q = (int)(i - e * kq);
-    const int ptx = col_pt[e];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ptx >= 0) v = __ldg(reinterpret_cast<const float4 *>(bsplit + (int64_t)ptx * Kp) + q);
-    reinterpret_cast<float4 *>(bperm + e * Kp)[q] = v;
-    if (q == 0) col_nrm[e] = ptx >= 0 ? nrm[ptx] : 0.f;
+    const int ptx = idx[e];
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+    if (ptx >= 0) {
+        const float *xr = Xf + (int64_t)ptx * ldf;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int t = 4 * q + u;
+            const int part = t >= dp8 ? 1 : 0;
+            const int f = t - part * dp8;
+            if (t < 2 * dp8 && f < d) {
+                const float xf = __ldg(xr + f);
+                const float hi = __uint_as_float(__float_as_uint(xf) & 0xffffe000u);
+                o[u] = part ? __uint_as_float(__float_as_uint(xf - hi) & 0xffffe000u) : hi;
+            }
+        }
+    }
+    reinterpret_cast<float4 *>(out + e * Kp2)[q] = make_float4(o[0], o[1], o[2], o[3]);
+    if (out_nrm && q == 0) out_nrm[e] = ptx >= 0 ? nrm[ptx] : 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -218,38 +256,51 @@ struct TopList {
 #pragma unroll
         for (int s = 0; s < KR; ++s) { key[s] = INFINITY; idx[s] = INT32_MAX; }
     }
-    // keeps the KR smallest (key, idx) pairs in ascending order; branch-free
+    // keeps the KR smallest keys (with their points) in ascending key order; branch-free.  The slot is found by counting
+    // (independent compares) and every slot then updates on its own, so the dependency chain is short -- with two
+    // epilogue warps per scheduler, latency rather than issue slots is what the epilogue runs out of.  Equal keys are not
+    // ordered by index: the re-rank ranks by (key, index) itself, and its overflow test only needs "every dropped entry
+    // has a key >= the largest kept key".
     __device__ __forceinline__ void insert(float ka, int ki)
     {
+        int cnt = 0;
 #pragma unroll
-        for (int s = 0; s < KR; ++s) {
-            const bool lt = (ka < key[s]) || (ka == key[s] && ki < idx[s]);
-            const float tk = lt ? key[s] : ka;
-            const int ti = lt ? idx[s] : ki;
-            key[s] = lt ? ka : key[s];
-            idx[s] = lt ? ki : idx[s];
-            ka = tk;
-            ki = ti;
+        for (int s = 0; s < KR; ++s) cnt += (key[s] <= ka) ? 1 : 0;
+#pragma unroll
+        for (int s = KR - 1; s >= 1; --s) {
+            const bool shift = s > cnt, here = s == cnt;
+            key[s] = shift ? key[s - 1] : (here ? ka : key[s]);
+            idx[s] = shift ? idx[s - 1] : (here ? ki : idx[s]);
         }
+        key[0] = cnt == 0 ? ka : key[0];
+        idx[0] = cnt == 0 ? ki : idx[0];
     }
 };
 
-template <int KR>
+// NKT > 0: the number of K=8 steps per operand half is known at compile time and a tile's MMA sequence is straight-line
+// code with immediate descriptor offsets (d = 137..160, the reference's 4-mer + coverage profiles); NKT = 0: any d, the
+// sequence is tabulated in shared memory once per CTA.
+template <int KR, int NKT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
-gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int num_kb,
+gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int nbox, int nk, int nstage,
                    const int32_t *__restrict__ ntiles_p, const int32_t *__restrict__ tile_bin, const int32_t *__restrict__ col_pt,
                    const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b, const float *__restrict__ col_nrm,
                    const float *__restrict__ nrm, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
-                   int64_t nrows, int32_t C, float *__restrict__ cand_key, int32_t *__restrict__ cand_idx)
+                   int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ cand_key,
+                   int32_t *__restrict__ cand_idx)
 {
+    // dynamic shared memory: [resident query operand: nbox boxes][column ring: nstage boxes][SmemTail]
     extern __shared__ uint8_t smem_raw[];
-    SharedStorage &S = *reinterpret_cast<SharedStorage *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *a_res = base;
+    uint8_t *ring = base + (size_t)nbox * TILE_BYTES;
+    SmemTail &S = *reinterpret_cast<SmemTail *>(ring + (size_t)nstage * TILE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ntiles = *ntiles_p;
     const int nrb = (int)((nrows + BM - 1) / BM);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
+        for (int s = 0; s < nstage; ++s) {
             mbar_init(&S.full_bar[s], 1);
             mbar_init(&S.empty_bar[s], 1);
         }
@@ -257,6 +308,8 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             mbar_init(&S.tmem_full_bar[b], 1);
             mbar_init(&S.tmem_empty_bar[b], 8); // one arrival per epilogue warp
         }
+        mbar_init(&S.a_full_bar, 1);
+        mbar_init(&S.a_empty_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -271,55 +324,138 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t tmem_base = S.tmem_base;
 
     if (warp == 0) {
+        // ---------------- TMA producer
         if (lane == 0) {
-            int64_t it = 0;
-            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+            int s = 0;
+            uint32_t ph = 0;
+            int rbi = 0;
+            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rbi) {
+                // the resident operand may be overwritten once every MMA of the previous row block has completed
+                mbar_wait(&S.a_empty_bar, (uint32_t)((rbi & 1) ^ 1));
+                mbar_expect_tx(&S.a_full_bar, (uint32_t)nbox * TILE_BYTES);
+                for (int jb = 0; jb < nbox; ++jb) tma_load_2d(a_res + (size_t)jb * TILE_BYTES, &map_a, &S.a_full_bar, jb * BK, rb * BM);
                 for (int t = 0; t < ntiles; ++t) {
-                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = (int)(it % STAGES);
-                        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
+                    for (int jb = 0; jb < nbox; ++jb) {
                         mbar_wait(&S.empty_bar[s], ph ^ 1);
-                        mbar_expect_tx(&S.full_bar[s], 2 * TILE_BYTES);
-                        tma_load_2d(S.a[s], &map_a, &S.full_bar[s], kb * BK, rb * BM);
-                        tma_load_2d(S.b[s], &map_b, &S.full_bar[s], kb * BK, t * BN);
+                        mbar_expect_tx(&S.full_bar[s], TILE_BYTES);
+                        tma_load_2d(ring + (size_t)s * TILE_BYTES, &map_b, &S.full_bar[s], jb * BK, t * BN);
+                        if (++s == nstage) { s = 0; ph ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        // ---------------- MMA issuer.  One thread feeds the tensor core, so its instruction stream is kept minimal:
+        // the (query step, column step) pairing of a tile is the same for every tile and is tabulated once.  The whole
+        // warp runs the loop (uniform control flow keeps descriptors in uniform registers); an elected lane issues.
+        {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-            int64_t it = 0, tt = 0;
-            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+            const uint32_t a_addr = smem_u32(a_res);
+            constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29); // SBO = 1024 B, version 1, 128-byte swizzle
+            if (NKT == 0 && lane == 0) {
+                int m = 0;
+                for (int jb = 0; jb < nbox; ++jb) {
+                    S.prog_start[jb] = m;
+                    for (int u = 0; u < BK / UMMA_K; ++u) {
+                        const int j = jb * (BK / UMMA_K) + u; // K=8 step of the column operand
+                        if (j >= 2 * nk) break;
+                        // column hi step j pairs with query hi step j and query lo step nk + j;
+                        // column lo step j - nk pairs with query hi step j - nk
+                        const int i0 = j < nk ? j : j - nk;
+                        const uint32_t boff = (uint32_t)((u * UMMA_K * 4) >> 4);
+                        S.prog[m++] = make_uint2((((a_addr + (uint32_t)(i0 >> 2) * TILE_BYTES) & 0x3FFFFu) >> 4 | (1u << 16)) +
+                                                     (uint32_t)(((i0 & 3) * UMMA_K * 4) >> 4), boff);
+                        if (j < nk) {
+                            const int i1 = nk + j;
+                            S.prog[m++] = make_uint2((((a_addr + (uint32_t)(i1 >> 2) * TILE_BYTES) & 0x3FFFFu) >> 4 | (1u << 16)) +
+                                                         (uint32_t)(((i1 & 3) * UMMA_K * 4) >> 4), boff);
+                        }
+                    }
+                }
+                S.prog_start[nbox] = m;
+            }
+            __syncwarp();
+            const uint32_t ring_lo = ((smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t tt = 0;
+            int rbi = 0;
+            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rbi) {
+                mbar_wait(&S.a_full_bar, (uint32_t)(rbi & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 for (int t = 0; t < ntiles; ++t, ++tt) {
                     const int buf = (int)(tt & 1);
                     const uint32_t tph = (uint32_t)((tt >> 1) & 1);
                     mbar_wait(&S.tmem_empty_bar[buf], tph ^ 1); // epilogue has drained this accumulator buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
-                    for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                        const int s = (int)(it % STAGES);
-                        const uint32_t ph = (uint32_t)((it / STAGES) & 1);
-                        mbar_wait(&S.full_bar[s], ph);
-                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint64_t adesc = make_smem_desc(smem_u32(S.a[s]));
-                        const uint64_t bdesc = make_smem_desc(smem_u32(S.b[s]));
+                    if constexpr (NKT > 0) {
+                        constexpr int NBOX = (2 * NKT + 3) / 4;
+                        const uint32_t a_lo = ((a_addr & 0x3FFFFu) >> 4) | (1u << 16);
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 4) >> 4);
-                            umma_tf32(tmem_d, adesc + koff, bdesc + koff, idesc, (kb | k) != 0);
+                        for (int jb = 0; jb < NBOX; ++jb) {
+                            const uint32_t b_lo = ring_lo + (uint32_t)s * (TILE_BYTES >> 4);
+                            mbar_wait(&S.full_bar[s], ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (elect_one_sync()) {
+#pragma unroll
+                            for (int u = 0; u < BK / UMMA_K; ++u) {
+                                const int j = jb * (BK / UMMA_K) + u;
+                                if (j < 2 * NKT) {
+                                    const int i0 = j < NKT ? j : j - NKT;
+                                    const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | (b_lo + (uint32_t)((u * UMMA_K * 4) >> 4));
+                                    umma_tf32(tmem_d,
+                                              ((uint64_t)DESC_HI << 32) |
+                                                  (a_lo + (uint32_t)((i0 >> 2) * (TILE_BYTES >> 4) + (((i0 & 3) * UMMA_K * 4) >> 4))),
+                                              bdesc, idesc, (jb | u) != 0);
+                                    if (j < NKT) {
+                                        const int i1 = NKT + j;
+                                        umma_tf32(tmem_d,
+                                                  ((uint64_t)DESC_HI << 32) |
+                                                      (a_lo + (uint32_t)((i1 >> 2) * (TILE_BYTES >> 4) + (((i1 & 3) * UMMA_K * 4) >> 4))),
+                                                  bdesc, idesc, 1u);
+                                    }
+                                }
+                            }
+                            umma_commit(&S.empty_bar[s]);
+                            }
+                            if (++s == nstage) { s = 0; ph ^= 1; }
                         }
-                        umma_commit(&S.empty_bar[s]);
+                    } else {
+                        uint32_t acc = 0;
+                        int m = 0;
+                        for (int jb = 0; jb < nbox; ++jb) {
+                            const int m_end = S.prog_start[jb + 1];
+                            const uint32_t b_lo = ring_lo + (uint32_t)s * (TILE_BYTES >> 4);
+                            mbar_wait(&S.full_bar[s], ph);
+                            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                            if (elect_one_sync()) {
+                                for (int mm = m; mm < m_end; ++mm) {
+                                    const uint2 e = S.prog[mm];
+                                    const uint64_t adesc = ((uint64_t)DESC_HI << 32) | e.x;
+                                    const uint64_t bdesc = ((uint64_t)DESC_HI << 32) | (b_lo + e.y);
+                                    umma_tf32(tmem_d, adesc, bdesc, idesc, (mm | (int)acc) != 0);
+                                }
+                                umma_commit(&S.empty_bar[s]);
+                            }
+                            m = m_end;
+                            acc = 1;
+                            if (++s == nstage) { s = 0; ph ^= 1; }
+                        }
                     }
-                    umma_commit(&S.tmem_full_bar[buf]);
+                    if (elect_one_sync()) umma_commit(&S.tmem_full_bar[buf]);
                 }
+                if (elect_one_sync()) umma_commit(&S.a_empty_bar);
             }
         }
     } else {
-        // ---------------- epilogue warps 2..9: thread <-> (query row, column half)
+        // ---------------- epilogue warps 2..9: thread <-> (query row, column half).  The warps run decoupled: each
+        // stages the metadata of its own 64 columns and synchronises with the MMA warp only (TMEM full / empty barriers),
+        // so a warp that meets many candidates in one tile does not hold up the other seven.
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;       // 0: columns [0,64) of a tile, 1: columns [64,128)
         const int row = q * 32 + lane;          // TMEM lane == row within the block
+        WarpMeta &M = S.meta[warp - 2];
         const int et = threadIdx.x - 64;        // 0..255 index among the epilogue threads
         TopList<KR> L;
         int64_t tt = 0;
@@ -335,90 +471,101 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             L.reset();
             int cur_bin = ntiles > 0 ? tile_bin[0] : -1;
+            // admission threshold of (this query, current bin): see threshold_kernel
+            float t0 = (rvalid && cur_bin >= 0) ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
+            // column metadata of the next tile travels in registers while the current tile is processed
+            float m_n0 = 0.f, m_n1 = 0.f;
+            int m_a0 = INT32_MAX, m_a1 = INT32_MAX, m_b0 = INT32_MIN, m_b1 = INT32_MIN;
+            if (ntiles > 0) {
+                const int64_t e = half * 64 + lane;
+                m_n0 = col_nrm[e]; m_a0 = col_a[e]; m_b0 = col_b[e];
+                m_n1 = col_nrm[e + 32]; m_a1 = col_a[e + 32]; m_b1 = col_b[e + 32];
+            }
+            int tb_next = cur_bin;
             for (int t = 0; t < ntiles; ++t, ++tt) {
                 const int buf = (int)(tt & 1);
                 const uint32_t tph = (uint32_t)((tt >> 1) & 1);
-                const int tb = tile_bin[t];
+                const int tb = tb_next;
+                if (t + 1 < ntiles) tb_next = tile_bin[t + 1];
                 if (tb != cur_bin) { // bin boundary: flush the finished (half-)list
                     if (rvalid) {
-                        float *ok = cand_key + ((gr * C + cur_bin) * 2 + half) * KR;
-                        int32_t *oi = cand_idx + ((gr * C + cur_bin) * 2 + half) * KR;
+                        float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
+                        int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
 #pragma unroll
-                        for (int s = 0; s < KR; ++s) { ok[s] = L.key[s]; oi[s] = L.idx[s]; }
+                        for (int s = 0; s < KR; s += 4) {
+                            ok[s >> 2] = make_float4(L.key[s], L.key[s + 1], L.key[s + 2], L.key[s + 3]);
+                            oi[s >> 2] = make_int4(L.idx[s], L.idx[s + 1], L.idx[s + 2], L.idx[s + 3]);
+                        }
                     }
                     L.reset();
                     cur_bin = tb;
+                    t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
                 }
-                if (et < BN) { // stage this tile's column metadata
-                    const int64_t e = (int64_t)t * BN + et;
-                    ColMeta &Mw = S.meta[buf];
-                    Mw.nrm[et] = col_nrm[e];
-                    Mw.pt[et] = col_pt[e];
-                    Mw.a[et] = col_a[e];
-                    Mw.b[et] = col_b[e];
+                __syncwarp(); // every lane is done with the previous tile's metadata
+                M.nrm[lane] = m_n0; M.a[lane] = m_a0; M.b[lane] = m_b0;
+                M.nrm[lane + 32] = m_n1; M.a[lane + 32] = m_a1; M.b[lane + 32] = m_b1;
+                __syncwarp();
+                if (t + 1 < ntiles) {
+                    const int64_t e = (int64_t)(t + 1) * BN + half * 64 + lane;
+                    m_n0 = col_nrm[e]; m_a0 = col_a[e]; m_b0 = col_b[e];
+                    m_n1 = col_nrm[e + 32]; m_a1 = col_a[e + 32]; m_b1 = col_b[e + 32];
                 }
-                epi_bar_sync();
-                const ColMeta &M = S.meta[buf];
+                const int32_t *tile_pt = col_pt + (int64_t)t * BN + half * 64;
                 mbar_wait(&S.tmem_full_bar[buf], tph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-                for (int cb = 0; cb < 2; ++cb) {
-                    const int c0 = half * 64 + cb * 32;
-                    uint32_t v[32];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                        : "r"(taddr));
+                // the thread's 64 accumulator columns in one TMEM read; the buffer goes back to the MMA warp right away
+                uint32_t v[64];
+                {
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * 64);
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x64.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+                                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+                                 : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (cb == 1) {
-                        // this warp has read its part of the accumulator tile: hand the buffer back to the MMA warp
-                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
+                }
+                // screen the 64 columns four at a time; survivors go onto the thread's candidate stack
+                int ncand = 0;
+#pragma unroll
+                for (int j = 0; j < 64; j += 4) {
+                    const float thr = fminf(L.key[KR - 1], t0);
+                    const float4 n4 = *reinterpret_cast<const float4 *>(&M.nrm[j]);
+                    const int4 a4 = *reinterpret_cast<const int4 *>(&M.a[j]);
+                    const int4 b4 = *reinterpret_cast<const int4 *>(&M.b[j]);
+                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
+                    const int aa[4] = {a4.x, a4.y, a4.z, a4.w};
+                    const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float av = fmaf(-2.f, __uint_as_float(v[j + u]), nr + nn[u]);
+                        const bool cand = ((p > aa[u]) || (p < bb[u])) && (av <= thr);
+                        if (cand) {
+                            S.cand_val[ncand][et] = av;
+                            S.cand_col[ncand][et] = (uint8_t)(j + u);
+                            ++ncand;
+                        }
                     }
-                    const float thr = L.key[KR - 1];
-                    unsigned mask = 0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 n4 = *reinterpret_cast<const float4 *>(&M.nrm[c0 + j]);
-                        const int4 a4 = *reinterpret_cast<const int4 *>(&M.a[c0 + j]);
-                        const int4 b4 = *reinterpret_cast<const int4 *>(&M.b[c0 + j]);
-                        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-                        const int aa[4] = {a4.x, a4.y, a4.z, a4.w};
-                        const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) {
-                            const float av = fmaf(-2.f, __uint_as_float(v[j + u]), nr + nn[u]);
-                            const bool cand = ((p > aa[u]) || (p < bb[u])) && (av <= thr);
-                            if (cand) {
-                                S.stage_vals[half][j + u][row] = av;
-                                mask |= 1u << (j + u);
+                    // drain when some stack could overflow in the next group, and at the end of the tile
+                    if (j == 60 || __any_sync(CHB_FULL, ncand > NC - 4)) {
+                        while (__any_sync(CHB_FULL, ncand > 0)) {
+                            if (ncand > 0) {
+                                --ncand;
+                                const float av = S.cand_val[ncand][et];
+                                if (av < L.key[KR - 1]) L.insert(av, __ldg(tile_pt + S.cand_col[ncand][et]));
                             }
                         }
                     }
-                    // insert candidates: the warp iterates max-over-lanes popcount times
-                    while (__any_sync(CHB_FULL, mask != 0)) {
-                        if (mask) {
-                            const int j = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            const float av = S.stage_vals[half][j][row];
-                            if (av <= L.key[KR - 1]) L.insert(av, M.pt[c0 + j]);
-                        }
-                    }
                 }
-                epi_bar_sync(); // everyone is done with meta[buf] before it is overwritten two tiles later
             }
             if (rvalid && cur_bin >= 0) {
-                float *ok = cand_key + ((gr * C + cur_bin) * 2 + half) * KR;
-                int32_t *oi = cand_idx + ((gr * C + cur_bin) * 2 + half) * KR;
+                float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
+                int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
 #pragma unroll
-                for (int s = 0; s < KR; ++s) { ok[s] = L.key[s]; oi[s] = L.idx[s]; }
+                for (int s = 0; s < KR; s += 4) {
+                    ok[s >> 2] = make_float4(L.key[s], L.key[s + 1], L.key[s + 2], L.key[s + 3]);
+                    oi[s >> 2] = make_int4(L.idx[s], L.idx[s + 1], L.idx[s + 2], L.idx[s + 3]);
+                }
             }
         }
     }
@@ -427,6 +574,48 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 2) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// admission thresholds.  The k cached neighbours of (query, bin) from the previous round bound this round's k-th
+// smallest key as long as all of them are still visible members of the bin: with |A - d^2| <= E for every evaluation
+// and thr = the largest cached key of the set, every re-evaluated member key is <= thr + 2E, so the k-th smallest key
+// a_k of this round is too, and everything the re-rank may need (keys <= a_k + 2E) lies below T0 = thr + 4E.
+// Columns above T0 are skipped by the fused kernel without touching the per-thread lists.  T0 = +inf when there is no
+// usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
+                                 const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
+                                 const int32_t *__restrict__ tent, const int32_t *__restrict__ old, const float *__restrict__ nrm,
+                                 const unsigned int *__restrict__ nrm_max_bits, double eps_rel, int64_t nown, int32_t C, int32_t k,
+                                 int64_t ldt, float *__restrict__ t0_tab)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nown * C) return;
+    const int c = (int)(i / nown);
+    const int64_t r = i - (int64_t)c * nown;
+    const int64_t pair = r * C + c;
+    float out = INFINITY;
+    if (knn_cnt[pair] == k) {
+        const float th = thr[pair];
+        if (th < INFINITY) {
+            const int jq = row_point[r];
+            const int p = pos[jq];
+            bool ok = true;
+            for (int s = 0; s < k; ++s) {
+                const int j = knn_idx[pair * k + s];
+                const int ps = pos[j];
+                const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
+                ok = ok && (lab == c);
+            }
+            if (ok) {
+                const double nmax = (double)__uint_as_float(*nrm_max_bits);
+                const float slack2 = __double2float_ru(2.0 * (eps_rel * ((double)nrm[jq] + nmax) + 1e-30));
+                out = __fadd_ru(th, __fmul_ru(2.f, slack2));
+            }
+        }
+    }
+    t0_tab[(int64_t)c * ldt + r] = out;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -462,20 +651,27 @@ __device__ __forceinline__ double exact_distance_g(const double *__restrict__ xq
     return __dsqrt_rn(acc);
 }
 
-// One CTA (128 threads) per owned query; warp w handles bins w, w+4, ...; lane s < 2*KR holds one kept candidate
-// (two half-lists of KR per pair, one per column half of the fused kernel's tiles).
+// One CTA (128 threads) per owned query.  A group of G lanes (G = 16 when the two half-lists of KR = 8 fit, else 32) handles
+// one (query, bin) pair: lane s < 2*KR of the group holds one kept candidate.  Everything is predicated rather than
+// branched so that the groups of a warp stay convergent for the shuffles; loops run over the set bits of the
+// candidate masks (with admission thresholds most lists hold few more than k entries).
 // Bins that never received a flush (no columns at all) are recognised through bin_cnt.
+template <int G>
 __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ cand_key, const int32_t *__restrict__ cand_idx, int KR,
                                                      const int32_t *__restrict__ bin_cnt, const double *__restrict__ X, int32_t ldx,
                                                      int32_t d, const int32_t *__restrict__ row_point, const float *__restrict__ nrm,
                                                      const unsigned int *__restrict__ nrm_max_bits, double eps_rel, int32_t C,
                                                      int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
-                                                     int32_t *__restrict__ fb_rows, int32_t *__restrict__ fb_count)
+                                                     int32_t *__restrict__ fb_rows, int32_t *__restrict__ fb_count,
+                                                     const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ thr_out)
 {
     extern __shared__ __align__(16) double xq_s[];
+    constexpr int NG = 32 / G;
+    constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
     const int64_t r = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gl = lane & (G - 1), gsh = lane & ~(G - 1);
     const int jq = row_point[r];
     for (int t = threadIdx.x; t < d; t += 128) xq_s[t] = X[(int64_t)jq * ldx + t];
     __shared__ int s_overflow;
@@ -484,86 +680,107 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
     const double nmax = (double)__uint_as_float(*nrm_max_bits);
     const float slack2 = __double2float_ru(2.0 * (eps_rel * ((double)nrm[jq] + nmax) + 1e-30));
     const int K2 = 2 * KR;
+    bool overflow = false;
 
-    for (int c = warp; c < C; c += 4) {
-        const int64_t pair = r * C + c;
+    for (int cb = warp * NG; cb < C; cb += 4 * NG) {
+        const int c = cb + lane / G;
+        const bool act = c < C;
+        const int64_t pair = r * C + (act ? c : 0);
         float ka = INFINITY;
         int ki = INT32_MAX;
-        if (bin_cnt[c] > 0 && lane < K2) {
-            ka = cand_key[pair * K2 + lane];
-            ki = cand_idx[pair * K2 + lane];
+        if (act && bin_cnt[c] > 0 && gl < K2) {
+            ka = cand_key[pair * K2 + gl];
+            ki = cand_idx[pair * K2 + gl];
         }
+        const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
+        const int mo = act ? knn_cnt[pair] : 0;
         const bool valid = ka < INFINITY; // +inf = empty slot
-        const unsigned vm = __ballot_sync(CHB_FULL, valid);
+        const unsigned vm = (__ballot_sync(CHB_FULL, valid) >> gsh) & GM;
         const int nc = __popc(vm);
-        const int m = nc < k ? nc : k;  // |bin| <= k: all members (distance_matrix.py:58-59)
-        // rank of every candidate by (key, index)
+        const int m = nc < k ? nc : k; // |bin| <= k: all members (distance_matrix.py:58-59)
+        const bool big = nc > k;
+        // rank of every candidate by (key, index) among the valid ones
         int rnk = 0;
-        for (int t = 0; t < K2; ++t) {
-            const float ok = __shfl_sync(CHB_FULL, ka, t);
-            const int oi = __shfl_sync(CHB_FULL, ki, t);
-            if (((vm >> t) & 1u) && (ok < ka || (ok == ka && oi < ki))) ++rnk;
+        {
+            unsigned mm = vm;
+            while (__any_sync(CHB_FULL, mm != 0)) {
+                const bool had = mm != 0;
+                const int t = had ? __ffs(mm) - 1 : 0;
+                mm &= mm - 1;
+                const float ok = __shfl_sync(CHB_FULL, ka, t, G);
+                const int oi = __shfl_sync(CHB_FULL, ki, t, G);
+                if (had && (ok < ka || (ok == ka && oi < ki))) ++rnk;
+            }
         }
-        bool sel = false;
-        if (nc <= k) {
-            sel = valid;
-        } else {
-            const int src_k = __ffs(__ballot_sync(CHB_FULL, valid && rnk == k - 1)) - 1;
-            const int src_k1 = __ffs(__ballot_sync(CHB_FULL, valid && rnk == k)) - 1;
-            const float a_k = __shfl_sync(CHB_FULL, ka, src_k);   // k-th smallest key
-            const float a_k1 = __shfl_sync(CHB_FULL, ka, src_k1); // (k+1)-th
-            const float hi = __fadd_ru(a_k, slack2);
+        const unsigned bk = (__ballot_sync(CHB_FULL, valid && rnk == k - 1) >> gsh) & GM;
+        const unsigned bk1 = (__ballot_sync(CHB_FULL, valid && rnk == k) >> gsh) & GM;
+        const float a_k = __shfl_sync(CHB_FULL, ka, bk ? __ffs(bk) - 1 : 0, G);    // k-th smallest key   (big only)
+        const float a_k1 = __shfl_sync(CHB_FULL, ka, bk1 ? __ffs(bk1) - 1 : 0, G); // (k+1)-th            (big only)
+        const float hi = __fadd_ru(a_k, slack2);
+        const bool could = valid && ka <= hi;                      // may belong to the exact top-k
+        const bool sure = valid && (__fadd_ru(ka, slack2) < a_k1); // certainly belongs to it
+        const unsigned cm = (__ballot_sync(CHB_FULL, could) >> gsh) & GM;
+        const unsigned sm = (__ballot_sync(CHB_FULL, sure) >> gsh) & GM;
+        const int nsure = __popc(sm);
+        if (big) {
+            // every key <= hi must have been admitted by the fused kernel's threshold (holds by construction of T0), and
             // a half-list that is full and entirely inside the slack may have dropped a closer point
-            const bool h0 = lane < KR, h1 = lane >= KR && lane < K2;
-            const unsigned in0 = __ballot_sync(CHB_FULL, h0 && valid && ka <= hi), in1 = __ballot_sync(CHB_FULL, h1 && valid && ka <= hi);
-            if (__popc(in0) == KR || __popc(in1) == KR) {
-                if (lane == 0) s_overflow = 1;
-            }
-            const bool could = valid && ka <= hi;                      // may belong to the exact top-k
-            const bool sure = valid && (__fadd_ru(ka, slack2) < a_k1); // certainly belongs to it
-            const unsigned sm = __ballot_sync(CHB_FULL, sure), cm = __ballot_sync(CHB_FULL, could);
-            const int nsure = __popc(sm);
-            if (__popc(cm) == k) {
-                sel = could; // unambiguous: the k smallest keys ARE the neighbours
-            } else {
-                // ambiguous candidates: exact scipy-recipe distance, rank by (distance, index)
-                const bool amb = could && !sure;
-                double de = 0.0;
-                if (amb) de = exact_distance_g(xq_s, X + (int64_t)ki * ldx, d);
-                const unsigned am = __ballot_sync(CHB_FULL, amb);
-                int rk = 0;
-                for (int t = 0; t < K2; ++t) {
-                    const double od = __shfl_sync(CHB_FULL, de, t);
-                    const int oi = __shfl_sync(CHB_FULL, ki, t);
-                    if (((am >> t) & 1u) && (od < de || (od == de && oi < ki))) ++rk;
-                }
-                sel = sure || (amb && rk < k - nsure);
+            const unsigned lo_half = (1u << KR) - 1u;
+            if (hi > t0v || __popc(cm & lo_half) == KR || __popc(cm >> KR) == KR) overflow = true;
+        }
+        // ambiguous candidates: exact scipy-recipe distance, rank by (distance, index)
+        const bool amb = big && __popc(cm) != k && could && !sure;
+        double de = 0.0;
+        if (amb) de = exact_distance_g(xq_s, X + (int64_t)ki * ldx, d);
+        const unsigned am = (__ballot_sync(CHB_FULL, amb) >> gsh) & GM;
+        int rk = 0;
+        {
+            unsigned mm = am;
+            while (__any_sync(CHB_FULL, mm != 0)) {
+                const bool had = mm != 0;
+                const int t = had ? __ffs(mm) - 1 : 0;
+                mm &= mm - 1;
+                const double od = __shfl_sync(CHB_FULL, de, t, G);
+                const int oi = __shfl_sync(CHB_FULL, ki, t, G);
+                if (had && (od < de || (od == de && oi < ki))) ++rk;
             }
         }
+        const bool sel = !big ? valid : (__popc(cm) == k ? could : (sure || (amb && rk < k - nsure)));
+        // largest FP32 key of the chosen set: next round's admission threshold derives from it (threshold_kernel)
+        float mx = sel ? ka : -INFINITY;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(CHB_FULL, mx, o));
         // neighbour set, stored in ascending index order (canonical for set comparison)
+        const unsigned selm = (__ballot_sync(CHB_FULL, sel) >> gsh) & GM;
         int srt = 0;
-        const unsigned selm = __ballot_sync(CHB_FULL, sel);
-        for (int t = 0; t < K2; ++t) {
-            const int oi = __shfl_sync(CHB_FULL, ki, t);
-            if (((selm >> t) & 1u) && oi < ki) ++srt;
+        {
+            unsigned mm = selm;
+            while (__any_sync(CHB_FULL, mm != 0)) {
+                const bool had = mm != 0;
+                const int t = had ? __ffs(mm) - 1 : 0;
+                mm &= mm - 1;
+                const int oi = __shfl_sync(CHB_FULL, ki, t, G);
+                if (had && oi < ki) ++srt;
+            }
         }
-        const int mo = knn_cnt[pair];
-        bool same = (mo == m);
-        if (same) {
-            const bool diff = sel && (knn_idx[pair * k + srt] != ki);
-            same = !__any_sync(CHB_FULL, diff);
-        }
-        if (!same) {
-            if (lane < k) knn_idx[pair * k + lane] = -1;
-            __syncwarp();
-            if (sel) knn_idx[pair * k + srt] = ki;
-            if (lane == 0) {
-                knn_cnt[pair] = m;
-                const int w = atomicAdd(work_count, 1);
-                work[w] = make_int2((int)r, c);
+        const bool diff = sel && (mo != m || knn_idx[pair * k + srt] != ki);
+        const unsigned dm = (__ballot_sync(CHB_FULL, diff) >> gsh) & GM;
+        const bool same = (mo == m) && dm == 0;
+        if (act) {
+            if (gl == 0) thr_out[pair] = (m == k) ? mx : INFINITY;
+            if (!same) {
+                // slots [0, m) come from the selected lanes, slots [m, k) are cleared by the lanes sitting at those positions
+                if (sel) knn_idx[pair * k + srt] = ki;
+                if (gl >= m && gl < k) knn_idx[pair * k + gl] = -1;
+                if (gl == 0) {
+                    knn_cnt[pair] = m;
+                    const int w = atomicAdd(work_count, 1);
+                    work[w] = make_int2((int)r, c);
+                }
             }
         }
     }
+    if (__any_sync(CHB_FULL, overflow) && lane == 0) s_overflow = 1;
     __syncthreads();
     if (threadIdx.x == 0 && s_overflow) fb_rows[atomicAdd(fb_count, 1)] = (int)r;
 }
@@ -597,25 +814,51 @@ int make_map(chb_ctx *ctx, CUtensorMap *map, float *base, int64_t nrows, int32_t
     return CHB_OK;
 }
 
-template <int KR>
-int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows)
+struct FusedGeom {
+    int dp8, nk, nbox, Kp2, nstage;
+    size_t smem;
+};
+FusedGeom fused_geom(int d)
 {
-    const size_t smem = sizeof(SharedStorage) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        CHB_CUDA(c, cudaFuncSetAttribute(gram_select_kernel<KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    FusedGeom g{};
+    g.dp8 = (d + 7) & ~7;
+    g.nk = g.dp8 / UMMA_K;
+    g.nbox = (2 * g.dp8 + BK - 1) / BK;
+    g.Kp2 = g.nbox * BK;
+    const int fixed = 1024 + (int)sizeof(SmemTail);
+    g.nstage = std::min(8, (SMEM_LIMIT - fixed - g.nbox * (int)TILE_BYTES) / (int)TILE_BYTES);
+    g.smem = (size_t)fixed + (size_t)(g.nbox + std::max(g.nstage, 0)) * TILE_BYTES;
+    return g;
+}
+
+template <int KR, int NKT>
+int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
+{
+    CHB_CUDA(c, cudaFuncSetAttribute(gram_select_kernel<KR, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int nrb = (int)((nrows + BM - 1) / BM);
     const int grid = std::min(nrb, c->sm_count);
     {
         chb_stage_timer t(c, CHB_ST_KNN);
-        gram_select_kernel<KR><<<grid, FUSED_THREADS, smem, c->stream>>>(
-            ma, mb, c->Kp / BK, c->f_ntiles, c->f_tile_bin, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->nrm,
-            c->qpoint + c->u0, c->pos, nrows, c->C, c->f_cand_key, c->f_cand_idx);
+        gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
+            ma, mb, g.nbox, g.nk, g.nstage, c->f_ntiles, c->f_tile_bin, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->nrm,
+            c->qpoint + c->u0, c->pos, nrows, c->C, c->f_t0, c->f_ldt, c->f_cand_key, c->f_cand_idx);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
+}
+
+template <int KR>
+int dispatch_nk(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
+{
+    const bool generic = getenv("CHB_FUSED_GENERIC") != nullptr; // test aid: force the tabulated MMA sequence
+    if (!generic && g.nk == 18) return launch_fused<KR, 18>(c, ma, mb, nrows, g);
+    if (!generic && g.nk == 19) return launch_fused<KR, 19>(c, ma, mb, nrows, g);
+    if (!generic && g.nk == 20) return launch_fused<KR, 20>(c, ma, mb, nrows, g);
+    return launch_fused<KR, 0>(c, ma, mb, nrows, g);
+}
+int dispatch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g, int KR)
+{
+    return KR == 8 ? dispatch_nk<8>(c, ma, mb, nrows, g) : dispatch_nk<16>(c, ma, mb, nrows, g);
 }
 
 template <typename T>
@@ -639,13 +882,22 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 } // namespace
 
-bool chb_fused_supported(const chb_ctx *c) { return c->k + 3 <= 16; }
+// k + 3 candidates per half-list fit 16 registers; the resident query operand (2 * dp8 floats per row) fits MAX_BOX
+// boxes with at least 3 ring stages left
+bool chb_fused_supported(const chb_ctx *c)
+{
+    const FusedGeom g = fused_geom(c->d);
+    return c->k + 3 <= 16 && g.nbox <= MAX_BOX && g.nstage >= 3;
+}
 
 void chb_fused_free(chb_ctx *c)
 {
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
-    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows);
+    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2);
+    c->f_thr = c->f_t0 = c->f_a2 = nullptr;
+    c->f_cap_a2 = c->f_cap_bperm = 0;
+    c->f_cap_bins = c->f_cap_cols = c->f_cap_cand = c->f_cap_thr = 0;
     c->f_bin_cnt = c->f_seg_off = c->f_cursor = c->f_tile_bin = c->f_ntiles = c->f_col_pt = c->f_col_a = c->f_col_b = nullptr;
     c->f_col_nrm = c->f_bperm = c->f_cand_key = nullptr;
     c->f_cand_idx = c->f_fb_rows = nullptr;
@@ -661,10 +913,10 @@ int chb_round_fused(chb_ctx *c)
     const int64_t n = c->n;
     const int32_t C = c->C, k = c->k;
     const int KR = (k + 3 <= 8) ? 8 : 16;
-    c->Kp = (3 * c->d + 31) & ~31;
+    const FusedGeom g = fused_geom(c->d);
     const int64_t ncol_max = ((2 * n + (int64_t)BN * C + BN - 1) / BN) * BN;
 
-    CHB_CHECK(c, chb_fused_supported(c), CHB_EINVAL, "fused mode supports num_neighbors <= 13");
+    CHB_CHECK(c, chb_fused_supported(c), CHB_EINVAL, "fused mode supports num_neighbors <= 13 and d <= 160");
     if (c->f_cap_bins < C + 1) {
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_bin_cnt, &z, C + 1)) return CHB_ENOMEM;
@@ -680,9 +932,9 @@ int chb_round_fused(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_col_b, &z, ncol_max)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_col_nrm, &z, ncol_max)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_tile_bin, &z, ncol_max / BN + 1)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_bperm, &z, ncol_max * c->Kp)) return CHB_ENOMEM;
         c->f_cap_cols = ncol_max;
     }
+    if (reserve(c, &c->f_bperm, &c->f_cap_bperm, ncol_max * g.Kp2)) return CHB_ENOMEM;
     if (c->f_cap_cand < nown * C * KR * 2) {
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_cand_key, &z, nown * C * KR * 2)) return CHB_ENOMEM;
@@ -690,21 +942,20 @@ int chb_round_fused(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_fb_rows, &z, nown)) return CHB_ENOMEM;
         c->f_cap_cand = nown * C * KR * 2;
     }
-    // split operands: points (once per feature set) and owned query rows (once per label set)
-    if (!c->bsplit_ready || c->cap_Bsplit < n * c->Kp) {
-        int64_t z = c->cap_Bsplit;
-        if (reserve(c, &c->Bsplit, &z, n * c->Kp)) return CHB_ENOMEM;
-        c->cap_Bsplit = z;
+    c->f_ldt = (nown + 127) & ~int64_t(127);
+    if (c->f_cap_thr < c->f_ldt * C) {
+        int64_t z = 0;
+        z = 0; if (reserve(c, &c->f_thr, &z, nown * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_t0, &z, c->f_ldt * C)) return CHB_ENOMEM;
+        c->f_cap_thr = c->f_ldt * C;
     }
-    if (!c->f_asplit_ready || c->cap_Asplit < nown * c->Kp) {
-        int64_t z = c->cap_Asplit;
-        if (reserve(c, &c->Asplit, &z, nown * c->Kp)) return CHB_ENOMEM;
-        c->cap_Asplit = z;
-    }
-    if (!c->bsplit_ready || !c->f_asplit_ready) {
-        int rc = chb_gram_tc_prepare(c, c->qpoint + c->u0, c->f_asplit_ready ? 0 : nown, c->Asplit, c->Bsplit, c->Kp, !c->bsplit_ready);
-        if (rc != CHB_OK) return rc;
-        c->bsplit_ready = true;
+    // query operand: once per (feature set, label set)
+    if (!c->f_asplit_ready || c->f_cap_a2 < nown * g.Kp2) {
+        if (reserve(c, &c->f_a2, &c->f_cap_a2, nown * g.Kp2)) return CHB_ENOMEM;
+        split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nullptr, nown, c->Xf, c->ldf, c->d,
+                                                                                  g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
+        CHB_CUDA(c, cudaGetLastError());
+        ++c->tm.launches_other;
         c->f_asplit_ready = true;
     }
 
@@ -715,18 +966,25 @@ int chb_round_fused(chb_ctx *c)
     entries_fill_kernel<<<nblk(ncol_max, 256), 256, 0, c->stream>>>(ncol_max, c->f_col_pt, c->f_col_a, c->f_col_b);
     entries_scatter_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
                                                                  c->f_col_pt, c->f_col_a, c->f_col_b);
-    entries_gather_kernel<<<nblk(ncol_max * (c->Kp / 4), 256), 256, 0, c->stream>>>(c->f_col_pt, c->f_ntiles, c->Bsplit, c->nrm, c->Kp,
-                                                                                    c->f_bperm, c->f_col_nrm);
+    split2_gather_kernel<<<nblk(ncol_max * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_col_pt, c->f_ntiles, ncol_max, c->Xf, c->ldf, c->d,
+                                                                                   g.dp8, g.Kp2, c->nrm, c->f_bperm, c->f_col_nrm);
     CHB_CUDA(c, cudaGetLastError());
     c->tm.launches_other += 5;
 
-    // ---- 2. fused Gram + selection
+    // ---- 2. admission thresholds from the cached lists, then the fused Gram + selection
+    const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
+    threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(c->knn_idx, c->knn_cnt, c->f_thr, c->qpoint + c->u0, c->pos, c->tent_pt,
+                                                                 c->old_label, c->nrm,
+                                                                 reinterpret_cast<const unsigned int *>(&c->counters[5]), eps_rel, nown,
+                                                                 C, k, c->f_ldt, c->f_t0);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
     CUtensorMap ma, mb;
-    int rc = make_map(c, &ma, c->Asplit, nown, c->Kp);
+    int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
     if (rc != CHB_OK) return rc;
-    rc = make_map(c, &mb, c->f_bperm, ncol_max, c->Kp);
+    rc = make_map(c, &mb, c->f_bperm, ncol_max, g.Kp2);
     if (rc != CHB_OK) return rc;
-    rc = (KR == 8) ? launch_fused<8>(c, ma, mb, nown) : launch_fused<16>(c, ma, mb, nown);
+    rc = dispatch_fused(c, ma, mb, nown, g, KR);
     if (rc != CHB_OK) return rc;
     c->tm.rows_scanned += nown;
 
@@ -734,11 +992,11 @@ int chb_round_fused(chb_ctx *c)
     CHB_CUDA(c, cudaMemsetAsync(&c->counters[6], 0, sizeof(int32_t), c->stream));
     {
         chb_stage_timer t(c, CHB_ST_KNN);
-        const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
-        rerank_kernel<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
+        auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
+        kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
             c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->qpoint + c->u0, c->nrm,
             reinterpret_cast<const unsigned int *>(&c->counters[5]), eps_rel, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
-            c->f_fb_rows, &c->counters[6]);
+            c->f_fb_rows, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
