@@ -302,51 +302,66 @@ def run_b200(args):
 
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
-        ms = {"distance": tm["ms_distance"], "knn": tm["ms_knn"], "qp": tm["ms_qp"], "commit": tm["ms_commit"]}
-        ln = {"distance": tm["launches_distance"], "knn": tm["launches_knn"], "qp": tm["launches_qp"],
-              "commit": tm["launches_commit"]}
-        dom = max(("distance", "knn", "qp"), key=lambda s: ms[s])
-        traffic = None
+        ms = {"distance": tm["ms_distance"], "gram": tm["ms_gram"], "knn": tm["ms_knn"], "qp": tm["ms_qp"],
+              "commit": tm["ms_commit"]}
+        ln = {"distance": tm["launches_distance"], "gram": tm["launches_gram"], "knn": tm["launches_knn"],
+              "qp": tm["launches_qp"], "commit": tm["launches_commit"]}
+        dom = max(("distance", "gram", "knn", "qp"), key=lambda s: ms[s])
+        traffic_all = {}
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get(dom)
+                traffic_all = json.load(open(tp))
             except Exception:
-                traffic = None
+                traffic_all = {}
         nown = u1 - u0
+        try:
+            tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
+            tf32_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"
+        except Exception:
+            tf32_peak, tf32_src = 1590.0 / 2.0, "fallback (B200_PROFILING.md bf16 figure / 2)"
         stages = {}
-        # kNN scan: one row of FP32 candidate values (4n bytes) per (launch item)
+        if ln["gram"]:
+            # fused tcgen05 Gram + per-bin selection (distance mode 2): TF32 3-term split, K = 3 * dp8 per 128x128 tile
+            dp8 = (d + 7) // 8 * 8
+            fl = tm["gram_tiles"] * 2.0 * 128 * 128 * 3 * dp8
+            stages["gram"] = {"kernel": "gram_select_kernel", "bound": "tensor", "achieved": fl / (ms["gram"] * 1e-3) / 1e12,
+                              "peak": tf32_peak, "unit": "TFLOP/s", "ms_total": ms["gram"], "launches": ln["gram"],
+                              "flops_per_launch": fl / ln["gram"], "tiles_128x128": tm["gram_tiles"], "peak_source": tf32_src}
         if ln["knn"]:
-            b = tm["rows_scanned"] * n * 4.0
-            stages["knn"] = {"bound": "hbm", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"]}
+            if ln["gram"]:
+                # re-rank of the kept candidates: 2*KR (key, index) pairs per (query, bin) pair in, neighbour set out
+                kr = 8 if k + 3 <= 8 else 16
+                b = tm["rounds"] * nown * C * (2 * kr * 8.0 + 4 * k + 8)
+                name = "rerank_kernel"
+            else:
+                b = tm["rows_scanned"] * n * 4.0  # kNN scan: one row of FP32 candidate values (4n bytes) per item
+                name = "knn_scan_kernel"
+            stages["knn"] = {"kernel": name, "bound": "hbm", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"],
+                             "peak_source": hbm_src}
         if ln["qp"]:
             b = tm["qps_solved"] * bytes_per_qp(k, d, C)
             f = tm["qps_solved"] * flops_per_qp(k, d)
-            stages["qp"] = {"bound": "hbm", "achieved": b / (ms["qp"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+            stages["qp"] = {"kernel": "qp_small_kernel" if k <= 5 else ("qp_mid_kernel" if k <= 10 else "qp_kernel"),
+                            "bound": "hbm", "achieved": b / (ms["qp"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "ms_total": ms["qp"], "launches": ln["qp"], "bytes_per_launch": b / ln["qp"],
                             "qps_solved": tm["qps_solved"], "qps_per_s": tm["qps_solved"] / (ms["qp"] * 1e-3),
-                            "fp64_tflops": f / (ms["qp"] * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak}
+                            "fp64_tflops": f / (ms["qp"] * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak,
+                            "fp64_frac": (f / (ms["qp"] * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
+                            "peak_source": hbm_src,
+                            "note": "algorithmic bytes B(k,d) per QP (SURVEY 8d); the gathered rows are L2-resident at this n"}
         if ln["distance"]:
-            # candidate-distance Gram on tcgen05: TF32 with a 3-term split, K = 3d rounded up to 32
-            kp = (3 * d + 31) // 32 * 32
-            fl = 2.0 * nown * n * kp * args.steps
-            tf32_peak = None
-            try:
-                tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
-            except Exception:
-                tf32_peak = 1590.0 / 2.0
-            stages["distance"] = {"bound": "tensor", "achieved": fl / (ms["distance"] * 1e-3) / 1e12, "peak": tf32_peak,
-                                  "unit": "TFLOP/s (TF32; peak = half the measured cuBLAS bf16 burst figure)",
-                                  "ms_total": ms["distance"], "launches": ln["distance"],
-                                  "bytes_written_per_launch": nown * n * 4.0}
+            # candidate-distance Gram of distance mode 1 / the exact-path fallback rows (gram_tc.cu)
+            stages["distance"] = {"kernel": "gram_tc_kernel", "bound": "tensor", "achieved": None, "peak": tf32_peak,
+                                  "unit": "TFLOP/s", "ms_total": ms["distance"], "launches": ln["distance"],
+                                  "peak_source": tf32_src}
         for s in stages.values():
-            s["frac"] = s["achieved"] / s["peak"] if s["peak"] else None
+            s["frac"] = (s["achieved"] / s["peak"]) if (s["peak"] and s["achieved"] is not None) else None
+            s["share_of_step"] = s["ms_total"] / elapsed_ms
         roof = dict(stages[dom])
-        roof["kernel"] = {"knn": "knn_scan_kernel", "qp": "qp_small_kernel" if k <= 5 else "qp_kernel", "distance": "gram_tc_kernel"}[dom]
-        roof["peak_source"] = hbm_src if roof["bound"] == "hbm" else "MEASURED_PEAKS.json bf16_tflops / 2"
-        roof["traffic"] = traffic
-        roof["share_of_step"] = ms[dom] / elapsed_ms
+        roof["traffic"] = traffic_all.get(roof["kernel"])
+        roof["avg_launch_ms"] = roof["ms_total"] / roof["launches"]
 
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -368,6 +383,7 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_s * 1e3 / args.steps,
                     "labels_equal_value_arm": same},
             "gpu_launches": int(sum(ln.values()) + tm["launches_other"]),
+            "launches_by_stage": dict(ln, other=tm["launches_other"]),
             "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
     "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
+    "chb_get_fused_candidates",
 ]
 
 
@@ -36,6 +37,7 @@ class Timers(ctypes.Structure):
         ("launches_commit", ctypes.c_int64), ("launches_other", ctypes.c_int64),
         ("qps_solved", ctypes.c_int64), ("qps_reference", ctypes.c_int64), ("rounds", ctypes.c_int64),
         ("rows_scanned", ctypes.c_int64),
+        ("ms_gram", ctypes.c_double), ("launches_gram", ctypes.c_int64), ("gram_tiles", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -82,6 +84,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_distance_mode.argtypes = [_vp, ctypes.c_int]
     L.chb_set_gram_engine.argtypes = [_vp, ctypes.c_int]
     L.chb_get_pair_cache.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp]
+    L.chb_get_fused_candidates.argtypes = [_vp, _i64, _i64, _vp, _vp, _vp, ctypes.POINTER(_i32)]
     L.chb_get_candidate_rows.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_dbl), _vp]
     L.chb_get_distance_rows.argtypes = [_vp, _i64, _i64, _vp]
     L.chb_knn_per_bin.argtypes = [_vp, _vp, _vp, _i64, _vp, _vp]
@@ -215,6 +218,18 @@ class Context:
         eps = _dbl(0.0)
         self._check(self._lib.chb_get_candidate_rows(self._h, slot0, nrows, _ptr(out), ctypes.byref(eps), _ptr(nrm)))
         return out, float(eps.value), nrm
+
+    def get_fused_candidates(self, slot0: int, nslots: int):
+        """(keys, idx) of shape (nslots, C, 2*KR) and slack (nslots, C): test aid of distance mode 2."""
+        key = np.empty((nslots, self.C, 32), dtype=np.float32)
+        idx = np.empty((nslots, self.C, 32), dtype=np.int32)
+        slack = np.empty((self.C, nslots), dtype=np.float32)
+        kr = _i32(0)
+        self._check(self._lib.chb_get_fused_candidates(self._h, slot0, nslots, _ptr(key), _ptr(idx), _ptr(slack), ctypes.byref(kr)))
+        m = nslots * self.C * 2 * kr.value
+        key = key.reshape(-1)[:m].reshape(nslots, self.C, 2 * kr.value)
+        idx = idx.reshape(-1)[:m].reshape(nslots, self.C, 2 * kr.value)
+        return key, idx, np.ascontiguousarray(slack.T)
 
     def get_pair_cache(self, slot0: int, nslots: int):
         idx = np.empty((nslots, self.C, self.k), dtype=np.int32)

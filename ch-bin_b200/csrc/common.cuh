@@ -102,6 +102,11 @@ struct chb_ctx {
     int64_t f_ldt = 0;
     float *f_a2 = nullptr;  // nown x Kp2 : TF32 [hi | lo] operand rows of the owned queries
     int64_t f_cap_a2 = 0, f_cap_bperm = 0;
+    double *f_mc = nullptr, *f_mc2 = nullptr; // C x d : bin reference point minus the global mean; C : its squared norm
+    int32_t *f_mcnt = nullptr;
+    int64_t f_cap_mc = 0;
+    float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
+    float *f_ym2 = nullptr;                    // 2 (C + 1) : per-bin maxima of |y|^2 and |column term| of this round
     bool f_asplit_ready = false;
     int32_t *f_fb_items = nullptr; // positions of the fallback queries
     int64_t f_cap_fb = 0;
@@ -140,7 +145,7 @@ int chb_fail(chb_ctx *ctx, int code, const char *fmt, ...);
         if (!(cond)) return chb_fail(ctx, code, __VA_ARGS__); \
     } while (0)
 
-enum chb_stage { CHB_ST_DISTANCE = 0, CHB_ST_KNN = 1, CHB_ST_QP = 2, CHB_ST_COMMIT = 3, CHB_ST_OTHER = 4 };
+enum chb_stage { CHB_ST_DISTANCE = 0, CHB_ST_KNN = 1, CHB_ST_QP = 2, CHB_ST_COMMIT = 3, CHB_ST_OTHER = 4, CHB_ST_GRAM = 5 };
 
 // Brackets one kernel launch with events when timers are on; resolved by chb_resolve_timers.
 struct chb_stage_timer {
@@ -166,6 +171,7 @@ struct chb_stage_timer {
                      : st == CHB_ST_KNN      ? &c->tm.launches_knn
                      : st == CHB_ST_QP       ? &c->tm.launches_qp
                      : st == CHB_ST_COMMIT   ? &c->tm.launches_commit
+                     : st == CHB_ST_GRAM     ? &c->tm.launches_gram
                                              : &c->tm.launches_other;
         ++*cnt;
         if (e0) {

@@ -245,6 +245,146 @@ __global__ void split2_gather_kernel(const int32_t *__restrict__ idx, const int3
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// per-bin centring.  The error of a tensor-core dot product scales with |a| |b|, and with one global centre the
+// coverage dimensions keep both operands long (|x - mu| ~ 0.5 against in-bin distances ~ 0.03), so the filter slack
+// 2E swallowed tens of bin members at 100k contigs.  Distances are translation invariant per COLUMN: with a fixed
+// reference point mu_c per bin (mean of the bin's seed contigs; the global mean if it has none), m_c = mu_c - mu,
+// the query operand a_q = fl32(x_q - mu) (unchanged) and the column operand y_i = fl32(x_i - mu_c),
+//     |x_q - x_i|^2  ~  |a_q - m_c|^2  +  ( |y_i|^2 + 2 m_c.y_i )  -  2 a_q.y_i
+//                        per (q, bin)        per column                  tensor core
+// and the contraction error is bounded by eps |a_q| max_i |y_i| -- the column vectors are now in-bin offsets.
+// The brackets are evaluated in FP64 from the FP32 operand values actually contracted and rounded once.
+// ---------------------------------------------------------------------------------------------------------
+// one warp per labelled point: bin sums of the seed contigs (initial labels)
+__global__ void __launch_bounds__(256) centre_accum_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, int64_t n,
+                                                           const int32_t *__restrict__ label, int32_t C, double *__restrict__ sum,
+                                                           int32_t *__restrict__ cnt)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const int c = label[i];
+    if (c < 0 || c >= C) return;
+    for (int t = lane; t < d; t += 32) atomicAdd(&sum[(int64_t)c * d + t], X[i * ldx + t]);
+    if (lane == 0) atomicAdd(&cnt[c], 1);
+}
+
+// m_c = mu_c - mu (zero for bins without seeds), mc2[c] = |m_c|^2
+__global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__restrict__ cnt, const double *__restrict__ colsum,
+                                     double inv_n, int32_t d, double *__restrict__ mc2)
+{
+    const int c = blockIdx.x;
+    __shared__ double red[128];
+    const double inv = cnt[c] > 0 ? 1.0 / (double)cnt[c] : 0.0;
+    double s = 0.0;
+    for (int t = threadIdx.x; t < d; t += blockDim.x) {
+        const double v = cnt[c] > 0 ? mc[(int64_t)c * d + t] * inv - colsum[t] * inv_n : 0.0;
+        mc[(int64_t)c * d + t] = v;
+        s += v * v;
+    }
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) mc2[c] = red[0];
+}
+
+// one warp per owned query: tq[c][r] = fl32( |a_q - m_c|^2 ), a_q = the FP32 centred feature row the tensor core contracts
+__global__ void __launch_bounds__(256) query_terms_kernel(const int32_t *__restrict__ row_point, int64_t nown,
+                                                          const float *__restrict__ Xf, int32_t ldf, int32_t d,
+                                                          const double *__restrict__ mc, const double *__restrict__ mc2, int32_t C,
+                                                          int64_t ldt, float *__restrict__ tq)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= nown) return;
+    const float *xr = Xf + (int64_t)row_point[r] * ldf;
+    double a[8]; // d <= 256
+    double aa = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        const int t = lane + 32 * u;
+        a[u] = t < d ? (double)xr[t] : 0.0;
+        aa = fma(a[u], a[u], aa);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) aa += __shfl_xor_sync(CHB_FULL, aa, o);
+    for (int c = 0; c < C; ++c) {
+        const double *m = mc + (int64_t)c * d;
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int t = lane + 32 * u;
+            if (t < d) s = fma(a[u], m[t], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
+        if (lane == 0) tq[(int64_t)c * ldt + r] = (float)fmax(aa - 2.0 * s + mc2[c], 0.0);
+    }
+}
+
+// one warp per column entry: y = fl32(x_i - mu_c) split into the [hi | lo] operand row, the column term
+// |y|^2 + 2 m_c.y, and the per-bin maxima of |y|^2 and of |column term| (for the error bound); padding columns are zero
+__global__ void __launch_bounds__(256) column_gather_kernel(const int32_t *__restrict__ col_pt, const int32_t *__restrict__ ntiles,
+                                                            const int32_t *__restrict__ tile_bin, const double *__restrict__ X,
+                                                            int32_t ldx, int32_t d, const double *__restrict__ colsum, double inv_n,
+                                                            const double *__restrict__ mc, int32_t dp8, int32_t Kp2,
+                                                            float *__restrict__ out, float *__restrict__ col_term,
+                                                            unsigned int *__restrict__ ym2_bits, unsigned int *__restrict__ tcmax_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (e >= (int64_t)(*ntiles) * BN) return;
+    const int ptx = col_pt[e];
+    float *orow = out + e * Kp2;
+    if (ptx < 0) {
+        for (int t = lane; t < Kp2; t += 32) orow[t] = 0.f;
+        if (lane == 0) col_term[e] = 0.f;
+        return;
+    }
+    const int c = tile_bin[e / BN];
+    const double *xr = X + (int64_t)ptx * ldx;
+    const double *m = mc + (int64_t)c * d;
+    double yy = 0.0, my = 0.0;
+    for (int t = lane; t < dp8; t += 32) {
+        float hi = 0.f, lo = 0.f;
+        if (t < d) {
+            const float yf = (float)(xr[t] - colsum[t] * inv_n - m[t]);
+            hi = __uint_as_float(__float_as_uint(yf) & 0xffffe000u);
+            lo = __uint_as_float(__float_as_uint(yf - hi) & 0xffffe000u);
+            yy = fma((double)yf, (double)yf, yy);
+            my = fma(m[t], (double)yf, my);
+        }
+        orow[t] = hi;
+        orow[dp8 + t] = lo;
+    }
+    for (int t = 2 * dp8 + lane; t < Kp2; t += 32) orow[t] = 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        yy += __shfl_xor_sync(CHB_FULL, yy, o);
+        my += __shfl_xor_sync(CHB_FULL, my, o);
+    }
+    if (lane == 0) {
+        const double term = yy + 2.0 * my;
+        col_term[e] = (float)term;
+        atomicMax(&ym2_bits[c], __float_as_uint(__double2float_ru(yy)));          // non-negative floats order like their bits
+        atomicMax(&tcmax_bits[c], __float_as_uint(__double2float_ru(fabs(term))));
+    }
+}
+
+// slack of (query r, bin c): bound on |key - |x_q - x_i|^2| for every column i of the bin (see the block comment above).
+//   contraction: 2 * eps_rel * |a_q| * max|y|      (eps_rel = (3d + 64) 2^-23 bounds the dot-product error, gram_tc.cu)
+//   FP32 roundings of the three terms and of the operands: 2^-21 * (tq + max|column term| + 2 |a_q| max|y| + D (|a_q| + max|y|) + D^2),  D = |a_q - m_c| + max|y|
+__device__ __forceinline__ float pair_slack(double eps_rel, float nrm_q, float ym2, float tcmax, float tq)
+{
+    const double sq = sqrt((double)nrm_q), ym = sqrt((double)ym2), dq = sqrt((double)tq);
+    const double e = 2.0 * eps_rel * sq * ym + 4.76837158203125e-07 * ((double)tq + (double)tcmax + 2.0 * sq * ym + (dq + ym) * (sq + ym) + (dq + ym) * (dq + ym));
+    return __double2float_ru(e * (1.0 + 1e-6) + 1e-30);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // fused Gram + selection
 // ---------------------------------------------------------------------------------------------------------
 template <int KR>
@@ -285,7 +425,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 1)
 gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int nbox, int nk, int nstage,
                    const int32_t *__restrict__ ntiles_p, const int32_t *__restrict__ tile_bin, const int32_t *__restrict__ col_pt,
                    const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b, const float *__restrict__ col_nrm,
-                   const float *__restrict__ nrm, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
+                   const float *__restrict__ tq_tab, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
                    int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ cand_key,
                    int32_t *__restrict__ cand_idx)
 {
@@ -463,16 +603,12 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const int64_t gr = (int64_t)rb * BM + row;
             const bool rvalid = gr < nrows;
             int p = INT32_MIN + 1;
-            float nr = 0.f;
-            if (rvalid) {
-                const int pt = row_point[gr];
-                p = pos[pt];
-                nr = nrm[pt];
-            }
+            if (rvalid) p = pos[row_point[gr]];
             L.reset();
             int cur_bin = ntiles > 0 ? tile_bin[0] : -1;
-            // admission threshold of (this query, current bin): see threshold_kernel
+            // admission threshold and query term |a_q - m_c|^2 of (this query, current bin): see threshold_kernel
             float t0 = (rvalid && cur_bin >= 0) ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
+            float nr = (rvalid && cur_bin >= 0) ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
             // column metadata of the next tile travels in registers while the current tile is processed
             float m_n0 = 0.f, m_n1 = 0.f;
             int m_a0 = INT32_MAX, m_a1 = INT32_MAX, m_b0 = INT32_MIN, m_b1 = INT32_MIN;
@@ -500,6 +636,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     L.reset();
                     cur_bin = tb;
                     t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
+                    nr = rvalid ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
                 }
                 __syncwarp(); // every lane is done with the previous tile's metadata
                 M.nrm[lane] = m_n0; M.a[lane] = m_a0; M.b[lane] = m_b0;
@@ -578,28 +715,32 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
 // ---------------------------------------------------------------------------------------------------------
 // admission thresholds.  The k cached neighbours of (query, bin) from the previous round bound this round's k-th
-// smallest key as long as all of them are still visible members of the bin: with |A - d^2| <= E for every evaluation
-// and thr = the largest cached key of the set, every re-evaluated member key is <= thr + 2E, so the k-th smallest key
-// a_k of this round is too, and everything the re-rank may need (keys <= a_k + 2E) lies below T0 = thr + 4E.
+// smallest key as long as all of them are still visible members of the bin: the re-rank stores ub = (largest key of
+// the chosen set) + (that round's slack) >= every member's true squared distance; with this round's slack E every
+// re-evaluated member key is <= ub + E, so the k-th smallest key a_k of this round is too, and everything the re-rank
+// may need (keys <= a_k + 2E) lies below T0 = ub + 3E.
 // Columns above T0 are skipped by the fused kernel without touching the per-thread lists.  T0 = +inf when there is no
 // usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
                                  const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
                                  const int32_t *__restrict__ tent, const int32_t *__restrict__ old, const float *__restrict__ nrm,
-                                 const unsigned int *__restrict__ nrm_max_bits, double eps_rel, int64_t nown, int32_t C, int32_t k,
-                                 int64_t ldt, float *__restrict__ t0_tab)
+                                 const float *__restrict__ ym2, const float *__restrict__ tcmax, const float *__restrict__ tq_tab,
+                                 double eps_rel, int64_t nown, int32_t C, int32_t k, int64_t ldt, float *__restrict__ t0_tab,
+                                 float *__restrict__ slack_tab)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nown * C) return;
     const int c = (int)(i / nown);
     const int64_t r = i - (int64_t)c * nown;
     const int64_t pair = r * C + c;
+    const int jq = row_point[r];
+    const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq_tab[(int64_t)c * ldt + r]);
+    slack_tab[(int64_t)c * ldt + r] = E;
     float out = INFINITY;
     if (knn_cnt[pair] == k) {
-        const float th = thr[pair];
-        if (th < INFINITY) {
-            const int jq = row_point[r];
+        const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
+        if (ub < INFINITY) {
             const int p = pos[jq];
             bool ok = true;
             for (int s = 0; s < k; ++s) {
@@ -608,11 +749,9 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
                 const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
                 ok = ok && (lab == c);
             }
-            if (ok) {
-                const double nmax = (double)__uint_as_float(*nrm_max_bits);
-                const float slack2 = __double2float_ru(2.0 * (eps_rel * ((double)nrm[jq] + nmax) + 1e-30));
-                out = __fadd_ru(th, __fmul_ru(2.f, slack2));
-            }
+            // this round's keys of the cached neighbours are <= ub + E, so is the k-th smallest key a_k, and the re-rank
+            // looks no further than a_k + 2E
+            if (ok) out = __fadd_ru(ub, __fmul_ru(3.f, E));
         }
     }
     t0_tab[(int64_t)c * ldt + r] = out;
@@ -659,8 +798,8 @@ __device__ __forceinline__ double exact_distance_g(const double *__restrict__ xq
 template <int G>
 __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ cand_key, const int32_t *__restrict__ cand_idx, int KR,
                                                      const int32_t *__restrict__ bin_cnt, const double *__restrict__ X, int32_t ldx,
-                                                     int32_t d, const int32_t *__restrict__ row_point, const float *__restrict__ nrm,
-                                                     const unsigned int *__restrict__ nrm_max_bits, double eps_rel, int32_t C,
+                                                     int32_t d, const int32_t *__restrict__ row_point,
+                                                     const float *__restrict__ slack_tab, int32_t C,
                                                      int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
                                                      int32_t *__restrict__ fb_rows, int32_t *__restrict__ fb_count,
@@ -677,8 +816,6 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
     __shared__ int s_overflow;
     if (threadIdx.x == 0) s_overflow = 0;
     __syncthreads();
-    const double nmax = (double)__uint_as_float(*nrm_max_bits);
-    const float slack2 = __double2float_ru(2.0 * (eps_rel * ((double)nrm[jq] + nmax) + 1e-30));
     const int K2 = 2 * KR;
     bool overflow = false;
 
@@ -693,6 +830,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
             ki = cand_idx[pair * K2 + gl];
         }
         const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
+        const float E = act ? slack_tab[(int64_t)c * ldt + r] : 0.f; // |key - d^2| <= E for every column of this bin
+        const float slack2 = __fmul_ru(2.f, E);
         const int mo = act ? knn_cnt[pair] : 0;
         const bool valid = ka < INFINITY; // +inf = empty slot
         const unsigned vm = (__ballot_sync(CHB_FULL, valid) >> gsh) & GM;
@@ -767,7 +906,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
         const unsigned dm = (__ballot_sync(CHB_FULL, diff) >> gsh) & GM;
         const bool same = (mo == m) && dm == 0;
         if (act) {
-            if (gl == 0) thr_out[pair] = (m == k) ? mx : INFINITY;
+            if (gl == 0) thr_out[pair] = (m == k) ? __fadd_ru(mx, E) : INFINITY;
             if (!same) {
                 // slots [0, m) come from the selected lanes, slots [m, k) are cleared by the lanes sitting at those positions
                 if (sel) knn_idx[pair * k + srt] = ki;
@@ -838,9 +977,9 @@ int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64
     const int nrb = (int)((nrows + BM - 1) / BM);
     const int grid = std::min(nrb, c->sm_count);
     {
-        chb_stage_timer t(c, CHB_ST_KNN);
+        chb_stage_timer t(c, CHB_ST_GRAM);
         gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
-            ma, mb, g.nbox, g.nk, g.nstage, c->f_ntiles, c->f_tile_bin, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->nrm,
+            ma, mb, g.nbox, g.nk, g.nstage, c->f_ntiles, c->f_tile_bin, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq,
             c->qpoint + c->u0, c->pos, nrows, c->C, c->f_t0, c->f_ldt, c->f_cand_key, c->f_cand_idx);
     }
     CHB_CUDA(c, cudaGetLastError());
@@ -894,8 +1033,12 @@ void chb_fused_free(chb_ctx *c)
 {
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
-    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2);
-    c->f_thr = c->f_t0 = c->f_a2 = nullptr;
+    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
+    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt);
+    c->f_thr = c->f_t0 = c->f_a2 = c->f_tq = c->f_slack = c->f_ym2 = nullptr;
+    c->f_mc = c->f_mc2 = nullptr;
+    c->f_mcnt = nullptr;
+    c->f_cap_mc = 0;
     c->f_cap_a2 = c->f_cap_bperm = 0;
     c->f_cap_bins = c->f_cap_cols = c->f_cap_cand = c->f_cap_thr = 0;
     c->f_bin_cnt = c->f_seg_off = c->f_cursor = c->f_tile_bin = c->f_ntiles = c->f_col_pt = c->f_col_a = c->f_col_b = nullptr;
@@ -923,8 +1066,12 @@ int chb_round_fused(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_seg_off, &z, C + 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cursor, &z, C + 1)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ntiles, &z, 4)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_ym2, &z, 2 * (C + 1))) return CHB_ENOMEM; // [0,C): max |y|^2, [C+1, 2C+1): max |column term|
+        z = 0; if (reserve(c, &c->f_mcnt, &z, C + 1)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_mc2, &z, C + 1)) return CHB_ENOMEM;
         c->f_cap_bins = C + 1;
     }
+    if (reserve(c, &c->f_mc, &c->f_cap_mc, (int64_t)C * c->d)) return CHB_ENOMEM;
     if (c->f_cap_cols < ncol_max) {
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_col_pt, &z, ncol_max)) return CHB_ENOMEM;
@@ -947,15 +1094,25 @@ int chb_round_fused(chb_ctx *c)
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_thr, &z, nown * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_t0, &z, c->f_ldt * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_tq, &z, c->f_ldt * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_slack, &z, c->f_ldt * C)) return CHB_ENOMEM;
         c->f_cap_thr = c->f_ldt * C;
+        c->f_asplit_ready = false;
     }
     // query operand: once per (feature set, label set)
     if (!c->f_asplit_ready || c->f_cap_a2 < nown * g.Kp2) {
         if (reserve(c, &c->f_a2, &c->f_cap_a2, nown * g.Kp2)) return CHB_ENOMEM;
         split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                   g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
+        // bin reference points from the seed contigs (the labels at this point are the initial bins) and the query terms
+        CHB_CUDA(c, cudaMemsetAsync(c->f_mc, 0, sizeof(double) * (size_t)C * c->d, c->stream));
+        CHB_CUDA(c, cudaMemsetAsync(c->f_mcnt, 0, sizeof(int32_t) * (size_t)(C + 1), c->stream));
+        centre_accum_kernel<<<nblk(n * 32, 256), 256, 0, c->stream>>>(c->X, c->ldx, c->d, n, c->old_label, C, c->f_mc, c->f_mcnt);
+        centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2);
+        query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nown, c->Xf, c->ldf, c->d, c->f_mc, c->f_mc2,
+                                                                       C, c->f_ldt, c->f_tq);
         CHB_CUDA(c, cudaGetLastError());
-        ++c->tm.launches_other;
+        c->tm.launches_other += 4;
         c->f_asplit_ready = true;
     }
 
@@ -966,17 +1123,18 @@ int chb_round_fused(chb_ctx *c)
     entries_fill_kernel<<<nblk(ncol_max, 256), 256, 0, c->stream>>>(ncol_max, c->f_col_pt, c->f_col_a, c->f_col_b);
     entries_scatter_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
                                                                  c->f_col_pt, c->f_col_a, c->f_col_b);
-    split2_gather_kernel<<<nblk(ncol_max * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_col_pt, c->f_ntiles, ncol_max, c->Xf, c->ldf, c->d,
-                                                                                   g.dp8, g.Kp2, c->nrm, c->f_bperm, c->f_col_nrm);
+    CHB_CUDA(c, cudaMemsetAsync(c->f_ym2, 0, sizeof(float) * (size_t)(2 * (C + 1)), c->stream));
+    column_gather_kernel<<<nblk(ncol_max * 32, 256), 256, 0, c->stream>>>(
+        c->f_col_pt, c->f_ntiles, c->f_tile_bin, c->X, c->ldx, c->d, c->colsum, 1.0 / (double)n, c->f_mc, g.dp8, g.Kp2, c->f_bperm,
+        c->f_col_nrm, reinterpret_cast<unsigned int *>(c->f_ym2), reinterpret_cast<unsigned int *>(c->f_ym2 + C + 1));
     CHB_CUDA(c, cudaGetLastError());
     c->tm.launches_other += 5;
 
-    // ---- 2. admission thresholds from the cached lists, then the fused Gram + selection
+    // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(c->knn_idx, c->knn_cnt, c->f_thr, c->qpoint + c->u0, c->pos, c->tent_pt,
-                                                                 c->old_label, c->nrm,
-                                                                 reinterpret_cast<const unsigned int *>(&c->counters[5]), eps_rel, nown,
-                                                                 C, k, c->f_ldt, c->f_t0);
+                                                                 c->old_label, c->nrm, c->f_ym2, c->f_ym2 + C + 1, c->f_tq, eps_rel,
+                                                                 nown, C, k, c->f_ldt, c->f_t0, c->f_slack);
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
     CUtensorMap ma, mb;
@@ -994,10 +1152,28 @@ int chb_round_fused(chb_ctx *c)
         chb_stage_timer t(c, CHB_ST_KNN);
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
         kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
-            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->qpoint + c->u0, c->nrm,
-            reinterpret_cast<const unsigned int *>(&c->counters[5]), eps_rel, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
+            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->qpoint + c->u0, c->f_slack, C, k, c->knn_idx,
+            c->knn_cnt, c->work, c->counters,
             c->f_fb_rows, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr);
     }
     CHB_CUDA(c, cudaGetLastError());
+    return CHB_OK;
+}
+
+extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslots, float *key_out, int32_t *idx_out, float *slack_out,
+                                        int32_t *kr_out)
+{
+    CHB_CHECK(c, c && key_out && idx_out && slack_out && kr_out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->f_cand_key && c->f_slack && slot0 >= c->u0 && nslots >= 0 && slot0 + nslots <= c->u1, CHB_EINVAL,
+              "slots not owned / no fused round has run yet");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int KR = (c->k + 3 <= 8) ? 8 : 16;
+    const int64_t r0 = slot0 - c->u0, per = (int64_t)c->C * 2 * KR;
+    *kr_out = KR;
+    CHB_CUDA(c, cudaMemcpyAsync(key_out, c->f_cand_key + r0 * per, sizeof(float) * (size_t)(nslots * per), cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(idx_out, c->f_cand_idx + r0 * per, sizeof(int32_t) * (size_t)(nslots * per), cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpy2DAsync(slack_out, sizeof(float) * (size_t)nslots, c->f_slack + r0, sizeof(float) * (size_t)c->f_ldt,
+                                  sizeof(float) * (size_t)nslots, (size_t)c->C, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaStreamSynchronize(c->stream));
     return CHB_OK;
 }

@@ -59,6 +59,11 @@ typedef struct chb_timers {
     int64_t qps_reference;  /* QPs the reference would have solved: sum over iterations of U*C     */
     int64_t rounds;         /* speculate/repair rounds executed                                    */
     int64_t rows_scanned;   /* distance rows streamed by the kNN kernel                            */
+    /* distance mode 2: the fused tensor-core Gram + per-bin selection kernel (fused.cu) is timed on its own; ms_knn
+     * then holds the re-rank (and the rare exact-path scans) only */
+    double ms_gram;
+    int64_t launches_gram;
+    int64_t gram_tiles;     /* 128 x 128 (query, column) tiles contracted: 2*128*128*3*dp8 flop each, dp8 = d rounded up to 8 */
 } chb_timers;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
@@ -111,6 +116,12 @@ int chb_get_candidate_rows(chb_ctx *ctx, int64_t slot0, int64_t nrows, float *ou
 /* Test aid: the per-(query, bin) state the assignment rounds keep for owned slots [slot0, slot0+nslots): neighbour
  * lists (nslots*C*k int32, -1 padded, order unspecified), their lengths (nslots*C) and hull distances (nslots*C). */
 int chb_get_pair_cache(chb_ctx *ctx, int64_t slot0, int64_t nslots, int32_t *idx_out, int32_t *cnt_out, double *dist_out);
+/* Test aid (distance mode 2): what the fused Gram + selection kernel kept in the last round for owned slots
+ * [slot0, slot0+nslots): 2*KR FP32 keys and point indices per (slot, bin) pair (key = +inf: empty entry), KR in
+ * *kr_out (8 or 16), and the proven error bound of those keys, slack_out[c * nslots + s] >= |key - |x_q - x_i|^2|.
+ * key_out / idx_out: nslots * C * 32 entries must be available (only nslots * C * 2 * KR are written). */
+int chb_get_fused_candidates(chb_ctx *ctx, int64_t slot0, int64_t nslots, float *key_out, int32_t *idx_out, float *slack_out,
+                             int32_t *kr_out);
 /* create_in_mem_distance_matrix / create_distance_matrix (distance_matrix.py:12-44) for the owned query
  * rows.  materialise=1: rows are computed once (exact cdist recipe) and kept in HBM (InMemDistMatrix=yes,
  * cli/clustering.py:57-59); fails with CHB_ENOMEM if they do not fit.  materialise=0: nothing is stored,

@@ -216,6 +216,45 @@ def test_fit_cluster_fused_with_duplicate_contigs():
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n,C,S,k", [(1500, 6, 1, 5), (2000, 8, 10, 10), (900, 4, 20, 5)])
+def test_fused_keys_within_proven_bound_and_lists_complete(n, C, S, k):
+    """Distance mode 2 (fused.cu): every FP32 key the fused Gram + selection kernel kept must lie within the per-(query,
+    bin) slack of the exact squared distance (per-bin centred operands), and the kept lists must contain every point
+    whose exact distance is among the k smallest of its bin -- the two facts the exact re-rank relies on."""
+    X, bins, _ = synth.make_contig_features(n, C, S, 12, seed=29)
+    perms = oracle.draw_permutations(bins, 2, seed=0)
+    D = oracle.create_in_mem_distance_matrix(X)
+    pts = np.where(bins == -1)[0]
+    ctx = capi.Context(0)
+    ctx.set_features(X); ctx.set_params(k, "convex"); ctx.set_distance_mode(2); ctx.set_labels(bins, C)
+    ctx.build_distance_matrix(True)
+    cur = bins.copy()
+    worst = 0.0
+    for it in range(2):
+        lab, _ = ctx.fit_iteration(perms[it])
+        key, idx, slack = ctx.get_fused_candidates(0, len(pts))
+        pos = np.full(len(X), -1)
+        pos[perms[it]] = np.arange(len(perms[it]))
+        for u, j in enumerate(pts):
+            for c in range(C):
+                valid = np.isfinite(key[u, c])
+                ii = idx[u, c][valid]
+                d2 = D[j, ii] ** 2
+                err = np.abs(key[u, c][valid].astype(np.float64) - d2)
+                assert np.all(err <= slack[u, c]), (it, j, c, err.max(), slack[u, c])
+                if len(err):
+                    worst = max(worst, float((err / slack[u, c]).max()))
+            if u % 5 == 0:  # the last round's lists were formed on the final labels as seen from this query's position
+                eff = np.where(pos < pos[j], lab, cur)
+                eff[j] = -1
+                for c in range(C):
+                    want = oracle.find_nearest_from_cluster(c, eff, D[j], k)
+                    assert set(want.tolist()) <= set(idx[u, c][np.isfinite(key[u, c])].tolist()), (it, j, c)
+        cur = lab
+    ctx.close()
+    assert worst < 0.5, f"observed error / bound = {worst}: the bound should have a wide margin"
+
+
 @pytest.mark.parametrize("path", ["exact", "filter", "fused"])
 def test_cached_neighbour_sets_match_each_querys_view(path):
     """After every iteration, the (query, bin) neighbour sets the rounds left in the cache must equal
