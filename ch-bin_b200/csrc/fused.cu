@@ -47,19 +47,12 @@ constexpr int SMEM_LIMIT = 232448;  // 227 KB opt-in shared memory per CTA
 // nbox boxes of 32 floats.  hi/lo are the TF32 halves of the centred FP32 feature (gram_tc.cu).  The contraction
 // hi.hi + hi.lo + lo.hi is issued as UMMA K=8 steps that pair step i of the RESIDENT query operand with step j of the
 // streamed column operand, so the query operand is read from L2 once per row block instead of once per tile.
-struct WarpMeta { // column metadata of one epilogue warp's 64 columns of the current tile (warp-private)
-    float nrm[64];
-    int a[64]; // visible to the query at position p iff p > a || p < b
-    int b[64];
-};
-
-constexpr int NC = 8; // per-thread candidate stack depth
+constexpr int NC = 16; // per-thread candidate stack depth
 struct SmemTail {
-    alignas(16) WarpMeta meta[8];
-    // candidates that passed the screen wait here (thread-private stacks, [slot][thread]) until the warp drains them into
-    // the register lists: draining costs max-over-lanes insertions, so it pays to drain rarely
+    // candidates that passed the screen wait here (thread-private stacks, [slot][thread]; their columns are remembered in
+    // a per-thread 64-bit mask) until the warp drains them into the register lists: draining costs max-over-lanes
+    // insertions, so it pays to drain rarely
     alignas(16) float cand_val[NC][EPI_THREADS];
-    uint8_t cand_col[NC][EPI_THREADS];
     alignas(8) uint64_t full_bar[8];
     alignas(8) uint64_t empty_bar[8];
     alignas(8) uint64_t tmem_full_bar[2];
@@ -589,13 +582,13 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
         }
     } else {
-        // ---------------- epilogue warps 2..9: thread <-> (query row, column half).  The warps run decoupled: each
-        // stages the metadata of its own 64 columns and synchronises with the MMA warp only (TMEM full / empty barriers),
-        // so a warp that meets many candidates in one tile does not hold up the other seven.
+        // ---------------- epilogue warps 2..9: thread <-> (query row, column half).  The warps run decoupled: they
+        // synchronise with the MMA warp only (TMEM full / empty barriers), so a warp that meets many candidates in one
+        // tile does not hold up the other seven.  Column metadata is the same for all rows: it is read with warp-uniform
+        // loads straight from global memory (L1 hits after a prefetch one tile ahead).
         const int q = warp & 3;                 // TMEM lane quadrant this warp may read
         const int half = (warp - 2) >> 2;       // 0: columns [0,64) of a tile, 1: columns [64,128)
         const int row = q * 32 + lane;          // TMEM lane == row within the block
-        WarpMeta &M = S.meta[warp - 2];
         const int et = threadIdx.x - 64;        // 0..255 index among the epilogue threads
         TopList<KR> L;
         int64_t tt = 0;
@@ -609,20 +602,19 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             // admission threshold and query term |a_q - m_c|^2 of (this query, current bin): see threshold_kernel
             float t0 = (rvalid && cur_bin >= 0) ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
             float nr = (rvalid && cur_bin >= 0) ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
-            // column metadata of the next tile travels in registers while the current tile is processed
-            float m_n0 = 0.f, m_n1 = 0.f;
-            int m_a0 = INT32_MAX, m_a1 = INT32_MAX, m_b0 = INT32_MIN, m_b1 = INT32_MIN;
-            if (ntiles > 0) {
-                const int64_t e = half * 64 + lane;
-                m_n0 = col_nrm[e]; m_a0 = col_a[e]; m_b0 = col_b[e];
-                m_n1 = col_nrm[e + 32]; m_a1 = col_a[e + 32]; m_b1 = col_b[e + 32];
-            }
             int tb_next = cur_bin;
             for (int t = 0; t < ntiles; ++t, ++tt) {
                 const int buf = (int)(tt & 1);
                 const uint32_t tph = (uint32_t)((tt >> 1) & 1);
                 const int tb = tb_next;
-                if (t + 1 < ntiles) tb_next = tile_bin[t + 1];
+                if (t + 1 < ntiles) {
+                    tb_next = tile_bin[t + 1];
+                    if (lane < 6) { // next tile's metadata -> L1: three arrays, two 128-byte lines each
+                        const int64_t e = (int64_t)(t + 1) * BN + half * 64 + (lane & 1) * 32;
+                        const void *pf = lane < 2 ? (const void *)(col_nrm + e) : (lane < 4 ? (const void *)(col_a + e) : (const void *)(col_b + e));
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                    }
+                }
                 if (tb != cur_bin) { // bin boundary: flush the finished (half-)list
                     if (rvalid) {
                         float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
@@ -638,16 +630,11 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
                     nr = rvalid ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
                 }
-                __syncwarp(); // every lane is done with the previous tile's metadata
-                M.nrm[lane] = m_n0; M.a[lane] = m_a0; M.b[lane] = m_b0;
-                M.nrm[lane + 32] = m_n1; M.a[lane + 32] = m_a1; M.b[lane + 32] = m_b1;
-                __syncwarp();
-                if (t + 1 < ntiles) {
-                    const int64_t e = (int64_t)(t + 1) * BN + half * 64 + lane;
-                    m_n0 = col_nrm[e]; m_a0 = col_a[e]; m_b0 = col_b[e];
-                    m_n1 = col_nrm[e + 32]; m_a1 = col_a[e + 32]; m_b1 = col_b[e + 32];
-                }
-                const int32_t *tile_pt = col_pt + (int64_t)t * BN + half * 64;
+                const int64_t e0 = (int64_t)t * BN + half * 64;
+                const float4 *mn = reinterpret_cast<const float4 *>(col_nrm + e0);
+                const int4 *ma = reinterpret_cast<const int4 *>(col_a + e0);
+                const int4 *mb = reinterpret_cast<const int4 *>(col_b + e0);
+                const int32_t *tile_pt = col_pt + e0;
                 mbar_wait(&S.tmem_full_bar[buf], tph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // the thread's 64 accumulator columns in one TMEM read; the buffer goes back to the MMA warp right away
@@ -662,38 +649,68 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
                 }
-                // screen the 64 columns four at a time; survivors go onto the thread's candidate stack
+                // Screen the 64 columns four at a time; survivors go onto the thread's candidate stack (value in shared
+                // memory, column in a bit mask).  The stacks are drained -- at ONE place in the code, the insertion is long
+                // and the instruction cache small -- when one of them could overflow in the next group, and after the tile.
                 int ncand = 0;
-#pragma unroll
-                for (int j = 0; j < 64; j += 4) {
-                    const float thr = fminf(L.key[KR - 1], t0);
-                    const float4 n4 = *reinterpret_cast<const float4 *>(&M.nrm[j]);
-                    const int4 a4 = *reinterpret_cast<const int4 *>(&M.a[j]);
-                    const int4 b4 = *reinterpret_cast<const int4 *>(&M.b[j]);
-                    const float nn[4] = {n4.x, n4.y, n4.z, n4.w};
-                    const int aa[4] = {a4.x, a4.y, a4.z, a4.w};
-                    const int bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float av = fmaf(-2.f, __uint_as_float(v[j + u]), nr + nn[u]);
-                        const bool cand = ((p > aa[u]) || (p < bb[u])) && (av <= thr);
-                        if (cand) {
-                            S.cand_val[ncand][et] = av;
-                            S.cand_col[ncand][et] = (uint8_t)(j + u);
-                            ++ncand;
+                unsigned cm_lo = 0, cm_hi = 0;
+                int g = 0;
+#define SCREEN_STEP(G)                                                                                              \
+    case G: {                                                                                                       \
+        const float thr = fminf(L.key[KR - 1], t0);                                                                 \
+        const float4 n4 = __ldg(mn + G);                                                                            \
+        const int4 a4 = __ldg(ma + G);                                                                              \
+        const int4 b4 = __ldg(mb + G);                                                                              \
+        const float nn[4] = {n4.x, n4.y, n4.z, n4.w};                                                               \
+        const int aa[4] = {a4.x, a4.y, a4.z, a4.w};                                                                 \
+        const int bb[4] = {b4.x, b4.y, b4.z, b4.w};                                                                 \
+        _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                             \
+            const float av = fmaf(-2.f, __uint_as_float(v[4 * G + u]), nr + nn[u]);                                 \
+            if (((p > aa[u]) || (p < bb[u])) && (av <= thr)) {                                                      \
+                S.cand_val[ncand][et] = av;                                                                         \
+                if (G < 8) cm_lo |= 1u << ((4 * G + u) & 31);                                                       \
+                else cm_hi |= 1u << ((4 * G + u) & 31);                                                             \
+                ++ncand;                                                                                            \
+            }                                                                                                       \
+        }                                                                                                           \
+        if (G < 15 && __any_sync(CHB_FULL, ncand > NC - 4)) {                                                       \
+            g = G + 1;                                                                                              \
+            break;                                                                                                  \
+        }                                                                                                           \
+    }
+                while (true) {
+                    switch (g) {
+                    SCREEN_STEP(0)
+                    SCREEN_STEP(1)
+                    SCREEN_STEP(2)
+                    SCREEN_STEP(3)
+                    SCREEN_STEP(4)
+                    SCREEN_STEP(5)
+                    SCREEN_STEP(6)
+                    SCREEN_STEP(7)
+                    SCREEN_STEP(8)
+                    SCREEN_STEP(9)
+                    SCREEN_STEP(10)
+                    SCREEN_STEP(11)
+                    SCREEN_STEP(12)
+                    SCREEN_STEP(13)
+                    SCREEN_STEP(14)
+                    SCREEN_STEP(15)
+                        g = 16;
+                    }
+                    while (__any_sync(CHB_FULL, ncand > 0)) {
+                        if (ncand > 0) {
+                            --ncand;
+                            int col;
+                            if (cm_hi) { col = 63 - __clz(cm_hi); cm_hi &= ~(1u << (col - 32)); }
+                            else { col = 31 - __clz(cm_lo); cm_lo &= ~(1u << col); }
+                            const float av = S.cand_val[ncand][et];
+                            if (av < L.key[KR - 1]) L.insert(av, __ldg(tile_pt + col));
                         }
                     }
-                    // drain when some stack could overflow in the next group, and at the end of the tile
-                    if (j == 60 || __any_sync(CHB_FULL, ncand > NC - 4)) {
-                        while (__any_sync(CHB_FULL, ncand > 0)) {
-                            if (ncand > 0) {
-                                --ncand;
-                                const float av = S.cand_val[ncand][et];
-                                if (av < L.key[KR - 1]) L.insert(av, __ldg(tile_pt + S.cand_col[ncand][et]));
-                            }
-                        }
-                    }
+                    if (g >= 16) break;
                 }
+#undef SCREEN_STEP
             }
             if (rvalid && cur_bin >= 0) {
                 float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
