@@ -7,9 +7,10 @@ The directory is named `ch-bin_b200` (not importable as written); `import chbin_
 Public surface (mirrors /root/reference/ch_bin/core/clustering/algorithm.py and ch_bin/cli/clustering.py):
     fit_cluster, perform_clustering, install, B200_SOLVER
     capi.Context        thin ctypes wrapper over the C-ABI (include/chbin_b200.h)
+    distance_cache      on-disk distance matrix (.npy, reference format) and the features.csv side-car
     synth               synthetic contig feature sets of the BASELINE configs
 """
-from . import build, capi, synth  # noqa: F401
+from . import build, capi, distance_cache, synth  # noqa: F401
 from .clustering import (  # noqa: F401
     B200_SOLVER,
     GpuEngine,
@@ -24,5 +25,5 @@ from .clustering import (  # noqa: F401
 
 __all__ = [
     "B200_SOLVER", "GpuEngine", "TorchComm", "fit_cluster", "install", "owned_slots", "perform_clustering",
-    "run_iteration", "shutdown", "build", "capi", "synth",
+    "run_iteration", "shutdown", "build", "capi", "distance_cache", "synth",
 ]

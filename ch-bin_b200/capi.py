@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 
 CHB_OK, CHB_EINVAL, CHB_ENODEV, CHB_ECUDA, CHB_ENOMEM, CHB_ENOTIMPL, CHB_EUNASSIGNED = range(7)
-METRICS = {"convex": 0, "affine-qp": 1}
+METRICS = {"convex": 0, "affine-qp": 1, "affine": 2}
 UNOWNED = -(2**31)
 OWN_STREAM = 2**64 - 1  # CHB_OWN_STREAM: (void*)-1
 

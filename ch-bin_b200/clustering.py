@@ -21,7 +21,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from . import capi
+from . import capi, distance_cache
 
 logger = logging.getLogger(__name__)
 
@@ -191,7 +191,7 @@ def fit_cluster(
     :param initial_bins: Initial bin vector. Use -1 for un-binned.
     :param num_neighbors: Number of neighbors to consider for polytope.
     :param max_iterations: Number of maximum iterations to perform.
-    :param metric: Polytope distance metric (convex/affine-qp).
+    :param metric: Polytope distance metric (convex/affine/affine-qp).
     :return: Final binning result (int64, n).
     """
     if qp_solver != B200_SOLVER:
@@ -289,10 +289,24 @@ def perform_clustering(
     operating_dir.mkdir(parents=True, exist_ok=True)
 
     logger.info(">> Reading feature CSV...")
-    df_features = pd.read_csv(features_csv)
+    samples = None
+    if distance_cache.sidecar_path(features_csv).exists():
+        # binary side-car of the samples block (distance_cache.write_features_sidecar): only the three label columns are
+        # parsed from the CSV text
+        df_features = pd.read_csv(features_csv, usecols=distance_cache.META_COLUMNS)
+        samples = distance_cache.load_samples(features_csv, len(df_features))
+    if samples is None:
+        df_features = pd.read_csv(features_csv)
+        samples = df_features.drop(distance_cache.META_COLUMNS, axis=1).values
     num_clusters = int(df_features.CLUSTER.max() + 1)
     initial_bins = df_features.CLUSTER.values.copy()
-    samples = df_features.drop(["CONTIG_NAME", "PARENT_NAME", "CLUSTER"], axis=1).values
+    num_samples = len(samples)
+
+    if not in_mem_dist_matrix:
+        # cli/clustering.py:60-63: the on-disk matrix is produced (or found) exactly where the reference keeps it; the
+        # assignment rounds below regenerate distances on the device and never read it back
+        logger.info(">> Creating a distance matrix of %s in-disk...", (num_samples, num_samples))
+        distance_cache.create_distance_matrix(samples, operating_dir)
 
     logger.info(">> Performing binning using %s solver...", qp_solver)
     convex_labels = fit_cluster(
@@ -303,8 +317,7 @@ def perform_clustering(
         raise ValueError("There were some un-clustered points left... Aborting.")  # cli/clustering.py:79-80
 
     logger.info(">> Assigning bins...")
-    df_samples = df_features.drop("CLUSTER", axis=1)
-    df_combined = pd.concat([df_samples, pd.DataFrame({"BIN": convex_labels})], axis=1)
+    df_combined = pd.concat([df_features[["PARENT_NAME"]], pd.DataFrame({"BIN": convex_labels})], axis=1)
     parent_groups = df_combined[["PARENT_NAME", "BIN"]].groupby("PARENT_NAME")
     df_dist_bin = parent_groups.BIN.apply(lambda x: np.bincount(x).argmax()).reset_index()
     df_dist_bin.rename(columns={"PARENT_NAME": "CONTIG_NAME"}, inplace=True)

@@ -544,8 +544,8 @@ int chb_set_params(chb_ctx *c, int32_t k, int32_t metric)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CHECK(c, k >= 1 && k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d], got %d", CHB_KMAX, k);
-    CHB_CHECK(c, metric == CHB_METRIC_CONVEX || metric == CHB_METRIC_AFFINE_QP, CHB_ENOTIMPL, "Metric %d not implemented",
-              metric);
+    CHB_CHECK(c, metric == CHB_METRIC_CONVEX || metric == CHB_METRIC_AFFINE_QP || metric == CHB_METRIC_AFFINE, CHB_ENOTIMPL,
+              "Metric %d not implemented", metric);
     if (k != c->k || metric != c->metric) c->cache_nown = -1;
     c->k = k;
     c->metric = metric;

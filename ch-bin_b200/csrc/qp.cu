@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
         int status = CHB_QP_OK;
         if (!(scale > 0.0)) {
             alpha = (lane == 0) ? 1.0 : 0.0; // every neighbour coincides with the query
-        } else if (a.metric == CHB_METRIC_AFFINE_QP) {
+        } else if (a.metric != CHB_METRIC_CONVEX) { // affine-qp / affine: no sign constraints
             unsigned smask = (m >= 32) ? 0xffffffffu : ((1u << m) - 1u);
             for (int guard = 0; guard < m; ++guard) {
                 double y;
@@ -297,8 +297,8 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
 {
     if (a.n_work <= 0) return CHB_OK;
     CHB_CHECK(ctx, a.k >= 1 && a.k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d]", CHB_KMAX);
-    CHB_CHECK(ctx, a.metric == CHB_METRIC_CONVEX || a.metric == CHB_METRIC_AFFINE_QP, CHB_ENOTIMPL,
-              "Metric %d not implemented", a.metric);
+    CHB_CHECK(ctx, a.metric == CHB_METRIC_CONVEX || a.metric == CHB_METRIC_AFFINE_QP || a.metric == CHB_METRIC_AFFINE,
+              CHB_ENOTIMPL, "Metric %d not implemented", a.metric);
     if (a.k <= 5 && a.metric == CHB_METRIC_CONVEX) {
         // fast path; pairs whose a'Ga is too small to trust go through the general kernel afterwards
         if (ctx->fallback_cap < a.n_work) {

@@ -35,7 +35,11 @@ enum {
 };
 
 /* AlgoDistanceMetric (config/default.ini:18 -> hull_distance.py:90-108) */
-enum { CHB_METRIC_CONVEX = 0, CHB_METRIC_AFFINE_QP = 1 };
+/* "affine" (hull_distance.py:69-87) is the SVD/orthogonal-projection form of the same geometric quantity as "affine-qp"
+ * (hull_distance.py:38-66): the distance to the affine hull of the neighbours.  Both run the equality-constrained
+ * solve of qp.cu; affinely dependent neighbours are dropped (the reference's scipy.linalg.orth drops the matching
+ * null directions), so the two agree to rounding whenever the hull is the same. */
+enum { CHB_METRIC_CONVEX = 0, CHB_METRIC_AFFINE_QP = 1, CHB_METRIC_AFFINE = 2 };
 
 /* per-QP status written by chb_hull_distance_batch (SURVEY.md 8(b) "Errors") */
 enum {

@@ -179,10 +179,27 @@ def affine_hull_distance_qp(query: np.ndarray, points: np.ndarray) -> float:
     return lib().chb_oracle_affine_hull_distance_qp(query, points, m, d, ctypes.byref(st))
 
 
+def affine_hull_distance(query: np.ndarray, points: np.ndarray) -> float:
+    """hull_distance.py:69-87: project (query - mean) onto the orthogonal complement of span(points - mean).  The basis
+    is scipy.linalg.orth's: left singular vectors whose singular value exceeds max(shape) * eps * s_max."""
+    query = np.asarray(query, dtype=np.float64)
+    points = np.asarray(points, dtype=np.float64)
+    mean_vec = points.mean(axis=0)
+    rel = (points - mean_vec).T  # d x m
+    u, sv, _ = np.linalg.svd(rel, full_matrices=False)
+    tol = max(rel.shape) * np.finfo(np.float64).eps * (sv.max() if sv.size else 0.0)
+    basis = u[:, sv > tol]
+    dq = query - mean_vec
+    proj = basis @ np.linalg.solve(basis.T @ basis, basis.T @ dq) if basis.shape[1] else np.zeros_like(dq)
+    return float(np.linalg.norm(dq - proj))
+
+
 def calculate_distance(x: np.ndarray, mat_p: np.ndarray, qp_solver: str = "quadprog", metric: str = "convex") -> float:
     """hull_distance.py:90-108."""
     if metric == "convex":
         return convex_hull_distance(x, mat_p)
+    if metric == "affine":
+        return affine_hull_distance(x, mat_p)
     if metric == "affine-qp":
         return affine_hull_distance_qp(x, mat_p)
     raise NotImplementedError(f"Metric {metric} not implemented")
@@ -224,7 +241,8 @@ def fit_cluster(
         perms = draw_permutations(initial_bins, max_iterations, seed=None)
     perms = np.ascontiguousarray(perms, dtype=np.int64)
     U = perms.shape[1]
-    met = {"convex": 0, "affine-qp": 1}.get(metric)
+    # "affine" and "affine-qp" are the same geometric distance (see affine_hull_distance): the sequential loop uses one solver
+    met = {"convex": 0, "affine-qp": 1, "affine": 1}.get(metric)
     if met is None:
         raise NotImplementedError(f"Metric {metric} not implemented")
     if distance_matrix is not None:

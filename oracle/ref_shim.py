@@ -134,3 +134,25 @@ def fit_cluster_reference(samples, num_clusters, initial_bins, num_neighbors, ma
     finally:
         ref.algorithm.tqdm = orig
         del _tqdm
+
+
+def load_cli_clustering():
+    """The reference's own ch_bin.cli.clustering module (perform_clustering / run_perform_clustering), imported with a
+    stand-in for Biopython's SeqIO: step 05 (dump_bins, FASTA output -- outside the hot path) becomes a no-op, steps
+    01-04 (cli/clustering.py:47-92) execute verbatim."""
+    load()
+    if "ch_bin.cli.clustering" in sys.modules:
+        return sys.modules["ch_bin.cli.clustering"]
+    if "Bio" not in sys.modules:
+        try:
+            import Bio  # noqa: F401
+        except ImportError:
+            bio = types.ModuleType("Bio")
+            seqio = types.ModuleType("Bio.SeqIO")
+            seqio.parse = lambda *a, **k: iter(())
+            bio.SeqIO = seqio
+            sys.modules["Bio"] = bio
+            sys.modules["Bio.SeqIO"] = seqio
+    mod = importlib.import_module("ch_bin.cli.clustering")
+    mod.dump_bins = lambda df_bins, contig_fasta, operating_dir: None
+    return mod

@@ -92,7 +92,7 @@ def main():
 
     # ---- 2. hull distances through hull_distance.py -> solve_qp.py -> (numba nearest-PD) -> solver
     Xh, _, _ = synth.make_contig_features(300, 5, 3, 10, seed=22)
-    hq, hidx, hm, hd, ha = [], [], [], [], []
+    hq, hidx, hm, hd, ha, hs = [], [], [], [], [], []
     KMAXG = 12
     for t in range(160):
         m = int(rng.integers(1, KMAXG + 1))
@@ -103,8 +103,9 @@ def main():
         hidx.append(np.pad(idx, (0, KMAXG - m), constant_values=-1))
         hd.append(ref.hull_distance.convex_hull_distance(Xh[q], Xh[idx], "quadprog"))
         ha.append(ref.hull_distance.affine_hull_distance_qp(Xh[q], Xh[idx], "quadprog") if m >= 2 else np.nan)
+        hs.append(ref.hull_distance.affine_hull_distance(Xh[q], Xh[idx]) if m >= 2 else np.nan)  # SVD form, :69-87
     out.update(hull_X=Xh, hull_q=np.array(hq), hull_idx=np.array(hidx), hull_m=np.array(hm), hull_dist=np.array(hd),
-               hull_affine_qp=np.array(ha))
+               hull_affine_qp=np.array(ha), hull_affine=np.array(hs))
 
     # ---- 3. fit_cluster, verbatim reference loop, np.random.seed(0) as ch_bin/ch_bin.py:22
     cases = {
@@ -122,12 +123,58 @@ def main():
         out[f"fit_{name}_params"] = np.array([c["C"], c["k"], c["iters"]], dtype=np.int64)
         print(name, "changed vs seeds:", int(np.sum(lab != bc)))
 
+    # ---- 3b. the "affine" metric (hull_distance.py:69-87, scipy.linalg.orth) through the same verbatim loop
+    ca = dict(n=350, C=4, S=2, n_seed=20, k=4, conc=800.0, iters=6)
+    Xa, ba, _ = synth.make_contig_features(ca["n"], ca["C"], ca["S"], ca["n_seed"], seed=33, concentration=ca["conc"])
+    laba = ref_shim.fit_cluster_reference(Xa, ca["C"], ba, ca["k"], ca["iters"], metric="affine", seed=0)
+    out.update(fit_affine_X=Xa, fit_affine_bins=ba, fit_affine_labels=laba.astype(np.int64),
+               fit_affine_params=np.array([ca["C"], ca["k"], ca["iters"]], dtype=np.int64))
+    print("affine changed vs seeds:", int(np.sum(laba != ba)))
+
     # ---- 4. five-genomes-like (config #1)
     Xg, bg, parents = five_genomes_like()
     print("five-genomes-like: n =", len(Xg), "U =", int(np.sum(bg == -1)), "seed pieces =", np.bincount(bg[bg >= 0]))
     lab = ref_shim.fit_cluster_reference(Xg, 5, bg, 5, 10, seed=0)
     out.update(fg_X=Xg, fg_bins=bg, fg_parents=parents, fg_labels=lab.astype(np.int64),
                fg_params=np.array([5, 5, 10], dtype=np.int64))
+
+    # ---- 5. the caller: perform_clustering (cli/clustering.py:19-99) steps 01-04, CSV in -> CSV out, both matrix modes
+    import tempfile
+    import pandas as pd
+    from pathlib import Path
+
+    cli = ref_shim.load_cli_clustering()
+    Xp, bp, _ = synth.make_contig_features(180, 3, 1, 12, seed=41, concentration=900.0)
+    prng = np.random.default_rng(7)
+    parents = np.empty(len(Xp), dtype=object)
+    # seeds of a bin are pieces of one parent contig; the rest are grouped 1-3 sub-contigs per parent
+    for c in range(3):
+        parents[bp == c] = f"seed_parent_{c}"
+    rest = np.where(bp == -1)[0]
+    pid, i = 0, 0
+    while i < len(rest):
+        g = int(prng.integers(1, 4))
+        parents[rest[i:i + g]] = f"contig_{pid}"
+        pid += 1
+        i += g
+    df = pd.DataFrame({"CONTIG_NAME": [f"sub_{j}" for j in range(len(Xp))], "PARENT_NAME": parents, "CLUSTER": bp})
+    df = pd.concat([df, pd.DataFrame(Xp, columns=[f"F{j}" for j in range(Xp.shape[1])])], axis=1)
+    with tempfile.TemporaryDirectory() as td:
+        td = Path(td)
+        csv = td / "features.csv"
+        df.to_csv(csv, index=False)
+        np.random.seed(0)
+        out_mem = cli.perform_clustering(td / "no.fasta", csv, td / "mem", 5, 6, "convex", "quadprog", True)
+        np.random.seed(0)
+        out_disk = cli.perform_clustering(td / "no.fasta", csv, td / "disk", 5, 6, "convex", "quadprog", False)
+        mem_txt, disk_txt = open(out_mem, "rb").read(), open(out_disk, "rb").read()
+        assert mem_txt == disk_txt
+        dm = np.load(td / "disk" / "distance_matrix.npy")
+        out.update(pc_features_csv=np.frombuffer(open(csv, "rb").read(), dtype=np.uint8),
+                   pc_assignment_csv=np.frombuffer(mem_txt, dtype=np.uint8),
+                   pc_npy_header=np.frombuffer(open(td / "disk" / "distance_matrix.npy", "rb").read(128), dtype=np.uint8),
+                   pc_dm_rows=dm[[0, 57, 179]].copy(), pc_params=np.array([5, 6], dtype=np.int64))
+        print("perform_clustering golden:", len(mem_txt), "bytes of binning-assignment.csv,", dm.shape)
 
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)

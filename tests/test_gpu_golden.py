@@ -25,6 +25,16 @@ def test_fit_cluster_matches_reference_run(G, name):
     assert np.array_equal(got, ref), f"{np.sum(got != ref)} labels differ from the reference's fit_cluster"
 
 
+def test_fit_cluster_affine_matches_reference_run(G):
+    """metric="affine" (hull_distance.py:69-87) against the verbatim reference loop."""
+    X, bins, ref = G["fit_affine_X"], G["fit_affine_bins"], G["fit_affine_labels"]
+    C, k, iters = (int(v) for v in G["fit_affine_params"])
+    for metric in ("affine", "affine-qp"):
+        np.random.seed(0)
+        got = chbin_b200.fit_cluster(X, C, bins, None, k, iters, metric=metric)
+        assert np.array_equal(got, ref), f"{metric}: {np.sum(got != ref)} labels differ from the reference's fit_cluster"
+
+
 @pytest.mark.parametrize("dist_mode", [0, 1])
 def test_knn_sets_match_reference(G, dist_mode):
     X, labels, queries, k = G["knn_X"], G["knn_labels"], G["knn_queries"], int(G["knn_k"])
@@ -50,7 +60,7 @@ def test_hull_distances_match_reference(G):
     X = G["hull_X"]
     hq, hidx, hm = G["hull_q"], G["hull_idx"], G["hull_m"]
     kmax = hidx.shape[1]
-    for metric, key, tol in (("convex", "hull_dist", 1e-6), ("affine-qp", "hull_affine_qp", 1e-6)):
+    for metric, key, tol in (("convex", "hull_dist", 1e-6), ("affine-qp", "hull_affine_qp", 1e-6), ("affine", "hull_affine", 1e-6)):
         ctx = capi.Context(0)
         ctx.set_features(X)
         ctx.set_labels(np.full(len(X), -1), 1)

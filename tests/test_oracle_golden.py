@@ -78,6 +78,31 @@ def test_hull_distance_golden(G):
                 assert abs(da - aref) <= 1e-7 * aref + 1e-12, (m, da, aref)
 
 
+def test_affine_svd_form_golden(G):
+    """hull_distance.py:69-87 (scipy.linalg.orth projection) against the reference's own outputs, and its agreement
+    with the QP form on these affinely independent neighbour sets (the GPU path evaluates both metrics with one solve)."""
+    X = G["hull_X"]
+    for q, idx, m, sref, aref in zip(G["hull_q"], G["hull_idx"], G["hull_m"], G["hull_affine"], G["hull_affine_qp"]):
+        if m < 2:
+            continue
+        pts = X[idx[:m]]
+        ds = oracle.affine_hull_distance(X[q], pts)
+        assert abs(ds - sref) <= 1e-12 * sref + 1e-15, (m, ds, sref)
+        assert abs(ds - oracle.affine_hull_distance_qp(X[q], pts)) <= 1e-7 * sref + 1e-12
+        assert abs(sref - aref) <= 1e-9 * sref
+    # affinely dependent neighbours: orth drops the null direction, the distance is that of the reduced hull
+    pts = X[[3, 9, 3, 20]]
+    assert abs(oracle.affine_hull_distance(X[50], pts) - oracle.affine_hull_distance(X[50], X[[3, 9, 20]])) <= 1e-12
+
+
+def test_fit_cluster_affine_golden(G):
+    X, bins, ref = G["fit_affine_X"], G["fit_affine_bins"], G["fit_affine_labels"]
+    C, k, iters = (int(v) for v in G["fit_affine_params"])
+    perms = oracle.draw_permutations(bins, iters, seed=0)
+    got = oracle.fit_cluster(X, C, bins, None, k, iters, metric="affine", perms=perms, threads=2)
+    assert np.array_equal(got, ref), f"{np.sum(got != ref)} labels differ from the verbatim reference run (metric=affine)"
+
+
 @pytest.mark.parametrize("name", ["easy", "hard", "k10", "smallbins"])
 def test_fit_cluster_golden(G, name):
     X, bins, ref = G[f"fit_{name}_X"], G[f"fit_{name}_bins"], G[f"fit_{name}_labels"]
