@@ -224,7 +224,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference = CPU oracle port (GI restatement); quadprog/cvxopt and the Python reference are not installable offline",
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def config_dict(args, cfg, U):
@@ -449,15 +449,28 @@ def run_b200(args):
             "launches_by_stage": dict(ln, other=tm["launches_other"]),
             "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(line: dict):
+    """The ONE JSON line goes to the real stdout; everything else written to fd 1 meanwhile (NCCL's version banner,
+    library chatter) was diverted to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
