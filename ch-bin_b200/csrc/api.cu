@@ -296,7 +296,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
-    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->f_fb_items); dev_free(&c->stage_X);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->f_fb_items); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
     chb_fused_free(c); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;
@@ -483,6 +483,7 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     CHB_CHECK(c, bins && C >= 1, CHB_EINVAL, "initial_bins is NULL or num_clusters < 1");
     CHB_CUDA(c, cudaSetDevice(c->device));
     std::vector<int32_t> &lab = c->h_lab, &qs = c->h_qslot, &qp = c->h_qpoint;
+    std::vector<int32_t> seed_off((size_t)C + 1, 0);
     lab.resize((size_t)n);
     qs.resize((size_t)n);
     qp.clear();
@@ -496,9 +497,18 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
             qp.push_back((int32_t)i);
         } else {
             qs[(size_t)i] = -1;
+            ++seed_off[(size_t)b + 1];
         }
     }
     const int64_t U = (int64_t)qp.size();
+    // seed contigs sorted by (bin, index): the bin reference points are summed in this fixed order on every rank
+    for (int32_t b = 0; b < C; ++b) seed_off[(size_t)b + 1] += seed_off[(size_t)b];
+    std::vector<int32_t> seed_idx((size_t)std::max<int64_t>(n - U, 1));
+    {
+        std::vector<int32_t> cur(seed_off.begin(), seed_off.end() - 1);
+        for (int64_t i = 0; i < n; ++i)
+            if (lab[(size_t)i] >= 0) seed_idx[(size_t)cur[(size_t)lab[(size_t)i]]++] = (int32_t)i;
+    }
     if (slot_end < 0) slot_end = U;
     CHB_CHECK(c, 0 <= slot_begin && slot_begin <= slot_end && slot_end <= U, CHB_EINVAL, "owned slot range [%lld,%lld) invalid for U=%lld",
               (long long)slot_begin, (long long)slot_end, (long long)U);
@@ -525,6 +535,10 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
         c->own_pos_host = new int64_t[(size_t)std::max<int64_t>(slot_end - slot_begin, 1)];
         c->cap_own = std::max<int64_t>(slot_end - slot_begin, 1);
     }
+    CHB_TRY(dev_reserve(c, &c->seed_off, &c->cap_seed_off, (int64_t)C + 1));
+    CHB_TRY(dev_reserve(c, &c->seed_idx, &c->cap_seed_idx, std::max<int64_t>(n - U, 1)));
+    CHB_CUDA(c, cudaMemcpy(c->seed_off, seed_off.data(), sizeof(int32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice));
+    CHB_CUDA(c, cudaMemcpy(c->seed_idx, seed_idx.data(), sizeof(int32_t) * (size_t)std::max<int64_t>(n - U, 1), cudaMemcpyHostToDevice));
     CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
@@ -533,6 +547,7 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
     c->labels_set = true;
+    c->guess_pending = true;
     c->in_iteration = false;
     c->dist_ready = false;
     c->f_asplit_ready = false;
@@ -787,6 +802,15 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
         ++c->tm.launches_other;
     }
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->guess_pending && use_fused(c) && U > 0) {
+        // First iteration: every query still carries -1.  Any starting vector T0 leads the speculate/repair rounds to
+        // the same fixed point (position p is final once positions < p are, whatever it started from), so start from
+        // the bin of the nearest seed centroid instead of "unassigned": when that guess is right the first round already
+        // reproduces itself and the seed-only round (a full batch of QPs that the second round re-solves) is saved.
+        CHB_TRY(chb_fused_setup(c));
+        CHB_TRY(chb_fused_guess(c));
+    }
+    c->guess_pending = false;
     // no sync: the host arrays are context-owned and pageable (the runtime stages them before returning)
     c->in_iteration = true;
     c->tm.qps_reference += (c->u1 - c->u0) * c->C;

@@ -23,16 +23,27 @@ namespace {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int PADM = BM + 4;
 
-// column sums of X (for the centring translation): block b adds rows [256 b, 256 b + 256) to colsum[]
-__global__ void __launch_bounds__(256) colsum_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, int64_t n,
-                                                       double *__restrict__ colsum)
+// column sums of X (for the centring translation), in a fixed summation order so that every rank of a multi-GPU run
+// derives bit-identical centred features: block b sums rows [256 b, 256 b + 256) into part[b][:], then one block adds
+// the partial sums in block order.
+__global__ void __launch_bounds__(256) colsum_part_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, int64_t n,
+                                                            double *__restrict__ part)
 {
     const int64_t r0 = (int64_t)blockIdx.x * 256;
     const int64_t r1 = r0 + 256 < n ? r0 + 256 : n;
     for (int t = threadIdx.x; t < d; t += 256) {
         double s = 0.0;
         for (int64_t r = r0; r < r1; ++r) s += X[r * ldx + t];
-        atomicAdd(&colsum[t], s);
+        part[(int64_t)blockIdx.x * d + t] = s;
+    }
+}
+__global__ void __launch_bounds__(256) colsum_final_kernel(const double *__restrict__ part, int64_t nparts, int32_t d,
+                                                             double *__restrict__ colsum)
+{
+    for (int t = threadIdx.x; t < d; t += 256) {
+        double s = 0.0;
+        for (int64_t b = 0; b < nparts; ++b) s += part[b * d + t];
+        colsum[t] = s;
     }
 }
 
@@ -143,13 +154,21 @@ int chb_launch_prep_f32(chb_ctx *ctx)
 {
     const int64_t n = ctx->n;
     CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[5], 0, sizeof(int32_t), ctx->stream));
-    CHB_CUDA(ctx, cudaMemsetAsync(ctx->colsum, 0, sizeof(double) * (size_t)ctx->d, ctx->stream));
-    colsum_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(ctx->X, ctx->ldx, ctx->d, n, ctx->colsum);
+    const int64_t nparts = (n + 255) / 256;
+    if (ctx->cap_colpart < nparts * ctx->d) {
+        if (ctx->colpart) cudaFree(ctx->colpart);
+        ctx->colpart = nullptr;
+        ctx->cap_colpart = 0;
+        CHB_CUDA(ctx, cudaMalloc(reinterpret_cast<void **>(&ctx->colpart), sizeof(double) * (size_t)(nparts * ctx->d)));
+        ctx->cap_colpart = nparts * ctx->d;
+    }
+    colsum_part_kernel<<<(unsigned)nparts, 256, 0, ctx->stream>>>(ctx->X, ctx->ldx, ctx->d, n, ctx->colpart);
+    colsum_final_kernel<<<1, 256, 0, ctx->stream>>>(ctx->colpart, nparts, ctx->d, ctx->colsum);
     prep_f32_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
         ctx->X, ctx->ldx, ctx->d, n, ctx->colsum, 1.0 / (double)n, ctx->Xf, ctx->ldf, ctx->nrm,
         reinterpret_cast<unsigned int *>(&ctx->counters[5]));
     CHB_CUDA(ctx, cudaGetLastError());
-    ctx->tm.launches_other += 2;
+    ctx->tm.launches_other += 3;
     return CHB_OK;
 }
 

@@ -29,6 +29,11 @@ struct chb_ctx {
     float *Xf = nullptr;  // n x ldf FP32 copy of the features (candidate filter)
     float *nrm = nullptr; // n : |x - mu|^2 rounded up to FP32
     double *colsum = nullptr; // d : column sums of X (mu = colsum / n)
+    double *colpart = nullptr; // per-256-row partial column sums (deterministic reduction)
+    int64_t cap_colpart = 0;
+    int32_t *seed_off = nullptr, *seed_idx = nullptr; // C + 1 offsets / seed points (initial label >= 0) sorted by (bin, index)
+    int64_t cap_seed_off = 0, cap_seed_idx = 0;
+    bool guess_pending = false; // first iteration after chb_set_labels: speculation starts from the nearest seed centroid
     int32_t ldf = 0;
     int dist_mode = 2;    // 2: fused tensor-core Gram + selection (default); 1: FP32 candidate matrix + scan; 0: exact FP64 rows
     int gram_engine = 1;  // filter mode: 1 = tcgen05 TF32x3 tensor-core Gram (gram_tc.cu), 0 = FFMA Gram (approx.cu)
@@ -198,6 +203,8 @@ int chb_launch_gram_tc(chb_ctx *ctx, const float *a_split, const float *b_split,
 // fused.cu : distance mode 2, Gram + per-bin selection in one tcgen05 kernel, then exact re-rank
 bool chb_fused_supported(const chb_ctx *c);
 int chb_round_fused(chb_ctx *c);
+int chb_fused_setup(chb_ctx *c);  // allocations + once-per-label-set operands (idempotent)
+int chb_fused_guess(chb_ctx *c);  // tent_pt of every query point := bin of the nearest seed centroid
 void chb_fused_free(chb_ctx *c);
 
 // knn.cu

@@ -248,18 +248,19 @@ __global__ void split2_gather_kernel(const int32_t *__restrict__ idx, const int3
 // and the contraction error is bounded by eps |a_q| max_i |y_i| -- the column vectors are now in-bin offsets.
 // The brackets are evaluated in FP64 from the FP32 operand values actually contracted and rounded once.
 // ---------------------------------------------------------------------------------------------------------
-// one warp per labelled point: bin sums of the seed contigs (initial labels)
-__global__ void __launch_bounds__(256) centre_accum_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, int64_t n,
-                                                           const int32_t *__restrict__ label, int32_t C, double *__restrict__ sum,
-                                                           int32_t *__restrict__ cnt)
+// one block per bin: sum of its seed contigs (initial labels), in index order -- the same bits on every rank
+__global__ void __launch_bounds__(256) centre_sum_kernel(const double *__restrict__ X, int32_t ldx, int32_t d,
+                                                         const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
+                                                         double *__restrict__ sum, int32_t *__restrict__ cnt)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (i >= n) return;
-    const int c = label[i];
-    if (c < 0 || c >= C) return;
-    for (int t = lane; t < d; t += 32) atomicAdd(&sum[(int64_t)c * d + t], X[i * ldx + t]);
-    if (lane == 0) atomicAdd(&cnt[c], 1);
+    const int c = blockIdx.x;
+    const int b = seed_off[c], e = seed_off[c + 1];
+    for (int t = threadIdx.x; t < d; t += blockDim.x) {
+        double s = 0.0;
+        for (int i = b; i < e; ++i) s += X[(int64_t)seed_idx[i] * ldx + t];
+        sum[(int64_t)c * d + t] = s;
+    }
+    if (threadIdx.x == 0) cnt[c] = e - b;
 }
 
 // m_c = mu_c - mu (zero for bins without seeds), mc2[c] = |m_c|^2
@@ -316,6 +317,43 @@ __global__ void __launch_bounds__(256) query_terms_kernel(const int32_t *__restr
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
         if (lane == 0) tq[(int64_t)c * ldt + r] = (float)fmax(aa - 2.0 * s + mc2[c], 0.0);
     }
+}
+
+// one warp per query slot (ALL of them, not only the owned ones: every rank must start from the same vector):
+// tent[point] = bin whose seed centroid is nearest (lowest bin on ties); bins without seeds are skipped
+__global__ void __launch_bounds__(256) guess_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
+                                                    int32_t ldf, int32_t d, const double *__restrict__ mc,
+                                                    const double *__restrict__ mc2, const int32_t *__restrict__ mcnt, int32_t C,
+                                                    int32_t *__restrict__ tent)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= U) return;
+    const int pt = qpoint[u];
+    const float *xr = Xf + (int64_t)pt * ldf;
+    double a[8]; // d <= 256
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const int t = lane + 32 * v;
+        a[v] = t < d ? (double)xr[t] : 0.0;
+    }
+    double best = INFINITY;
+    int bc = -1;
+    for (int c = 0; c < C; ++c) {
+        if (mcnt[c] <= 0) continue;
+        const double *m = mc + (int64_t)c * d;
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int t = lane + 32 * v;
+            if (t < d) s = fma(a[v], m[t], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
+        const double val = mc2[c] - 2.0 * s; // |a - m_c|^2 minus the bin-independent |a|^2
+        if (val < best) { best = val; bc = c; }
+    }
+    if (lane == 0 && bc >= 0) tent[pt] = bc;
 }
 
 // one warp per column entry: y = fl32(x_i - mu_c) split into the [hi | lo] operand row, the column term
@@ -1066,10 +1104,19 @@ void chb_fused_free(chb_ctx *c)
 // Runs steps 1-3 of the header comment for ALL owned query slots against the current (pos, tent, old) labels.
 // Appends changed (slot_local, bin) pairs to ctx->work (count in counters[0]); queries needing the exact fallback are
 // listed in f_fb_rows (count in counters[6]).
-int chb_round_fused(chb_ctx *c)
+int chb_fused_guess(chb_ctx *c)
+{
+    if (c->U <= 0) return CHB_OK;
+    guess_kernel<<<nblk(c->U * 32, 256), 256, 0, c->stream>>>(c->qpoint, c->U, c->Xf, c->ldf, c->d, c->f_mc, c->f_mc2, c->f_mcnt, c->C,
+                                                              c->tent_pt);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    return CHB_OK;
+}
+
+int chb_fused_setup(chb_ctx *c)
 {
     const int64_t nown = c->u1 - c->u0;
-    if (nown <= 0) return CHB_OK;
     const int64_t n = c->n;
     const int32_t C = c->C, k = c->k;
     const int KR = (k + 3 <= 8) ? 8 : 16;
@@ -1118,19 +1165,35 @@ int chb_round_fused(chb_ctx *c)
     }
     // query operand: once per (feature set, label set)
     if (!c->f_asplit_ready || c->f_cap_a2 < nown * g.Kp2) {
-        if (reserve(c, &c->f_a2, &c->f_cap_a2, nown * g.Kp2)) return CHB_ENOMEM;
-        split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nullptr, nown, c->Xf, c->ldf, c->d,
-                                                                                  g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
-        // bin reference points from the seed contigs (the labels at this point are the initial bins) and the query terms
-        CHB_CUDA(c, cudaMemsetAsync(c->f_mc, 0, sizeof(double) * (size_t)C * c->d, c->stream));
-        CHB_CUDA(c, cudaMemsetAsync(c->f_mcnt, 0, sizeof(int32_t) * (size_t)(C + 1), c->stream));
-        centre_accum_kernel<<<nblk(n * 32, 256), 256, 0, c->stream>>>(c->X, c->ldx, c->d, n, c->old_label, C, c->f_mc, c->f_mcnt);
+        if (reserve(c, &c->f_a2, &c->f_cap_a2, std::max<int64_t>(nown, 1) * g.Kp2)) return CHB_ENOMEM;
+        if (nown > 0)
+            split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nullptr, nown, c->Xf, c->ldf,
+                                                                                      c->d, g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
+        // bin reference points from the seed contigs (initial bins, fixed summation order) and the query terms
+        centre_sum_kernel<<<(unsigned)C, 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_off, c->seed_idx, c->f_mc, c->f_mcnt);
         centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2);
-        query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nown, c->Xf, c->ldf, c->d, c->f_mc, c->f_mc2,
-                                                                       C, c->f_ldt, c->f_tq);
+        if (nown > 0)
+            query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nown, c->Xf, c->ldf, c->d, c->f_mc,
+                                                                           c->f_mc2, C, c->f_ldt, c->f_tq);
         CHB_CUDA(c, cudaGetLastError());
         c->tm.launches_other += 4;
         c->f_asplit_ready = true;
+    }
+    return CHB_OK;
+}
+
+int chb_round_fused(chb_ctx *c)
+{
+    const int64_t nown = c->u1 - c->u0;
+    if (nown <= 0) return CHB_OK;
+    const int64_t n = c->n;
+    const int32_t C = c->C, k = c->k;
+    const int KR = (k + 3 <= 8) ? 8 : 16;
+    const FusedGeom g = fused_geom(c->d);
+    const int64_t ncol_max = ((2 * n + (int64_t)BN * C + BN - 1) / BN) * BN;
+    {
+        const int rc0 = chb_fused_setup(c);
+        if (rc0 != CHB_OK) return rc0;
     }
 
     // ---- 1. column entries
