@@ -844,9 +844,9 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         CHB_TRY(chb_round_fused(c));
         // exact-path fallback for queries whose kept candidate list may be incomplete (duplicate contigs): rare
         CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[7], c->f_ntiles, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[7], &c->counters[7], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         CHB_TRY(sync_stream(c));
-        c->tm.gram_tiles += (int64_t)c->counters_host[7] * ((nown + 127) / 128);
+        c->tm.gram_tiles += (int64_t)c->counters_host[7]; // tiles left after bin pruning (skip_kernel)
         const int64_t nfb = c->counters_host[6];
         if (nfb > 0) {
             if (c->f_cap_fb < 2 * nfb) {

@@ -101,7 +101,7 @@ struct chb_ctx {
     int32_t *f_col_pt = nullptr, *f_col_a = nullptr, *f_col_b = nullptr;
     float *f_col_nrm = nullptr, *f_bperm = nullptr, *f_cand_key = nullptr;
     int32_t *f_cand_idx = nullptr, *f_fb_rows = nullptr;
-    int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0, f_cap_thr = 0;
+    int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0, f_cap_thr = 0, f_cap_ldt = 0;
     float *f_thr = nullptr; // nown x C : largest FP32 key of the cached neighbour set (+inf: fewer than k members)
     float *f_t0 = nullptr;  // C x f_ldt : this round's admission threshold per (bin, owned slot)
     int64_t f_ldt = 0;
@@ -111,6 +111,9 @@ struct chb_ctx {
     int32_t *f_mcnt = nullptr;
     int64_t f_cap_mc = 0;
     float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
+    uint8_t *f_skip = nullptr;                 // (#row blocks) x C : tiles of this (row block, bin) are skipped this round
+    int32_t *f_row_slot = nullptr, *f_row_pt = nullptr, *f_guess_slot = nullptr; // row -> owned slot / point; guessed bin per slot
+    float *f_ub = nullptr, *f_ub_slot = nullptr; // upper bound of min_c hull distance per row / per slot
     float *f_ym2 = nullptr;                    // 2 (C + 1) : per-bin maxima of |y|^2 and |column term| of this round
     bool f_asplit_ready = false;
     int32_t *f_fb_items = nullptr; // positions of the fallback queries

@@ -319,6 +319,116 @@ __global__ void __launch_bounds__(256) query_terms_kernel(const int32_t *__restr
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// bin pruning.  The label of a query is the bin with the smallest hull distance (algorithm.py:47-58).  Two bounds
+// decide most (query, bin) pairs without a neighbour search or a QP:
+//   upper  UB(q)   = distance from q to the nearest SEED contig of its guessed bin g: seeds never change label and are
+//                    visible to every query, the nearest visible member of a bin is one of its k neighbours, and the
+//                    hull distance is at most the distance to a neighbour -- so min_c D(q, c) <= D(q, g) <= UB(q);
+//   lower  LB(q,c) = |x_q - mu_c| - max_i |x_i - mu_c| over the bin's current members: the hull of any k of them lies in
+//                    that ball -- so D(q, c) >= LB(q, c).
+// A bin with LB(q, c) > UB(q) (strictly, with a rounding margin) cannot be the argmin, not even on a tie, and is
+// pruned: admission threshold -inf, no candidates, no QP, hull distance +inf.  Rows are ordered by guessed bin so that
+// whole 128-query row blocks prune the same bins and their tiles are skipped by the fused kernel.
+// ---------------------------------------------------------------------------------------------------------
+// one warp per owned slot: guessed bin (same arithmetic as guess_kernel) and UB
+__global__ void __launch_bounds__(256) row_bound_kernel(const int32_t *__restrict__ qpoint_own, int64_t nown, const double *__restrict__ X,
+                                                        int32_t ldx, const float *__restrict__ Xf, int32_t ldf, int32_t d,
+                                                        const double *__restrict__ mc, const double *__restrict__ mc2,
+                                                        const int32_t *__restrict__ mcnt, int32_t C,
+                                                        const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
+                                                        int32_t *__restrict__ guess_out, float *__restrict__ ub_out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= nown) return;
+    const int pt = qpoint_own[u];
+    const float *xr = Xf + (int64_t)pt * ldf;
+    double a[8]; // d <= 256
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+        const int t = lane + 32 * v;
+        a[v] = t < d ? (double)xr[t] : 0.0;
+    }
+    double best = INFINITY;
+    int bc = -1;
+    for (int c = 0; c < C; ++c) {
+        if (mcnt[c] <= 0) continue;
+        const double *m = mc + (int64_t)c * d;
+        double s = 0.0;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int t = lane + 32 * v;
+            if (t < d) s = fma(a[v], m[t], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
+        const double val = mc2[c] - 2.0 * s;
+        if (val < best) { best = val; bc = c; }
+    }
+    double ub2 = INFINITY;
+    if (bc >= 0) {
+        const double *xq = X + (int64_t)pt * ldx;
+        double q[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) {
+            const int t = lane + 32 * v;
+            q[v] = t < d ? xq[t] : 0.0;
+        }
+        for (int i = seed_off[bc]; i < seed_off[bc + 1]; ++i) {
+            const double *xs = X + (int64_t)seed_idx[i] * ldx;
+            double s = 0.0;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) {
+                const int t = lane + 32 * v;
+                if (t < d) { const double df = q[v] - xs[t]; s = fma(df, df, s); }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
+            ub2 = fmin(ub2, s);
+        }
+    }
+    if (lane == 0) {
+        guess_out[u] = bc < 0 ? C : bc; // queries without a guess sort last
+        ub_out[u] = ub2 < INFINITY ? __double2float_ru(sqrt(ub2) * (1.0 + 1e-9)) : INFINITY;
+    }
+}
+
+__global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const int32_t *__restrict__ qpoint_own,
+                                  const float *__restrict__ ub_slot, int64_t nown, int32_t *__restrict__ row_pt,
+                                  float *__restrict__ ub_row)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    const int sl = row_slot[r];
+    row_pt[r] = qpoint_own[sl];
+    ub_row[r] = ub_slot[sl];
+}
+
+// one warp per (row block, bin): skip = every row of the block pruned the bin (t0 == -inf) or lies beyond nrows;
+// counts the tiles that remain
+__global__ void __launch_bounds__(256) skip_kernel(const float *__restrict__ t0_tab, int64_t ldt, int64_t nrows, int32_t C,
+                                                   const int32_t *__restrict__ seg_off, uint8_t *__restrict__ skip,
+                                                   int32_t *__restrict__ tiles_left)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nrb = (nrows + BM - 1) / BM;
+    if (w >= nrb * C) return;
+    const int64_t rb = w / C;
+    const int c = (int)(w - rb * C);
+    bool all = true;
+    for (int i = lane; i < BM; i += 32) {
+        const int64_t r = rb * BM + i;
+        if (r < nrows && !(t0_tab[(int64_t)c * ldt + r] == -INFINITY)) all = false;
+    }
+    all = __all_sync(CHB_FULL, all);
+    if (lane == 0) {
+        skip[rb * C + c] = all ? 1 : 0;
+        if (!all) atomicAdd(tiles_left, (seg_off[c + 1] - seg_off[c]) / BN);
+    }
+}
+
 // one warp per query slot (ALL of them, not only the owned ones: every rank must start from the same vector):
 // tent[point] = bin whose seed centroid is nearest (lowest bin on ties); bins without seeds are skipped
 __global__ void __launch_bounds__(256) guess_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
@@ -457,9 +567,11 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                    const int32_t *__restrict__ ntiles_p, const int32_t *__restrict__ tile_bin, const int32_t *__restrict__ col_pt,
                    const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b, const float *__restrict__ col_nrm,
                    const float *__restrict__ tq_tab, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
-                   int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ cand_key,
-                   int32_t *__restrict__ cand_idx)
+                   int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, const uint8_t *__restrict__ skip,
+                   float *__restrict__ cand_key, int32_t *__restrict__ cand_idx)
 {
+    // skip[rb * C + bin] != 0: no query of row block rb can have bin `bin` as its nearest hull (skip_kernel) -- its tiles
+    // are neither loaded, contracted nor screened.  All three warp roles apply the same test.
     // dynamic shared memory: [resident query operand: nbox boxes][column ring: nstage boxes][SmemTail]
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -506,6 +618,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 mbar_expect_tx(&S.a_full_bar, (uint32_t)nbox * TILE_BYTES);
                 for (int jb = 0; jb < nbox; ++jb) tma_load_2d(a_res + (size_t)jb * TILE_BYTES, &map_a, &S.a_full_bar, jb * BK, rb * BM);
                 for (int t = 0; t < ntiles; ++t) {
+                    if (skip[(int64_t)rb * C + tile_bin[t]]) continue;
                     for (int jb = 0; jb < nbox; ++jb) {
                         mbar_wait(&S.empty_bar[s], ph ^ 1);
                         mbar_expect_tx(&S.full_bar[s], TILE_BYTES);
@@ -554,9 +667,11 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rbi) {
                 mbar_wait(&S.a_full_bar, (uint32_t)(rbi & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int t = 0; t < ntiles; ++t, ++tt) {
+                for (int t = 0; t < ntiles; ++t) {
+                    if (skip[(int64_t)rb * C + tile_bin[t]]) continue;
                     const int buf = (int)(tt & 1);
                     const uint32_t tph = (uint32_t)((tt >> 1) & 1);
+                    ++tt;
                     mbar_wait(&S.tmem_empty_bar[buf], tph ^ 1); // epilogue has drained this accumulator buffer
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
@@ -636,17 +751,18 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             int p = INT32_MIN + 1;
             if (rvalid) p = pos[row_point[gr]];
             L.reset();
-            int cur_bin = ntiles > 0 ? tile_bin[0] : -1;
+            int cur_bin = -1; // bin of the list under construction (-1: none yet)
             // admission threshold and query term |a_q - m_c|^2 of (this query, current bin): see threshold_kernel
-            float t0 = (rvalid && cur_bin >= 0) ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
-            float nr = (rvalid && cur_bin >= 0) ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
-            int tb_next = cur_bin;
-            for (int t = 0; t < ntiles; ++t, ++tt) {
+            float t0 = INFINITY, nr = 0.f;
+            int tb_next = ntiles > 0 ? tile_bin[0] : -1;
+            for (int t = 0; t < ntiles; ++t) {
+                const int tb = tb_next;
+                if (t + 1 < ntiles) tb_next = tile_bin[t + 1];
+                if (skip[(int64_t)rb * C + tb]) continue;
                 const int buf = (int)(tt & 1);
                 const uint32_t tph = (uint32_t)((tt >> 1) & 1);
-                const int tb = tb_next;
+                ++tt;
                 if (t + 1 < ntiles) {
-                    tb_next = tile_bin[t + 1];
                     if (lane < 6) { // next tile's metadata -> L1: three arrays, two 128-byte lines each
                         const int64_t e = (int64_t)(t + 1) * BN + half * 64 + (lane & 1) * 32;
                         const void *pf = lane < 2 ? (const void *)(col_nrm + e) : (lane < 4 ? (const void *)(col_a + e) : (const void *)(col_b + e));
@@ -654,7 +770,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                 }
                 if (tb != cur_bin) { // bin boundary: flush the finished (half-)list
-                    if (rvalid) {
+                    if (rvalid && cur_bin >= 0) {
                         float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
                         int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
 #pragma unroll
@@ -778,20 +894,32 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
 // ---------------------------------------------------------------------------------------------------------
 __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
-                                 const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
-                                 const int32_t *__restrict__ tent, const int32_t *__restrict__ old, const float *__restrict__ nrm,
+                                 const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
+                                 const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
+                                 const float *__restrict__ nrm, const unsigned int *__restrict__ nrm_max_bits,
                                  const float *__restrict__ ym2, const float *__restrict__ tcmax, const float *__restrict__ tq_tab,
-                                 double eps_rel, int64_t nown, int32_t C, int32_t k, int64_t ldt, float *__restrict__ t0_tab,
-                                 float *__restrict__ slack_tab)
+                                 const float *__restrict__ ub_row, double eps_rel, int64_t nown, int32_t C, int32_t k, int64_t ldt,
+                                 float *__restrict__ t0_tab, float *__restrict__ slack_tab)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nown * C) return;
     const int c = (int)(i / nown);
-    const int64_t r = i - (int64_t)c * nown;
-    const int64_t pair = r * C + c;
+    const int64_t r = i - (int64_t)c * nown;           // row (rows are the owned slots ordered by guessed bin)
+    const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
     const int jq = row_point[r];
-    const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq_tab[(int64_t)c * ldt + r]);
+    const float tq = tq_tab[(int64_t)c * ldt + r];
+    const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
     slack_tab[(int64_t)c * ldt + r] = E;
+    // pruning: LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands
+    {
+        const double lb = sqrt((double)tq) - sqrt((double)ym2[c]);
+        const double ub = (double)ub_row[r];
+        const double scale = sqrt((double)nrm[jq]) + sqrt((double)__uint_as_float(*nrm_max_bits));
+        if (lb > ub + 1e-5 * (sqrt((double)tq) + sqrt((double)ym2[c]) + ub) + 4e-6 * scale) {
+            t0_tab[(int64_t)c * ldt + r] = -INFINITY;
+            return;
+        }
+    }
     float out = INFINITY;
     if (knn_cnt[pair] == k) {
         const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
@@ -854,6 +982,7 @@ template <int G>
 __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ cand_key, const int32_t *__restrict__ cand_idx, int KR,
                                                      const int32_t *__restrict__ bin_cnt, const double *__restrict__ X, int32_t ldx,
                                                      int32_t d, const int32_t *__restrict__ row_point,
+                                                     const int32_t *__restrict__ row_slot, double *__restrict__ pair_dist,
                                                      const float *__restrict__ slack_tab, int32_t C,
                                                      int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
@@ -863,7 +992,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
     extern __shared__ __align__(16) double xq_s[];
     constexpr int NG = 32 / G;
     constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-    const int64_t r = blockIdx.x;
+    const int64_t r = blockIdx.x;              // row: candidate lists, thresholds and slacks are per row ...
+    const int64_t sl = row_slot[r];            // ... neighbour caches, hull distances and the work list per owned slot
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (G - 1), gsh = lane & ~(G - 1);
     const int jq = row_point[r];
@@ -877,17 +1007,22 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
     for (int cb = warp * NG; cb < C; cb += 4 * NG) {
         const int c = cb + lane / G;
         const bool act = c < C;
-        const int64_t pair = r * C + (act ? c : 0);
+        const int64_t pair = sl * C + (act ? c : 0);
+        const int64_t rpair = r * C + (act ? c : 0);
+        const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
+        const bool pruned = t0v == -INFINITY; // the bin cannot be this query's nearest hull: no neighbours, distance +inf
+        const int mo = act ? knn_cnt[pair] : 0;
+        // bins ruled out by the bounds whose cache already says "no neighbours": nothing to do (the common case once the
+        // rows are ordered by guessed bin)
+        if (__all_sync(CHB_FULL, !act || (pruned && mo == 0))) continue;
         float ka = INFINITY;
         int ki = INT32_MAX;
-        if (act && bin_cnt[c] > 0 && gl < K2) {
-            ka = cand_key[pair * K2 + gl];
-            ki = cand_idx[pair * K2 + gl];
+        if (act && !pruned && bin_cnt[c] > 0 && gl < K2) {
+            ka = cand_key[rpair * K2 + gl];
+            ki = cand_idx[rpair * K2 + gl];
         }
-        const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
         const float E = act ? slack_tab[(int64_t)c * ldt + r] : 0.f; // |key - d^2| <= E for every column of this bin
         const float slack2 = __fmul_ru(2.f, E);
-        const int mo = act ? knn_cnt[pair] : 0;
         const bool valid = ka < INFINITY; // +inf = empty slot
         const unsigned vm = (__ballot_sync(CHB_FULL, valid) >> gsh) & GM;
         const int nc = __popc(vm);
@@ -968,15 +1103,19 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
                 if (gl >= m && gl < k) knn_idx[pair * k + gl] = -1;
                 if (gl == 0) {
                     knn_cnt[pair] = m;
-                    const int w = atomicAdd(work_count, 1);
-                    work[w] = make_int2((int)r, c);
+                    if (pruned) {
+                        pair_dist[pair] = INFINITY;
+                    } else {
+                        const int w = atomicAdd(work_count, 1);
+                        work[w] = make_int2((int)sl, c);
+                    }
                 }
             }
         }
     }
     if (__any_sync(CHB_FULL, overflow) && lane == 0) s_overflow = 1;
     __syncthreads();
-    if (threadIdx.x == 0 && s_overflow) fb_rows[atomicAdd(fb_count, 1)] = (int)r;
+    if (threadIdx.x == 0 && s_overflow) fb_rows[atomicAdd(fb_count, 1)] = (int)sl;
 }
 
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1035,7 +1174,7 @@ int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64
         chb_stage_timer t(c, CHB_ST_GRAM);
         gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
             ma, mb, g.nbox, g.nk, g.nstage, c->f_ntiles, c->f_tile_bin, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq,
-            c->qpoint + c->u0, c->pos, nrows, c->C, c->f_t0, c->f_ldt, c->f_cand_key, c->f_cand_idx);
+            c->f_row_pt, c->pos, nrows, c->C, c->f_t0, c->f_ldt, c->f_skip, c->f_cand_key, c->f_cand_idx);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
@@ -1089,13 +1228,17 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
-    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt);
+    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
+    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot);
+    c->f_skip = nullptr;
+    c->f_row_slot = c->f_row_pt = c->f_guess_slot = nullptr;
+    c->f_ub = c->f_ub_slot = nullptr;
     c->f_thr = c->f_t0 = c->f_a2 = c->f_tq = c->f_slack = c->f_ym2 = nullptr;
     c->f_mc = c->f_mc2 = nullptr;
     c->f_mcnt = nullptr;
     c->f_cap_mc = 0;
     c->f_cap_a2 = c->f_cap_bperm = 0;
-    c->f_cap_bins = c->f_cap_cols = c->f_cap_cand = c->f_cap_thr = 0;
+    c->f_cap_bins = c->f_cap_cols = c->f_cap_cand = c->f_cap_thr = c->f_cap_ldt = 0;
     c->f_bin_cnt = c->f_seg_off = c->f_cursor = c->f_tile_bin = c->f_ntiles = c->f_col_pt = c->f_col_a = c->f_col_b = nullptr;
     c->f_col_nrm = c->f_bperm = c->f_cand_key = nullptr;
     c->f_cand_idx = c->f_fb_rows = nullptr;
@@ -1154,29 +1297,53 @@ int chb_fused_setup(chb_ctx *c)
         c->f_cap_cand = nown * C * KR * 2;
     }
     c->f_ldt = (nown + 127) & ~int64_t(127);
-    if (c->f_cap_thr < c->f_ldt * C) {
+    if (c->f_cap_thr < c->f_ldt * C || c->f_cap_ldt < c->f_ldt) {
         int64_t z = 0;
-        z = 0; if (reserve(c, &c->f_thr, &z, nown * C)) return CHB_ENOMEM;
+        c->f_cap_ldt = c->f_ldt;
+        z = 0; if (reserve(c, &c->f_thr, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_t0, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_tq, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_slack, &z, c->f_ldt * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_skip, &z, (c->f_ldt / BM) * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_row_slot, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_row_pt, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_ub, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_guess_slot, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_ub_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         c->f_cap_thr = c->f_ldt * C;
         c->f_asplit_ready = false;
     }
-    // query operand: once per (feature set, label set)
+    // once per (feature set, label set): bin reference points, row order, query operand and query terms
     if (!c->f_asplit_ready || c->f_cap_a2 < nown * g.Kp2) {
         if (reserve(c, &c->f_a2, &c->f_cap_a2, std::max<int64_t>(nown, 1) * g.Kp2)) return CHB_ENOMEM;
-        if (nown > 0)
-            split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nullptr, nown, c->Xf, c->ldf,
-                                                                                      c->d, g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
-        // bin reference points from the seed contigs (initial bins, fixed summation order) and the query terms
+        // bin reference points from the seed contigs (initial bins, fixed summation order)
         centre_sum_kernel<<<(unsigned)C, 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_off, c->seed_idx, c->f_mc, c->f_mcnt);
         centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2);
-        if (nown > 0)
-            query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nown, c->Xf, c->ldf, c->d, c->f_mc,
-                                                                           c->f_mc2, C, c->f_ldt, c->f_tq);
+        c->tm.launches_other += 2;
+        if (nown > 0) {
+            // rows = owned slots ordered by guessed bin (stable), so that a 128-row block prunes the same bins
+            row_bound_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nown, c->X, c->ldx, c->Xf, c->ldf, c->d,
+                                                                         c->f_mc, c->f_mc2, c->f_mcnt, C, c->seed_off, c->seed_idx,
+                                                                         c->f_guess_slot, c->f_ub_slot);
+            std::vector<int32_t> guess((size_t)nown), order((size_t)nown);
+            CHB_CUDA(c, cudaMemcpyAsync(guess.data(), c->f_guess_slot, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+            CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+            {
+                std::vector<int64_t> start((size_t)C + 2, 0);
+                for (int64_t u = 0; u < nown; ++u) ++start[(size_t)guess[(size_t)u] + 1];
+                for (int32_t b = 0; b <= C; ++b) start[(size_t)b + 1] += start[(size_t)b];
+                for (int64_t u = 0; u < nown; ++u) order[(size_t)start[(size_t)guess[(size_t)u]]++] = (int32_t)u;
+            }
+            CHB_CUDA(c, cudaMemcpy(c->f_row_slot, order.data(), sizeof(int32_t) * (size_t)nown, cudaMemcpyHostToDevice));
+            row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_ub_slot, nown, c->f_row_pt,
+                                                                      c->f_ub);
+            split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
+                                                                                      g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
+            query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, nown, c->Xf, c->ldf, c->d, c->f_mc, c->f_mc2, C,
+                                                                           c->f_ldt, c->f_tq);
+            c->tm.launches_other += 4;
+        }
         CHB_CUDA(c, cudaGetLastError());
-        c->tm.launches_other += 4;
         c->f_asplit_ready = true;
     }
     return CHB_OK;
@@ -1212,11 +1379,15 @@ int chb_round_fused(chb_ctx *c)
 
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
-    threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(c->knn_idx, c->knn_cnt, c->f_thr, c->qpoint + c->u0, c->pos, c->tent_pt,
-                                                                 c->old_label, c->nrm, c->f_ym2, c->f_ym2 + C + 1, c->f_tq, eps_rel,
-                                                                 nown, C, k, c->f_ldt, c->f_t0, c->f_slack);
+    threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
+        c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
+        reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, eps_rel, nown, C, k,
+        c->f_ldt, c->f_t0, c->f_slack);
+    CHB_CUDA(c, cudaMemsetAsync(&c->counters[7], 0, sizeof(int32_t), c->stream));
+    skip_kernel<<<nblk(((nown + BM - 1) / BM) * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_seg_off, c->f_skip,
+                                                                                 &c->counters[7]);
     CHB_CUDA(c, cudaGetLastError());
-    ++c->tm.launches_other;
+    c->tm.launches_other += 2;
     CUtensorMap ma, mb;
     int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
     if (rc != CHB_OK) return rc;
@@ -1232,8 +1403,8 @@ int chb_round_fused(chb_ctx *c)
         chb_stage_timer t(c, CHB_ST_KNN);
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
         kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
-            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->qpoint + c->u0, c->f_slack, C, k, c->knn_idx,
-            c->knn_cnt, c->work, c->counters,
+            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pair_dist, c->f_slack, C,
+            k, c->knn_idx, c->knn_cnt, c->work, c->counters,
             c->f_fb_rows, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr);
     }
     CHB_CUDA(c, cudaGetLastError());
@@ -1248,12 +1419,22 @@ extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslot
               "slots not owned / no fused round has run yet");
     CHB_CUDA(c, cudaSetDevice(c->device));
     const int KR = (c->k + 3 <= 8) ? 8 : 16;
-    const int64_t r0 = slot0 - c->u0, per = (int64_t)c->C * 2 * KR;
+    const int64_t nown = c->u1 - c->u0, s0 = slot0 - c->u0, per = (int64_t)c->C * 2 * KR;
     *kr_out = KR;
-    CHB_CUDA(c, cudaMemcpyAsync(key_out, c->f_cand_key + r0 * per, sizeof(float) * (size_t)(nslots * per), cudaMemcpyDeviceToHost, c->stream));
-    CHB_CUDA(c, cudaMemcpyAsync(idx_out, c->f_cand_idx + r0 * per, sizeof(int32_t) * (size_t)(nslots * per), cudaMemcpyDeviceToHost, c->stream));
-    CHB_CUDA(c, cudaMemcpy2DAsync(slack_out, sizeof(float) * (size_t)nslots, c->f_slack + r0, sizeof(float) * (size_t)c->f_ldt,
-                                  sizeof(float) * (size_t)nslots, (size_t)c->C, cudaMemcpyDeviceToHost, c->stream));
+    // the kernels keep these tables per ROW (owned slots ordered by guessed bin): translate back to slots
+    std::vector<int32_t> row_slot((size_t)std::max<int64_t>(nown, 1));
+    CHB_CUDA(c, cudaMemcpy(row_slot.data(), c->f_row_slot, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost));
+    std::vector<float> srow((size_t)c->C);
+    for (int64_t r = 0; r < nown; ++r) {
+        const int64_t sl = row_slot[(size_t)r] - s0;
+        if (sl < 0 || sl >= nslots) continue;
+        CHB_CUDA(c, cudaMemcpyAsync(key_out + sl * per, c->f_cand_key + r * per, sizeof(float) * (size_t)per, cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaMemcpyAsync(idx_out + sl * per, c->f_cand_idx + r * per, sizeof(int32_t) * (size_t)per, cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaMemcpy2DAsync(srow.data(), sizeof(float), c->f_slack + r, sizeof(float) * (size_t)c->f_ldt, sizeof(float),
+                                      (size_t)c->C, cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int32_t b = 0; b < c->C; ++b) slack_out[(int64_t)b * nslots + sl] = srow[(size_t)b];
+    }
     CHB_CUDA(c, cudaStreamSynchronize(c->stream));
     return CHB_OK;
 }

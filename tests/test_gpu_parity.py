@@ -233,10 +233,14 @@ def test_fused_keys_within_proven_bound_and_lists_complete(n, C, S, k):
     for it in range(2):
         lab, _ = ctx.fit_iteration(perms[it])
         key, idx, slack = ctx.get_fused_candidates(0, len(pts))
+        _, pcnt, pdist = ctx.get_pair_cache(0, len(pts))
+        pruned = (pcnt == 0) & np.isinf(pdist)  # bins ruled out by the bounds (or empty): lists not maintained
         pos = np.full(len(X), -1)
         pos[perms[it]] = np.arange(len(perms[it]))
         for u, j in enumerate(pts):
             for c in range(C):
+                if pruned[u, c]:
+                    continue
                 valid = np.isfinite(key[u, c])
                 ii = idx[u, c][valid]
                 d2 = D[j, ii] ** 2
@@ -247,9 +251,14 @@ def test_fused_keys_within_proven_bound_and_lists_complete(n, C, S, k):
             if u % 5 == 0:  # the last round's lists were formed on the final labels as seen from this query's position
                 eff = np.where(pos < pos[j], lab, cur)
                 eff[j] = -1
+                hd = [oracle.convex_hull_distance(X[j], X[oracle.find_nearest_from_cluster(c, eff, D[j], k)])
+                      if np.any(eff == c) else np.inf for c in range(C)]
                 for c in range(C):
                     want = oracle.find_nearest_from_cluster(c, eff, D[j], k)
-                    assert set(want.tolist()) <= set(idx[u, c][np.isfinite(key[u, c])].tolist()), (it, j, c)
+                    if pruned[u, c]:
+                        assert len(want) == 0 or hd[c] > min(hd), (it, j, c)  # a pruned bin is never the nearest hull
+                    else:
+                        assert set(want.tolist()) <= set(idx[u, c][np.isfinite(key[u, c])].tolist()), (it, j, c)
         cur = lab
     ctx.close()
     assert worst < 0.5, f"observed error / bound = {worst}: the bound should have a wide margin"
@@ -282,12 +291,20 @@ def test_cached_neighbour_sets_match_each_querys_view(path):
             u = u * 7
             eff = np.where(pos < pos[j], lab, cur)
             eff[j] = -1
+            drefs, pruned = [], []
             for c in range(5):
                 want = np.sort(oracle.find_nearest_from_cluster(c, eff, D[j], 5))
+                dref = oracle.convex_hull_distance(X[j], X[want]) if len(want) else np.inf
+                drefs.append(dref)
+                if cnt[u, c] == 0 and np.isinf(dist[u, c]) and len(want):
+                    pruned.append(c)  # distance mode 2 rules bins out by bounds: no neighbour set, distance +inf
+                    continue
                 got = np.sort(idx[u, c, : cnt[u, c]])
                 assert np.array_equal(want, got), (it, j, c)
-                dref = oracle.convex_hull_distance(X[j], X[want])
                 assert abs(dist[u, c] - dref) <= 1e-6 * dref + 1e-12
+            assert path == "fused" or not pruned
+            for c in pruned:
+                assert drefs[c] > min(drefs), (it, j, c)  # a pruned bin is never the nearest hull, not even tied
         cur = ref
     ctx.close()
 
