@@ -537,8 +537,10 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     }
     CHB_TRY(dev_reserve(c, &c->seed_off, &c->cap_seed_off, (int64_t)C + 1));
     CHB_TRY(dev_reserve(c, &c->seed_idx, &c->cap_seed_idx, std::max<int64_t>(n - U, 1)));
-    CHB_CUDA(c, cudaMemcpy(c->seed_off, seed_off.data(), sizeof(int32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice));
-    CHB_CUDA(c, cudaMemcpy(c->seed_idx, seed_idx.data(), sizeof(int32_t) * (size_t)std::max<int64_t>(n - U, 1), cudaMemcpyHostToDevice));
+    // stream-ordered copies (pageable sources are staged before the call returns, so the local vectors may go away)
+    CHB_CUDA(c, cudaMemcpyAsync(c->seed_off, seed_off.data(), sizeof(int32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->seed_idx, seed_idx.data(), sizeof(int32_t) * (size_t)std::max<int64_t>(n - U, 1), cudaMemcpyHostToDevice,
+                                c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));

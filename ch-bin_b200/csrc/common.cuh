@@ -109,8 +109,13 @@ struct chb_ctx {
     int64_t f_cap_a2 = 0, f_cap_bperm = 0;
     double *f_mc = nullptr, *f_mc2 = nullptr; // C x d : bin reference point minus the global mean; C : its squared norm
     int32_t *f_mcnt = nullptr;
+    double *f_mcT = nullptr;        // d x Cp : the same table transposed (bins contiguous)
+    int32_t *f_guess_all = nullptr; // U : bin of the nearest seed centroid of every query slot (C: none)
+    int64_t f_cap_guess = 0, f_cap_mcT = 0;
     int64_t f_cap_mc = 0;
     float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
+    int4 *f_items = nullptr;                   // surviving (row block, bin) work items of the fused kernel, row-block order
+    int32_t *f_cta_begin = nullptr;            // sm_count + 1 : item range per CTA (balanced by tile count)
     uint8_t *f_skip = nullptr;                 // (#row blocks) x C : tiles of this (row block, bin) are skipped this round
     int32_t *f_row_slot = nullptr, *f_row_pt = nullptr, *f_guess_slot = nullptr; // row -> owned slot / point; guessed bin per slot
     float *f_ub = nullptr, *f_ub_slot = nullptr; // upper bound of min_c hull distance per row / per slot

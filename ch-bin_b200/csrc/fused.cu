@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) centre_sum_kernel(const double *__restric
 
 // m_c = mu_c - mu (zero for bins without seeds), mc2[c] = |m_c|^2
 __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__restrict__ cnt, const double *__restrict__ colsum,
-                                     double inv_n, int32_t d, double *__restrict__ mc2)
+                                     double inv_n, int32_t d, double *__restrict__ mc2, double *__restrict__ mcT, int32_t Cp)
 {
     const int c = blockIdx.x;
     __shared__ double red[128];
@@ -274,6 +274,7 @@ __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__r
     for (int t = threadIdx.x; t < d; t += blockDim.x) {
         const double v = cnt[c] > 0 ? mc[(int64_t)c * d + t] * inv - colsum[t] * inv_n : 0.0;
         mc[(int64_t)c * d + t] = v;
+        mcT[(int64_t)t * Cp + c] = v; // [feature][bin]: lanes of a warp read consecutive bins
         s += v * v;
     }
     red[threadIdx.x] = s;
@@ -285,38 +286,80 @@ __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__r
     if (threadIdx.x == 0) mc2[c] = red[0];
 }
 
-// one warp per owned query: tq[c][r] = fl32( |a_q - m_c|^2 ), a_q = the FP32 centred feature row the tensor core contracts
+// a_q . m_c for the bins c = lane, lane + 32, ... of one query: the query row sits in shared memory, every lane walks
+// the features for its own bins (coalesced reads of the transposed centre table, no shuffles).  The summation order is
+// fixed, so every rank of a multi-GPU run obtains the same bits.
+constexpr int DMAX_F = 160; // fused mode: d <= 160
+__device__ __forceinline__ void load_query_row(const float *__restrict__ xr, int d, int lane, double *a_s, double &aa)
+{
+    double s = 0.0;
+    for (int t = lane; t < d; t += 32) {
+        const double v = (double)xr[t];
+        a_s[t] = v;
+        s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
+    aa = s;
+    __syncwarp();
+}
+
+// one warp per row (owned slots in row order): tq[c][r] = fl32( |a_q - m_c|^2 ), a_q = the FP32 centred feature row the
+// tensor core contracts
 __global__ void __launch_bounds__(256) query_terms_kernel(const int32_t *__restrict__ row_point, int64_t nown,
                                                           const float *__restrict__ Xf, int32_t ldf, int32_t d,
-                                                          const double *__restrict__ mc, const double *__restrict__ mc2, int32_t C,
-                                                          int64_t ldt, float *__restrict__ tq)
+                                                          const double *__restrict__ mcT, int32_t Cp, const double *__restrict__ mc2,
+                                                          int32_t C, int64_t ldt, float *__restrict__ tq)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ double a_sm[8][DMAX_F];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= nown) return;
-    const float *xr = Xf + (int64_t)row_point[r] * ldf;
-    double a[8]; // d <= 256
-    double aa = 0.0;
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        const int t = lane + 32 * u;
-        a[u] = t < d ? (double)xr[t] : 0.0;
-        aa = fma(a[u], a[u], aa);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) aa += __shfl_xor_sync(CHB_FULL, aa, o);
-    for (int c = 0; c < C; ++c) {
-        const double *m = mc + (int64_t)c * d;
+    double aa;
+    load_query_row(Xf + (int64_t)row_point[r] * ldf, d, lane, a_sm[w], aa);
+    for (int c = lane; c < C; c += 32) {
         double s = 0.0;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int t = lane + 32 * u;
-            if (t < d) s = fma(a[u], m[t], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
-        if (lane == 0) tq[(int64_t)c * ldt + r] = (float)fmax(aa - 2.0 * s + mc2[c], 0.0);
+        for (int t = 0; t < d; ++t) s = fma(a_sm[w][t], mcT[(int64_t)t * Cp + c], s);
+        tq[(int64_t)c * ldt + r] = (float)fmax(aa - 2.0 * s + mc2[c], 0.0);
     }
+}
+
+// one warp per query slot (ALL U of them: every rank must start the speculation from the same vector): bin whose seed
+// centroid is nearest (lowest bin on ties); bins without seeds are skipped; C when no bin has seeds
+__global__ void __launch_bounds__(256) guess_all_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
+                                                        int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
+                                                        const double *__restrict__ mc2, const int32_t *__restrict__ mcnt, int32_t C,
+                                                        int32_t *__restrict__ guess_all)
+{
+    __shared__ double a_sm[8][DMAX_F];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= U) return;
+    double aa;
+    load_query_row(Xf + (int64_t)qpoint[u] * ldf, d, lane, a_sm[w], aa);
+    double best = INFINITY;
+    int bc = C;
+    for (int c = lane; c < C; c += 32) {
+        if (mcnt[c] <= 0) continue;
+        double s = 0.0;
+        for (int t = 0; t < d; ++t) s = fma(a_sm[w][t], mcT[(int64_t)t * Cp + c], s);
+        const double val = mc2[c] - 2.0 * s; // |a - m_c|^2 minus the bin-independent |a|^2
+        if (val < best) { best = val; bc = c; } // ascending c per lane: first minimum kept
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(CHB_FULL, best, o);
+        const int oc = __shfl_xor_sync(CHB_FULL, bc, o);
+        if (ov < best || (ov == best && oc < bc)) { best = ov; bc = oc; }
+    }
+    if (lane == 0) guess_all[u] = bc;
+}
+
+__global__ void guess_scatter_kernel(const int32_t *__restrict__ qpoint, const int32_t *__restrict__ guess_all, int64_t U, int32_t C,
+                                     int32_t *__restrict__ tent)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < U && guess_all[u] < C) tent[qpoint[u]] = guess_all[u];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -331,67 +374,32 @@ __global__ void __launch_bounds__(256) query_terms_kernel(const int32_t *__restr
 // pruned: admission threshold -inf, no candidates, no QP, hull distance +inf.  Rows are ordered by guessed bin so that
 // whole 128-query row blocks prune the same bins and their tiles are skipped by the fused kernel.
 // ---------------------------------------------------------------------------------------------------------
-// one warp per owned slot: guessed bin (same arithmetic as guess_kernel) and UB
-__global__ void __launch_bounds__(256) row_bound_kernel(const int32_t *__restrict__ qpoint_own, int64_t nown, const double *__restrict__ X,
-                                                        int32_t ldx, const float *__restrict__ Xf, int32_t ldf, int32_t d,
-                                                        const double *__restrict__ mc, const double *__restrict__ mc2,
-                                                        const int32_t *__restrict__ mcnt, int32_t C,
-                                                        const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
-                                                        int32_t *__restrict__ guess_out, float *__restrict__ ub_out)
+// one warp per owned slot: UB = distance to the nearest seed of the guessed bin (one lane per seed)
+__global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__ qpoint_own, const int32_t *__restrict__ guess_own,
+                                                     int64_t nown, const double *__restrict__ X, int32_t ldx, int32_t d, int32_t C,
+                                                     const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
+                                                     float *__restrict__ ub_out)
 {
-    const int lane = threadIdx.x & 31;
+    __shared__ double q_sm[8][DMAX_F];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= nown) return;
-    const int pt = qpoint_own[u];
-    const float *xr = Xf + (int64_t)pt * ldf;
-    double a[8]; // d <= 256
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        const int t = lane + 32 * v;
-        a[v] = t < d ? (double)xr[t] : 0.0;
-    }
-    double best = INFINITY;
-    int bc = -1;
-    for (int c = 0; c < C; ++c) {
-        if (mcnt[c] <= 0) continue;
-        const double *m = mc + (int64_t)c * d;
-        double s = 0.0;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int t = lane + 32 * v;
-            if (t < d) s = fma(a[v], m[t], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
-        const double val = mc2[c] - 2.0 * s;
-        if (val < best) { best = val; bc = c; }
-    }
+    const double *xq = X + (int64_t)qpoint_own[u] * ldx;
+    for (int t = lane; t < d; t += 32) q_sm[w][t] = xq[t];
+    __syncwarp();
+    const int g = guess_own[u];
     double ub2 = INFINITY;
-    if (bc >= 0) {
-        const double *xq = X + (int64_t)pt * ldx;
-        double q[8];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int t = lane + 32 * v;
-            q[v] = t < d ? xq[t] : 0.0;
-        }
-        for (int i = seed_off[bc]; i < seed_off[bc + 1]; ++i) {
+    if (g < C) {
+        for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32) {
             const double *xs = X + (int64_t)seed_idx[i] * ldx;
             double s = 0.0;
-#pragma unroll
-            for (int v = 0; v < 8; ++v) {
-                const int t = lane + 32 * v;
-                if (t < d) { const double df = q[v] - xs[t]; s = fma(df, df, s); }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
+            for (int t = 0; t < d; ++t) { const double df = q_sm[w][t] - xs[t]; s = fma(df, df, s); }
             ub2 = fmin(ub2, s);
         }
     }
-    if (lane == 0) {
-        guess_out[u] = bc < 0 ? C : bc; // queries without a guess sort last
-        ub_out[u] = ub2 < INFINITY ? __double2float_ru(sqrt(ub2) * (1.0 + 1e-9)) : INFINITY;
-    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ub2 = fmin(ub2, __shfl_xor_sync(CHB_FULL, ub2, o));
+    if (lane == 0) ub_out[u] = ub2 < INFINITY ? __double2float_ru(sqrt(ub2) * (1.0 + 1e-9)) : INFINITY;
 }
 
 __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const int32_t *__restrict__ qpoint_own,
@@ -405,11 +413,9 @@ __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const in
     ub_row[r] = ub_slot[sl];
 }
 
-// one warp per (row block, bin): skip = every row of the block pruned the bin (t0 == -inf) or lies beyond nrows;
-// counts the tiles that remain
+// one warp per (row block, bin): skip = every row of the block pruned the bin (t0 == -inf) or lies beyond nrows
 __global__ void __launch_bounds__(256) skip_kernel(const float *__restrict__ t0_tab, int64_t ldt, int64_t nrows, int32_t C,
-                                                   const int32_t *__restrict__ seg_off, uint8_t *__restrict__ skip,
-                                                   int32_t *__restrict__ tiles_left)
+                                                   uint8_t *__restrict__ skip)
 {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -423,47 +429,7 @@ __global__ void __launch_bounds__(256) skip_kernel(const float *__restrict__ t0_
         if (r < nrows && !(t0_tab[(int64_t)c * ldt + r] == -INFINITY)) all = false;
     }
     all = __all_sync(CHB_FULL, all);
-    if (lane == 0) {
-        skip[rb * C + c] = all ? 1 : 0;
-        if (!all) atomicAdd(tiles_left, (seg_off[c + 1] - seg_off[c]) / BN);
-    }
-}
-
-// one warp per query slot (ALL of them, not only the owned ones: every rank must start from the same vector):
-// tent[point] = bin whose seed centroid is nearest (lowest bin on ties); bins without seeds are skipped
-__global__ void __launch_bounds__(256) guess_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
-                                                    int32_t ldf, int32_t d, const double *__restrict__ mc,
-                                                    const double *__restrict__ mc2, const int32_t *__restrict__ mcnt, int32_t C,
-                                                    int32_t *__restrict__ tent)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (u >= U) return;
-    const int pt = qpoint[u];
-    const float *xr = Xf + (int64_t)pt * ldf;
-    double a[8]; // d <= 256
-#pragma unroll
-    for (int v = 0; v < 8; ++v) {
-        const int t = lane + 32 * v;
-        a[v] = t < d ? (double)xr[t] : 0.0;
-    }
-    double best = INFINITY;
-    int bc = -1;
-    for (int c = 0; c < C; ++c) {
-        if (mcnt[c] <= 0) continue;
-        const double *m = mc + (int64_t)c * d;
-        double s = 0.0;
-#pragma unroll
-        for (int v = 0; v < 8; ++v) {
-            const int t = lane + 32 * v;
-            if (t < d) s = fma(a[v], m[t], s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
-        const double val = mc2[c] - 2.0 * s; // |a - m_c|^2 minus the bin-independent |a|^2
-        if (val < best) { best = val; bc = c; }
-    }
-    if (lane == 0 && bc >= 0) tent[pt] = bc;
+    if (lane == 0) skip[rb * C + c] = all ? 1 : 0;
 }
 
 // one warp per column entry: y = fl32(x_i - mu_c) split into the [hi | lo] operand row, the column term
@@ -525,6 +491,61 @@ __device__ __forceinline__ float pair_slack(double eps_rel, float nrm_q, float y
     return __double2float_ru(e * (1.0 + 1e-6) + 1e-30);
 }
 
+// Work list of the fused kernel: one item per surviving (row block, bin) = {row block, bin, first tile, #tiles}, in row-block
+// order, and for each of the G CTAs the contiguous range of items whose cumulative tile count falls into its 1/G share.
+// Whole items only (a (query, bin) list is built by one CTA), so CTAs differ by at most one bin's tiles.  One block.
+__global__ void __launch_bounds__(1024) items_kernel(const uint8_t *__restrict__ skip, int64_t nrb, int32_t C,
+                                                     const int32_t *__restrict__ seg_off, int32_t G, int4 *__restrict__ items,
+                                                     int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals)
+{
+    __shared__ int s_items[1024], s_tiles[1024];
+    __shared__ int tot_items, tot_tiles;
+    const int tid = threadIdx.x;
+    const int64_t ne = nrb * C;
+    const int64_t per = (ne + 1023) / 1024;
+    const int64_t e0 = tid * per < ne ? tid * per : ne, e1 = e0 + per < ne ? e0 + per : ne;
+    int ni = 0, nt = 0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int c = (int)(e % C);
+        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
+        if (!skip[e] && w > 0) { ++ni; nt += w; }
+    }
+    s_items[tid] = ni;
+    s_tiles[tid] = nt;
+    __syncthreads();
+    // inclusive scan (Hillis-Steele) over the 1024 partial counts
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int a = tid >= o ? s_items[tid - o] : 0, b = tid >= o ? s_tiles[tid - o] : 0;
+        __syncthreads();
+        s_items[tid] += a;
+        s_tiles[tid] += b;
+        __syncthreads();
+    }
+    if (tid == 1023) { tot_items = s_items[1023]; tot_tiles = s_tiles[1023]; }
+    for (int b = tid; b <= G; b += 1024) cta_begin[b] = INT32_MAX;
+    __syncthreads();
+    const int TI = tot_items, TT = tot_tiles;
+    int oi = s_items[tid] - ni, ot = s_tiles[tid] - nt; // exclusive prefixes of this thread's chunk
+    for (int64_t e = e0; e < e1; ++e) {
+        const int c = (int)(e % C);
+        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
+        if (!skip[e] && w > 0) {
+            items[oi] = make_int4((int)(e / C), c, seg_off[c] / BN, w);
+            const int cta = (int)(((int64_t)ot * G) / (TT > 0 ? TT : 1));
+            atomicMin(&cta_begin[cta], oi);
+            ++oi;
+            ot += w;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cta_begin[G] = TI;
+        for (int b = G - 1; b >= 0; --b)
+            if (cta_begin[b] > cta_begin[b + 1]) cta_begin[b] = cta_begin[b + 1]; // CTAs without an item of their own
+        totals[0] = TT;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // fused Gram + selection
 // ---------------------------------------------------------------------------------------------------------
@@ -564,14 +585,16 @@ struct TopList {
 template <int KR, int NKT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
 gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int nbox, int nk, int nstage,
-                   const int32_t *__restrict__ ntiles_p, const int32_t *__restrict__ tile_bin, const int32_t *__restrict__ col_pt,
+                   const int32_t *__restrict__ col_pt,
                    const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b, const float *__restrict__ col_nrm,
                    const float *__restrict__ tq_tab, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
-                   int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, const uint8_t *__restrict__ skip,
-                   float *__restrict__ cand_key, int32_t *__restrict__ cand_idx)
+                   int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, const int4 *__restrict__ items,
+                   const int32_t *__restrict__ cta_begin, float *__restrict__ cand_key, int32_t *__restrict__ cand_idx)
 {
-    // skip[rb * C + bin] != 0: no query of row block rb can have bin `bin` as its nearest hull (skip_kernel) -- its tiles
-    // are neither loaded, contracted nor screened.  All three warp roles apply the same test.
+    // This CTA's work: items [cta_begin[b], cta_begin[b + 1]) of the list built by items_kernel, each one surviving
+    // (row block, bin) = {row block, bin, first tile, #tiles}.  Pruned (row block, bin) pairs are not in the list: their
+    // tiles are neither loaded, contracted nor screened.  All three warp roles walk the same items.
+    const int item_begin = cta_begin[blockIdx.x], item_end = cta_begin[blockIdx.x + 1];
     // dynamic shared memory: [resident query operand: nbox boxes][column ring: nstage boxes][SmemTail]
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -579,8 +602,6 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     uint8_t *ring = base + (size_t)nbox * TILE_BYTES;
     SmemTail &S = *reinterpret_cast<SmemTail *>(ring + (size_t)nstage * TILE_BYTES);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ntiles = *ntiles_p;
-    const int nrb = (int)((nrows + BM - 1) / BM);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < nstage; ++s) {
@@ -611,14 +632,19 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            int rbi = 0;
-            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rbi) {
-                // the resident operand may be overwritten once every MMA of the previous row block has completed
-                mbar_wait(&S.a_empty_bar, (uint32_t)((rbi & 1) ^ 1));
-                mbar_expect_tx(&S.a_full_bar, (uint32_t)nbox * TILE_BYTES);
-                for (int jb = 0; jb < nbox; ++jb) tma_load_2d(a_res + (size_t)jb * TILE_BYTES, &map_a, &S.a_full_bar, jb * BK, rb * BM);
-                for (int t = 0; t < ntiles; ++t) {
-                    if (skip[(int64_t)rb * C + tile_bin[t]]) continue;
+            int cur_rb = -1, na = 0; // row block whose operand is resident, number of operand loads so far
+            for (int it = item_begin; it < item_end; ++it) {
+                const int4 item = items[it];
+                if (item.x != cur_rb) {
+                    // the resident operand may be overwritten once every MMA of the previous row block has completed
+                    mbar_wait(&S.a_empty_bar, (uint32_t)((na & 1) ^ 1));
+                    mbar_expect_tx(&S.a_full_bar, (uint32_t)nbox * TILE_BYTES);
+                    for (int jb = 0; jb < nbox; ++jb)
+                        tma_load_2d(a_res + (size_t)jb * TILE_BYTES, &map_a, &S.a_full_bar, jb * BK, item.x * BM);
+                    cur_rb = item.x;
+                    ++na;
+                }
+                for (int t = item.z; t < item.z + item.w; ++t) {
                     for (int jb = 0; jb < nbox; ++jb) {
                         mbar_wait(&S.empty_bar[s], ph ^ 1);
                         mbar_expect_tx(&S.full_bar[s], TILE_BYTES);
@@ -663,12 +689,18 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             int s = 0;
             uint32_t ph = 0;
             int64_t tt = 0;
-            int rbi = 0;
-            for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x, ++rbi) {
-                mbar_wait(&S.a_full_bar, (uint32_t)(rbi & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int t = 0; t < ntiles; ++t) {
-                    if (skip[(int64_t)rb * C + tile_bin[t]]) continue;
+            int cur_rb = -1, na = 0;
+            for (int it = item_begin; it < item_end; ++it) {
+                const int4 item = items[it];
+                if (item.x != cur_rb) {
+                    // every MMA on the previous row block's operand has been issued: release it, then wait for the new one
+                    if (cur_rb >= 0 && elect_one_sync()) umma_commit(&S.a_empty_bar);
+                    mbar_wait(&S.a_full_bar, (uint32_t)(na & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    cur_rb = item.x;
+                    ++na;
+                }
+                for (int t = item.z; t < item.z + item.w; ++t) {
                     const int buf = (int)(tt & 1);
                     const uint32_t tph = (uint32_t)((tt >> 1) & 1);
                     ++tt;
@@ -731,7 +763,6 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     }
                     if (elect_one_sync()) umma_commit(&S.tmem_full_bar[buf]);
                 }
-                if (elect_one_sync()) umma_commit(&S.a_empty_bar);
             }
         }
     } else {
@@ -745,44 +776,26 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int et = threadIdx.x - 64;        // 0..255 index among the epilogue threads
         TopList<KR> L;
         int64_t tt = 0;
-        for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
-            const int64_t gr = (int64_t)rb * BM + row;
+        for (int it = item_begin; it < item_end; ++it) {
+            const int4 item = items[it];
+            const int cur_bin = item.y;
+            const int64_t gr = (int64_t)item.x * BM + row;
             const bool rvalid = gr < nrows;
-            int p = INT32_MIN + 1;
-            if (rvalid) p = pos[row_point[gr]];
+            const int p = rvalid ? pos[row_point[gr]] : INT32_MIN + 1;
+            // admission threshold and query term |a_q - m_c|^2 of (this query, this bin): see threshold_kernel
+            const float t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : -INFINITY;
+            const float nr = rvalid ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
             L.reset();
-            int cur_bin = -1; // bin of the list under construction (-1: none yet)
-            // admission threshold and query term |a_q - m_c|^2 of (this query, current bin): see threshold_kernel
-            float t0 = INFINITY, nr = 0.f;
-            int tb_next = ntiles > 0 ? tile_bin[0] : -1;
-            for (int t = 0; t < ntiles; ++t) {
-                const int tb = tb_next;
-                if (t + 1 < ntiles) tb_next = tile_bin[t + 1];
-                if (skip[(int64_t)rb * C + tb]) continue;
+            for (int t = item.z; t < item.z + item.w; ++t) {
                 const int buf = (int)(tt & 1);
                 const uint32_t tph = (uint32_t)((tt >> 1) & 1);
                 ++tt;
-                if (t + 1 < ntiles) {
-                    if (lane < 6) { // next tile's metadata -> L1: three arrays, two 128-byte lines each
-                        const int64_t e = (int64_t)(t + 1) * BN + half * 64 + (lane & 1) * 32;
-                        const void *pf = lane < 2 ? (const void *)(col_nrm + e) : (lane < 4 ? (const void *)(col_a + e) : (const void *)(col_b + e));
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-                    }
-                }
-                if (tb != cur_bin) { // bin boundary: flush the finished (half-)list
-                    if (rvalid && cur_bin >= 0) {
-                        float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
-                        int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
-#pragma unroll
-                        for (int s = 0; s < KR; s += 4) {
-                            ok[s >> 2] = make_float4(L.key[s], L.key[s + 1], L.key[s + 2], L.key[s + 3]);
-                            oi[s >> 2] = make_int4(L.idx[s], L.idx[s + 1], L.idx[s + 2], L.idx[s + 3]);
-                        }
-                    }
-                    L.reset();
-                    cur_bin = tb;
-                    t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : INFINITY;
-                    nr = rvalid ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
+                if (lane < 6 && (t + 1 < item.z + item.w || it + 1 < item_end)) {
+                    // next tile's metadata -> L1: three arrays, two 128-byte lines each
+                    const int tn = t + 1 < item.z + item.w ? t + 1 : items[it + 1].z;
+                    const int64_t e = (int64_t)tn * BN + half * 64 + (lane & 1) * 32;
+                    const void *pf = lane < 2 ? (const void *)(col_nrm + e) : (lane < 4 ? (const void *)(col_a + e) : (const void *)(col_b + e));
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
                 }
                 const int64_t e0 = (int64_t)t * BN + half * 64;
                 const float4 *mn = reinterpret_cast<const float4 *>(col_nrm + e0);
@@ -866,7 +879,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
 #undef SCREEN_STEP
             }
-            if (rvalid && cur_bin >= 0) {
+            if (rvalid) { // the item's (half-)list is complete
                 float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
                 int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
 #pragma unroll
@@ -1168,13 +1181,12 @@ template <int KR, int NKT>
 int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
 {
     CHB_CUDA(c, cudaFuncSetAttribute(gram_select_kernel<KR, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    const int nrb = (int)((nrows + BM - 1) / BM);
-    const int grid = std::min(nrb, c->sm_count);
+    const int grid = c->sm_count; // persistent: one CTA per SM, work split by items_kernel
     {
         chb_stage_timer t(c, CHB_ST_GRAM);
         gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
-            ma, mb, g.nbox, g.nk, g.nstage, c->f_ntiles, c->f_tile_bin, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq,
-            c->f_row_pt, c->pos, nrows, c->C, c->f_t0, c->f_ldt, c->f_skip, c->f_cand_key, c->f_cand_idx);
+            ma, mb, g.nbox, g.nk, g.nstage, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq, c->f_row_pt, c->pos, nrows, c->C,
+            c->f_t0, c->f_ldt, c->f_items, c->f_cta_begin, c->f_cand_key, c->f_cand_idx);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
@@ -1228,9 +1240,14 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
-    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
-    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot);
+    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
+    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all);
+    c->f_mcT = nullptr;
+    c->f_guess_all = nullptr;
+    c->f_cap_guess = c->f_cap_mcT = 0;
     c->f_skip = nullptr;
+    c->f_items = nullptr;
+    c->f_cta_begin = nullptr;
     c->f_row_slot = c->f_row_pt = c->f_guess_slot = nullptr;
     c->f_ub = c->f_ub_slot = nullptr;
     c->f_thr = c->f_t0 = c->f_a2 = c->f_tq = c->f_slack = c->f_ym2 = nullptr;
@@ -1250,8 +1267,7 @@ void chb_fused_free(chb_ctx *c)
 int chb_fused_guess(chb_ctx *c)
 {
     if (c->U <= 0) return CHB_OK;
-    guess_kernel<<<nblk(c->U * 32, 256), 256, 0, c->stream>>>(c->qpoint, c->U, c->Xf, c->ldf, c->d, c->f_mc, c->f_mc2, c->f_mcnt, c->C,
-                                                              c->tent_pt);
+    guess_scatter_kernel<<<nblk(c->U, 256), 256, 0, c->stream>>>(c->qpoint, c->f_guess_all, c->U, c->C, c->tent_pt);
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
     return CHB_OK;
@@ -1278,7 +1294,9 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_mc2, &z, C + 1)) return CHB_ENOMEM;
         c->f_cap_bins = C + 1;
     }
+    if (reserve(c, &c->f_mcT, &c->f_cap_mcT, (int64_t)((C + 31) & ~31) * c->d)) return CHB_ENOMEM;
     if (reserve(c, &c->f_mc, &c->f_cap_mc, (int64_t)C * c->d)) return CHB_ENOMEM;
+    if (reserve(c, &c->f_guess_all, &c->f_cap_guess, std::max<int64_t>(c->U, 1))) return CHB_ENOMEM;
     if (c->f_cap_cols < ncol_max) {
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_col_pt, &z, ncol_max)) return CHB_ENOMEM;
@@ -1305,6 +1323,8 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_tq, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_slack, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_skip, &z, (c->f_ldt / BM) * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_items, &z, (c->f_ldt / BM) * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_cta_begin, &z, c->sm_count + 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_pt, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ub, &z, c->f_ldt)) return CHB_ENOMEM;
@@ -1318,15 +1338,21 @@ int chb_fused_setup(chb_ctx *c)
         if (reserve(c, &c->f_a2, &c->f_cap_a2, std::max<int64_t>(nown, 1) * g.Kp2)) return CHB_ENOMEM;
         // bin reference points from the seed contigs (initial bins, fixed summation order)
         centre_sum_kernel<<<(unsigned)C, 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_off, c->seed_idx, c->f_mc, c->f_mcnt);
-        centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2);
+        const int32_t Cp = (C + 31) & ~31;
+        centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2,
+                                                                 c->f_mcT, Cp);
         c->tm.launches_other += 2;
+        if (c->U > 0) {
+            guess_all_kernel<<<nblk(c->U * 32, 256), 256, 0, c->stream>>>(c->qpoint, c->U, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2,
+                                                                         c->f_mcnt, C, c->f_guess_all);
+            ++c->tm.launches_other;
+        }
         if (nown > 0) {
             // rows = owned slots ordered by guessed bin (stable), so that a 128-row block prunes the same bins
-            row_bound_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, nown, c->X, c->ldx, c->Xf, c->ldf, c->d,
-                                                                         c->f_mc, c->f_mc2, c->f_mcnt, C, c->seed_off, c->seed_idx,
-                                                                         c->f_guess_slot, c->f_ub_slot);
+            row_ub_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, c->f_guess_all + c->u0, nown, c->X, c->ldx,
+                                                                      c->d, C, c->seed_off, c->seed_idx, c->f_ub_slot);
             std::vector<int32_t> guess((size_t)nown), order((size_t)nown);
-            CHB_CUDA(c, cudaMemcpyAsync(guess.data(), c->f_guess_slot, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+            CHB_CUDA(c, cudaMemcpyAsync(guess.data(), c->f_guess_all + c->u0, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
             CHB_CUDA(c, cudaStreamSynchronize(c->stream));
             {
                 std::vector<int64_t> start((size_t)C + 2, 0);
@@ -1334,13 +1360,15 @@ int chb_fused_setup(chb_ctx *c)
                 for (int32_t b = 0; b <= C; ++b) start[(size_t)b + 1] += start[(size_t)b];
                 for (int64_t u = 0; u < nown; ++u) order[(size_t)start[(size_t)guess[(size_t)u]]++] = (int32_t)u;
             }
-            CHB_CUDA(c, cudaMemcpy(c->f_row_slot, order.data(), sizeof(int32_t) * (size_t)nown, cudaMemcpyHostToDevice));
+            // stream-ordered: a synchronous cudaMemcpy from pageable memory only waits for the staging copy, and the legacy
+            // stream it runs on is not ordered against this context's non-blocking stream
+            CHB_CUDA(c, cudaMemcpyAsync(c->f_row_slot, order.data(), sizeof(int32_t) * (size_t)nown, cudaMemcpyHostToDevice, c->stream));
             row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_ub_slot, nown, c->f_row_pt,
                                                                       c->f_ub);
             split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
-            query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, nown, c->Xf, c->ldf, c->d, c->f_mc, c->f_mc2, C,
-                                                                           c->f_ldt, c->f_tq);
+            query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, nown, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2,
+                                                                           C, c->f_ldt, c->f_tq);
             c->tm.launches_other += 4;
         }
         CHB_CUDA(c, cudaGetLastError());
@@ -1383,11 +1411,11 @@ int chb_round_fused(chb_ctx *c)
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, eps_rel, nown, C, k,
         c->f_ldt, c->f_t0, c->f_slack);
-    CHB_CUDA(c, cudaMemsetAsync(&c->counters[7], 0, sizeof(int32_t), c->stream));
-    skip_kernel<<<nblk(((nown + BM - 1) / BM) * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_seg_off, c->f_skip,
-                                                                                 &c->counters[7]);
+    const int64_t nrb = (nown + BM - 1) / BM;
+    skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
+    items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7]);
     CHB_CUDA(c, cudaGetLastError());
-    c->tm.launches_other += 2;
+    c->tm.launches_other += 3;
     CUtensorMap ma, mb;
     int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
     if (rc != CHB_OK) return rc;
@@ -1423,7 +1451,8 @@ extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslot
     *kr_out = KR;
     // the kernels keep these tables per ROW (owned slots ordered by guessed bin): translate back to slots
     std::vector<int32_t> row_slot((size_t)std::max<int64_t>(nown, 1));
-    CHB_CUDA(c, cudaMemcpy(row_slot.data(), c->f_row_slot, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost));
+    CHB_CUDA(c, cudaMemcpyAsync(row_slot.data(), c->f_row_slot, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaStreamSynchronize(c->stream));
     std::vector<float> srow((size_t)c->C);
     for (int64_t r = 0; r < nown; ++r) {
         const int64_t sl = row_slot[(size_t)r] - s0;

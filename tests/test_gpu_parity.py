@@ -309,6 +309,19 @@ def test_cached_neighbour_sets_match_each_querys_view(path):
     ctx.close()
 
 
+def test_fresh_contexts_back_to_back():
+    """Every call builds a NEW library context on recycled device memory: host-to-device set-up copies must be ordered on
+    the context's own stream (a synchronous cudaMemcpy from pageable memory only waits for its staging copy)."""
+    X, bins, _ = synth.make_contig_features(6000, 12, 10, 20, seed=5, concentration=500.0)
+    perms = oracle.draw_permutations(bins, 4, seed=0)
+    ref = oracle.fit_cluster(X, 12, bins, None, 10, 4, perms=perms, threads=4)
+    for rep in range(4):
+        np.random.seed(0)
+        got, info = chbin_b200.fit_cluster(X, 12, bins, None, 10, 4, reuse_context=False, return_info=True)
+        assert np.array_equal(got, ref), rep
+        assert info["timers"]["launches_gram"] > 0
+
+
 def test_fit_cluster_fortran_order_and_errors():
     X, bins, _ = synth.make_contig_features(400, 3, 1, 20, seed=1)
     perms = oracle.draw_permutations(bins, 10, seed=0)
