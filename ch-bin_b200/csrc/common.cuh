@@ -111,7 +111,9 @@ struct chb_ctx {
     int32_t *f_mcnt = nullptr;
     double *f_mcT = nullptr;        // d x Cp : the same table transposed (bins contiguous)
     int32_t *f_guess_all = nullptr; // U : bin of the nearest seed centroid of every query slot (C: none)
-    int64_t f_cap_guess = 0, f_cap_mcT = 0;
+    int64_t f_cap_guess = 0, f_cap_mcT = 0, f_cap_seedT = 0;
+    double *f_seedT = nullptr;      // d x (#seeds) : seed contigs transposed, (bin, index) order
+    int32_t *f_row_nb = nullptr, *f_row_bins = nullptr; // per row: number / list of the bins that survived pruning this round
     int64_t f_cap_mc = 0;
     float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
     int4 *f_items = nullptr;                   // surviving (row block, bin) work items of the fused kernel, row-block order

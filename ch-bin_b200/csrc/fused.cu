@@ -374,10 +374,21 @@ __global__ void guess_scatter_kernel(const int32_t *__restrict__ qpoint, const i
 // pruned: admission threshold -inf, no candidates, no QP, hull distance +inf.  Rows are ordered by guessed bin so that
 // whole 128-query row blocks prune the same bins and their tiles are skipped by the fused kernel.
 // ---------------------------------------------------------------------------------------------------------
+// seed contigs transposed, [feature][seed] in (bin, index) order: lanes that each take one seed read consecutive addresses
+__global__ void seed_transpose_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, const int32_t *__restrict__ seed_idx,
+                                      int64_t ns, double *__restrict__ seedT)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ns * d) return;
+    const int64_t sidx = i / d;
+    const int t = (int)(i - sidx * d);
+    seedT[(int64_t)t * ns + sidx] = X[(int64_t)seed_idx[sidx] * ldx + t];
+}
+
 // one warp per owned slot: UB = distance to the nearest seed of the guessed bin (one lane per seed)
 __global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__ qpoint_own, const int32_t *__restrict__ guess_own,
                                                      int64_t nown, const double *__restrict__ X, int32_t ldx, int32_t d, int32_t C,
-                                                     const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
+                                                     const int32_t *__restrict__ seed_off, const double *__restrict__ seedT, int64_t ns,
                                                      float *__restrict__ ub_out)
 {
     __shared__ double q_sm[8][DMAX_F];
@@ -391,9 +402,8 @@ __global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__
     double ub2 = INFINITY;
     if (g < C) {
         for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32) {
-            const double *xs = X + (int64_t)seed_idx[i] * ldx;
             double s = 0.0;
-            for (int t = 0; t < d; ++t) { const double df = q_sm[w][t] - xs[t]; s = fma(df, df, s); }
+            for (int t = 0; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; s = fma(df, df, s); }
             ub2 = fmin(ub2, s);
         }
     }
@@ -906,13 +916,14 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // Columns above T0 are skipped by the fused kernel without touching the per-thread lists.  T0 = +inf when there is no
 // usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
+__global__ void threshold_kernel(int32_t *knn_idx, int32_t *knn_cnt, const float *__restrict__ thr,
                                  const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
                                  const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
                                  const float *__restrict__ nrm, const unsigned int *__restrict__ nrm_max_bits,
                                  const float *__restrict__ ym2, const float *__restrict__ tcmax, const float *__restrict__ tq_tab,
                                  const float *__restrict__ ub_row, double eps_rel, int64_t nown, int32_t C, int32_t k, int64_t ldt,
-                                 float *__restrict__ t0_tab, float *__restrict__ slack_tab)
+                                 float *__restrict__ t0_tab, float *__restrict__ slack_tab, double *__restrict__ pair_dist,
+                                 int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nown * C) return;
@@ -930,9 +941,15 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
         const double scale = sqrt((double)nrm[jq]) + sqrt((double)__uint_as_float(*nrm_max_bits));
         if (lb > ub + 1e-5 * (sqrt((double)tq) + sqrt((double)ym2[c]) + ub) + 4e-6 * scale) {
             t0_tab[(int64_t)c * ldt + r] = -INFINITY;
+            if (knn_cnt[pair] != 0) { // settle the pair here: no neighbours, hull distance +inf (the re-rank never sees it)
+                knn_cnt[pair] = 0;
+                for (int s = 0; s < k; ++s) knn_idx[pair * k + s] = -1;
+                pair_dist[pair] = INFINITY;
+            }
             return;
         }
     }
+    row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
     float out = INFINITY;
     if (knn_cnt[pair] == k) {
         const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
@@ -1000,7 +1017,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
                                                      int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
                                                      int32_t *__restrict__ fb_rows, int32_t *__restrict__ fb_count,
-                                                     const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ thr_out)
+                                                     const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ thr_out,
+                                                     const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins)
 {
     extern __shared__ __align__(16) double xq_s[];
     constexpr int NG = 32 / G;
@@ -1017,17 +1035,17 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
     const int K2 = 2 * KR;
     bool overflow = false;
 
-    for (int cb = warp * NG; cb < C; cb += 4 * NG) {
-        const int c = cb + lane / G;
-        const bool act = c < C;
-        const int64_t pair = sl * C + (act ? c : 0);
-        const int64_t rpair = r * C + (act ? c : 0);
+    // only the bins that survived the pruning bounds (threshold_kernel lists them per row; pruned pairs were settled there)
+    const int nb = row_nb[r];
+    for (int jb = warp * NG; jb < nb; jb += 4 * NG) {
+        const int j = jb + lane / G;
+        const bool act = j < nb;
+        const int c = act ? row_bins[r * C + j] : 0;
+        const int64_t pair = sl * C + c;
+        const int64_t rpair = r * C + c;
         const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
-        const bool pruned = t0v == -INFINITY; // the bin cannot be this query's nearest hull: no neighbours, distance +inf
+        const bool pruned = false;
         const int mo = act ? knn_cnt[pair] : 0;
-        // bins ruled out by the bounds whose cache already says "no neighbours": nothing to do (the common case once the
-        // rows are ordered by guessed bin)
-        if (__all_sync(CHB_FULL, !act || (pruned && mo == 0))) continue;
         float ka = INFINITY;
         int ki = INT32_MAX;
         if (act && !pruned && bin_cnt[c] > 0 && gl < K2) {
@@ -1241,7 +1259,10 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
-    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all);
+    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins);
+    c->f_seedT = nullptr;
+    c->f_row_nb = c->f_row_bins = nullptr;
+    c->f_cap_seedT = 0;
     c->f_mcT = nullptr;
     c->f_guess_all = nullptr;
     c->f_cap_guess = c->f_cap_mcT = 0;
@@ -1328,6 +1349,8 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_row_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_pt, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ub, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_row_nb, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_row_bins, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_guess_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ub_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         c->f_cap_thr = c->f_ldt * C;
@@ -1349,8 +1372,11 @@ int chb_fused_setup(chb_ctx *c)
         }
         if (nown > 0) {
             // rows = owned slots ordered by guessed bin (stable), so that a 128-row block prunes the same bins
+            const int64_t ns = std::max<int64_t>(n - c->U, 1);
+            if (reserve(c, &c->f_seedT, &c->f_cap_seedT, ns * c->d)) return CHB_ENOMEM;
+            seed_transpose_kernel<<<nblk(ns * c->d, 256), 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_idx, n - c->U, c->f_seedT);
             row_ub_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, c->f_guess_all + c->u0, nown, c->X, c->ldx,
-                                                                      c->d, C, c->seed_off, c->seed_idx, c->f_ub_slot);
+                                                                      c->d, C, c->seed_off, c->f_seedT, n - c->U, c->f_ub_slot);
             std::vector<int32_t> guess((size_t)nown), order((size_t)nown);
             CHB_CUDA(c, cudaMemcpyAsync(guess.data(), c->f_guess_all + c->u0, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
             CHB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1407,10 +1433,11 @@ int chb_round_fused(chb_ctx *c)
 
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
+    CHB_CUDA(c, cudaMemsetAsync(c->f_row_nb, 0, sizeof(int32_t) * (size_t)nown, c->stream));
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, eps_rel, nown, C, k,
-        c->f_ldt, c->f_t0, c->f_slack);
+        c->f_ldt, c->f_t0, c->f_slack, c->pair_dist, c->f_row_nb, c->f_row_bins);
     const int64_t nrb = (nown + BM - 1) / BM;
     skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7]);
@@ -1433,7 +1460,7 @@ int chb_round_fused(chb_ctx *c)
         kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
             c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pair_dist, c->f_slack, C,
             k, c->knn_idx, c->knn_cnt, c->work, c->counters,
-            c->f_fb_rows, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr);
+            c->f_fb_rows, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
