@@ -332,6 +332,7 @@ def run_b200(args):
     qps_ref_total = total_iters * U * C
     value = qps_ref_total / (elapsed_ms * 1e-3)
     fp64_peak = ctx.measure_fp64_tflops() if rank == 0 else 0.0
+    ctx.close()  # the end-to-end arm below builds its own context through the public API: release this one's HBM first
 
     # ---------------- e2e arm: public API, host (pinned) buffers ----------------
     Xp = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
@@ -450,7 +451,6 @@ def run_b200(args):
             "clocks": clocks,
         }
         _emit(line)
-    ctx.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
