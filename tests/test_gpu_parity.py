@@ -309,6 +309,51 @@ def test_cached_neighbour_sets_match_each_querys_view(path):
     ctx.close()
 
 
+@pytest.mark.parametrize("cuts", [(0.5,), (0.1, 0.1, 0.73)])
+def test_sharded_contexts_exchange_labels(cuts):
+    """The multi-GPU form on one device: several contexts, each owning a slice of the query slots (one of them may be
+    empty), run the round protocol of include/chbin_b200.h and exchange tentative labels by element-wise MAX -- what the
+    NCCL all-reduce does between ranks.  Labels must equal the sequential oracle after every iteration."""
+    import torch
+
+    X, bins, _ = synth.make_contig_features(3000, 7, 3, 15, seed=23, concentration=120.0)
+    perms = oracle.draw_permutations(bins, 4, seed=0)
+    U = perms.shape[1]
+    edges = [0] + [int(U * f) for f in cuts] + [U]   # repeated edges give an empty shard
+    dev = torch.device("cuda", 0)
+    stream = torch.cuda.Stream(dev)
+    ctxs = []
+    for u0, u1 in zip(edges[:-1], edges[1:]):
+        ctx = capi.Context(0)
+        ctx.set_stream(stream.cuda_stream)
+        ctx.set_features(X); ctx.set_params(5, "convex"); ctx.set_distance_mode(2)
+        ctx.set_labels(bins, 7, u0, u1); ctx.build_distance_matrix(True)
+        ctxs.append(ctx)
+    cur = bins.copy()
+    with torch.cuda.stream(stream):
+        for it in range(4):
+            for ctx in ctxs:
+                ctx.iteration_begin(perms[it])
+            lo = 0
+            while lo < U:
+                tents = [torch.empty(U - lo, dtype=torch.int32, device=dev) for _ in ctxs]
+                for ctx, t in zip(ctxs, tents):
+                    ctx.round_run(lo, U, t.data_ptr())
+                merged = torch.stack(tents).max(dim=0).values.contiguous()
+                assert int(merged.min()) >= 0, "a position was left un-owned after the exchange"
+                firsts = [ctx.round_commit(lo, U, merged.data_ptr()) for ctx in ctxs]
+                assert len(set(firsts)) == 1
+                lo = U if firsts[0] < 0 else firsts[0] + 1
+            changed = [ctx.iteration_end() for ctx in ctxs]
+            assert len(set(changed)) == 1
+            ref = oracle.fit_cluster(X, 7, cur, None, 5, 1, perms=perms[it:it + 1], threads=4)
+            for ctx in ctxs:
+                assert np.array_equal(ctx.get_labels(), ref), it
+            cur = ref
+    for ctx in ctxs:
+        ctx.close()
+
+
 def test_fresh_contexts_back_to_back():
     """Every call builds a NEW library context on recycled device memory: host-to-device set-up copies must be ordered on
     the context's own stream (a synchronous cudaMemcpy from pageable memory only waits for its staging copy)."""
