@@ -844,37 +844,9 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         CHB_TRY(ensure_work(c, 2 * nown)); // a pair can be listed by the re-rank AND again by the exact-path fallback
         CHB_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(int32_t), c->stream));
         CHB_TRY(chb_round_fused(c));
-        // exact-path fallback for queries whose kept candidate list may be incomplete (duplicate contigs): rare
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[7], &c->counters[7], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-        CHB_TRY(sync_stream(c));
-        c->tm.gram_tiles += (int64_t)c->counters_host[7]; // tiles left after bin pruning (skip_kernel)
-        const int64_t nfb = c->counters_host[6];
-        if (nfb > 0) {
-            if (c->f_cap_fb < 2 * nfb) {
-                CHB_TRY(dev_alloc(c, &c->f_fb_items, 2 * nfb));
-                c->f_cap_fb = 2 * nfb;
-            }
-            int32_t *items = c->f_fb_items, *points = c->f_fb_items + nfb;
-            fallback_prepare_kernel<<<(unsigned)nfb, 128, 0, c->stream>>>(c->f_fb_rows, (int32_t)nfb, c->qpoint + c->u0, c->pos, c->C,
-                                                                          items, points, c->knn_cnt, c->f_thr);
-            ++c->tm.launches_other;
-            for (int64_t s0 = 0; s0 < nfb; s0 += c->scratch_rows) {
-                const int64_t sc = std::min(c->scratch_rows, nfb - s0);
-                CHB_TRY(candidate_rows(c, points + s0, sc, c->Ascratch, c->lda));
-                chb_knn_args a{};
-                a.row_stride = c->lda; a.items = items + s0; a.n_items = sc; a.mode = 0; a.perm_pt = c->perm_pt;
-                a.qslot = c->qslot; a.pos = c->pos; a.tent_pt = c->tent_pt; a.old_label = c->old_label; a.n = c->n; a.C = c->C;
-                a.k = c->k; a.u0 = c->u0; a.knn_idx = c->knn_idx; a.knn_cnt = c->knn_cnt; a.work = c->work;
-                a.work_count = c->counters;
-                fill_filter_args(c, a, true);
-                a.knn_dist = c->knn_dist;
-                a.packed = nullptr;
-                a.arows = c->Ascratch;
-                a.row_is_item = 1;
-                CHB_TRY(chb_launch_knn_scan(c, a));
-            }
-        }
+        // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the
+        // tile / redo counters travel with the commit's read-back
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         chb_qp_args q{};
         q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = 2 * nown * c->C;
         q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
@@ -959,6 +931,11 @@ int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev
     CHB_TRY(sync_stream(c));
     c->tm.qps_solved += c->counters_host[4];
     c->counters_host[4] = 0;
+    c->tm.gram_tiles += c->counters_host[7]; // tiles left after bin pruning (items_kernel), this round
+    c->counters_host[7] = 0;
+    if (c->f_fb_cap > 0 && c->counters_host[6] > c->f_fb_cap)
+        return chb_fail(c, CHB_ECUDA, "exact-redo list overflow: %d pairs, capacity %d", c->counters_host[6], c->f_fb_cap);
+    c->counters_host[6] = 0;
     *first_changed = (c->counters_host[1] == 0x7f7f7f7f) ? -1 : (int64_t)c->counters_host[1];
     return CHB_OK;
 }

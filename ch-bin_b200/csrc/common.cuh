@@ -100,7 +100,9 @@ struct chb_ctx {
     int32_t *f_bin_cnt = nullptr, *f_seg_off = nullptr, *f_cursor = nullptr, *f_tile_bin = nullptr, *f_ntiles = nullptr;
     int32_t *f_col_pt = nullptr, *f_col_a = nullptr, *f_col_b = nullptr;
     float *f_col_nrm = nullptr, *f_bperm = nullptr, *f_cand_key = nullptr;
-    int32_t *f_cand_idx = nullptr, *f_fb_rows = nullptr;
+    int32_t *f_cand_idx = nullptr;
+    int2 *f_fb_pairs = nullptr; // (row, bin) pairs to redo exactly this round
+    int32_t f_fb_cap = 0;
     int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0, f_cap_thr = 0, f_cap_ldt = 0;
     float *f_thr = nullptr; // nown x C : largest FP32 key of the cached neighbour set (+inf: fewer than k members)
     float *f_t0 = nullptr;  // C x f_ldt : this round's admission threshold per (bin, owned slot)

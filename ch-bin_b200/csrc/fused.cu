@@ -1016,7 +1016,7 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
                                                      const float *__restrict__ slack_tab, int32_t C,
                                                      int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
-                                                     int32_t *__restrict__ fb_rows, int32_t *__restrict__ fb_count,
+                                                     int2 *__restrict__ fb_pairs, int32_t fb_cap, int32_t *__restrict__ fb_count,
                                                      const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ thr_out,
                                                      const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins)
 {
@@ -1029,11 +1029,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
     const int gl = lane & (G - 1), gsh = lane & ~(G - 1);
     const int jq = row_point[r];
     for (int t = threadIdx.x; t < d; t += 128) xq_s[t] = X[(int64_t)jq * ldx + t];
-    __shared__ int s_overflow;
-    if (threadIdx.x == 0) s_overflow = 0;
     __syncthreads();
     const int K2 = 2 * KR;
-    bool overflow = false;
 
     // only the bins that survived the pruning bounds (threshold_kernel lists them per row; pruned pairs were settled there)
     const int nb = row_nb[r];
@@ -1082,11 +1079,12 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
         const unsigned cm = (__ballot_sync(CHB_FULL, could) >> gsh) & GM;
         const unsigned sm = (__ballot_sync(CHB_FULL, sure) >> gsh) & GM;
         const int nsure = __popc(sm);
+        bool ovf = false; // the kept lists may be incomplete for this pair: it is redone exactly (exact_pairs_kernel)
         if (big) {
             // every key <= hi must have been admitted by the fused kernel's threshold (holds by construction of T0), and
             // a half-list that is full and entirely inside the slack may have dropped a closer point
             const unsigned lo_half = (1u << KR) - 1u;
-            if (hi > t0v || __popc(cm & lo_half) == KR || __popc(cm >> KR) == KR) overflow = true;
+            if (hi > t0v || __popc(cm & lo_half) == KR || __popc(cm >> KR) == KR) ovf = true;
         }
         // ambiguous candidates: exact scipy-recipe distance, rank by (distance, index)
         const bool amb = big && __popc(cm) != k && could && !sure;
@@ -1126,7 +1124,13 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
         const bool diff = sel && (mo != m || knn_idx[pair * k + srt] != ki);
         const unsigned dm = (__ballot_sync(CHB_FULL, diff) >> gsh) & GM;
         const bool same = (mo == m) && dm == 0;
-        if (act) {
+        if (act && ovf) {
+            if (gl == 0) {
+                thr_out[pair] = INFINITY;
+                const int w = atomicAdd(fb_count, 1);
+                if (w < fb_cap) fb_pairs[w] = make_int2((int)r, c);
+            }
+        } else if (act) {
             if (gl == 0) thr_out[pair] = (m == k) ? __fadd_ru(mx, E) : INFINITY;
             if (!same) {
                 // slots [0, m) come from the selected lanes, slots [m, k) are cleared by the lanes sitting at those positions
@@ -1144,9 +1148,106 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
             }
         }
     }
-    if (__any_sync(CHB_FULL, overflow) && lane == 0) s_overflow = 1;
-    __syncthreads();
-    if (threadIdx.x == 0 && s_overflow) fb_rows[atomicAdd(fb_count, 1)] = (int)sl;
+}
+
+// Exact redo of the (row, bin) pairs whose kept candidate lists may be incomplete (duplicate contigs: more than KR keys
+// inside the slack window).  One CTA per pair walks the bin's column segment of this round, evaluates scipy's exact
+// recipe for every visible member and selects the k smallest (distance, index) -- find_nearest_from_cluster
+// (distance_matrix.py:47-62) verbatim.  Rare, so simple: per-thread sorted lists, then k block-wide argmin rounds.
+template <int KX>
+__global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict__ fb_pairs, const int32_t *__restrict__ fb_count,
+                                                          int32_t fb_cap, const int32_t *__restrict__ seg_off,
+                                                          const int32_t *__restrict__ bin_cnt, const int32_t *__restrict__ col_pt,
+                                                          const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b,
+                                                          const double *__restrict__ X, int32_t ldx, int32_t d,
+                                                          const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
+                                                          const int32_t *__restrict__ pos, int32_t C, int32_t k,
+                                                          int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
+                                                          int2 *__restrict__ work, int32_t *__restrict__ work_count)
+{
+    extern __shared__ __align__(16) double xq_s[];
+    __shared__ double s_best[4];
+    __shared__ int s_bidx[4], s_bthr[4];
+    __shared__ int s_sel[KX];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nfb = min(*fb_count, fb_cap);
+    for (int f = blockIdx.x; f < nfb; f += gridDim.x) {
+        const int r = fb_pairs[f].x, c = fb_pairs[f].y;
+        const int jq = row_point[r];
+        const int p = pos[jq];
+        __syncthreads();
+        for (int t = tid; t < d; t += 128) xq_s[t] = X[(int64_t)jq * ldx + t];
+        __syncthreads();
+        double ld[KX];
+        int li[KX];
+#pragma unroll
+        for (int s = 0; s < KX; ++s) { ld[s] = INFINITY; li[s] = INT32_MAX; }
+        const int e0 = seg_off[c], e1 = e0 + bin_cnt[c];
+        for (int e = e0 + tid; e < e1; e += 128) {
+            const int pt = col_pt[e];
+            if (pt < 0 || !((p > col_a[e]) || (p < col_b[e]))) continue;
+            double dv = exact_distance_g(xq_s, X + (int64_t)pt * ldx, d);
+            int iv = pt;
+#pragma unroll
+            for (int s = 0; s < KX; ++s) { // sorted insertion by (distance, index)
+                const bool lt = dv < ld[s] || (dv == ld[s] && iv < li[s]);
+                const double td = lt ? ld[s] : dv;
+                const int ti = lt ? li[s] : iv;
+                ld[s] = lt ? dv : ld[s];
+                li[s] = lt ? iv : li[s];
+                dv = td;
+                iv = ti;
+            }
+        }
+        int m = 0;
+        for (int round = 0; round < k; ++round) {
+            // block-wide argmin over the heads of the per-thread lists
+            double bd = ld[0];
+            int bi = li[0], bt = tid;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double od = __shfl_xor_sync(CHB_FULL, bd, o);
+                const int oi = __shfl_xor_sync(CHB_FULL, bi, o);
+                const int ot = __shfl_xor_sync(CHB_FULL, bt, o);
+                if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; bt = ot; }
+            }
+            if (lane == 0) { s_best[warp] = bd; s_bidx[warp] = bi; s_bthr[warp] = bt; }
+            __syncthreads();
+            int win = 0;
+            for (int w = 1; w < 4; ++w)
+                if (s_best[w] < s_best[win] || (s_best[w] == s_best[win] && s_bidx[w] < s_bidx[win])) win = w;
+            const bool any = s_best[win] < INFINITY;
+            const int wthr = s_bthr[win], widx = s_bidx[win];
+            __syncthreads();
+            if (!any) break;
+            if (tid == 0) s_sel[m] = widx;
+            ++m;
+            if (tid == wthr) { // pop the head
+#pragma unroll
+                for (int s = 0; s + 1 < KX; ++s) { ld[s] = ld[s + 1]; li[s] = li[s + 1]; }
+                ld[KX - 1] = INFINITY;
+                li[KX - 1] = INT32_MAX;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // ascending index order (canonical), compare with the cache, list for the QP kernel if the set changed
+            for (int a = 1; a < m; ++a) {
+                const int v = s_sel[a];
+                int b = a - 1;
+                while (b >= 0 && s_sel[b] > v) { s_sel[b + 1] = s_sel[b]; --b; }
+                s_sel[b + 1] = v;
+            }
+            const int64_t pair = (int64_t)row_slot[r] * C + c;
+            bool same = knn_cnt[pair] == m;
+            for (int a = 0; same && a < m; ++a) same = knn_idx[pair * k + a] == s_sel[a];
+            if (!same) {
+                for (int a = 0; a < k; ++a) knn_idx[pair * k + a] = a < m ? s_sel[a] : -1;
+                knn_cnt[pair] = m;
+                work[atomicAdd(work_count, 1)] = make_int2(row_slot[r], c);
+            }
+        }
+    }
 }
 
 typedef CUresult (*encode_fn_t)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1257,7 +1358,7 @@ void chb_fused_free(chb_ctx *c)
 {
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
-    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_rows); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
+    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
     cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins);
     c->f_seedT = nullptr;
@@ -1279,12 +1380,13 @@ void chb_fused_free(chb_ctx *c)
     c->f_cap_bins = c->f_cap_cols = c->f_cap_cand = c->f_cap_thr = c->f_cap_ldt = 0;
     c->f_bin_cnt = c->f_seg_off = c->f_cursor = c->f_tile_bin = c->f_ntiles = c->f_col_pt = c->f_col_a = c->f_col_b = nullptr;
     c->f_col_nrm = c->f_bperm = c->f_cand_key = nullptr;
-    c->f_cand_idx = c->f_fb_rows = nullptr;
+    c->f_cand_idx = nullptr;
+    c->f_fb_pairs = nullptr;
 }
 
 // Runs steps 1-3 of the header comment for ALL owned query slots against the current (pos, tent, old) labels.
 // Appends changed (slot_local, bin) pairs to ctx->work (count in counters[0]); queries needing the exact fallback are
-// listed in f_fb_rows (count in counters[6]).
+// redone exactly on the device (exact_pairs_kernel; their count stays in counters[6]).
 int chb_fused_guess(chb_ctx *c)
 {
     if (c->U <= 0) return CHB_OK;
@@ -1332,7 +1434,8 @@ int chb_fused_setup(chb_ctx *c)
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_cand_key, &z, nown * C * KR * 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cand_idx, &z, nown * C * KR * 2)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_fb_rows, &z, nown)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_fb_pairs, &z, std::max<int64_t>(nown, 1024))) return CHB_ENOMEM;
+        c->f_fb_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(nown, 1024), INT32_MAX);
         c->f_cap_cand = nown * C * KR * 2;
     }
     c->f_ldt = (nown + 127) & ~int64_t(127);
@@ -1460,7 +1563,18 @@ int chb_round_fused(chb_ctx *c)
         kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
             c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pair_dist, c->f_slack, C,
             k, c->knn_idx, c->knn_cnt, c->work, c->counters,
-            c->f_fb_rows, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins);
+            c->f_fb_pairs, c->f_fb_cap, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins);
+        // pairs the re-rank could not settle from the kept lists (rare): exact redo, no host round trip -- the grid is
+        // fixed and walks the device-side list
+        const size_t xs = sizeof(double) * (size_t)((c->d + 1) & ~1);
+        if (KR == 8)
+            exact_pairs_kernel<5><<<64, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt, c->f_col_pt,
+                                                              c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pos, C,
+                                                              k, c->knn_idx, c->knn_cnt, c->work, c->counters);
+        else
+            exact_pairs_kernel<13><<<64, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
+                                                               c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot,
+                                                               c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
