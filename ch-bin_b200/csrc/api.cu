@@ -454,7 +454,10 @@ int chb_get_pair_cache(chb_ctx *c, int64_t slot0, int64_t nslots, int32_t *idx_o
     CHB_CUDA(c, cudaMemcpyAsync(idx_out, c->knn_idx + r0 * c->C * c->k, sizeof(int32_t) * (size_t)np * c->k, cudaMemcpyDeviceToHost, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(cnt_out, c->knn_cnt + r0 * c->C, sizeof(int32_t) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(dist_out, c->pair_dist + r0 * c->C, sizeof(double) * (size_t)np, cudaMemcpyDeviceToHost, c->stream));
-    return sync_stream(c);
+    CHB_TRY(sync_stream(c));
+    // distance mode 2 keeps no state for the bins its bounds ruled out: report them as "no neighbours, distance +inf"
+    if (use_fused(c) && c->f_row_nb) CHB_TRY(chb_fused_mask_pair_cache(c, slot0, nslots, cnt_out, dist_out));
+    return CHB_OK;
 }
 
 int chb_set_distance_mode(chb_ctx *c, int mode)
@@ -853,12 +856,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
         CHB_TRY(chb_launch_qp(c, q));
         cudaMemcpyAsync(&c->counters_host[4], c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-        {
-            chb_stage_timer t(c, CHB_ST_COMMIT);
-            argmin_kernel<<<nblk(cnt * 32, 256), 256, 0, c->stream>>>(c->own_pos + b, cnt, c->perm_pt, c->qslot, c->u0, c->pair_dist,
-                                                                      c->C, c->old_label, lo, tent_dev);
-        }
-        CHB_CUDA(c, cudaGetLastError());
+        CHB_TRY(chb_fused_argmin(c, c->own_pos + b, cnt, lo, tent_dev));
         return CHB_OK;
     }
     CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));

@@ -115,6 +115,8 @@ struct chb_ctx {
     int32_t *f_guess_all = nullptr; // U : bin of the nearest seed centroid of every query slot (C: none)
     int64_t f_cap_guess = 0, f_cap_mcT = 0, f_cap_seedT = 0;
     double *f_seedT = nullptr;      // d x (#seeds) : seed contigs transposed, (bin, index) order
+    int32_t *f_slot_row = nullptr;  // owned slot -> row
+    float *f_sq_row = nullptr;      // per row: >= |a_q|
     int32_t *f_row_nb = nullptr, *f_row_bins = nullptr; // per row: number / list of the bins that survived pruning this round
     int64_t f_cap_mc = 0;
     float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
@@ -216,7 +218,9 @@ int chb_launch_gram_tc(chb_ctx *ctx, const float *a_split, const float *b_split,
 bool chb_fused_supported(const chb_ctx *c);
 int chb_round_fused(chb_ctx *c);
 int chb_fused_setup(chb_ctx *c);  // allocations + once-per-label-set operands (idempotent)
-int chb_fused_guess(chb_ctx *c);  // tent_pt of every query point := bin of the nearest seed centroid
+int chb_fused_guess(chb_ctx *c);
+int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int32_t *tent_dev); // argmin over surviving bins
+int chb_fused_mask_pair_cache(chb_ctx *c, int64_t slot0, int64_t nslots, int32_t *cnt_out, double *dist_out); // test aid  // tent_pt of every query point := bin of the nearest seed centroid
 void chb_fused_free(chb_ctx *c);
 
 // knn.cu

@@ -413,14 +413,18 @@ __global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__
 }
 
 __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const int32_t *__restrict__ qpoint_own,
-                                  const float *__restrict__ ub_slot, int64_t nown, int32_t *__restrict__ row_pt,
-                                  float *__restrict__ ub_row)
+                                  const float *__restrict__ ub_slot, const float *__restrict__ nrm, int64_t nown,
+                                  int32_t *__restrict__ row_pt, float *__restrict__ ub_row, int32_t *__restrict__ slot_row,
+                                  float *__restrict__ sq_row)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nown) return;
     const int sl = row_slot[r];
-    row_pt[r] = qpoint_own[sl];
+    const int pt = qpoint_own[sl];
+    row_pt[r] = pt;
     ub_row[r] = ub_slot[sl];
+    slot_row[sl] = (int32_t)r;
+    sq_row[r] = __fmul_ru(__fsqrt_ru(nrm[pt]), 1.000001f); // >= |a_q|
 }
 
 // one warp per (row block, bin): skip = every row of the block pruned the bin (t0 == -inf) or lies beyond nrows
@@ -916,40 +920,35 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // Columns above T0 are skipped by the fused kernel without touching the per-thread lists.  T0 = +inf when there is no
 // usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void threshold_kernel(int32_t *knn_idx, int32_t *knn_cnt, const float *__restrict__ thr,
+__global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
                                  const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
                                  const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
                                  const float *__restrict__ nrm, const unsigned int *__restrict__ nrm_max_bits,
                                  const float *__restrict__ ym2, const float *__restrict__ tcmax, const float *__restrict__ tq_tab,
-                                 const float *__restrict__ ub_row, double eps_rel, int64_t nown, int32_t C, int32_t k, int64_t ldt,
-                                 float *__restrict__ t0_tab, float *__restrict__ slack_tab, double *__restrict__ pair_dist,
+                                 const float *__restrict__ ub_row, const float *__restrict__ sq_row, double eps_rel, int64_t nown,
+                                 int32_t C, int32_t k, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
                                  int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nown * C) return;
     const int c = (int)(i / nown);
     const int64_t r = i - (int64_t)c * nown;           // row (rows are the owned slots ordered by guessed bin)
-    const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
-    const int jq = row_point[r];
     const float tq = tq_tab[(int64_t)c * ldt + r];
-    const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
-    slack_tab[(int64_t)c * ldt + r] = E;
-    // pruning: LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands
+    // pruning (97-99 % of the pairs end here, so this test is all FP32 and touches nothing per pair but tq and t0):
+    // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test
     {
-        const double lb = sqrt((double)tq) - sqrt((double)ym2[c]);
-        const double ub = (double)ub_row[r];
-        const double scale = sqrt((double)nrm[jq]) + sqrt((double)__uint_as_float(*nrm_max_bits));
-        if (lb > ub + 1e-5 * (sqrt((double)tq) + sqrt((double)ym2[c]) + ub) + 4e-6 * scale) {
-            t0_tab[(int64_t)c * ldt + r] = -INFINITY;
-            if (knn_cnt[pair] != 0) { // settle the pair here: no neighbours, hull distance +inf (the re-rank never sees it)
-                knn_cnt[pair] = 0;
-                for (int s = 0; s < k; ++s) knn_idx[pair * k + s] = -1;
-                pair_dist[pair] = INFINITY;
-            }
+        const float dq = __fsqrt_rd(tq), ym = __fmul_ru(__fsqrt_ru(ym2[c]), 1.000001f), ub = ub_row[r];
+        const float scale = sq_row[r] + __fsqrt_ru(__uint_as_float(*nrm_max_bits));
+        if (dq * 0.999999f - ym > ub + 1e-5f * (dq + ym + ub) + 4e-6f * scale) {
+            t0_tab[(int64_t)c * ldt + r] = -INFINITY; // no candidates, no re-rank, no QP; argmin never looks at the pair
             return;
         }
     }
     row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
+    const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
+    const int jq = row_point[r];
+    const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
+    slack_tab[(int64_t)c * ldt + r] = E;
     float out = INFINITY;
     if (knn_cnt[pair] == k) {
         const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
@@ -968,6 +967,38 @@ __global__ void threshold_kernel(int32_t *knn_idx, int32_t *knn_cnt, const float
         }
     }
     t0_tab[(int64_t)c * ldt + r] = out;
+}
+
+// algorithm.py:47-48,57-58,60 over the surviving bins of each query: strict '<' so the lowest bin wins ties; a query
+// always keeps its guessed bin, so there is a finite distance whenever that bin has a visible member
+__global__ void argmin_rows_kernel(const int32_t *__restrict__ own_pos, int64_t cnt, const int32_t *__restrict__ perm_pt,
+                                   const int32_t *__restrict__ qslot, int64_t u0, const int32_t *__restrict__ slot_row,
+                                   const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins,
+                                   const double *__restrict__ pair_dist, int32_t C, const int32_t *__restrict__ old_label,
+                                   int64_t lo, int32_t *__restrict__ tent)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= cnt) return;
+    const int p = own_pos[w];
+    const int j = perm_pt[p];
+    const int64_t sl = (int64_t)qslot[j] - u0;
+    const int64_t r = slot_row[sl];
+    const int nb = row_nb[r];
+    double best = INFINITY;
+    int bc = INT32_MAX;
+    for (int i = lane; i < nb; i += 32) {
+        const int c = row_bins[r * C + i];
+        const double v = pair_dist[sl * C + c];
+        if (v < best || (v == best && c < bc)) { best = v; bc = c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(CHB_FULL, best, o);
+        const int oc = __shfl_xor_sync(CHB_FULL, bc, o);
+        if (ov < best || (ov == best && oc < bc)) { best = ov; bc = oc; }
+    }
+    if (lane == 0) tent[p - lo] = (best < INFINITY) ? bc : old_label[j];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1360,7 +1391,9 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
-    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins);
+    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
+    c->f_slot_row = nullptr;
+    c->f_sq_row = nullptr;
     c->f_seedT = nullptr;
     c->f_row_nb = c->f_row_bins = nullptr;
     c->f_cap_seedT = 0;
@@ -1387,6 +1420,18 @@ void chb_fused_free(chb_ctx *c)
 // Runs steps 1-3 of the header comment for ALL owned query slots against the current (pos, tent, old) labels.
 // Appends changed (slot_local, bin) pairs to ctx->work (count in counters[0]); queries needing the exact fallback are
 // redone exactly on the device (exact_pairs_kernel; their count stays in counters[6]).
+int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int32_t *tent_dev)
+{
+    if (cnt <= 0) return CHB_OK;
+    {
+        chb_stage_timer t(c, CHB_ST_COMMIT);
+        argmin_rows_kernel<<<nblk(cnt * 32, 256), 256, 0, c->stream>>>(own_pos_dev, cnt, c->perm_pt, c->qslot, c->u0, c->f_slot_row, c->f_row_nb,
+                                                                       c->f_row_bins, c->pair_dist, c->C, c->old_label, lo, tent_dev);
+    }
+    CHB_CUDA(c, cudaGetLastError());
+    return CHB_OK;
+}
+
 int chb_fused_guess(chb_ctx *c)
 {
     if (c->U <= 0) return CHB_OK;
@@ -1453,6 +1498,8 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_row_pt, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ub, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_nb, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_slot_row, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_sq_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_bins, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_guess_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ub_slot, &z, c->f_ldt)) return CHB_ENOMEM;
@@ -1492,8 +1539,8 @@ int chb_fused_setup(chb_ctx *c)
             // stream-ordered: a synchronous cudaMemcpy from pageable memory only waits for the staging copy, and the legacy
             // stream it runs on is not ordered against this context's non-blocking stream
             CHB_CUDA(c, cudaMemcpyAsync(c->f_row_slot, order.data(), sizeof(int32_t) * (size_t)nown, cudaMemcpyHostToDevice, c->stream));
-            row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_ub_slot, nown, c->f_row_pt,
-                                                                      c->f_ub);
+            row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_ub_slot, c->nrm, nown,
+                                                                      c->f_row_pt, c->f_ub, c->f_slot_row, c->f_sq_row);
             split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
             query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, nown, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2,
@@ -1539,8 +1586,8 @@ int chb_round_fused(chb_ctx *c)
     CHB_CUDA(c, cudaMemsetAsync(c->f_row_nb, 0, sizeof(int32_t) * (size_t)nown, c->stream));
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
-        reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, eps_rel, nown, C, k,
-        c->f_ldt, c->f_t0, c->f_slack, c->pair_dist, c->f_row_nb, c->f_row_bins);
+        reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, eps_rel,
+        nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins);
     const int64_t nrb = (nown + BM - 1) / BM;
     skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7]);
@@ -1606,5 +1653,26 @@ extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslot
         for (int32_t b = 0; b < c->C; ++b) slack_out[(int64_t)b * nslots + sl] = srow[(size_t)b];
     }
     CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return CHB_OK;
+}
+
+int chb_fused_mask_pair_cache(chb_ctx *c, int64_t slot0, int64_t nslots, int32_t *cnt_out, double *dist_out)
+{
+    const int64_t nown = c->u1 - c->u0, s0 = slot0 - c->u0;
+    const int32_t C = c->C;
+    std::vector<int32_t> slot_row((size_t)std::max<int64_t>(nown, 1)), nb((size_t)std::max<int64_t>(nown, 1)), bins((size_t)C);
+    CHB_CUDA(c, cudaMemcpyAsync(slot_row.data(), c->f_slot_row, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(nb.data(), c->f_row_nb, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+    std::vector<char> alive((size_t)C);
+    for (int64_t s = 0; s < nslots; ++s) {
+        const int64_t r = slot_row[(size_t)(s0 + s)];
+        CHB_CUDA(c, cudaMemcpyAsync(bins.data(), c->f_row_bins + r * C, sizeof(int32_t) * (size_t)nb[(size_t)r], cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        std::fill(alive.begin(), alive.end(), 0);
+        for (int32_t i = 0; i < nb[(size_t)r]; ++i) alive[(size_t)bins[(size_t)i]] = 1;
+        for (int32_t b = 0; b < C; ++b)
+            if (!alive[(size_t)b]) { cnt_out[s * C + b] = 0; dist_out[s * C + b] = INFINITY; }
+    }
     return CHB_OK;
 }
