@@ -114,6 +114,8 @@ struct chb_ctx {
     double *f_mcT = nullptr;        // d x Cp : the same table transposed (bins contiguous)
     int32_t *f_guess_all = nullptr; // U : bin of the nearest seed centroid of every query slot (C: none)
     int64_t f_cap_guess = 0, f_cap_mcT = 0, f_cap_seedT = 0;
+    float *f_tqs = nullptr;         // U x Cp : |a_u - m_c|^2 of every query slot (slot order)
+    int64_t f_cap_tqs = 0;
     double *f_seedT = nullptr;      // d x (#seeds) : seed contigs transposed, (bin, index) order
     int32_t *f_slot_row = nullptr;  // owned slot -> row
     float *f_sq_row = nullptr;      // per row: >= |a_q|

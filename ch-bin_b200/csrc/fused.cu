@@ -304,55 +304,125 @@ __device__ __forceinline__ void load_query_row(const float *__restrict__ xr, int
     __syncwarp();
 }
 
-// one warp per row (owned slots in row order): tq[c][r] = fl32( |a_q - m_c|^2 ), a_q = the FP32 centred feature row the
-// tensor core contracts
-__global__ void __launch_bounds__(256) query_terms_kernel(const int32_t *__restrict__ row_point, int64_t nown,
-                                                          const float *__restrict__ Xf, int32_t ldf, int32_t d,
-                                                          const double *__restrict__ mcT, int32_t Cp, const double *__restrict__ mc2,
-                                                          int32_t C, int64_t ldt, float *__restrict__ tq)
+// |a_u - m_c|^2 for every query slot u and every bin c, once per label set: an FP64 GEMM (U x C x d) in 64 x 64 tiles, 4 x 4
+// outputs per thread, 16 features per shared-memory stage.  tqs[u][c] = fl32( |a_u|^2 - 2 a_u.m_c + |m_c|^2 ), a_u = the FP32
+// centred feature row the tensor core contracts.  Both the speculation start (argmin over bins, all U slots -- every rank
+// must derive the same vector, and the summation order here is fixed) and the query terms of the owned rows come from it.
+__global__ void __launch_bounds__(256) centroid_terms_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
+                                                             int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
+                                                             const double *__restrict__ mc2, int32_t C, float *__restrict__ tqs)
 {
-    __shared__ double a_sm[8][DMAX_F];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= nown) return;
-    double aa;
-    load_query_row(Xf + (int64_t)row_point[r] * ldf, d, lane, a_sm[w], aa);
-    for (int c = lane; c < C; c += 32) {
-        double s = 0.0;
-        for (int t = 0; t < d; ++t) s = fma(a_sm[w][t], mcT[(int64_t)t * Cp + c], s);
-        tq[(int64_t)c * ldt + r] = (float)fmax(aa - 2.0 * s + mc2[c], 0.0);
+    __shared__ __align__(16) double As[16][64 + 2];
+    __shared__ __align__(16) double Bs[16][64 + 2];
+    __shared__ double aa_s[64];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int64_t u0 = (int64_t)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 64;
+    // loader roles: A: query lq, features 4*lk..4*lk+3 of the stage; B: feature bk, bins 4*bc..4*bc+3
+    const int lq = tid >> 2, lk = tid & 3;
+    const int bk = tid >> 4, bc = tid & 15;
+    const int64_t uq = u0 + lq;
+    const float *xrow = uq < U ? Xf + (int64_t)qpoint[uq] * ldf : nullptr;
+    double acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    double aa[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < d; k0 += 16) {
+        {
+            const int t = k0 + 4 * lk;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xrow && t < ldf) v = *reinterpret_cast<const float4 *>(xrow + t); // pads beyond d are zero (prep_f32_kernel)
+            As[4 * lk + 0][lq] = t + 0 < d ? (double)v.x : 0.0;
+            As[4 * lk + 1][lq] = t + 1 < d ? (double)v.y : 0.0;
+            As[4 * lk + 2][lq] = t + 2 < d ? (double)v.z : 0.0;
+            As[4 * lk + 3][lq] = t + 3 < d ? (double)v.w : 0.0;
+            const int tb = k0 + bk;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + 4 * bc + j;
+                Bs[bk][4 * bc + j] = (tb < d && c < Cp) ? mcT[(int64_t)tb * Cp + c] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) av[i] = As[k][4 * ty + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bv[j] = Bs[k][4 * tx + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (tx == 0) aa[i] = fma(av[i], av[i], aa[i]);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+            }
+        }
+        __syncthreads();
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) aa_s[4 * ty + i] = aa[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t u = u0 + 4 * ty + i;
+        if (u >= U) continue;
+        const double au = aa_s[4 * ty + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * tx + j;
+            if (c < C) tqs[u * Cp + c] = (float)fmax(au - 2.0 * acc[i][j] + mc2[c], 0.0);
+        }
     }
 }
 
-// one warp per query slot (ALL U of them: every rank must start the speculation from the same vector): bin whose seed
-// centroid is nearest (lowest bin on ties); bins without seeds are skipped; C when no bin has seeds
-__global__ void __launch_bounds__(256) guess_all_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
-                                                        int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
-                                                        const double *__restrict__ mc2, const int32_t *__restrict__ mcnt, int32_t C,
-                                                        int32_t *__restrict__ guess_all)
+// one warp per query slot: bin with the smallest |a_u - m_c|^2 among the bins that have seeds (lowest bin on ties); C if none
+__global__ void __launch_bounds__(256) guess_from_terms_kernel(const float *__restrict__ tqs, int64_t U, int32_t Cp, int32_t C,
+                                                               const int32_t *__restrict__ mcnt, int32_t *__restrict__ guess_all)
 {
-    __shared__ double a_sm[8][DMAX_F];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= U) return;
-    double aa;
-    load_query_row(Xf + (int64_t)qpoint[u] * ldf, d, lane, a_sm[w], aa);
-    double best = INFINITY;
+    float best = INFINITY;
     int bc = C;
     for (int c = lane; c < C; c += 32) {
         if (mcnt[c] <= 0) continue;
-        double s = 0.0;
-        for (int t = 0; t < d; ++t) s = fma(a_sm[w][t], mcT[(int64_t)t * Cp + c], s);
-        const double val = mc2[c] - 2.0 * s; // |a - m_c|^2 minus the bin-independent |a|^2
-        if (val < best) { best = val; bc = c; } // ascending c per lane: first minimum kept
+        const float v = tqs[u * Cp + c];
+        if (v < best) { best = v; bc = c; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(CHB_FULL, best, o);
+        const float ov = __shfl_xor_sync(CHB_FULL, best, o);
         const int oc = __shfl_xor_sync(CHB_FULL, bc, o);
         if (ov < best || (ov == best && oc < bc)) { best = ov; bc = oc; }
     }
     if (lane == 0) guess_all[u] = bc;
+}
+
+// tq[c][r] = tqs[slot of row r][c] for the owned rows: 32 x 32 tiles through shared memory, coalesced both ways
+__global__ void __launch_bounds__(256) query_terms_gather_kernel(const float *__restrict__ tqs, int32_t Cp, int64_t u_first,
+                                                                 const int32_t *__restrict__ row_slot, int64_t nown, int32_t C,
+                                                                 int64_t ldt, float *__restrict__ tq)
+{
+    __shared__ float tile[32][33];
+    const int x = threadIdx.x & 31, y = threadIdx.x >> 5; // 8 rows of the tile per pass
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int i = y; i < 32; i += 8) {
+        const int64_t r = r0 + i;
+        const int c = c0 + x;
+        tile[i][x] = (r < nown && c < C) ? tqs[(u_first + row_slot[r]) * Cp + c] : 0.f;
+    }
+    __syncthreads();
+    for (int j = y; j < 32; j += 8) {
+        const int c = c0 + j;
+        const int64_t r = r0 + x;
+        if (r < nown && c < C) tq[(int64_t)c * ldt + r] = tile[x][j];
+    }
 }
 
 __global__ void guess_scatter_kernel(const int32_t *__restrict__ qpoint, const int32_t *__restrict__ guess_all, int64_t U, int32_t C,
@@ -1391,7 +1461,9 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
-    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
+    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
+    c->f_tqs = nullptr;
+    c->f_cap_tqs = 0; cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
     c->f_slot_row = nullptr;
     c->f_sq_row = nullptr;
     c->f_seedT = nullptr;
@@ -1516,9 +1588,11 @@ int chb_fused_setup(chb_ctx *c)
                                                                  c->f_mcT, Cp);
         c->tm.launches_other += 2;
         if (c->U > 0) {
-            guess_all_kernel<<<nblk(c->U * 32, 256), 256, 0, c->stream>>>(c->qpoint, c->U, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2,
-                                                                         c->f_mcnt, C, c->f_guess_all);
-            ++c->tm.launches_other;
+            if (reserve(c, &c->f_tqs, &c->f_cap_tqs, c->U * (int64_t)Cp)) return CHB_ENOMEM;
+            dim3 gt((unsigned)((c->U + 63) / 64), (unsigned)((C + 63) / 64));
+            centroid_terms_kernel<<<gt, 256, 0, c->stream>>>(c->qpoint, c->U, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2, C, c->f_tqs);
+            guess_from_terms_kernel<<<nblk(c->U * 32, 256), 256, 0, c->stream>>>(c->f_tqs, c->U, Cp, C, c->f_mcnt, c->f_guess_all);
+            c->tm.launches_other += 2;
         }
         if (nown > 0) {
             // rows = owned slots ordered by guessed bin (stable), so that a 128-row block prunes the same bins
@@ -1543,8 +1617,8 @@ int chb_fused_setup(chb_ctx *c)
                                                                       c->f_row_pt, c->f_ub, c->f_slot_row, c->f_sq_row);
             split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
-            query_terms_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, nown, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2,
-                                                                           C, c->f_ldt, c->f_tq);
+            dim3 gq((unsigned)((nown + 31) / 32), (unsigned)((C + 31) / 32));
+            query_terms_gather_kernel<<<gq, 256, 0, c->stream>>>(c->f_tqs, Cp, c->u0, c->f_row_slot, nown, C, c->f_ldt, c->f_tq);
             c->tm.launches_other += 4;
         }
         CHB_CUDA(c, cudaGetLastError());
