@@ -124,23 +124,6 @@ __global__ void repack_features_kernel(const double *__restrict__ src, int64_t n
     dst[i] = t < d ? src[r * d + t] : 0.0;
 }
 
-// fused-mode fallback: owned slot -> permutation position and point; the row's cached lists are invalidated so that
-// the exact-path kNN kernel recomputes every bin of that query from scratch
-__global__ void fallback_prepare_kernel(const int32_t *__restrict__ fb_rows, int32_t cnt, const int32_t *__restrict__ qpoint_own,
-                                        const int32_t *__restrict__ pos, int32_t C, int32_t *__restrict__ items,
-                                        int32_t *__restrict__ points, int32_t *__restrict__ knn_cnt, float *__restrict__ thr)
-{
-    const int i = blockIdx.x;
-    if (i >= cnt) return;
-    const int r = fb_rows[i];
-    const int pt = qpoint_own[r];
-    if (threadIdx.x == 0) { items[i] = pos[pt]; points[i] = pt; }
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        knn_cnt[(int64_t)r * C + c] = -1;
-        thr[(int64_t)r * C + c] = INFINITY; // no admission threshold next round (fused.cu threshold_kernel)
-    }
-}
-
 __global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
                                    int32_t *__restrict__ rows)
 {
@@ -296,7 +279,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
-    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->f_fb_items); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
+    dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
     chb_fused_free(c); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     delete[] c->own_pos_host;

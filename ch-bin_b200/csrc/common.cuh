@@ -125,12 +125,10 @@ struct chb_ctx {
     int4 *f_items = nullptr;                   // surviving (row block, bin) work items of the fused kernel, row-block order
     int32_t *f_cta_begin = nullptr;            // sm_count + 1 : item range per CTA (balanced by tile count)
     uint8_t *f_skip = nullptr;                 // (#row blocks) x C : tiles of this (row block, bin) are skipped this round
-    int32_t *f_row_slot = nullptr, *f_row_pt = nullptr, *f_guess_slot = nullptr; // row -> owned slot / point; guessed bin per slot
+    int32_t *f_row_slot = nullptr, *f_row_pt = nullptr; // row -> owned slot / point
     float *f_ub = nullptr, *f_ub_slot = nullptr; // upper bound of min_c hull distance per row / per slot
     float *f_ym2 = nullptr;                    // 2 (C + 1) : per-bin maxima of |y|^2 and |column term| of this round
     bool f_asplit_ready = false;
-    int32_t *f_fb_items = nullptr; // positions of the fallback queries
-    int64_t f_cap_fb = 0;
 
     int2 *fallback = nullptr; // pairs the small-k QP kernel hands to the general one
     int64_t fallback_cap = 0;

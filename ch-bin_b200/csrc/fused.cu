@@ -2,29 +2,32 @@
 //
 // Replaces, for one speculate/repair round, create_in_mem_distance_matrix + find_nearest_from_cluster
 // (/root/reference/ch_bin/core/clustering/distance_matrix.py:33-62) for every (query, bin) pair, without ever
-// writing a distance matrix:
+// writing a distance matrix.  Per label set (chb_fused_setup): bin reference points from the seed contigs, the
+// U x C centroid terms (FP64 GEMM), the speculation start, per-query upper bounds, the row order (owned slots sorted
+// by guessed bin) and the resident TF32 query operand.  Per round (chb_round_fused):
 //
 //  1. "column entries": every point becomes a column of the bin(s) in which some query can see it this round.
 //     The label the query at permutation position p sees for point i is  pos[i] < p ? tent[i] : old[i]
 //     (algorithm.py:46-60), so point i is a column of bin tent[i] visible when p > pos[i], and -- if different --
 //     of bin old[i] visible when p < pos[i]; when both labels agree it is one column visible when p != pos[i]
 //     (which also removes the query itself, algorithm.py:50).  Columns are counting-sorted by bin, each bin padded
-//     to a multiple of 128, and the TF32 hi/lo operand rows are gathered in that order.
-//  2. gram_select_kernel: persistent CTA per 128-query row block, looping over the 128-column tiles (= one bin
-//     each).  TMA -> 3-stage smem ring -> tcgen05.mma kind::tf32 (3-term split, see gram_tc.cu) -> FP32
-//     accumulators double-buffered in TMEM.  While the tensor core works on tile t+1, the four epilogue warps read
-//     tile t from TMEM: thread r owns query row r, forms A = nrm[r] + nrm[c] - 2 acc for its 128 columns, masks
-//     (two threads per row, one per 64-column half) by visibility, and keeps the KR smallest (A, point) pairs of the
-//     current bin in REGISTERS
-//     (branch-free swap insertion; candidates are found with a 32-column bitmask and the warp loops only
-//     max-over-lanes popcount times).  At a bin boundary the list is flushed to global memory.
-//  3. rerank_kernel: per (query, bin): with |A - d^2| <= E, the k smallest-A candidates are EXACTLY the reference's
-//     neighbours whenever A_(k+1) > A_(k) + 2E; otherwise only the ambiguous candidates (A within 2E of the
-//     boundary) get scipy's exact recipe (sequential sum, no FMA) and are ranked by exact (distance, index).
-//     A pair goes to the QP work list only if its neighbour SET changed; if the kept list could have missed a
-//     candidate (more than KR keys inside the slack: duplicate contigs) the query falls back to knn.cu.
+//     to a multiple of 128; column_gather_kernel writes the per-bin-centred TF32 [hi | lo] operand rows in that order.
+//  2. threshold_kernel: per (row, bin) the pruning test (bin cannot be the argmin: admission threshold -inf, nothing
+//     else happens for the pair), else the key error bound E and the admission threshold T0 from the cached set;
+//     skip_kernel / items_kernel turn the surviving (row block, bin) pairs into a balanced work list.
+//  3. gram_select_kernel: one persistent CTA per SM walking its work items.  TMA: the row block's query operand is
+//     loaded once and stays resident, the column operand streams through a 3-4-stage ring -> tcgen05.mma kind::tf32
+//     (3-term hi/lo split, see gram_tc.cu) -> FP32 accumulators double-buffered in TMEM.  Eight decoupled epilogue
+//     warps read a tile with one tcgen05.ld per thread (thread = query row x 64-column half), form
+//     key = tq + column term - 2 acc, screen by visibility and T0, and keep the KR smallest (key, point) pairs of the
+//     item's bin in REGISTERS (candidate stack in shared memory, one drain site, rank-by-counting insertion).
+//  4. rerank_kernel, over each row's surviving bins: with |key - d^2| <= E the k smallest keys ARE the reference's
+//     neighbours whenever key_(k+1) > key_(k) + 2E; otherwise only the candidates inside the 2E window get scipy's exact
+//     recipe (sequential sum, no FMA) and are ranked by exact (distance, index).  A pair goes to the QP work list only
+//     if its neighbour SET changed.  Pairs whose kept lists could be incomplete (more than KR keys inside the window:
+//     duplicate contigs) are redone exactly on the device by exact_pairs_kernel.
 //
-// Roofline: tensor pipe / L2->SM operand traffic (both operands stream: 2*128*Kp*4 bytes per 128x128 tile).
+// Roofline of gram_select_kernel: tensor pipe, co-limited by the CUDA-core selection epilogue.
 #include <cuda.h>
 
 #include <algorithm>
@@ -97,16 +100,6 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *m
                  ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
                  : "memory");
 }
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr)
-{
-    uint64_t desc = 0;
-    desc |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    desc |= (uint64_t)1 << 16;
-    desc |= (uint64_t)(1024u >> 4) << 32;
-    desc |= (uint64_t)1 << 46;
-    desc |= (uint64_t)2 << 61;
-    return desc;
-}
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
@@ -152,7 +145,6 @@ __global__ void entries_count_kernel(const int32_t *__restrict__ tent, const int
 __global__ void entries_scan_kernel(const int32_t *__restrict__ bin_cnt, int32_t C, int32_t *__restrict__ seg_off,
                                     int32_t *__restrict__ cursor, int32_t *__restrict__ tile_bin, int32_t *__restrict__ ntiles_out)
 {
-    __shared__ int total;
     if (threadIdx.x == 0) {
         int off = 0;
         for (int c = 0; c < C; ++c) {
@@ -160,7 +152,6 @@ __global__ void entries_scan_kernel(const int32_t *__restrict__ bin_cnt, int32_t
             off += (bin_cnt[c] + BN - 1) / BN * BN;
         }
         seg_off[C] = off;
-        total = off;
         *ntiles_out = off / BN;
     }
     __syncthreads();
@@ -168,7 +159,6 @@ __global__ void entries_scan_kernel(const int32_t *__restrict__ bin_cnt, int32_t
         cursor[c] = 0;
         for (int t = seg_off[c] / BN; t < seg_off[c + 1] / BN; ++t) tile_bin[t] = c;
     }
-    (void)total;
 }
 
 __global__ void entries_scatter_kernel(const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
@@ -286,23 +276,7 @@ __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__r
     if (threadIdx.x == 0) mc2[c] = red[0];
 }
 
-// a_q . m_c for the bins c = lane, lane + 32, ... of one query: the query row sits in shared memory, every lane walks
-// the features for its own bins (coalesced reads of the transposed centre table, no shuffles).  The summation order is
-// fixed, so every rank of a multi-GPU run obtains the same bits.
 constexpr int DMAX_F = 160; // fused mode: d <= 160
-__device__ __forceinline__ void load_query_row(const float *__restrict__ xr, int d, int lane, double *a_s, double &aa)
-{
-    double s = 0.0;
-    for (int t = lane; t < d; t += 32) {
-        const double v = (double)xr[t];
-        a_s[t] = v;
-        s = fma(v, v, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(CHB_FULL, s, o);
-    aa = s;
-    __syncwarp();
-}
 
 // |a_u - m_c|^2 for every query slot u and every bin c, once per label set: an FP64 GEMM (U x C x d) in 64 x 64 tiles, 4 x 4
 // outputs per thread, 16 features per shared-memory stage.  tqs[u][c] = fl32( |a_u|^2 - 2 a_u.m_c + |m_c|^2 ), a_u = the FP32
@@ -1113,7 +1087,7 @@ template <int G>
 __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ cand_key, const int32_t *__restrict__ cand_idx, int KR,
                                                      const int32_t *__restrict__ bin_cnt, const double *__restrict__ X, int32_t ldx,
                                                      int32_t d, const int32_t *__restrict__ row_point,
-                                                     const int32_t *__restrict__ row_slot, double *__restrict__ pair_dist,
+                                                     const int32_t *__restrict__ row_slot,
                                                      const float *__restrict__ slack_tab, int32_t C,
                                                      int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
@@ -1142,11 +1116,10 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
         const int64_t pair = sl * C + c;
         const int64_t rpair = r * C + c;
         const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
-        const bool pruned = false;
         const int mo = act ? knn_cnt[pair] : 0;
         float ka = INFINITY;
         int ki = INT32_MAX;
-        if (act && !pruned && bin_cnt[c] > 0 && gl < K2) {
+        if (act && bin_cnt[c] > 0 && gl < K2) {
             ka = cand_key[rpair * K2 + gl];
             ki = cand_idx[rpair * K2 + gl];
         }
@@ -1239,12 +1212,8 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
                 if (gl >= m && gl < k) knn_idx[pair * k + gl] = -1;
                 if (gl == 0) {
                     knn_cnt[pair] = m;
-                    if (pruned) {
-                        pair_dist[pair] = INFINITY;
-                    } else {
-                        const int w = atomicAdd(work_count, 1);
-                        work[w] = make_int2((int)sl, c);
-                    }
+                    const int w = atomicAdd(work_count, 1);
+                    work[w] = make_int2((int)sl, c);
                 }
             }
         }
@@ -1461,7 +1430,7 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
-    cudaFree(c->f_ub); cudaFree(c->f_guess_slot); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
+    cudaFree(c->f_ub); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
     c->f_tqs = nullptr;
     c->f_cap_tqs = 0; cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
     c->f_slot_row = nullptr;
@@ -1475,7 +1444,7 @@ void chb_fused_free(chb_ctx *c)
     c->f_skip = nullptr;
     c->f_items = nullptr;
     c->f_cta_begin = nullptr;
-    c->f_row_slot = c->f_row_pt = c->f_guess_slot = nullptr;
+    c->f_row_slot = c->f_row_pt = nullptr;
     c->f_ub = c->f_ub_slot = nullptr;
     c->f_thr = c->f_t0 = c->f_a2 = c->f_tq = c->f_slack = c->f_ym2 = nullptr;
     c->f_mc = c->f_mc2 = nullptr;
@@ -1573,7 +1542,6 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_slot_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_sq_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_bins, &z, c->f_ldt * C)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_guess_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ub_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         c->f_cap_thr = c->f_ldt * C;
         c->f_asplit_ready = false;
@@ -1682,8 +1650,7 @@ int chb_round_fused(chb_ctx *c)
         chb_stage_timer t(c, CHB_ST_KNN);
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
         kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
-            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pair_dist, c->f_slack, C,
-            k, c->knn_idx, c->knn_cnt, c->work, c->counters,
+            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->f_slack, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
             c->f_fb_pairs, c->f_fb_cap, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins);
         // pairs the re-rank could not settle from the kept lists (rare): exact redo, no host round trip -- the grid is
         // fixed and walks the device-side list
