@@ -844,10 +844,21 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             const float t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : -INFINITY;
             const float nr = rvalid ? tq_tab[(int64_t)cur_bin * ldt + gr] : 0.f;
             L.reset();
+            // rows are ordered by guessed bin, so in the "side" bins of a row block only a few rows survive the pruning:
+            // a warp none of whose 32 rows admits anything (t0 = -inf) only hands the accumulator buffers back
+            const bool wskip = __all_sync(CHB_FULL, !(t0 > -INFINITY));
             for (int t = item.z; t < item.z + item.w; ++t) {
                 const int buf = (int)(tt & 1);
                 const uint32_t tph = (uint32_t)((tt >> 1) & 1);
                 ++tt;
+                if (wskip) {
+                    mbar_wait(&S.tmem_full_bar[buf], tph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.tmem_empty_bar[buf]);
+                    continue;
+                }
                 if (lane < 6 && (t + 1 < item.z + item.w || it + 1 < item_end)) {
                     // next tile's metadata -> L1: three arrays, two 128-byte lines each
                     const int tn = t + 1 < item.z + item.w ? t + 1 : items[it + 1].z;
@@ -937,7 +948,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 }
 #undef SCREEN_STEP
             }
-            if (rvalid) { // the item's (half-)list is complete
+            if (rvalid && !wskip) { // the item's (half-)list is complete (pruned rows' lists are never read)
                 float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
                 int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
 #pragma unroll
