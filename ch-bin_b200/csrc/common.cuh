@@ -126,7 +126,8 @@ struct chb_ctx {
     int32_t *f_cta_begin = nullptr;            // sm_count + 1 : item range per CTA (balanced by tile count)
     uint8_t *f_skip = nullptr;                 // (#row blocks) x C : tiles of this (row block, bin) are skipped this round
     int32_t *f_row_slot = nullptr, *f_row_pt = nullptr; // row -> owned slot / point
-    float *f_ub = nullptr, *f_ub_slot = nullptr; // upper bound of min_c hull distance per row / per slot
+    float *f_ub = nullptr, *f_ubk2 = nullptr; // per row: upper bound of min_c hull distance; squared distance to the k-th nearest seed
+    int32_t *f_row_guess = nullptr, *f_rhist = nullptr; // guessed bin per row; histogram / cursors of the row grouping
     float *f_ym2 = nullptr;                    // 2 (C + 1) : per-bin maxima of |y|^2 and |column term| of this round
     bool f_asplit_ready = false;
 

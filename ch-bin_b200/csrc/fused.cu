@@ -429,36 +429,82 @@ __global__ void seed_transpose_kernel(const double *__restrict__ X, int32_t ldx,
     seedT[(int64_t)t * ns + sidx] = X[(int64_t)seed_idx[sidx] * ldx + t];
 }
 
-// one warp per owned slot: UB = distance to the nearest seed of the guessed bin (one lane per seed)
-__global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__ qpoint_own, const int32_t *__restrict__ guess_own,
+// one warp per row: UB = distance to the nearest seed of the guessed bin, and the squared distance to its k-th nearest
+// seed (an admission threshold for the first round, when there is no cached neighbour set yet: all seeds are visible
+// members of the bin, so the bin's k-th smallest squared distance cannot exceed it).  One lane per seed; rows come in
+// guessed-bin order, so the warps of a CTA read the same seed tile.
+__global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__ row_pt, const int32_t *__restrict__ row_guess,
                                                      int64_t nown, const double *__restrict__ X, int32_t ldx, int32_t d, int32_t C,
-                                                     const int32_t *__restrict__ seed_off, const double *__restrict__ seedT, int64_t ns,
-                                                     float *__restrict__ ub_out)
+                                                     int32_t k, const int32_t *__restrict__ seed_off, const double *__restrict__ seedT,
+                                                     int64_t ns, float *__restrict__ ub_out, float *__restrict__ ubk2_out)
 {
     __shared__ double q_sm[8][DMAX_F];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (u >= nown) return;
-    const double *xq = X + (int64_t)qpoint_own[u] * ldx;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= nown) return;
+    const double *xq = X + (int64_t)row_pt[r] * ldx;
     for (int t = lane; t < d; t += 32) q_sm[w][t] = xq[t];
     __syncwarp();
-    const int g = guess_own[u];
+    const int g = row_guess[r];
+    double v[4] = {INFINITY, INFINITY, INFINITY, INFINITY}; // this lane's seeds (up to 128 per bin)
     double ub2 = INFINITY;
+    int nseed = 0;
     if (g < C) {
-        for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32) {
+        nseed = seed_off[g + 1] - seed_off[g];
+        int slot = 0;
+        for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32, ++slot) {
             double s = 0.0;
             for (int t = 0; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; s = fma(df, df, s); }
             ub2 = fmin(ub2, s);
+            if (slot == 0) v[0] = s; else if (slot == 1) v[1] = s; else if (slot == 2) v[2] = s; else if (slot == 3) v[3] = s;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) ub2 = fmin(ub2, __shfl_xor_sync(CHB_FULL, ub2, o));
-    if (lane == 0) ub_out[u] = ub2 < INFINITY ? __double2float_ru(sqrt(ub2) * (1.0 + 1e-9)) : INFINITY;
+    // k-th smallest over the warp: k rounds of "extract the minimum"
+    double kth = INFINITY;
+    if (nseed >= k && nseed <= 128) {
+        for (int round = 0; round < k; ++round) {
+            const double mine = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
+            double m = mine;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(CHB_FULL, m, o));
+            kth = m;
+            const unsigned owners = __ballot_sync(CHB_FULL, mine == m);
+            if (lane == __ffs(owners) - 1) { // remove one copy of the minimum
+                if (v[0] == m) v[0] = INFINITY; else if (v[1] == m) v[1] = INFINITY; else if (v[2] == m) v[2] = INFINITY; else v[3] = INFINITY;
+            }
+        }
+    }
+    if (lane == 0) {
+        ub_out[r] = ub2 < INFINITY ? __double2float_ru(sqrt(ub2) * (1.0 + 1e-9)) : INFINITY;
+        ubk2_out[r] = kth < INFINITY ? __double2float_ru(kth * (1.0 + 1e-9)) : INFINITY;
+    }
+}
+
+// rows = owned slots grouped by guessed bin (any order inside a group): histogram, scan, scatter -- no host round trip
+__global__ void row_hist_kernel(const int32_t *__restrict__ guess_own, int64_t nown, int32_t *__restrict__ hist)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nown) atomicAdd(&hist[guess_own[u]], 1);
+}
+__global__ void row_scan_kernel(const int32_t *__restrict__ hist, int32_t nb, int32_t *__restrict__ cursor)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int acc = 0;
+        for (int b = 0; b < nb; ++b) { cursor[b] = acc; acc += hist[b]; }
+    }
+}
+__global__ void row_scatter_kernel(const int32_t *__restrict__ guess_own, int64_t nown, int32_t *__restrict__ cursor,
+                                   int32_t *__restrict__ row_slot)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < nown) row_slot[atomicAdd(&cursor[guess_own[u]], 1)] = (int32_t)u;
 }
 
 __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const int32_t *__restrict__ qpoint_own,
-                                  const float *__restrict__ ub_slot, const float *__restrict__ nrm, int64_t nown,
-                                  int32_t *__restrict__ row_pt, float *__restrict__ ub_row, int32_t *__restrict__ slot_row,
+                                  const int32_t *__restrict__ guess_own, const float *__restrict__ nrm, int64_t nown,
+                                  int32_t *__restrict__ row_pt, int32_t *__restrict__ row_guess, int32_t *__restrict__ slot_row,
                                   float *__restrict__ sq_row)
 {
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -466,7 +512,7 @@ __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const in
     const int sl = row_slot[r];
     const int pt = qpoint_own[sl];
     row_pt[r] = pt;
-    ub_row[r] = ub_slot[sl];
+    row_guess[r] = guess_own[sl];
     slot_row[sl] = (int32_t)r;
     sq_row[r] = __fmul_ru(__fsqrt_ru(nrm[pt]), 1.000001f); // >= |a_q|
 }
@@ -980,7 +1026,8 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
                                  const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
                                  const float *__restrict__ nrm, const unsigned int *__restrict__ nrm_max_bits,
                                  const float *__restrict__ ym2, const float *__restrict__ tcmax, const float *__restrict__ tq_tab,
-                                 const float *__restrict__ ub_row, const float *__restrict__ sq_row, double eps_rel, int64_t nown,
+                                 const float *__restrict__ ub_row, const float *__restrict__ sq_row,
+                                 const float *__restrict__ ubk2_row, const int32_t *__restrict__ row_guess, double eps_rel, int64_t nown,
                                  int32_t C, int32_t k, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
                                  int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins)
 {
@@ -1021,6 +1068,8 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
             if (ok) out = __fadd_ru(ub, __fmul_ru(3.f, E));
         }
     }
+    // no usable cache: in the query's guessed bin the k-th nearest SEED bounds the k-th smallest squared distance
+    if (out == INFINITY && c == row_guess[r] && ubk2_row[r] < INFINITY) out = __fadd_ru(ubk2_row[r], __fmul_ru(3.f, E));
     t0_tab[(int64_t)c * ldt + r] = out;
 }
 
@@ -1441,7 +1490,7 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
-    cudaFree(c->f_ub); cudaFree(c->f_ub_slot); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
+    cudaFree(c->f_ub); cudaFree(c->f_ubk2); cudaFree(c->f_row_guess); cudaFree(c->f_rhist); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
     c->f_tqs = nullptr;
     c->f_cap_tqs = 0; cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
     c->f_slot_row = nullptr;
@@ -1456,7 +1505,8 @@ void chb_fused_free(chb_ctx *c)
     c->f_items = nullptr;
     c->f_cta_begin = nullptr;
     c->f_row_slot = c->f_row_pt = nullptr;
-    c->f_ub = c->f_ub_slot = nullptr;
+    c->f_ub = c->f_ubk2 = nullptr;
+    c->f_row_guess = c->f_rhist = nullptr;
     c->f_thr = c->f_t0 = c->f_a2 = c->f_tq = c->f_slack = c->f_ym2 = nullptr;
     c->f_mc = c->f_mc2 = nullptr;
     c->f_mcnt = nullptr;
@@ -1512,6 +1562,7 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_ym2, &z, 2 * (C + 1))) return CHB_ENOMEM; // [0,C): max |y|^2, [C+1, 2C+1): max |column term|
         z = 0; if (reserve(c, &c->f_mcnt, &z, C + 1)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_mc2, &z, C + 1)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_rhist, &z, 2 * (C + 2))) return CHB_ENOMEM;
         c->f_cap_bins = C + 1;
     }
     if (reserve(c, &c->f_mcT, &c->f_cap_mcT, (int64_t)((C + 31) & ~31) * c->d)) return CHB_ENOMEM;
@@ -1553,7 +1604,8 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_slot_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_sq_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_bins, &z, c->f_ldt * C)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_ub_slot, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_ubk2, &z, c->f_ldt)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_row_guess, &z, c->f_ldt)) return CHB_ENOMEM;
         c->f_cap_thr = c->f_ldt * C;
         c->f_asplit_ready = false;
     }
@@ -1574,26 +1626,19 @@ int chb_fused_setup(chb_ctx *c)
             c->tm.launches_other += 2;
         }
         if (nown > 0) {
-            // rows = owned slots ordered by guessed bin (stable), so that a 128-row block prunes the same bins
+            // rows = owned slots grouped by guessed bin, so that a 128-row block prunes the same bins
             const int64_t ns = std::max<int64_t>(n - c->U, 1);
             if (reserve(c, &c->f_seedT, &c->f_cap_seedT, ns * c->d)) return CHB_ENOMEM;
             seed_transpose_kernel<<<nblk(ns * c->d, 256), 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_idx, n - c->U, c->f_seedT);
-            row_ub_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->qpoint + c->u0, c->f_guess_all + c->u0, nown, c->X, c->ldx,
-                                                                      c->d, C, c->seed_off, c->f_seedT, n - c->U, c->f_ub_slot);
-            std::vector<int32_t> guess((size_t)nown), order((size_t)nown);
-            CHB_CUDA(c, cudaMemcpyAsync(guess.data(), c->f_guess_all + c->u0, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
-            CHB_CUDA(c, cudaStreamSynchronize(c->stream));
-            {
-                std::vector<int64_t> start((size_t)C + 2, 0);
-                for (int64_t u = 0; u < nown; ++u) ++start[(size_t)guess[(size_t)u] + 1];
-                for (int32_t b = 0; b <= C; ++b) start[(size_t)b + 1] += start[(size_t)b];
-                for (int64_t u = 0; u < nown; ++u) order[(size_t)start[(size_t)guess[(size_t)u]]++] = (int32_t)u;
-            }
-            // stream-ordered: a synchronous cudaMemcpy from pageable memory only waits for the staging copy, and the legacy
-            // stream it runs on is not ordered against this context's non-blocking stream
-            CHB_CUDA(c, cudaMemcpyAsync(c->f_row_slot, order.data(), sizeof(int32_t) * (size_t)nown, cudaMemcpyHostToDevice, c->stream));
-            row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_ub_slot, c->nrm, nown,
-                                                                      c->f_row_pt, c->f_ub, c->f_slot_row, c->f_sq_row);
+            CHB_CUDA(c, cudaMemsetAsync(c->f_rhist, 0, sizeof(int32_t) * (size_t)(C + 2), c->stream));
+            row_hist_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_guess_all + c->u0, nown, c->f_rhist);
+            row_scan_kernel<<<1, 32, 0, c->stream>>>(c->f_rhist, C + 1, c->f_rhist + C + 2);
+            row_scatter_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_guess_all + c->u0, nown, c->f_rhist + C + 2, c->f_row_slot);
+            row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_guess_all + c->u0, c->nrm, nown,
+                                                                      c->f_row_pt, c->f_row_guess, c->f_slot_row, c->f_sq_row);
+            row_ub_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, c->f_row_guess, nown, c->X, c->ldx, c->d, C, k,
+                                                                      c->seed_off, c->f_seedT, n - c->U, c->f_ub, c->f_ubk2);
+            c->tm.launches_other += 2;
             split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
             dim3 gq((unsigned)((nown + 31) / 32), (unsigned)((C + 31) / 32));
@@ -1639,8 +1684,8 @@ int chb_round_fused(chb_ctx *c)
     CHB_CUDA(c, cudaMemsetAsync(c->f_row_nb, 0, sizeof(int32_t) * (size_t)nown, c->stream));
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
-        reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, eps_rel,
-        nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins);
+        reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
+        c->f_row_guess, eps_rel, nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins);
     const int64_t nrb = (nown + BM - 1) / BM;
     skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7]);
