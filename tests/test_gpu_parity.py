@@ -380,3 +380,58 @@ def test_fit_cluster_fortran_order_and_errors():
         chbin_b200.fit_cluster(X, 3, bins, None, 5, 10, qp_solver="quadprog")
     with pytest.raises(ValueError):
         chbin_b200.fit_cluster(X, 3, bins, None, 64, 10)
+
+
+def _same_as_oracle(X, C, bins, k, iters, **kw):
+    perms = oracle.draw_permutations(bins, iters, seed=0)
+    ref = oracle.fit_cluster(X, C, bins, None, k, iters, perms=perms, threads=2) if perms.shape[1] else bins.copy()
+    np.random.seed(0)
+    got, info = chbin_b200.fit_cluster(X, C, bins, None, k, iters, return_info=True, **kw)
+    assert got.dtype == np.int64 and np.array_equal(got, ref)
+    return info
+
+
+def test_edge_nothing_to_assign():
+    """Every contig already carries a label: zero query slots, zero QPs, labels returned unchanged (algorithm.py:38-66)."""
+    X, bins, truth = synth.make_contig_features(300, 3, 1, 20, seed=2)
+    info = _same_as_oracle(X, 3, truth.copy(), 5, 10)
+    assert info["iterations"] == 1 and info["converged"]
+
+
+def test_edge_single_bin_and_single_neighbour():
+    X, bins, _ = synth.make_contig_features(500, 1, 2, 30, seed=3)
+    _same_as_oracle(X, 1, bins, 5, 4)       # C = 1: nothing to choose, still one hull distance per query
+    X, bins, _ = synth.make_contig_features(600, 4, 1, 10, seed=4)
+    _same_as_oracle(X, 4, bins, 1, 4)       # k = 1: the hull is a point, the distance is the nearest member's
+
+
+def test_edge_bins_without_seeds_and_tiny_bins():
+    """Bins with no seed contig at all (num_clusters = max label + 1 leaves gaps), a bin with a single seed, and k larger
+    than every bin at the start: find_nearest_from_cluster returns all members (distance_matrix.py:58-59)."""
+    X, bins, truth = synth.make_contig_features(700, 5, 3, 6, seed=6, concentration=400.0)
+    bins[bins == 2] = -1                     # bin 2 has no seeds: it can never win, and has no reference point
+    keep = np.where(bins == 4)[0]
+    bins[keep[1:]] = -1                      # bin 4 starts with one member
+    _same_as_oracle(X, 5, bins, 9, 6)
+
+
+def test_edge_wide_features_take_the_matrix_path():
+    """d > 160 does not fit the resident operand of the fused kernel: the library falls back to distance mode 1 on its
+    own (FP32 candidate matrix + scan), still exact."""
+    rng = np.random.default_rng(8)
+    X, bins, _ = synth.make_contig_features(500, 4, 40, 15, seed=8)     # d = 176
+    assert X.shape[1] > 160
+    info = _same_as_oracle(X, 4, bins, 5, 5)
+    assert info["timers"]["launches_gram"] == 0 and info["timers"]["launches_knn"] > 0
+    X2 = np.ascontiguousarray(rng.normal(size=(400, 7)))                # d = 7: tabulated MMA sequence, one operand box
+    b2 = np.full(400, -1, dtype=np.int64)
+    b2[:30] = np.arange(30) % 3
+    _same_as_oracle(X2, 3, b2, 4, 5)
+
+
+def test_edge_identical_contigs_everywhere():
+    """Many exact duplicates (ties at every rank, zero distances, singular Gram matrices)."""
+    X, bins, _ = synth.make_contig_features(600, 3, 1, 20, seed=9, concentration=200.0)
+    X[100:300] = X[100]
+    X[400:420] = X[0]
+    _same_as_oracle(X, 3, bins, 5, 5)
