@@ -124,6 +124,9 @@ struct chb_ctx {
     float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
     int4 *f_items = nullptr;                   // surviving (row block, bin) work items of the fused kernel, row-block order
     int32_t *f_cta_begin = nullptr;            // sm_count + 1 : item range per CTA (balanced by tile count)
+    int32_t *f_pair_row = nullptr, *f_pair_meta = nullptr, *f_mode = nullptr; // compact (row, bin) pairs: row per pair id; per-bin counters; mode flag
+    float *f_ap = nullptr;                     // cap_pairs x Kp2 : query operand rows gathered in compact pair order
+    int64_t f_cap_ap = 0, f_cap_pairs = 0;
     uint8_t *f_skip = nullptr;                 // (#row blocks) x C : tiles of this (row block, bin) are skipped this round
     int32_t *f_row_slot = nullptr, *f_row_pt = nullptr; // row -> owned slot / point
     float *f_ub = nullptr, *f_ubk2 = nullptr; // per row: upper bound of min_c hull distance; squared distance to the k-th nearest seed

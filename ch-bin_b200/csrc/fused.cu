@@ -595,13 +595,106 @@ __device__ __forceinline__ float pair_slack(double eps_rel, float nrm_q, float y
     return __double2float_ru(e * (1.0 + 1e-6) + 1e-30);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// compaction.  After pruning, the rows that still need a bin are few and scattered over the row blocks (in a "side" bin
+// of a row block typically 5-10 of the 128 rows survive), so contracting (row block x bin) tiles wastes most of every
+// tile.  The surviving (row, bin) pairs are therefore regrouped PER BIN: bin c's survivors become ceil(n_c / 128) dense
+// 128-row blocks whose query operand rows are gathered into a compact buffer.  mode = 1: work items are (pair block,
+// bin); mode = 0 (the compact buffer would overflow: little pruning): items stay (row block, bin) as before.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restrict__ bin_surv, const int32_t *__restrict__ seg_off,
+                                                          int32_t C, int64_t cap_pairs, int32_t G, int32_t *__restrict__ pair_off,
+                                                          int32_t *__restrict__ scratch /* 2 (C + 1) */, int4 *__restrict__ items,
+                                                          int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
+                                                          int32_t *__restrict__ mode)
+{
+    __shared__ int s_mode, s_ti, s_tt;
+    int32_t *item_off = scratch, *tile_cum = scratch + C + 1;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int64_t po = 0;
+        int io = 0, tc = 0;
+        for (int c = 0; c < C; ++c) {
+            const int nb = (bin_surv[c] + BM - 1) / BM, w = (seg_off[c + 1] - seg_off[c]) / BN;
+            pair_off[c] = (int32_t)po;
+            item_off[c] = io;
+            tile_cum[c] = tc;
+            po += (int64_t)nb * BM;
+            if (w > 0) { io += nb; tc += nb * w; }
+        }
+        pair_off[C] = (int32_t)(po < INT32_MAX ? po : INT32_MAX);
+        item_off[C] = io;
+        tile_cum[C] = tc;
+        s_mode = po <= cap_pairs ? 1 : 0;
+        s_ti = io;
+        s_tt = tc;
+        *mode = s_mode;
+    }
+    __syncthreads();
+    if (!s_mode) return; // items_kernel builds the (row block, bin) list instead
+    for (int b = tid; b <= G; b += 1024) cta_begin[b] = INT32_MAX;
+    __syncthreads();
+    const int TI = s_ti, TT = s_tt;
+    for (int c = tid; c < C; c += 1024) {
+        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
+        if (w <= 0) continue;
+        const int nb = item_off[c + 1] - item_off[c];
+        for (int b = 0; b < nb; ++b) {
+            const int it = item_off[c] + b;
+            items[it] = make_int4(pair_off[c] / BM + b, c, seg_off[c] / BN, w);
+            atomicMin(&cta_begin[(int)(((int64_t)(tile_cum[c] + b * w) * G) / (TT > 0 ? TT : 1))], it);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cta_begin[G] = TI;
+        for (int b = G - 1; b >= 0; --b)
+            if (cta_begin[b] > cta_begin[b + 1]) cta_begin[b] = cta_begin[b + 1];
+        totals[0] = TT;
+    }
+}
+
+// compact pair id -> row, per bin (any order inside a bin); padding entries stay -1 (memset)
+__global__ void pairs_fill_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ row_nb,
+                                  const int32_t *__restrict__ row_bins, int64_t nown, int32_t C, const int32_t *__restrict__ pair_off,
+                                  int32_t *__restrict__ pair_cur, int32_t *__restrict__ pair_row)
+{
+    if (!*mode) return;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    const int nb = row_nb[r];
+    for (int j = 0; j < nb; ++j) {
+        const int c = row_bins[r * C + j];
+        pair_row[pair_off[c] + atomicAdd(&pair_cur[c], 1)] = (int32_t)r;
+    }
+}
+
+// compact query operand: row id of the compact buffer <- operand row of its query (zeros for padding)
+__global__ void pairs_gather_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ pair_off, int32_t C,
+                                    const int32_t *__restrict__ pair_row, const float *__restrict__ a2, int32_t Kp2,
+                                    int64_t cap_pairs, float *__restrict__ ap)
+{
+    if (!*mode) return;
+    const int64_t kq = Kp2 / 4;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t id = i / kq;
+    if (id >= cap_pairs || id >= pair_off[C]) return;
+    const int q = (int)(i - id * kq);
+    const int r = pair_row[id];
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r >= 0) v = __ldg(reinterpret_cast<const float4 *>(a2 + (int64_t)r * Kp2) + q);
+    reinterpret_cast<float4 *>(ap + id * Kp2)[q] = v;
+}
+
 // Work list of the fused kernel: one item per surviving (row block, bin) = {row block, bin, first tile, #tiles}, in row-block
 // order, and for each of the G CTAs the contiguous range of items whose cumulative tile count falls into its 1/G share.
 // Whole items only (a (query, bin) list is built by one CTA), so CTAs differ by at most one bin's tiles.  One block.
 __global__ void __launch_bounds__(1024) items_kernel(const uint8_t *__restrict__ skip, int64_t nrb, int32_t C,
                                                      const int32_t *__restrict__ seg_off, int32_t G, int4 *__restrict__ items,
-                                                     int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals)
+                                                     int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
+                                                     const int32_t *__restrict__ mode)
 {
+    if (*mode) return; // pairs_plan_kernel already built the compact (pair block, bin) list
     __shared__ int s_items[1024], s_tiles[1024];
     __shared__ int tot_items, tot_tiles;
     const int tid = threadIdx.x;
@@ -688,7 +781,9 @@ struct TopList {
 // sequence is tabulated in shared memory once per CTA.
 template <int KR, int NKT>
 __global__ void __launch_bounds__(FUSED_THREADS, 1)
-gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int nbox, int nk, int nstage,
+gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_ap,
+                   const __grid_constant__ CUtensorMap map_b, const int32_t *__restrict__ mode_p,
+                   const int32_t *__restrict__ pair_row, int nbox, int nk, int nstage,
                    const int32_t *__restrict__ col_pt,
                    const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b, const float *__restrict__ col_nrm,
                    const float *__restrict__ tq_tab, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
@@ -699,6 +794,9 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // (row block, bin) = {row block, bin, first tile, #tiles}.  Pruned (row block, bin) pairs are not in the list: their
     // tiles are neither loaded, contracted nor screened.  All three warp roles walk the same items.
     const int item_begin = cta_begin[blockIdx.x], item_end = cta_begin[blockIdx.x + 1];
+    // mode 1: item.x is a block of 128 compact (row, bin) pairs of bin item.y, operand rows in the compact buffer (map_ap),
+    // pair_row[] names the query row of each; mode 0: item.x is a row block of the resident operand (map_a)
+    const int mode = *mode_p;
     // dynamic shared memory: [resident query operand: nbox boxes][column ring: nstage boxes][SmemTail]
     extern __shared__ uint8_t smem_raw[];
     uint8_t *base = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -720,6 +818,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_init(&S.a_empty_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_ap) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     }
     if (warp == 2) {
@@ -744,7 +843,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     mbar_wait(&S.a_empty_bar, (uint32_t)((na & 1) ^ 1));
                     mbar_expect_tx(&S.a_full_bar, (uint32_t)nbox * TILE_BYTES);
                     for (int jb = 0; jb < nbox; ++jb)
-                        tma_load_2d(a_res + (size_t)jb * TILE_BYTES, &map_a, &S.a_full_bar, jb * BK, item.x * BM);
+                        tma_load_2d(a_res + (size_t)jb * TILE_BYTES, mode ? &map_ap : &map_a, &S.a_full_bar, jb * BK, item.x * BM);
                     cur_rb = item.x;
                     ++na;
                 }
@@ -883,8 +982,9 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int it = item_begin; it < item_end; ++it) {
             const int4 item = items[it];
             const int cur_bin = item.y;
-            const int64_t gr = (int64_t)item.x * BM + row;
-            const bool rvalid = gr < nrows;
+            const int64_t gid = (int64_t)item.x * BM + row;
+            const int64_t gr = mode ? (int64_t)pair_row[gid] : gid; // the query row this thread works for
+            const bool rvalid = gr >= 0 && gr < nrows;
             const int p = rvalid ? pos[row_point[gr]] : INT32_MIN + 1;
             // admission threshold and query term |a_q - m_c|^2 of (this query, this bin): see threshold_kernel
             const float t0 = rvalid ? t0_tab[(int64_t)cur_bin * ldt + gr] : -INFINITY;
@@ -1029,7 +1129,7 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
                                  const float *__restrict__ ub_row, const float *__restrict__ sq_row,
                                  const float *__restrict__ ubk2_row, const int32_t *__restrict__ row_guess, double eps_rel, int64_t nown,
                                  int32_t C, int32_t k, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
-                                 int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins)
+                                 int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nown * C) return;
@@ -1047,6 +1147,7 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
         }
     }
     row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
+    atomicAdd(&bin_surv[c], 1);
     const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
     const int jq = row_point[r];
     const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
@@ -1427,14 +1528,14 @@ FusedGeom fused_geom(int d)
 }
 
 template <int KR, int NKT>
-int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
+int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &map, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
 {
     CHB_CUDA(c, cudaFuncSetAttribute(gram_select_kernel<KR, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int grid = c->sm_count; // persistent: one CTA per SM, work split by items_kernel
     {
         chb_stage_timer t(c, CHB_ST_GRAM);
         gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
-            ma, mb, g.nbox, g.nk, g.nstage, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq, c->f_row_pt, c->pos, nrows, c->C,
+            ma, map, mb, c->f_mode, c->f_pair_row, g.nbox, g.nk, g.nstage, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq, c->f_row_pt, c->pos, nrows, c->C,
             c->f_t0, c->f_ldt, c->f_items, c->f_cta_begin, c->f_cand_key, c->f_cand_idx);
     }
     CHB_CUDA(c, cudaGetLastError());
@@ -1442,17 +1543,18 @@ int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64
 }
 
 template <int KR>
-int dispatch_nk(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
+int dispatch_nk(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &map, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
 {
     const bool generic = getenv("CHB_FUSED_GENERIC") != nullptr; // test aid: force the tabulated MMA sequence
-    if (!generic && g.nk == 18) return launch_fused<KR, 18>(c, ma, mb, nrows, g);
-    if (!generic && g.nk == 19) return launch_fused<KR, 19>(c, ma, mb, nrows, g);
-    if (!generic && g.nk == 20) return launch_fused<KR, 20>(c, ma, mb, nrows, g);
-    return launch_fused<KR, 0>(c, ma, mb, nrows, g);
+    if (!generic && g.nk == 18) return launch_fused<KR, 18>(c, ma, map, mb, nrows, g);
+    if (!generic && g.nk == 19) return launch_fused<KR, 19>(c, ma, map, mb, nrows, g);
+    if (!generic && g.nk == 20) return launch_fused<KR, 20>(c, ma, map, mb, nrows, g);
+    return launch_fused<KR, 0>(c, ma, map, mb, nrows, g);
 }
-int dispatch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g, int KR)
+int dispatch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &map, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g,
+                   int KR)
 {
-    return KR == 8 ? dispatch_nk<8>(c, ma, mb, nrows, g) : dispatch_nk<16>(c, ma, mb, nrows, g);
+    return KR == 8 ? dispatch_nk<8>(c, ma, map, mb, nrows, g) : dispatch_nk<16>(c, ma, map, mb, nrows, g);
 }
 
 template <typename T>
@@ -1489,7 +1591,7 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
-    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
+    cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_pair_row); cudaFree(c->f_pair_meta); cudaFree(c->f_ap); cudaFree(c->f_mode); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
     cudaFree(c->f_ub); cudaFree(c->f_ubk2); cudaFree(c->f_row_guess); cudaFree(c->f_rhist); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
     c->f_tqs = nullptr;
     c->f_cap_tqs = 0; cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
@@ -1502,6 +1604,9 @@ void chb_fused_free(chb_ctx *c)
     c->f_guess_all = nullptr;
     c->f_cap_guess = c->f_cap_mcT = 0;
     c->f_skip = nullptr;
+    c->f_pair_row = c->f_pair_meta = c->f_mode = nullptr;
+    c->f_ap = nullptr;
+    c->f_cap_ap = c->f_cap_pairs = 0;
     c->f_items = nullptr;
     c->f_cta_begin = nullptr;
     c->f_row_slot = c->f_row_pt = nullptr;
@@ -1559,6 +1664,8 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_seg_off, &z, C + 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cursor, &z, C + 1)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ntiles, &z, 4)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_mode, &z, 4)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_pair_meta, &z, 5 * ((int64_t)C + 2))) return CHB_ENOMEM; // surv, off, cur, item_off, tile_cum
         z = 0; if (reserve(c, &c->f_ym2, &z, 2 * (C + 1))) return CHB_ENOMEM; // [0,C): max |y|^2, [C+1, 2C+1): max |column term|
         z = 0; if (reserve(c, &c->f_mcnt, &z, C + 1)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_mc2, &z, C + 1)) return CHB_ENOMEM;
@@ -1595,7 +1702,9 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_tq, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_slack, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_skip, &z, (c->f_ldt / BM) * C)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_items, &z, (c->f_ldt / BM) * C)) return CHB_ENOMEM;
+        c->f_cap_pairs = ((4 * std::max<int64_t>(nown, 1) + (int64_t)BM * C + BM - 1) / BM) * BM;
+        z = 0; if (reserve(c, &c->f_items, &z, std::max<int64_t>((c->f_ldt / BM) * C, c->f_cap_pairs / BM + C))) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_pair_row, &z, c->f_cap_pairs)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cta_begin, &z, c->sm_count + 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_slot, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_pt, &z, c->f_ldt)) return CHB_ENOMEM;
@@ -1609,6 +1718,7 @@ int chb_fused_setup(chb_ctx *c)
         c->f_cap_thr = c->f_ldt * C;
         c->f_asplit_ready = false;
     }
+    if (reserve(c, &c->f_ap, &c->f_cap_ap, c->f_cap_pairs * g.Kp2)) return CHB_ENOMEM;
     // once per (feature set, label set): bin reference points, row order, query operand and query terms
     if (!c->f_asplit_ready || c->f_cap_a2 < nown * g.Kp2) {
         if (reserve(c, &c->f_a2, &c->f_cap_a2, std::max<int64_t>(nown, 1) * g.Kp2)) return CHB_ENOMEM;
@@ -1682,21 +1792,33 @@ int chb_round_fused(chb_ctx *c)
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
     CHB_CUDA(c, cudaMemsetAsync(c->f_row_nb, 0, sizeof(int32_t) * (size_t)nown, c->stream));
+    CHB_CUDA(c, cudaMemsetAsync(c->f_pair_meta, 0, sizeof(int32_t) * (size_t)(3 * (C + 2)), c->stream)); // survivors, offsets, cursors
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
-        c->f_row_guess, eps_rel, nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins);
+        c->f_row_guess, eps_rel, nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins, c->f_pair_meta);
     const int64_t nrb = (nown + BM - 1) / BM;
+    int32_t *bin_surv = c->f_pair_meta, *pair_off = c->f_pair_meta + (C + 2), *pair_cur = c->f_pair_meta + 2 * (C + 2);
     skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
-    items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7]);
+    pairs_plan_kernel<<<1, 1024, 0, c->stream>>>(bin_surv, c->f_seg_off, C, c->f_cap_pairs, c->sm_count, pair_off,
+                                                 c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode);
+    items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
+                                            c->f_mode);
+    CHB_CUDA(c, cudaMemsetAsync(c->f_pair_row, 0xff, sizeof(int32_t) * (size_t)c->f_cap_pairs, c->stream));
+    pairs_fill_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
+                                                              c->f_pair_row);
+    pairs_gather_kernel<<<nblk(c->f_cap_pairs * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_mode, pair_off, C, c->f_pair_row, c->f_a2, g.Kp2,
+                                                                                      c->f_cap_pairs, c->f_ap);
     CHB_CUDA(c, cudaGetLastError());
-    c->tm.launches_other += 3;
-    CUtensorMap ma, mb;
+    c->tm.launches_other += 6;
+    CUtensorMap ma, mb, map;
     int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
+    if (rc != CHB_OK) return rc;
+    rc = make_map(c, &map, c->f_ap, c->f_cap_pairs, g.Kp2);
     if (rc != CHB_OK) return rc;
     rc = make_map(c, &mb, c->f_bperm, ncol_max, g.Kp2);
     if (rc != CHB_OK) return rc;
-    rc = dispatch_fused(c, ma, mb, nown, g, KR);
+    rc = dispatch_fused(c, ma, map, mb, nown, g, KR);
     if (rc != CHB_OK) return rc;
     c->tm.rows_scanned += nown;
 
