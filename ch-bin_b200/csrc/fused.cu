@@ -611,11 +611,17 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
     __shared__ int s_mode, s_ti, s_tt;
     int32_t *item_off = scratch, *tile_cum = scratch + C + 1;
     const int tid = threadIdx.x;
+    // per-bin block and tile counts first (all threads, coalesced), then one thread runs the three prefix sums over them
+    for (int c = tid; c < C; c += 1024) {
+        item_off[c] = (bin_surv[c] + BM - 1) / BM;
+        tile_cum[c] = (seg_off[c + 1] - seg_off[c]) / BN;
+    }
+    __syncthreads();
     if (tid == 0) {
         int64_t po = 0;
         int io = 0, tc = 0;
         for (int c = 0; c < C; ++c) {
-            const int nb = (bin_surv[c] + BM - 1) / BM, w = (seg_off[c + 1] - seg_off[c]) / BN;
+            const int nb = item_off[c], w = tile_cum[c];
             pair_off[c] = (int32_t)po;
             item_off[c] = io;
             tile_cum[c] = tc;
@@ -1239,13 +1245,13 @@ __device__ __forceinline__ double exact_distance_g(const double *__restrict__ xq
     return __dsqrt_rn(acc);
 }
 
-// One CTA (128 threads) per owned query.  A group of G lanes (G = 16 when the two half-lists of KR = 8 fit, else 32) handles
+// One warp per owned query.  A group of G lanes (G = 16 when the two half-lists of KR = 8 fit, else 32) handles
 // one (query, bin) pair: lane s < 2*KR of the group holds one kept candidate.  Everything is predicated rather than
 // branched so that the groups of a warp stay convergent for the shuffles; loops run over the set bits of the
 // candidate masks (with admission thresholds most lists hold few more than k entries).
 // Bins that never received a flush (no columns at all) are recognised through bin_cnt.
 template <int G>
-__global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ cand_key, const int32_t *__restrict__ cand_idx, int KR,
+__global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float *__restrict__ cand_key, const int32_t *__restrict__ cand_idx, int KR,
                                                      const int32_t *__restrict__ bin_cnt, const double *__restrict__ X, int32_t ldx,
                                                      int32_t d, const int32_t *__restrict__ row_point,
                                                      const int32_t *__restrict__ row_slot,
@@ -1256,21 +1262,20 @@ __global__ void __launch_bounds__(128) rerank_kernel(const float *__restrict__ c
                                                      const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ thr_out,
                                                      const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins)
 {
-    extern __shared__ __align__(16) double xq_s[];
     constexpr int NG = 32 / G;
     constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
-    const int64_t r = blockIdx.x;              // row: candidate lists, thresholds and slacks are per row ...
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; // one warp per row: candidate lists, thresholds and
+    if (r >= nrows) return;                                                   // slacks are per row ...
     const int64_t sl = row_slot[r];            // ... neighbour caches, hull distances and the work list per owned slot
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gl = lane & (G - 1), gsh = lane & ~(G - 1);
     const int jq = row_point[r];
-    for (int t = threadIdx.x; t < d; t += 128) xq_s[t] = X[(int64_t)jq * ldx + t];
-    __syncthreads();
+    const double *xq_s = X + (int64_t)jq * ldx; // query row, read only for the (rare) exact evaluations
     const int K2 = 2 * KR;
 
     // only the bins that survived the pruning bounds (threshold_kernel lists them per row; pruned pairs were settled there)
     const int nb = row_nb[r];
-    for (int jb = warp * NG; jb < nb; jb += 4 * NG) {
+    for (int jb = 0; jb < nb; jb += NG) {
         const int j = jb + lane / G;
         const bool act = j < nb;
         const int c = act ? row_bins[r * C + j] : 0;
@@ -1827,8 +1832,8 @@ int chb_round_fused(chb_ctx *c)
     {
         chb_stage_timer t(c, CHB_ST_KNN);
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
-        kern<<<(unsigned)nown, 128, sizeof(double) * (size_t)((c->d + 1) & ~1), c->stream>>>(
-            c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->f_slack, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
+        kern<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(
+            nown, c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->f_slack, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
             c->f_fb_pairs, c->f_fb_cap, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins);
         // pairs the re-rank could not settle from the kept lists (rare): exact redo, no host round trip -- the grid is
         // fixed and walks the device-side list
