@@ -828,8 +828,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     if (use_fused(c)) {
         const int64_t nown = c->u1 - c->u0;
         CHB_TRY(ensure_work(c, 2 * nown)); // a pair can be listed by the re-rank AND again by the exact-path fallback
-        CHB_CUDA(c, cudaMemsetAsync(c->counters, 0, sizeof(int32_t), c->stream));
-        CHB_TRY(chb_round_fused(c));
+        CHB_TRY(chb_round_fused(c)); // resets the work counter itself (round_reset_kernel)
         // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the
         // tile / redo counters travel with the commit's read-back
         CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));

@@ -128,6 +128,21 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// everything a round starts from zero, in one launch: per-bin column counts, per-bin maxima, per-row survivor counts,
+// per-bin pair counters, the work / redo counters, and the compact pair -> row table (-1 = padding)
+__global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_cnt, float *__restrict__ ym2, int32_t nym2,
+                                   int32_t *__restrict__ row_nb, int64_t nown, int32_t *__restrict__ pair_meta, int32_t nmeta,
+                                   int32_t *__restrict__ pair_row, int64_t cap_pairs, int32_t *__restrict__ counters)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nbin_cnt) bin_cnt[i] = 0;
+    if (i < nym2) ym2[i] = 0.f;
+    if (i < nown) row_nb[i] = 0;
+    if (i < nmeta) pair_meta[i] = 0;
+    if (i < cap_pairs) pair_row[i] = -1;
+    if (i == 0) { counters[0] = 0; counters[6] = 0; }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // column entries
 // ---------------------------------------------------------------------------------------------------------
@@ -453,8 +468,15 @@ __global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__
         nseed = seed_off[g + 1] - seed_off[g];
         int slot = 0;
         for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32, ++slot) {
-            double s = 0.0;
-            for (int t = 0; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; s = fma(df, df, s); }
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; // independent chains: the loop is DFMA-latency bound otherwise
+            int t = 0;
+            for (; t + 3 < d; t += 4) {
+                const double d0 = q_sm[w][t] - seedT[(int64_t)t * ns + i], d1 = q_sm[w][t + 1] - seedT[(int64_t)(t + 1) * ns + i];
+                const double d2 = q_sm[w][t + 2] - seedT[(int64_t)(t + 2) * ns + i], d3 = q_sm[w][t + 3] - seedT[(int64_t)(t + 3) * ns + i];
+                s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            }
+            for (; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; s0 = fma(df, df, s0); }
+            const double s = (s0 + s1) + (s2 + s3);
             ub2 = fmin(ub2, s);
             if (slot == 0) v[0] = s; else if (slot == 1) v[1] = s; else if (slot == 2) v[2] = s; else if (slot == 3) v[3] = s;
         }
@@ -1781,13 +1803,13 @@ int chb_round_fused(chb_ctx *c)
     }
 
     // ---- 1. column entries
-    CHB_CUDA(c, cudaMemsetAsync(c->f_bin_cnt, 0, sizeof(int32_t) * (size_t)(C + 1), c->stream));
+    round_reset_kernel<<<nblk(std::max<int64_t>(std::max<int64_t>(nown, c->f_cap_pairs), 5 * (C + 2)), 256), 256, 0, c->stream>>>(
+        c->f_bin_cnt, C + 1, c->f_ym2, 2 * (C + 1), c->f_row_nb, nown, c->f_pair_meta, 3 * (C + 2), c->f_pair_row, c->f_cap_pairs, c->counters);
     entries_count_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, n, C, c->f_bin_cnt);
     entries_scan_kernel<<<1, 256, 0, c->stream>>>(c->f_bin_cnt, C, c->f_seg_off, c->f_cursor, c->f_tile_bin, c->f_ntiles);
     entries_fill_kernel<<<nblk(ncol_max, 256), 256, 0, c->stream>>>(ncol_max, c->f_col_pt, c->f_col_a, c->f_col_b);
     entries_scatter_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
                                                                  c->f_col_pt, c->f_col_a, c->f_col_b);
-    CHB_CUDA(c, cudaMemsetAsync(c->f_ym2, 0, sizeof(float) * (size_t)(2 * (C + 1)), c->stream));
     column_gather_kernel<<<nblk(ncol_max * 32, 256), 256, 0, c->stream>>>(
         c->f_col_pt, c->f_ntiles, c->f_tile_bin, c->X, c->ldx, c->d, c->colsum, 1.0 / (double)n, c->f_mc, g.dp8, g.Kp2, c->f_bperm,
         c->f_col_nrm, reinterpret_cast<unsigned int *>(c->f_ym2), reinterpret_cast<unsigned int *>(c->f_ym2 + C + 1));
@@ -1796,8 +1818,6 @@ int chb_round_fused(chb_ctx *c)
 
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
-    CHB_CUDA(c, cudaMemsetAsync(c->f_row_nb, 0, sizeof(int32_t) * (size_t)nown, c->stream));
-    CHB_CUDA(c, cudaMemsetAsync(c->f_pair_meta, 0, sizeof(int32_t) * (size_t)(3 * (C + 2)), c->stream)); // survivors, offsets, cursors
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
@@ -1809,7 +1829,6 @@ int chb_round_fused(chb_ctx *c)
                                                  c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
                                             c->f_mode);
-    CHB_CUDA(c, cudaMemsetAsync(c->f_pair_row, 0xff, sizeof(int32_t) * (size_t)c->f_cap_pairs, c->stream));
     pairs_fill_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
                                                               c->f_pair_row);
     pairs_gather_kernel<<<nblk(c->f_cap_pairs * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_mode, pair_off, C, c->f_pair_row, c->f_a2, g.Kp2,
@@ -1828,7 +1847,6 @@ int chb_round_fused(chb_ctx *c)
     c->tm.rows_scanned += nown;
 
     // ---- 3. re-rank
-    CHB_CUDA(c, cudaMemsetAsync(&c->counters[6], 0, sizeof(int32_t), c->stream));
     {
         chb_stage_timer t(c, CHB_ST_KNN);
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
