@@ -186,7 +186,9 @@ int ensure_caches(chb_ctx *c)
     const int64_t nown = c->u1 - c->u0;
     if (c->cache_nown == nown && c->cache_C == c->C && c->cache_k == c->k && c->knn_idx) return CHB_OK;
     CHB_TRY(dev_reserve(c, &c->knn_idx, &c->cap_knn, nown * c->C * c->k));
-    CHB_TRY(dev_reserve(c, &c->knn_dist, &c->cap_knn_dist, nown * c->C * c->k));
+    // exact distances of the cached lists: only the matrix-backed modes (knn.cu) keep them
+    if (!(c->dist_mode == 2 && c->filter_ok && chb_fused_supported(c)))
+        CHB_TRY(dev_reserve(c, &c->knn_dist, &c->cap_knn_dist, nown * c->C * c->k));
     if (c->cap_pairs < nown * c->C) {
         CHB_TRY(dev_alloc(c, &c->knn_cnt, nown * c->C));
         CHB_TRY(dev_alloc(c, &c->pair_dist, nown * c->C));
@@ -827,13 +829,13 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     const bool filt = use_filter(c);
     if (use_fused(c)) {
         const int64_t nown = c->u1 - c->u0;
-        CHB_TRY(ensure_work(c, 2 * nown)); // a pair can be listed by the re-rank AND again by the exact-path fallback
+        CHB_TRY(ensure_work(c, nown)); // a pair is listed at most once per round (re-rank or exact redo)
         CHB_TRY(chb_round_fused(c)); // resets the work counter itself (round_reset_kernel)
         // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the
         // tile / redo counters travel with the commit's read-back
         CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         chb_qp_args q{};
-        q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = 2 * nown * c->C;
+        q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = nown * c->C;
         q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
         q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
         CHB_TRY(chb_launch_qp(c, q));
