@@ -816,9 +816,11 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     const int64_t *ob = c->own_pos_host, *oe = c->own_pos_host + c->n_own_pos;
     const int64_t b = std::lower_bound(ob, oe, lo) - ob, e = std::lower_bound(ob, oe, hi) - ob;
     const int64_t cnt = e - b;
-    fill_i32_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, hi - lo, CHB_UNOWNED);
-    CHB_CUDA(c, cudaGetLastError());
-    ++c->tm.launches_other;
+    if (c->n_own_pos < c->U) { // positions of other ranks' queries stay CHB_UNOWNED; a context that owns them all skips the fill
+        fill_i32_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, hi - lo, CHB_UNOWNED);
+        CHB_CUDA(c, cudaGetLastError());
+        ++c->tm.launches_other;
+    }
     ++c->tm.rounds;
     if (cnt == 0) return CHB_OK;
     if (use_filter(c) && !use_fused(c) && c->C < 32768) {

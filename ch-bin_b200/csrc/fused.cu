@@ -132,9 +132,15 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar)
 // per-bin pair counters, the work / redo counters, and the compact pair -> row table (-1 = padding)
 __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_cnt, float *__restrict__ ym2, int32_t nym2,
                                    int32_t *__restrict__ row_nb, int64_t nown, int32_t *__restrict__ pair_meta, int32_t nmeta,
-                                   int32_t *__restrict__ pair_row, int64_t cap_pairs, int32_t *__restrict__ counters)
+                                   int32_t *__restrict__ pair_row, int64_t cap_pairs, int32_t *__restrict__ counters,
+                                   int64_t ncol, int32_t *__restrict__ col_pt, int32_t *__restrict__ col_a, int32_t *__restrict__ col_b)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncol) { // padding columns: no point, never visible
+        col_pt[i] = -1;
+        col_a[i] = INT32_MAX;
+        col_b[i] = INT32_MIN;
+    }
     if (i < nbin_cnt) bin_cnt[i] = 0;
     if (i < nym2) ym2[i] = 0.f;
     if (i < nown) row_nb[i] = 0;
@@ -197,16 +203,6 @@ __global__ void entries_scatter_kernel(const int32_t *__restrict__ tent, const i
         col_a[e] = INT32_MAX;
         col_b[e] = ps;                      // visible only when p < pos[i]
     }
-}
-
-__global__ void entries_fill_kernel(int64_t ncol, int32_t *__restrict__ col_pt, int32_t *__restrict__ col_a,
-                                    int32_t *__restrict__ col_b)
-{
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= ncol) return;
-    col_pt[e] = -1;
-    col_a[e] = INT32_MAX; // never visible
-    col_b[e] = INT32_MIN;
 }
 
 // Gathers rows of the centred FP32 features (Xf, prep_f32_kernel) through `idx` and writes them as TF32 operands in the
@@ -682,36 +678,32 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
     }
 }
 
-// compact pair id -> row, per bin (any order inside a bin); padding entries stay -1 (memset)
-__global__ void pairs_fill_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ row_nb,
-                                  const int32_t *__restrict__ row_bins, int64_t nown, int32_t C, const int32_t *__restrict__ pair_off,
-                                  int32_t *__restrict__ pair_cur, int32_t *__restrict__ pair_row)
+// compact pair id -> row, per bin (any order inside a bin), and the pair's query operand row copied into the compact
+// buffer; one warp per row.  Padding ids keep pair_row = -1 (round_reset_kernel); their operand rows are never
+// initialised -- accumulator rows are independent and the epilogue ignores rows without a query.
+__global__ void __launch_bounds__(256) pairs_fill_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ row_nb,
+                                                         const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
+                                                         const int32_t *__restrict__ pair_off, int32_t *__restrict__ pair_cur,
+                                                         int32_t *__restrict__ pair_row, const float *__restrict__ a2, int32_t Kp2,
+                                                         float *__restrict__ ap)
 {
     if (!*mode) return;
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= nown) return;
     const int nb = row_nb[r];
+    const float4 *src = reinterpret_cast<const float4 *>(a2 + r * Kp2);
     for (int j = 0; j < nb; ++j) {
-        const int c = row_bins[r * C + j];
-        pair_row[pair_off[c] + atomicAdd(&pair_cur[c], 1)] = (int32_t)r;
+        int id = 0;
+        if (lane == 0) {
+            const int c = row_bins[r * C + j];
+            id = pair_off[c] + atomicAdd(&pair_cur[c], 1);
+            pair_row[id] = (int32_t)r;
+        }
+        id = __shfl_sync(CHB_FULL, id, 0);
+        float4 *dst = reinterpret_cast<float4 *>(ap + (int64_t)id * Kp2);
+        for (int q = lane; q < Kp2 / 4; q += 32) dst[q] = __ldg(src + q);
     }
-}
-
-// compact query operand: row id of the compact buffer <- operand row of its query (zeros for padding)
-__global__ void pairs_gather_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ pair_off, int32_t C,
-                                    const int32_t *__restrict__ pair_row, const float *__restrict__ a2, int32_t Kp2,
-                                    int64_t cap_pairs, float *__restrict__ ap)
-{
-    if (!*mode) return;
-    const int64_t kq = Kp2 / 4;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t id = i / kq;
-    if (id >= cap_pairs || id >= pair_off[C]) return;
-    const int q = (int)(i - id * kq);
-    const int r = pair_row[id];
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r >= 0) v = __ldg(reinterpret_cast<const float4 *>(a2 + (int64_t)r * Kp2) + q);
-    reinterpret_cast<float4 *>(ap + id * Kp2)[q] = v;
 }
 
 // Work list of the fused kernel: one item per surviving (row block, bin) = {row block, bin, first tile, #tiles}, in row-block
@@ -1803,11 +1795,11 @@ int chb_round_fused(chb_ctx *c)
     }
 
     // ---- 1. column entries
-    round_reset_kernel<<<nblk(std::max<int64_t>(std::max<int64_t>(nown, c->f_cap_pairs), 5 * (C + 2)), 256), 256, 0, c->stream>>>(
-        c->f_bin_cnt, C + 1, c->f_ym2, 2 * (C + 1), c->f_row_nb, nown, c->f_pair_meta, 3 * (C + 2), c->f_pair_row, c->f_cap_pairs, c->counters);
+    round_reset_kernel<<<nblk(std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(nown, c->f_cap_pairs), ncol_max), 5 * (C + 2)), 256), 256, 0,
+                         c->stream>>>(c->f_bin_cnt, C + 1, c->f_ym2, 2 * (C + 1), c->f_row_nb, nown, c->f_pair_meta, 3 * (C + 2),
+                                      c->f_pair_row, c->f_cap_pairs, c->counters, ncol_max, c->f_col_pt, c->f_col_a, c->f_col_b);
     entries_count_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, n, C, c->f_bin_cnt);
     entries_scan_kernel<<<1, 256, 0, c->stream>>>(c->f_bin_cnt, C, c->f_seg_off, c->f_cursor, c->f_tile_bin, c->f_ntiles);
-    entries_fill_kernel<<<nblk(ncol_max, 256), 256, 0, c->stream>>>(ncol_max, c->f_col_pt, c->f_col_a, c->f_col_b);
     entries_scatter_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
                                                                  c->f_col_pt, c->f_col_a, c->f_col_b);
     column_gather_kernel<<<nblk(ncol_max * 32, 256), 256, 0, c->stream>>>(
@@ -1829,12 +1821,10 @@ int chb_round_fused(chb_ctx *c)
                                                  c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
                                             c->f_mode);
-    pairs_fill_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
-                                                              c->f_pair_row);
-    pairs_gather_kernel<<<nblk(c->f_cap_pairs * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_mode, pair_off, C, c->f_pair_row, c->f_a2, g.Kp2,
-                                                                                      c->f_cap_pairs, c->f_ap);
+    pairs_fill_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
+                                                                   c->f_pair_row, c->f_a2, g.Kp2, c->f_ap);
     CHB_CUDA(c, cudaGetLastError());
-    c->tm.launches_other += 6;
+    c->tm.launches_other += 5;
     CUtensorMap ma, mb, map;
     int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
     if (rc != CHB_OK) return rc;
