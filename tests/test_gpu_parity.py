@@ -435,3 +435,42 @@ def test_edge_identical_contigs_everywhere():
     X[100:300] = X[100]
     X[400:420] = X[0]
     _same_as_oracle(X, 3, bins, 5, 5)
+
+
+def test_abi_argument_validation():
+    """Error behaviour at the C-ABI (include/chbin_b200.h): bad arguments come back as CHB_EINVAL -> ValueError with a
+    message, never as a crash or a silent wrong answer, and the context stays usable."""
+    X, bins, _ = synth.make_contig_features(300, 3, 1, 20, seed=11)
+    pts = np.where(bins == -1)[0]
+    perm = np.random.default_rng(0).permutation(pts).astype(np.int64)
+    ctx = capi.Context(0)
+    with pytest.raises(ValueError, match="set_features first"):
+        ctx.set_labels(bins, 3)
+    ctx.set_features(X)
+    with pytest.raises(ValueError, match="outside"):
+        ctx.set_labels(np.where(bins == 2, 3, bins), 3)          # label == num_clusters
+    with pytest.raises(ValueError, match="same n"):
+        ctx.set_labels(bins[:-1], 3)
+    with pytest.raises(ValueError, match="num_neighbors"):
+        ctx.set_params(0, "convex")
+    ctx.set_labels(bins, 3)
+    ctx.set_params(5, "convex")
+    with pytest.raises(ValueError, match="not set up"):
+        ctx.iteration_begin(perm)                                 # distance structure not built yet
+    ctx.build_distance_matrix(True)
+    with pytest.raises(ValueError, match="permutation length"):
+        ctx.iteration_begin(perm[:-1])
+    bad = perm.copy(); bad[3] = bad[4]
+    with pytest.raises(ValueError, match="repeats"):
+        ctx.iteration_begin(bad)
+    bad = perm.copy(); bad[0] = int(np.where(bins >= 0)[0][0])    # a seed contig is not a query
+    with pytest.raises(ValueError, match="not an un-assigned"):
+        ctx.iteration_begin(bad)
+    bad = perm.copy(); bad[0] = len(X)
+    with pytest.raises(ValueError, match="out of range"):
+        ctx.iteration_begin(bad)
+    # the context is still usable after the refused calls
+    ref = oracle.fit_cluster(X, 3, bins, None, 5, 1, perms=perm[None, :])
+    lab, _ = ctx.fit_iteration(perm)
+    assert np.array_equal(lab, ref)
+    ctx.close()
