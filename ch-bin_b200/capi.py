@@ -301,10 +301,11 @@ class Context:
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         self._check(self._lib.chb_iteration_begin(self._h, _ptr(perm), len(perm)))
 
-    def round_run(self, lo: int, hi: int, tent_dev_ptr: int):
+    def round_run(self, lo: int, hi: int, tent_dev_ptr: Optional[int] = None):
+        """Enqueues one speculate round (asynchronous).  tent_dev_ptr None: the library's own tentative buffer."""
         self._check(self._lib.chb_round_run(self._h, lo, hi, _vp(tent_dev_ptr)))
 
-    def round_commit(self, lo: int, hi: int, tent_dev_ptr: int) -> int:
+    def round_commit(self, lo: int, hi: int, tent_dev_ptr: Optional[int] = None) -> int:
         first = _i64(-1)
         self._check(self._lib.chb_round_commit(self._h, lo, hi, _vp(tent_dev_ptr), ctypes.byref(first)))
         return int(first.value)

@@ -231,15 +231,35 @@ def fit_cluster(
             comm = TorchComm()
 
         iterations, converged, rounds_total, changed = 0, False, 0, []
+        spec_perm = spec_state = None  # next iteration's permutation, drawn speculatively while a round runs
         for i_iter in range(max_iterations):
             if world > 1:
                 with engine.stream_context():
                     sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
                     change_count, rounds = run_iteration(engine, sample_perm, comm)
             else:
-                sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
-                _, change_count = ctx.fit_iteration(sample_perm, want_labels=False)
-                rounds = 0
+                # Single context: chb_round_run only enqueues, chb_round_commit synchronises.  The next iteration's
+                # np.random.permutation (algorithm.py:45) is drawn while the first round runs on the device; if the loop
+                # then stops (algorithm.py:63-66, or the iteration limit) the global RNG is put back, so that exactly one
+                # draw per EXECUTED iteration remains visible -- the reference's RNG contract.
+                sample_perm = spec_perm if spec_perm is not None else _draw_permutation(points_to_assign, dist_mod, device)
+                spec_perm = spec_state = None
+                ctx.iteration_begin(sample_perm)
+                U, W = len(sample_perm), ctx.get_window()
+                lo = rounds = 0
+                while lo < U:
+                    hi = min(U, lo + (W or U))
+                    ctx.round_run(lo, hi)
+                    if spec_state is None and i_iter + 1 < max_iterations:
+                        spec_state = np.random.get_state()
+                        spec_perm = _draw_permutation(points_to_assign, dist_mod, device)
+                    first = ctx.round_commit(lo, hi)
+                    lo = hi if first < 0 else first + 1
+                    rounds += 1
+                change_count = ctx.iteration_end()
+                if (change_count == 0 or i_iter + 1 == max_iterations) and spec_state is not None:
+                    np.random.set_state(spec_state)  # the speculative draw never happened
+                    spec_perm = spec_state = None
             rounds_total += rounds
             iterations += 1
             changed.append(change_count)

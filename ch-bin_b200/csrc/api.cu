@@ -807,12 +807,24 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
     return CHB_OK;
 }
 
+// tent_dev == NULL: the context's own tentative buffer (single-context use: nothing to exchange between the two calls)
+static int own_tent(chb_ctx *c, int64_t len, int32_t **out)
+{
+    if (c->tent_win_cap < len) {
+        CHB_TRY(dev_alloc(c, &c->tent_win, len));
+        c->tent_win_cap = len;
+    }
+    *out = c->tent_win;
+    return CHB_OK;
+}
+
 int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
 {
-    CHB_CHECK(c, c && tent_dev, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CHECK(c, c->in_iteration, CHB_EINVAL, "round_run outside chb_iteration_begin/end");
     CHB_CHECK(c, 0 <= lo && lo < hi && hi <= c->U, CHB_EINVAL, "round window [%lld,%lld) invalid", (long long)lo, (long long)hi);
     CHB_CUDA(c, cudaSetDevice(c->device));
+    if (!tent_dev) CHB_TRY(own_tent(c, hi - lo, &tent_dev));
     const int64_t *ob = c->own_pos_host, *oe = c->own_pos_host + c->n_own_pos;
     const int64_t b = std::lower_bound(ob, oe, lo) - ob, e = std::lower_bound(ob, oe, hi) - ob;
     const int64_t cnt = e - b;
@@ -901,10 +913,14 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
 
 int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed)
 {
-    CHB_CHECK(c, c && tent_dev && first_changed, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c && first_changed, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->in_iteration, CHB_EINVAL, "round_commit outside chb_iteration_begin/end");
     CHB_CHECK(c, 0 <= lo && lo < hi && hi <= c->U, CHB_EINVAL, "round window [%lld,%lld) invalid", (long long)lo, (long long)hi);
     CHB_CUDA(c, cudaSetDevice(c->device));
+    if (!tent_dev) {
+        CHB_CHECK(c, c->tent_win && c->tent_win_cap >= hi - lo, CHB_EINVAL, "round_commit(NULL) without a preceding round_run(NULL)");
+        tent_dev = c->tent_win;
+    }
     CHB_CUDA(c, cudaMemsetAsync(&c->counters[1], 0x7f, sizeof(int32_t), c->stream)); // 0x7f7f7f7f: above any position
     {
         chb_stage_timer t(c, CHB_ST_COMMIT);

@@ -167,7 +167,9 @@ int chb_get_labels(chb_ctx *ctx, int64_t *labels_out);
  *           <all-reduce MAX tent_dev[0 .. hi-lo)>
  *           chb_round_commit(lo, hi, tent_dev, &first_changed)   -> next lo = first_changed+1, or hi if -1
  *   chb_iteration_end(&n_changed)
- * window: suggested hi-lo (chb_get_window). */
+ * window: suggested hi-lo (chb_get_window).  A single context that owns every slot may pass tent_dev = NULL to both calls
+ * (the library keeps the tentative labels itself); chb_round_run only ENQUEUES work, chb_round_commit is the sync point,
+ * so the host can overlap its own work (drawing the next permutation) with a round. */
 int chb_iteration_begin(chb_ctx *ctx, const int64_t *perm, int64_t U);
 int chb_round_run(chb_ctx *ctx, int64_t lo, int64_t hi, int32_t *tent_dev);
 int chb_round_commit(chb_ctx *ctx, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed);

@@ -474,3 +474,21 @@ def test_abi_argument_validation():
     lab, _ = ctx.fit_iteration(perm)
     assert np.array_equal(lab, ref)
     ctx.close()
+
+
+@pytest.mark.parametrize("max_iterations", [10, 1, 2])
+def test_rng_contract_one_draw_per_executed_iteration(max_iterations):
+    """fit_cluster overlaps the NEXT iteration's np.random.permutation with the running round and takes it back when the
+    loop stops: afterwards the global legacy RNG must be exactly where the reference leaves it -- one draw per executed
+    iteration (algorithm.py:45), whether the loop ends by convergence (:63-66) or by the iteration limit (:74-75)."""
+    X, bins, _ = synth.make_contig_features(800, 4, 1, 20, seed=14, concentration=300.0)
+    pts = np.where(bins == -1)[0]
+    np.random.seed(123)
+    got, info = chbin_b200.fit_cluster(X, 4, bins, None, 5, max_iterations, return_info=True)
+    after = np.random.random()
+    np.random.seed(123)
+    perms = np.stack([np.random.permutation(pts) for _ in range(info["iterations"])])
+    expect = np.random.random()
+    assert after == expect
+    ref = oracle.fit_cluster(X, 4, bins, None, 5, info["iterations"], perms=perms.astype(np.int64))
+    assert np.array_equal(got, ref)
