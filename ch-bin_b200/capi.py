@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
     "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
-    "chb_get_fused_candidates",
+    "chb_get_fused_candidates", "chb_set_features_async",
 ]
 
 
@@ -78,6 +78,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_enable_timers.argtypes = [_vp, ctypes.c_int]
     L.chb_set_features.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_dev.argtypes = [_vp, _vp, _i64, _i32]
+    L.chb_set_features_async.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_labels.argtypes = [_vp, _vp, _i64, _i32, _i64, _i64]
     L.chb_set_params.argtypes = [_vp, _i32, _i32]
     L.chb_build_distance_matrix.argtypes = [_vp, ctypes.c_int]
@@ -181,12 +182,18 @@ class Context:
         self._check(self._lib.chb_enable_timers(self._h, int(bool(on))))
 
     # -- set-up
-    def set_features(self, samples: np.ndarray):
+    def set_features(self, samples: np.ndarray, asynchronous: bool = False):
+        """asynchronous=True: chb_set_features_async -- returns once the upload is enqueued; the array is kept alive
+        (and must stay unchanged) until build_distance_matrix() / synchronize()."""
         x = np.ascontiguousarray(samples, dtype=np.float64)  # DataFrame.values arrives F-ordered
         if x.ndim != 2:
             raise ValueError("samples must be a 2-D array")
         self.n, self.d = x.shape
-        self._check(self._lib.chb_set_features(self._h, _ptr(x), x.shape[0], x.shape[1]))
+        if asynchronous:
+            self._pending_features = x
+            self._check(self._lib.chb_set_features_async(self._h, _ptr(x), x.shape[0], x.shape[1]))
+        else:
+            self._check(self._lib.chb_set_features(self._h, _ptr(x), x.shape[0], x.shape[1]))
 
     def set_features_dev(self, dev_ptr: int, n: int, d: int):
         self.n, self.d = int(n), int(d)

@@ -217,21 +217,24 @@ def fit_cluster(
     try:
         ctx.set_stream(capi.OWN_STREAM)
         ctx.reset_timers()
-        ctx.set_features(samples)
+        ctx.set_features(samples, asynchronous=True)  # the upload overlaps the label set-up and the first permutation draw
         u0, u1 = owned_slots(num_points_to_assign, rank, world)
         ctx.set_labels(curr, int(num_clusters), u0, u1)
         ctx.set_params(int(num_neighbors), metric)
         ctx.set_window(int(window))
         ctx.set_distance_mode(int(distance_mode))
         ctx.set_gram_engine(int(gram_engine))
+        spec_perm = spec_state = None  # a permutation drawn ahead of the iteration that will use it
+        if world == 1 and max_iterations > 0:
+            spec_perm = _draw_permutation(points_to_assign, dist_mod, device)  # iteration 1 always executes
         ctx.build_distance_matrix(bool(in_mem_dist_matrix))
+        ctx._pending_features = None
         engine = comm = None
         if world > 1:
             engine = GpuEngine(ctx, device)
             comm = TorchComm()
 
         iterations, converged, rounds_total, changed = 0, False, 0, []
-        spec_perm = spec_state = None  # next iteration's permutation, drawn speculatively while a round runs
         for i_iter in range(max_iterations):
             if world > 1:
                 with engine.stream_context():

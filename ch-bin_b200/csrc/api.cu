@@ -220,6 +220,13 @@ int sync_stream(chb_ctx *c)
 {
     CHB_CUDA(c, cudaStreamSynchronize(c->stream));
     chb_resolve_timers(c);
+    if (c->nmax_pending) { // chb_set_features_async: the largest |x - mu|^2 has arrived now
+        float nmax;
+        memcpy(&nmax, &c->counters_host[5], sizeof(float));
+        // the FP32 filter's error bound needs |x|^2 far from FP32 overflow / underflow; otherwise use exact rows
+        c->filter_ok = (nmax > 1e-30f) && (nmax < 1e30f);
+        c->nmax_pending = false;
+    }
     return CHB_OK;
 }
 
@@ -284,6 +291,7 @@ int chb_destroy(chb_ctx *c)
     dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
     chb_fused_free(c); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
+    if (c->pin_i32) cudaFreeHost(c->pin_i32);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -360,7 +368,7 @@ static void fill_filter_args(chb_ctx *c, chb_knn_args &a, bool filt)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind)
+static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind, bool defer_sync = false)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CHECK(c, src && n > 0 && d > 0, CHB_EINVAL, "samples must be a non-empty (n, d) float64 array");
@@ -389,13 +397,8 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     }
     CHB_TRY(chb_launch_prep_f32(c));
     CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[5], &c->counters[5], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CHB_TRY(sync_stream(c));
-    {
-        float nmax;
-        memcpy(&nmax, &c->counters_host[5], sizeof(float));
-        // the FP32 filter's error bound needs |x|^2 far from FP32 overflow / underflow; otherwise use exact rows
-        c->filter_ok = (nmax > 1e-30f) && (nmax < 1e30f);
-    }
+    c->nmax_pending = true; // resolved by the next stream synchronisation (sync_stream)
+    if (!defer_sync) CHB_TRY(sync_stream(c));
     c->dist_ready = false;
     c->labels_set = false;
     c->bsplit_ready = false;
@@ -459,6 +462,10 @@ int chb_set_features(chb_ctx *c, const double *x, int64_t n, int32_t d)
 {
     return set_features_common(c, x, n, d, cudaMemcpyHostToDevice);
 }
+int chb_set_features_async(chb_ctx *c, const double *x, int64_t n, int32_t d)
+{
+    return set_features_common(c, x, n, d, cudaMemcpyHostToDevice, true);
+}
 int chb_set_features_dev(chb_ctx *c, const double *x_dev, int64_t n, int32_t d)
 {
     return set_features_common(c, x_dev, n, d, cudaMemcpyDeviceToDevice);
@@ -470,32 +477,43 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     CHB_CHECK(c, c->X && n == c->n, CHB_EINVAL, "set_labels: call chb_set_features first with the same n");
     CHB_CHECK(c, bins && C >= 1, CHB_EINVAL, "initial_bins is NULL or num_clusters < 1");
     CHB_CUDA(c, cudaSetDevice(c->device));
-    std::vector<int32_t> &lab = c->h_lab, &qs = c->h_qslot, &qp = c->h_qpoint;
-    std::vector<int32_t> seed_off((size_t)C + 1, 0);
-    lab.resize((size_t)n);
-    qs.resize((size_t)n);
-    qp.clear();
-    qp.reserve((size_t)n);
+    c->labels_set = false; // the staging block (and with it the host mirror of the slots) is rewritten below
+    // Host staging in ONE page-locked block: lab[n] | qslot[n] | qpoint[n] | seed_idx[n] | seed_off[C + 1].  Copies from
+    // page-locked memory neither stage nor wait for earlier work on the stream, so they (and the host loops here) overlap a
+    // feature upload still in flight (chb_set_features_async).  The block is rewritten by the next chb_set_labels only.
+    {
+        const int64_t need = 4 * n + C + 1;
+        if (c->pin_cap < need) {
+            if (c->pin_i32) cudaFreeHost(c->pin_i32);
+            c->pin_i32 = nullptr;
+            c->pin_cap = 0;
+            CHB_CUDA(c, cudaMallocHost(reinterpret_cast<void **>(&c->pin_i32), sizeof(int32_t) * (size_t)need));
+            c->pin_cap = need;
+        }
+    }
+    int32_t *lab = c->pin_i32, *qs = lab + n, *qp = qs + n, *seed_idx = qp + n, *seed_off = seed_idx + n;
+    c->h_qslot = qs; // host mirror used by chb_iteration_begin
+    for (int32_t b = 0; b <= C; ++b) seed_off[b] = 0;
+    int64_t U = 0;
     for (int64_t i = 0; i < n; ++i) {
         const int64_t b = bins[i];
         CHB_CHECK(c, b >= -1 && b < C, CHB_EINVAL, "initial_bins[%lld] = %lld outside [-1, %d)", (long long)i, (long long)b, C);
-        lab[(size_t)i] = (int32_t)b;
+        lab[i] = (int32_t)b;
         if (b == -1) {
-            qs[(size_t)i] = (int32_t)qp.size();
-            qp.push_back((int32_t)i);
+            qs[i] = (int32_t)U;
+            qp[U++] = (int32_t)i;
         } else {
-            qs[(size_t)i] = -1;
-            ++seed_off[(size_t)b + 1];
+            qs[i] = -1;
+            ++seed_off[b + 1];
         }
     }
-    const int64_t U = (int64_t)qp.size();
     // seed contigs sorted by (bin, index): the bin reference points are summed in this fixed order on every rank
-    for (int32_t b = 0; b < C; ++b) seed_off[(size_t)b + 1] += seed_off[(size_t)b];
-    std::vector<int32_t> seed_idx((size_t)std::max<int64_t>(n - U, 1));
+    for (int32_t b = 0; b < C; ++b) seed_off[b + 1] += seed_off[b];
     {
-        std::vector<int32_t> cur(seed_off.begin(), seed_off.end() - 1);
+        std::vector<int32_t> &cur = c->h_lab; // scratch: write cursor per bin
+        cur.assign(seed_off, seed_off + C);
         for (int64_t i = 0; i < n; ++i)
-            if (lab[(size_t)i] >= 0) seed_idx[(size_t)cur[(size_t)lab[(size_t)i]]++] = (int32_t)i;
+            if (lab[i] >= 0) seed_idx[cur[(size_t)lab[i]]++] = (int32_t)i;
     }
     if (slot_end < 0) slot_end = U;
     CHB_CHECK(c, 0 <= slot_begin && slot_begin <= slot_end && slot_end <= U, CHB_EINVAL, "owned slot range [%lld,%lld) invalid for U=%lld",
@@ -525,14 +543,13 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     }
     CHB_TRY(dev_reserve(c, &c->seed_off, &c->cap_seed_off, (int64_t)C + 1));
     CHB_TRY(dev_reserve(c, &c->seed_idx, &c->cap_seed_idx, std::max<int64_t>(n - U, 1)));
-    // stream-ordered copies (pageable sources are staged before the call returns, so the local vectors may go away)
-    CHB_CUDA(c, cudaMemcpyAsync(c->seed_off, seed_off.data(), sizeof(int32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, c->stream));
-    CHB_CUDA(c, cudaMemcpyAsync(c->seed_idx, seed_idx.data(), sizeof(int32_t) * (size_t)std::max<int64_t>(n - U, 1), cudaMemcpyHostToDevice,
-                                c->stream));
-    CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, lab.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs.data(), sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    if (U) CHB_CUDA(c, cudaMemcpyAsync(c->qpoint, qp.data(), sizeof(int32_t) * (size_t)U, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->seed_off, seed_off, sizeof(int32_t) * ((size_t)C + 1), cudaMemcpyHostToDevice, c->stream));
+    if (n - U > 0)
+        CHB_CUDA(c, cudaMemcpyAsync(c->seed_idx, seed_idx, sizeof(int32_t) * (size_t)(n - U), cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    if (U) CHB_CUDA(c, cudaMemcpyAsync(c->qpoint, qp, sizeof(int32_t) * (size_t)U, cudaMemcpyHostToDevice, c->stream));
     fill_i32_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->pos, n, -1);
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
@@ -562,6 +579,7 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CHECK(c, c->labels_set, CHB_EINVAL, "build_distance_matrix: call chb_set_features and chb_set_labels first");
     CHB_CUDA(c, cudaSetDevice(c->device));
+    if (c->nmax_pending) CHB_TRY(sync_stream(c)); // chb_set_features_async: the upload ends here at the latest
     const int64_t nown = c->u1 - c->u0;
     c->materialise = materialise != 0;
     const bool filt = use_filter(c);
@@ -645,6 +663,7 @@ int chb_knn_per_bin(chb_ctx *c, const int64_t *labels, const int64_t *queries, i
     CHB_CHECK(c, c && labels && queries && idx_out && m_out, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->X && c->C > 0, CHB_EINVAL, "knn_per_bin: set features and labels first");
     CHB_CUDA(c, cudaSetDevice(c->device));
+    if (c->nmax_pending) CHB_TRY(sync_stream(c));
     const int64_t n = c->n;
     const int32_t C = c->C, k = c->k;
     std::vector<int32_t> lab((size_t)n);
@@ -695,6 +714,7 @@ int chb_hull_distance_batch(chb_ctx *c, const int64_t *queries, int64_t nq, cons
     CHB_CHECK(c, c && queries && idx && m && dist_out, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->X && c->C > 0, CHB_EINVAL, "hull_distance_batch: set features and labels first");
     CHB_CUDA(c, cudaSetDevice(c->device));
+    if (c->nmax_pending) CHB_TRY(sync_stream(c));
     const int32_t C = c->C, k = c->k;
     const int64_t np = nq * C;
     if (np == 0) return CHB_OK;
@@ -771,7 +791,7 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
         for (int64_t p = 0; p < U; ++p) {
             const int64_t pt = perm[p];
             CHB_CHECK(c, pt >= 0 && pt < c->n, CHB_EINVAL, "permutation entry %lld out of range", (long long)pt);
-            const int64_t slot = c->h_qslot[(size_t)pt];
+            const int64_t slot = c->h_qslot[pt];
             CHB_CHECK(c, slot >= 0, CHB_EINVAL, "permutation entry %lld is not an un-assigned point", (long long)pt);
             CHB_CHECK(c, !seen[(size_t)slot], CHB_EINVAL, "permutation repeats point %lld", (long long)pt);
             seen[(size_t)slot] = 1;

@@ -42,6 +42,7 @@ struct chb_ctx {
     int32_t Kp = 0;
     bool bsplit_ready = false;
     bool filter_ok = true; // feature magnitudes inside the FP32 filter's validated range
+    bool nmax_pending = false; // the read-back deciding filter_ok is still in flight (chb_set_features_async)
 
     // ---- labels / slots
     int32_t C = 0;
@@ -56,7 +57,10 @@ struct chb_ctx {
     int64_t n_own_pos = 0;
     int64_t *own_pos_host = nullptr;
     bool labels_set = false, in_iteration = false;
-    std::vector<int32_t> h_lab, h_qslot, h_qpoint, h_perm32, h_own32; // host mirrors / per-iteration scratch
+    std::vector<int32_t> h_lab, h_perm32, h_own32; // per-call scratch
+    int32_t *pin_i32 = nullptr; // page-locked staging block of chb_set_labels
+    int64_t pin_cap = 0;
+    const int32_t *h_qslot = nullptr; // host mirror of qslot (inside pin_i32)
     std::vector<uint8_t> h_seen;
 
     // ---- parameters

@@ -93,6 +93,11 @@ int chb_enable_timers(chb_ctx *ctx, int enable);
  * F-ordered DataFrame.values of cli/clustering.py:53).  Copied to the device in a 16-byte-pitched layout. */
 int chb_set_features(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
 int chb_set_features_dev(chb_ctx *ctx, const double *x_rowmajor_dev, int64_t n, int32_t d);
+/* Same as chb_set_features, but returns as soon as the upload is ENQUEUED: when x_rowmajor is page-locked memory the
+ * copy overlaps the caller's next host work (reading labels, drawing the first permutation).  The one exception to "no
+ * pointer is retained": x_rowmajor must stay valid and unchanged until chb_build_distance_matrix (or chb_synchronize)
+ * returns.  Pageable memory is staged before the call returns, as with chb_set_features. */
+int chb_set_features_async(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
 /* `initial_bins` + `num_clusters` of fit_cluster (algorithm.py:14-15): int64, -1 = to be assigned.
  * Defines points_to_assign = where(initial_bins == -1) (algorithm.py:38), ascending: "query slot" u is the
  * u-th such point.  [slot_begin, slot_end) is the slice of query slots THIS context owns (multi-GPU query
