@@ -492,3 +492,16 @@ def test_rng_contract_one_draw_per_executed_iteration(max_iterations):
     assert after == expect
     ref = oracle.fit_cluster(X, 4, bins, None, 5, info["iterations"], perms=perms.astype(np.int64))
     assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("k", [14, 16, 24, 32])
+def test_large_neighbour_counts_take_the_matrix_path(k):
+    """BASELINE config #5 sweeps AlgoNumNeighbors up to 32.  The fused kernel keeps k + 3 <= 16 candidates per list, so
+    k >= 14 runs the matrix-backed selection (distance mode 1) and the general QP kernel -- same labels as the oracle."""
+    X, bins, _ = synth.make_contig_features(1400, 3, 2, 45, seed=16 + k, concentration=250.0)
+    perms = oracle.draw_permutations(bins, 3, seed=0)
+    ref = oracle.fit_cluster(X, 3, bins, None, k, 3, perms=perms, threads=4)
+    np.random.seed(0)
+    got, info = chbin_b200.fit_cluster(X, 3, bins, None, k, 3, return_info=True)
+    assert np.array_equal(got, ref)
+    assert info["timers"]["launches_gram"] == 0
