@@ -1400,6 +1400,20 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
     }
 }
 
+// large neighbour counts (k + 3 > 16: the register lists of the fused kernel cannot hold the candidates): every
+// surviving (row, bin) pair goes straight to the exact selection below -- after pruning there are few of them
+__global__ void all_pairs_kernel(const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
+                                 int2 *__restrict__ fb_pairs, int32_t fb_cap, int32_t *__restrict__ fb_count)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    const int nb = row_nb[r];
+    if (nb <= 0) return;
+    const int w0 = atomicAdd(fb_count, nb);
+    for (int j = 0; j < nb; ++j)
+        if (w0 + j < fb_cap) fb_pairs[w0 + j] = make_int2((int)r, row_bins[r * C + j]);
+}
+
 // Exact redo of the (row, bin) pairs whose kept candidate lists may be incomplete (duplicate contigs: more than KR keys
 // inside the slack window).  One CTA per pair walks the bin's column segment of this round, evaluates scipy's exact
 // recipe for every visible member and selects the k smallest (distance, index) -- find_nearest_from_cluster
@@ -1597,12 +1611,12 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 } // namespace
 
-// k + 3 candidates per half-list fit 16 registers; the resident query operand (2 * dp8 floats per row) fits MAX_BOX
-// boxes with at least 3 ring stages left
+// the resident query operand (2 * dp8 floats per row) fits MAX_BOX boxes with at least 3 ring stages left; k + 3 <= 16
+// candidates per half-list fit the register lists of the fused kernel, larger k uses pruning + exact selection only
 bool chb_fused_supported(const chb_ctx *c)
 {
     const FusedGeom g = fused_geom(c->d);
-    return c->k + 3 <= 16 && g.nbox <= MAX_BOX && g.nstage >= 3;
+    return c->k <= 32 && g.nbox <= MAX_BOX && g.nstage >= 3;
 }
 
 void chb_fused_free(chb_ctx *c)
@@ -1676,7 +1690,7 @@ int chb_fused_setup(chb_ctx *c)
     const FusedGeom g = fused_geom(c->d);
     const int64_t ncol_max = ((2 * n + (int64_t)BN * C + BN - 1) / BN) * BN;
 
-    CHB_CHECK(c, chb_fused_supported(c), CHB_EINVAL, "fused mode supports num_neighbors <= 13 and d <= 160");
+    CHB_CHECK(c, chb_fused_supported(c), CHB_EINVAL, "fused mode supports num_neighbors <= 32 and d <= 160");
     if (c->f_cap_bins < C + 1) {
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_bin_cnt, &z, C + 1)) return CHB_ENOMEM;
@@ -1708,8 +1722,9 @@ int chb_fused_setup(chb_ctx *c)
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_cand_key, &z, nown * C * KR * 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cand_idx, &z, nown * C * KR * 2)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_fb_pairs, &z, std::max<int64_t>(nown, 1024))) return CHB_ENOMEM;
-        c->f_fb_cap = (int32_t)std::min<int64_t>(std::max<int64_t>(nown, 1024), INT32_MAX);
+        const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * std::min<int64_t>(C, 8), 1024), INT32_MAX);
+        z = 0; if (reserve(c, &c->f_fb_pairs, &z, fbc)) return CHB_ENOMEM;
+        c->f_fb_cap = (int32_t)fbc;
         c->f_cap_cand = nown * C * KR * 2;
     }
     c->f_ldt = (nown + 127) & ~int64_t(127);
@@ -1814,6 +1829,19 @@ int chb_round_fused(chb_ctx *c)
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
         c->f_row_guess, eps_rel, nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins, c->f_pair_meta);
+    if (k + 3 > 16) {
+        // ---- 3'. large k: exact selection for every surviving pair (find_nearest_from_cluster on exact distances)
+        chb_stage_timer t(c, CHB_ST_KNN);
+        all_pairs_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_nb, c->f_row_bins, nown, C, c->f_fb_pairs, c->f_fb_cap,
+                                                                 &c->counters[6]);
+        const size_t xs = sizeof(double) * (size_t)((c->d + 1) & ~1);
+        exact_pairs_kernel<32><<<c->sm_count * 8, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
+                                                                        c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
+                                                                        c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
+        CHB_CUDA(c, cudaGetLastError());
+        c->tm.rows_scanned += nown;
+        return CHB_OK;
+    }
     const int64_t nrb = (nown + BM - 1) / BM;
     int32_t *bin_surv = c->f_pair_meta, *pair_off = c->f_pair_meta + (C + 2), *pair_cur = c->f_pair_meta + 2 * (C + 2);
     skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);

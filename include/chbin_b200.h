@@ -109,7 +109,9 @@ int chb_set_params(chb_ctx *ctx, int32_t num_neighbors, int32_t metric);
 /* How the distances behind find_nearest_from_cluster are produced.
  *   mode 2 (default): nothing is stored; every round the tensor cores regenerate error-bounded FP32 candidate values
  *           and the per-bin selection happens in the same kernel's epilogue (fused.cu); exact scipy-cdist values are
- *           evaluated only where the FP32 bound cannot decide.  Needs num_neighbors <= 13, else mode 1 is used.
+ *           evaluated only where the FP32 bound cannot decide.  Bins that provably cannot be a query's nearest hull are
+ *           pruned first.  num_neighbors >= 14: pruning, then exact selection for the surviving pairs (no Gram kernel).
+ *           Needs d <= 160, else mode 1 is used.
  *   mode 1: the FP32 candidate matrix of the owned query rows is kept in HBM (InMemDistMatrix=yes) or recomputed per
  *           round (no) and scanned by knn.cu; exact values for candidates only.
  *   mode 0: every exact FP64 distance is formed (3 non-fusable FP64 ops per feature) and ranked directly.
