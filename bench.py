@@ -260,9 +260,7 @@ def run_b200(args):
     X, bins, cfg, U = workload(args)
     n, d = X.shape
     C, k = cfg["C"], cfg["k"]
-    import oracle  # only for the cpu_baseline leg below and the permutation helper (host RNG contract)
-
-    perms = oracle.draw_permutations(bins, MAX_ITERATIONS, seed=0)
+    perms = clustering.draw_permutations(bins, MAX_ITERATIONS, seed=0)  # the host RNG contract (algorithm.py:45)
 
     # ---------------- value arm: features resident in HBM, one context reused ----------------
     ctx = capi.Context(local_rank)

@@ -15,6 +15,7 @@ from .clustering import (  # noqa: F401
     B200_SOLVER,
     GpuEngine,
     TorchComm,
+    draw_permutations,
     fit_cluster,
     install,
     owned_slots,
@@ -24,6 +25,6 @@ from .clustering import (  # noqa: F401
 )
 
 __all__ = [
-    "B200_SOLVER", "GpuEngine", "TorchComm", "fit_cluster", "install", "owned_slots", "perform_clustering",
+    "B200_SOLVER", "GpuEngine", "TorchComm", "draw_permutations", "fit_cluster", "install", "owned_slots", "perform_clustering",
     "run_iteration", "shutdown", "build", "capi", "distance_cache", "synth",
 ]

@@ -144,6 +144,17 @@ def _dist_state():
     return None, 0, 1
 
 
+def draw_permutations(initial_bins: np.ndarray, max_iterations: int, seed: Optional[int] = 0) -> np.ndarray:
+    """The permutations fit_cluster would draw (algorithm.py:45) for up to `max_iterations` iterations, as one
+    (max_iterations, U) int64 array: np.random.seed(seed) as in ch_bin/ch_bin.py:22, then one
+    np.random.permutation(points_to_assign) per iteration on the global legacy RNG.  For callers that drive the C-ABI
+    themselves (chb_fit, benchmarks)."""
+    pts = np.where(np.asarray(initial_bins) == -1)[0]
+    if seed is not None:
+        np.random.seed(seed)
+    return np.stack([np.random.permutation(pts) for _ in range(max_iterations)]).astype(np.int64).reshape(max_iterations, len(pts))
+
+
 def _draw_permutation(points_to_assign: np.ndarray, dist_mod, device_index: int) -> np.ndarray:
     """algorithm.py:45.  Every rank draws from its own global RNG (so the stream advances exactly as in the
     reference); rank 0's draw is authoritative and broadcast so that differently-seeded ranks cannot diverge."""
