@@ -1845,7 +1845,10 @@ int chb_round_fused(chb_ctx *c)
     const int64_t nrb = (nown + BM - 1) / BM;
     int32_t *bin_surv = c->f_pair_meta, *pair_off = c->f_pair_meta + (C + 2), *pair_cur = c->f_pair_meta + 2 * (C + 2);
     skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
-    pairs_plan_kernel<<<1, 1024, 0, c->stream>>>(bin_surv, c->f_seg_off, C, c->f_cap_pairs, c->sm_count, pair_off,
+    // test aid: CHB_FUSED_NO_COMPACT forces the (row block, bin) items that are otherwise only used when the compact buffer
+    // would overflow
+    const int64_t plan_cap = getenv("CHB_FUSED_NO_COMPACT") ? -1 : c->f_cap_pairs;
+    pairs_plan_kernel<<<1, 1024, 0, c->stream>>>(bin_surv, c->f_seg_off, C, plan_cap, c->sm_count, pair_off,
                                                  c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
                                             c->f_mode);

@@ -509,3 +509,17 @@ def test_large_neighbour_counts(k):
     np.random.seed(0)
     got1 = chbin_b200.fit_cluster(X, 3, bins, None, k, 3, distance_mode=1)
     assert np.array_equal(got1, ref)
+
+
+def test_uncompacted_items_fallback(monkeypatch):
+    """When the surviving (row, bin) pairs would not fit the compact operand buffer, the fused kernel works on (row block,
+    bin) items instead (decided on the device).  CHB_FUSED_NO_COMPACT forces that path."""
+    monkeypatch.setenv("CHB_FUSED_NO_COMPACT", "1")
+    for (n, C, S, n_seed, k, conc) in [(1500, 8, 1, 30, 5, 60.0), (1200, 6, 10, 25, 10, 300.0), (5000, 20, 1, 20, 5, 1000.0)]:
+        X, bins, _ = synth.make_contig_features(n, C, S, n_seed, seed=31, concentration=conc)
+        perms = oracle.draw_permutations(bins, 4, seed=0)
+        ref = oracle.fit_cluster(X, C, bins, None, k, 4, perms=perms, threads=4)
+        np.random.seed(0)
+        got, info = chbin_b200.fit_cluster(X, C, bins, None, k, 4, return_info=True, reuse_context=False)
+        assert np.array_equal(got, ref), (n, C, k)
+        assert info["timers"]["launches_gram"] > 0
