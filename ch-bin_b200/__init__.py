@@ -8,9 +8,10 @@ Public surface (mirrors /root/reference/ch_bin/core/clustering/algorithm.py and 
     fit_cluster, perform_clustering, install, B200_SOLVER
     capi.Context        thin ctypes wrapper over the C-ABI (include/chbin_b200.h)
     distance_cache      on-disk distance matrix (.npy, reference format) and the features.csv side-car
+    features            coverage normalisation + [k-mer | coverage] merge on the device (coverage.py, cli/features.py)
     synth               synthetic contig feature sets of the BASELINE configs
 """
-from . import build, capi, distance_cache, synth  # noqa: F401
+from . import build, capi, distance_cache, features, synth  # noqa: F401
 from .clustering import (  # noqa: F401
     B200_SOLVER,
     GpuEngine,
@@ -26,5 +27,5 @@ from .clustering import (  # noqa: F401
 
 __all__ = [
     "B200_SOLVER", "GpuEngine", "TorchComm", "draw_permutations", "fit_cluster", "install", "owned_slots", "perform_clustering",
-    "run_iteration", "shutdown", "build", "capi", "distance_cache", "synth",
+    "run_iteration", "shutdown", "build", "capi", "distance_cache", "features", "synth",
 ]

@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = [
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
     "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
-    "chb_get_fused_candidates", "chb_set_features_async",
+    "chb_get_fused_candidates", "chb_set_features_async", "chb_set_features_merged", "chb_get_features",
 ]
 
 
@@ -79,6 +79,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_features.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_dev.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_async.argtypes = [_vp, _vp, _i64, _i32]
+    L.chb_set_features_merged.argtypes = [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]
+    L.chb_get_features.argtypes = [_vp, _vp]
     L.chb_set_labels.argtypes = [_vp, _vp, _i64, _i32, _i64, _i64]
     L.chb_set_params.argtypes = [_vp, _i32, _i32]
     L.chb_build_distance_matrix.argtypes = [_vp, ctypes.c_int]
@@ -194,6 +196,33 @@ class Context:
             self._check(self._lib.chb_set_features_async(self._h, _ptr(x), x.shape[0], x.shape[1]))
         else:
             self._check(self._lib.chb_set_features(self._h, _ptr(x), x.shape[0], x.shape[1]))
+
+    def set_features_merged(self, kmer: Optional[np.ndarray], cov_raw: np.ndarray, parent: np.ndarray,
+                            want_coverages: bool = False):
+        """chb_set_features_merged: samples = [kmer | normalised coverage of the parent contig], built on the device
+        (coverage.py:35-41 + cli/features.py:106-109).  Returns the normalised (P, S) coverages when asked."""
+        cov = np.ascontiguousarray(cov_raw, dtype=np.float64)
+        if cov.ndim != 2:
+            raise ValueError("coverages must be a 2-D (P, S) array")
+        par = np.ascontiguousarray(parent, dtype=np.int64)
+        if par.ndim != 1:
+            raise ValueError("parent must be a 1-D index array")
+        if kmer is None:
+            km = np.zeros((par.shape[0], 0), dtype=np.float64)
+        else:
+            km = np.ascontiguousarray(kmer, dtype=np.float64)
+        if km.ndim != 2 or km.shape[0] != par.shape[0]:
+            raise ValueError("kmer must be (n, dk) with one row per entry of parent")
+        out = np.empty_like(cov) if want_coverages else None
+        self._check(self._lib.chb_set_features_merged(self._h, _ptr(km) if km.shape[1] else None, km.shape[0], km.shape[1],
+                                                      _ptr(cov), cov.shape[0], cov.shape[1], _ptr(par), _ptr(out)))
+        self.n, self.d = km.shape[0], km.shape[1] + cov.shape[1]
+        return out
+
+    def get_features(self) -> np.ndarray:
+        out = np.empty((self.n, self.d), dtype=np.float64)
+        self._check(self._lib.chb_get_features(self._h, _ptr(out)))
+        return out
 
     def set_features_dev(self, dev_ptr: int, n: int, d: int):
         self.n, self.d = int(n), int(d)

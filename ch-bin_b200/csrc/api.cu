@@ -368,10 +368,9 @@ static void fill_filter_args(chb_ctx *c, chb_knn_args &a, bool filt)
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind, bool defer_sync = false)
+// Shapes and device arrays of a new feature matrix (shared by every chb_set_features* entry point)
+static int features_begin(chb_ctx *c, int64_t n, int32_t d)
 {
-    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
-    CHB_CHECK(c, src && n > 0 && d > 0, CHB_EINVAL, "samples must be a non-empty (n, d) float64 array");
     CHB_CHECK(c, n < INT32_MAX, CHB_EINVAL, "n = %lld exceeds the 32-bit point index range", (long long)n);
     CHB_CUDA(c, cudaSetDevice(c->device));
     c->n = n;
@@ -382,6 +381,28 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
     if (c->cap_Xf < n * c->ldf) { CHB_TRY(dev_alloc(c, &c->Xf, n * c->ldf)); c->cap_Xf = n * c->ldf; }
     if (c->cap_nrm < n) { CHB_TRY(dev_alloc(c, &c->nrm, n)); c->cap_nrm = n; }
     if (c->cap_colsum < d) { CHB_TRY(dev_alloc(c, &c->colsum, d)); c->cap_colsum = d; }
+    return CHB_OK;
+}
+
+// Derived arrays (FP32 copy, centred norms) once c->X holds the rows; invalidates everything built on the old matrix
+static int features_finish(chb_ctx *c, bool defer_sync)
+{
+    CHB_TRY(chb_launch_prep_f32(c));
+    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[5], &c->counters[5], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    c->nmax_pending = true; // resolved by the next stream synchronisation (sync_stream)
+    if (!defer_sync) CHB_TRY(sync_stream(c));
+    c->dist_ready = false;
+    c->labels_set = false;
+    c->bsplit_ready = false;
+    c->f_asplit_ready = false;
+    return CHB_OK;
+}
+
+static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind, bool defer_sync = false)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, src && n > 0 && d > 0, CHB_EINVAL, "samples must be a non-empty (n, d) float64 array");
+    CHB_TRY(features_begin(c, n, d));
     {
         // one contiguous copy into a persistent staging buffer (a strided 2-D copy from pageable host memory is several
         // times slower, and allocating / freeing the staging area per call costs more than the copy), then repack
@@ -395,15 +416,159 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
         ++c->tm.launches_other;
         CHB_CUDA(c, cudaGetLastError());
     }
-    CHB_TRY(chb_launch_prep_f32(c));
-    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[5], &c->counters[5], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    c->nmax_pending = true; // resolved by the next stream synchronisation (sync_stream)
-    if (!defer_sync) CHB_TRY(sync_stream(c));
-    c->dist_ready = false;
-    c->labels_set = false;
-    c->bsplit_ready = false;
-    c->f_asplit_ready = false;
-    return CHB_OK;
+    return features_finish(c, defer_sync);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Coverage normalisation + feature merge on the device (coverage.py:35-41, cli/features.py:106-109).
+//
+// The reference divides every coverage column by its sum (DataFrame.sum(axis=0): numpy add.reduce over a contiguous
+// float64 axis = pairwise summation: halves split at multiples of 8 down to leaves of <= 128 elements, each leaf summed
+// with eight running sums), then -- with more than one sample -- every row by its sum (DataFrame.sum(axis=1): a
+// left-to-right sequential sum over the columns).  Both orders are reproduced so that the merged rows are the same doubles
+// pandas would have written (pinned by tests/golden, generated from coverage.py itself).
+//
+// The shape of the pairwise tree depends on P only: the host lists the leaves and a post-order program
+// (>= 0: push that leaf's sum, -1: add the two topmost); leaves are summed in parallel, the program is run per column.
+static void pairwise_plan(int64_t off, int64_t n, std::vector<int32_t> &leaf, std::vector<int32_t> &prog)
+{
+    if (n <= 128) {
+        prog.push_back((int32_t)(leaf.size() / 2));
+        leaf.push_back((int32_t)off);
+        leaf.push_back((int32_t)n);
+        return;
+    }
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    pairwise_plan(off, n2, leaf, prog);
+    pairwise_plan(off + n2, n - n2, leaf, prog);
+    prog.push_back(-1);
+}
+
+__global__ void cov_leaf_sum_kernel(const double *__restrict__ raw, int32_t S, const int32_t *__restrict__ leaf, int32_t nleaf,
+                                    double *__restrict__ leafsum)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)nleaf * S) return;
+    const int32_t l = (int32_t)(i / S), j = (int32_t)(i - (int64_t)l * S);
+    const int32_t n = leaf[2 * l + 1];
+    const double *a = raw + (int64_t)leaf[2 * l] * S + j;
+    double res;
+    if (n < 8) {
+        res = -0.0;
+        for (int32_t t = 0; t < n; ++t) res = __dadd_rn(res, a[(int64_t)t * S]);
+    } else {
+        double r[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) r[u] = a[(int64_t)u * S];
+        int32_t t = 8;
+        for (; t < n - (n % 8); t += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) r[u] = __dadd_rn(r[u], a[(int64_t)(t + u) * S]);
+        }
+        res = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])), __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
+        for (; t < n; ++t) res = __dadd_rn(res, a[(int64_t)t * S]);
+    }
+    leafsum[i] = res;
+}
+
+__global__ void cov_col_total_kernel(const double *__restrict__ leafsum, int32_t S, const int32_t *__restrict__ prog, int32_t nprog,
+                                     double *__restrict__ colsum)
+{
+    const int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= S) return;
+    double st[48]; // tree depth <= log2(2^31 / 64) + 1
+    int sp = 0;
+    for (int32_t t = 0; t < nprog; ++t) {
+        const int32_t op = prog[t];
+        if (op >= 0) {
+            st[sp++] = leafsum[(int64_t)op * S + j];
+        } else {
+            --sp;
+            st[sp - 1] = __dadd_rn(st[sp - 1], st[sp]);
+        }
+    }
+    colsum[j] = st[0];
+}
+
+__global__ void cov_normalise_kernel(const double *__restrict__ raw, int64_t P, int32_t S, const double *__restrict__ colsum,
+                                     double *__restrict__ out)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    const double *a = raw + p * S;
+    double *o = out + p * S;
+    if (S == 1) { // a single sample is normalised over the column only (coverage.py:38)
+        o[0] = __ddiv_rn(a[0], colsum[0]);
+        return;
+    }
+    double rs = __ddiv_rn(a[0], colsum[0]);
+    for (int32_t j = 1; j < S; ++j) rs = __dadd_rn(rs, __ddiv_rn(a[j], colsum[j]));
+    for (int32_t j = 0; j < S; ++j) o[j] = __ddiv_rn(__ddiv_rn(a[j], colsum[j]), rs);
+}
+
+// X[i] = [ kmer[i] | cov[parent[i]] | 0-pad ]   (column order of the merged frame once the name / label columns are dropped,
+// cli/features.py:106-109 and cli/clustering.py:53)
+__global__ void merge_features_kernel(const double *__restrict__ kmer, int32_t dk, const double *__restrict__ cov, int32_t S,
+                                      const int64_t *__restrict__ parent, int64_t n, int32_t ldx, double *__restrict__ dst)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * ldx) return;
+    const int64_t r = i / ldx;
+    const int32_t t = (int32_t)(i - r * ldx);
+    double v = 0.0;
+    if (t < dk) v = kmer[r * dk + t];
+    else if (t < dk + S) v = cov[parent[r] * S + (t - dk)];
+    dst[i] = v;
+}
+
+int chb_set_features_merged(chb_ctx *c, const double *kmer, int64_t n, int32_t dk, const double *cov_raw, int64_t P, int32_t S,
+                            const int64_t *parent, double *cov_norm_out)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, n > 0 && dk >= 0 && (dk == 0 || kmer), CHB_EINVAL, "k-mer profiles must be an (n, dk) float64 array");
+    CHB_CHECK(c, cov_raw && P > 0 && S > 0 && P < INT32_MAX, CHB_EINVAL, "coverages must be a non-empty (P, S) float64 array");
+    CHB_CHECK(c, parent, CHB_EINVAL, "parent index (n,) is NULL");
+    for (int64_t i = 0; i < n; ++i)
+        CHB_CHECK(c, parent[i] >= 0 && parent[i] < P, CHB_EINVAL, "parent[%lld] = %lld is not a coverage row (P = %lld)", (long long)i,
+                  (long long)parent[i], (long long)P);
+    const int32_t d = dk + S;
+    CHB_TRY(features_begin(c, n, d));
+
+    std::vector<int32_t> leaf, prog;
+    pairwise_plan(0, P, leaf, prog);
+    const int32_t nleaf = (int32_t)(leaf.size() / 2), nprog = (int32_t)prog.size();
+    // staging block (doubles): kmer | raw | normalised | column sums | leaf sums | parent (int64) | leaf table + program (int32)
+    const int64_t o_raw = n * (int64_t)dk, o_cov = o_raw + P * S, o_cs = o_cov + P * S, o_ls = o_cs + S, o_par = o_ls + (int64_t)nleaf * S,
+                  o_tab = o_par + n, total = o_tab + (2 * (int64_t)nleaf + nprog + 1) / 2 + 1;
+    CHB_TRY(dev_reserve(c, &c->stage_X, &c->cap_stage_X, total));
+    double *s = c->stage_X;
+    int32_t *tab = reinterpret_cast<int32_t *>(s + o_tab);
+    if (dk > 0) CHB_CUDA(c, cudaMemcpyAsync(s, kmer, sizeof(double) * (size_t)n * dk, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(s + o_raw, cov_raw, sizeof(double) * (size_t)P * S, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(s + o_par, parent, sizeof(int64_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(tab, leaf.data(), sizeof(int32_t) * leaf.size(), cudaMemcpyHostToDevice, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(tab + 2 * nleaf, prog.data(), sizeof(int32_t) * prog.size(), cudaMemcpyHostToDevice, c->stream));
+    cov_leaf_sum_kernel<<<nblk((int64_t)nleaf * S, 128), 128, 0, c->stream>>>(s + o_raw, S, tab, nleaf, s + o_ls);
+    cov_col_total_kernel<<<nblk(S, 32), 32, 0, c->stream>>>(s + o_ls, S, tab + 2 * nleaf, nprog, s + o_cs);
+    cov_normalise_kernel<<<nblk(P, 128), 128, 0, c->stream>>>(s + o_raw, P, S, s + o_cs, s + o_cov);
+    merge_features_kernel<<<nblk(n * c->ldx, 256), 256, 0, c->stream>>>(s, dk, s + o_cov, S, reinterpret_cast<const int64_t *>(s + o_par), n,
+                                                                        c->ldx, c->X);
+    c->tm.launches_other += 4;
+    CHB_CUDA(c, cudaGetLastError());
+    if (cov_norm_out)
+        CHB_CUDA(c, cudaMemcpyAsync(cov_norm_out, s + o_cov, sizeof(double) * (size_t)P * S, cudaMemcpyDeviceToHost, c->stream));
+    return features_finish(c, false);
+}
+
+int chb_get_features(chb_ctx *c, double *out)
+{
+    CHB_CHECK(c, c && out, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->X && c->n > 0, CHB_EINVAL, "get_features: no feature matrix yet");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_CUDA(c, cudaMemcpy2DAsync(out, sizeof(double) * c->d, c->X, sizeof(double) * c->ldx, sizeof(double) * c->d, (size_t)c->n,
+                                  cudaMemcpyDeviceToHost, c->stream));
+    return sync_stream(c);
 }
 
 int chb_set_gram_engine(chb_ctx *c, int engine)

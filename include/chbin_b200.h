@@ -98,6 +98,19 @@ int chb_set_features_dev(chb_ctx *ctx, const double *x_rowmajor_dev, int64_t n, 
  * pointer is retained": x_rowmajor must stay valid and unchanged until chb_build_distance_matrix (or chb_synchronize)
  * returns.  Pageable memory is staged before the call returns, as with chb_set_features. */
 int chb_set_features_async(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
+/* Builds `samples` on the device from its two sources instead of from features.csv:
+ *   kmer      (n, dk)  normalised k-mer profiles of the sub-contigs (seq2vec output, cli/features.py:84-93), row-major;
+ *   cov_raw   (P, S)   RAW per-sample coverages of the P parent contigs as read from the abundance file
+ *                      (coverage.py:30), row-major;
+ *   parent    (n,)     row of cov_raw each sub-contig inherits (the PARENT_NAME join of cli/features.py:107).
+ * The coverages are normalised as coverage.py:35-41 does -- every column by its sum, then (S > 1) every row by its sum,
+ * with pandas' summation orders so that the doubles are the ones parse_coverages returns -- and the device matrix becomes
+ * [kmer | coverage] (n, dk + S), the column order left after cli/clustering.py:53 drops the name / label columns.
+ * cov_norm_out (P, S), optional: the normalised coverages.  dk may be 0.  NaN (missing) coverages are not supported. */
+int chb_set_features_merged(chb_ctx *ctx, const double *kmer, int64_t n, int32_t dk, const double *cov_raw, int64_t P,
+                            int32_t S, const int64_t *parent, double *cov_norm_out);
+/* The device feature matrix back on the host, (n, d) row-major. */
+int chb_get_features(chb_ctx *ctx, double *out);
 /* `initial_bins` + `num_clusters` of fit_cluster (algorithm.py:14-15): int64, -1 = to be assigned.
  * Defines points_to_assign = where(initial_bins == -1) (algorithm.py:38), ascending: "query slot" u is the
  * u-th such point.  [slot_begin, slot_end) is the slice of query slots THIS context owns (multi-GPU query

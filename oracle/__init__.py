@@ -266,3 +266,52 @@ def fit_cluster(
         return labels, dict(iterations=iters.value, converged=bool(conv.value),
                             changed=changed[: iters.value].copy(), qps=nqp.value)
     return labels
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Coverage normalisation and feature merge
+def pairwise_sum(a) -> float:
+    """numpy's add.reduce over a contiguous float64 axis, restated (this is what `DataFrame.sum(axis=0)` of
+    coverage.py:37 runs per column): below 8 elements a plain running sum; up to 128 elements eight running sums combined
+    as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and then the tail; above, halves split at a multiple of 8.  Pure Python loop --
+    small inputs only; tests pin it against numpy itself."""
+    n = len(a)
+    if n < 8:
+        res = -0.0
+        for v in a:
+            res += float(v)
+        return res
+    if n <= 128:
+        r = [float(a[u]) for u in range(8)]
+        t = 8
+        while t < n - (n % 8):
+            for u in range(8):
+                r[u] += float(a[t + u])
+            t += 8
+        res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]))
+        while t < n:
+            res += float(a[t])
+            t += 1
+        return res
+    n2 = n // 2
+    n2 -= n2 % 8
+    return pairwise_sum(a[:n2]) + pairwise_sum(a[n2:])
+
+
+def normalise_coverages(raw: np.ndarray) -> np.ndarray:
+    """coverage.py:35-41: divide each column by its sum, then (more than one sample) each row by its sum.
+    Column sums: pairwise (contiguous axis of the frame's block); row sums: left to right over the columns."""
+    raw = np.asarray(raw, dtype=np.float64)
+    colsum = np.ascontiguousarray(raw.T).sum(axis=1)
+    t = raw / colsum
+    if raw.shape[1] > 1:
+        rs = t[:, 0].copy()
+        for j in range(1, raw.shape[1]):
+            rs = rs + t[:, j]
+        t = t / rs[:, None]
+    return t
+
+
+def merge_features(kmer: np.ndarray, cov_norm: np.ndarray, parent: np.ndarray) -> np.ndarray:
+    """cli/features.py:106-109 + cli/clustering.py:53: samples = [k-mer columns | coverage columns of the parent contig]."""
+    return np.ascontiguousarray(np.hstack([np.asarray(kmer, dtype=np.float64), np.asarray(cov_norm)[np.asarray(parent)]]))

@@ -176,6 +176,52 @@ def main():
                    pc_dm_rows=dm[[0, 57, 179]].copy(), pc_params=np.array([5, 6], dtype=np.int64))
         print("perform_clustering golden:", len(mem_txt), "bytes of binning-assignment.csv,", dm.shape)
 
+    # ---- 6. coverage normalisation (coverage.py:13-43, imported unmodified) and the feature merge (cli/features.py:106-109)
+    sys.path.insert(0, REF)
+    from ch_bin.core.features.coverage import parse_coverages  # noqa: E402
+
+    def run_parse(path, sep="\t"):
+        raw = pd.read_csv(path, sep=sep, header=None).drop(columns=[0]).to_numpy(dtype=np.float64)
+        norm = parse_coverages(Path(path), sep).drop(columns=["CONTIG_NAME"]).to_numpy(dtype=np.float64)
+        return np.ascontiguousarray(raw), np.ascontiguousarray(norm)
+
+    raw, norm = run_parse(os.path.join(REF, "test_data", "five-genomes-abundance.abund"))
+    out.update(cov_raw_real=raw, cov_norm_real=norm)
+    crng = np.random.default_rng(11)
+    shapes = [(7, 2), (129, 3), (300, 10), (1100, 20)]
+    with tempfile.TemporaryDirectory() as td:
+        for P, S in shapes:
+            vals = np.round(crng.lognormal(3.0, 1.0, (P, S)), 4)
+            fn = os.path.join(td, f"cov_{P}_{S}.tsv")
+            with open(fn, "w") as f:
+                for i in range(P):
+                    f.write(f"contig_{i}\t" + "\t".join(repr(float(v)) for v in vals[i]) + "\n")
+            raw, norm = run_parse(fn)
+            out[f"cov_raw_{P}_{S}"] = raw
+            out[f"cov_norm_{P}_{S}"] = norm
+        # the merge: the three pandas lines of cli/features.py:106-109 re-run on small frames, then the column drop of
+        # cli/clustering.py:53 -- pins the column order [k-mer | coverage] and the PARENT_NAME join
+        P, S, n, dk = 300, 10, 420, 24
+        fn = os.path.join(td, f"cov_{P}_{S}.tsv")
+        df_cov = parse_coverages(Path(fn))
+        par_idx = np.concatenate([np.arange(P), crng.integers(0, P, n - P)])
+        crng.shuffle(par_idx)
+        kmer = crng.dirichlet(np.full(dk, 8.0), n)
+        df_init = pd.DataFrame({"CONTIG_NAME": [f"sub_{j}" for j in range(n)], "PARENT_NAME": [f"contig_{q}" for q in par_idx],
+                                "CLUSTER": -1})
+        df_kmer = pd.concat([pd.DataFrame({"CONTIG_NAME": [f"sub_{j}" for j in range(n)]}),
+                             pd.DataFrame(kmer, columns=[f"K{j}" for j in range(dk)])], axis=1)
+        df_merged = pd.merge(df_init, df_kmer)
+        df_merged = pd.merge(df_merged, df_cov, left_on="PARENT_NAME", right_on="CONTIG_NAME")
+        df_merged = df_merged.rename(columns={"CONTIG_NAME_x": "CONTIG_NAME"})
+        df_merged = df_merged.drop("CONTIG_NAME_y", axis=1)
+        order = np.array([int(s[4:]) for s in df_merged["CONTIG_NAME"]])  # the merge may reorder rows
+        samples = df_merged.drop(["CONTIG_NAME", "PARENT_NAME", "CLUSTER"], axis=1).values
+        out.update(merge_kmer=kmer, merge_parent=par_idx.astype(np.int64), merge_order=order.astype(np.int64),
+                   merge_samples=np.ascontiguousarray(samples), merge_cov_key=np.array([P, S], dtype=np.int64))
+        print("coverage goldens:", [(k, out[k].shape) for k in out if k.startswith("cov_norm")], "merge:", samples.shape,
+              "row order kept:", bool((order == np.arange(n)).all()))
+
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path), "bytes")
