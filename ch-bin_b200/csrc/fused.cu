@@ -1400,20 +1400,6 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
     }
 }
 
-// large neighbour counts (k + 3 > 16: the register lists of the fused kernel cannot hold the candidates): every
-// surviving (row, bin) pair goes straight to the exact selection below -- after pruning there are few of them
-__global__ void all_pairs_kernel(const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
-                                 int2 *__restrict__ fb_pairs, int32_t fb_cap, int32_t *__restrict__ fb_count)
-{
-    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= nown) return;
-    const int nb = row_nb[r];
-    if (nb <= 0) return;
-    const int w0 = atomicAdd(fb_count, nb);
-    for (int j = 0; j < nb; ++j)
-        if (w0 + j < fb_cap) fb_pairs[w0 + j] = make_int2((int)r, row_bins[r * C + j]);
-}
-
 // Exact redo of the (row, bin) pairs whose kept candidate lists may be incomplete (duplicate contigs: more than KR keys
 // inside the slack window).  One CTA per pair walks the bin's column segment of this round, evaluates scipy's exact
 // recipe for every visible member and selects the k smallest (distance, index) -- find_nearest_from_cluster
@@ -1509,6 +1495,249 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict
                 for (int a = 0; a < k; ++a) knn_idx[pair * k + a] = a < m ? s_sel[a] : -1;
                 knn_cnt[pair] = m;
                 work[atomicAdd(work_count, 1)] = make_int2(row_slot[r], c);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Large neighbour counts (k + 3 > 16: the register lists of the fused kernel cannot hold the candidates): exact selection for
+// EVERY surviving (row, bin) pair.  With one pair per CTA every member row of the bin travels L2 -> SM once per pair and the
+// L2 fabric is the bound; here the surviving pairs are regrouped per bin and XS_G queries of one bin share every member row
+// they read (XS_G x fewer bytes, XS_G independent FP64 chains per thread), which leaves the FP64 pipe as the bound
+// (|bin| x d x 3 operations per pair: scipy's recipe admits no FMA).
+//   distances : a thread evaluates scipy's recipe for one member against the XS_G queries; (distance bits, index) composites of
+//               the members visible to a query are appended to that query's shared-memory array -- non-negative doubles order
+//               like their bit patterns and the index makes every composite unique;
+//   selection : warp w owns query w.  tau = k-th smallest of 64 strided minima: at least k members are <= tau and, for
+//               k << |bin|, few more; those are compacted and ranked by counting; ranks < k are find_nearest_from_cluster's
+//               answer (distance_matrix.py:47-62, ties resolved by index as everywhere in this library).
+// Bins larger than one pass are walked in chunks: the k kept so far stay at the front of the query's array.
+constexpr int XS_G = 8, XS_THREADS = 32 * XS_G, XS_CHUNK = 3 * XS_THREADS, XS_KEEP = 32, XS_CAP = XS_CHUNK + XS_KEEP, XS_CAND = 128;
+// XS_KEEP = the largest k the fused mode accepts (chb_fused_supported)
+
+__device__ __forceinline__ bool comp_lt(unsigned long long ka, int ia, unsigned long long kb, int ib)
+{
+    return ka < kb || (ka == kb && ia < ib);
+}
+
+inline size_t exact_group_smem(int d)
+{
+    return (size_t)XS_G * (sizeof(double) * (size_t)((d + 1) & ~1) + (size_t)(XS_CAP + 64 + XS_CAND + XS_KEEP) * 12);
+}
+
+// offsets of the per-bin slot ranges, each rounded up to a multiple of XS_G (so that a group never mixes bins)
+__global__ void xs_plan_kernel(const int32_t *__restrict__ bin_surv, int32_t C, int32_t *__restrict__ xs_off, int32_t *__restrict__ npairs)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int off = 0, np = 0;
+    for (int c = 0; c < C; ++c) {
+        xs_off[c] = off;
+        const int s = bin_surv[c];
+        np += s;
+        off += (s + XS_G - 1) / XS_G * XS_G;
+    }
+    xs_off[C] = off;
+    *npairs = np; // chb_round_commit reports an error if this exceeds the pair capacity
+}
+
+__global__ void xs_fill_kernel(const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
+                               const int32_t *__restrict__ xs_off, int32_t *__restrict__ xs_cur, int2 *__restrict__ slots, int32_t cap_slots)
+{
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    const int nb = row_nb[r];
+    for (int j = 0; j < nb; ++j) {
+        const int c = row_bins[r * C + j];
+        const int s = xs_off[c] + atomicAdd(&xs_cur[c], 1);
+        if (s < cap_slots) slots[s] = make_int2((int)r, c);
+    }
+}
+
+// scipy's recipe (sequential sum of rounded squares, no FMA, then sqrt) for one member row against XS_G query rows
+__device__ __forceinline__ void group_distances(const double *__restrict__ xq_s, int dpad, const double *__restrict__ xi, int d,
+                                                double (&acc)[XS_G])
+{
+#pragma unroll
+    for (int g = 0; g < XS_G; ++g) acc[g] = 0.0;
+    const int d8 = d & ~7;
+    double v[8];
+    if (d8 > 0) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = xi[u];
+    }
+    for (int t = 0; t < d8; t += 8) {
+        double w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = v[u];
+        if (t + 8 < d8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = xi[t + 8 + u];
+        }
+#pragma unroll
+        for (int g = 0; g < XS_G; ++g) {
+            const double *q = xq_s + g * dpad + t;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double df = __dsub_rn(q[u], w[u]);
+                acc[g] = __dadd_rn(acc[g], __dmul_rn(df, df));
+            }
+        }
+    }
+    for (int t = d8; t < d; ++t) {
+        const double x = xi[t];
+#pragma unroll
+        for (int g = 0; g < XS_G; ++g) {
+            const double df = __dsub_rn(xq_s[g * dpad + t], x);
+            acc[g] = __dadd_rn(acc[g], __dmul_rn(df, df));
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < XS_G; ++g) acc[g] = __dsqrt_rn(acc[g]);
+}
+
+__global__ void __launch_bounds__(XS_THREADS, 2)
+    exact_group_kernel(const int2 *__restrict__ slots, const int32_t *__restrict__ xs_off, int32_t cap_slots, const int32_t *__restrict__ seg_off,
+                       const int32_t *__restrict__ bin_cnt, const int32_t *__restrict__ col_pt, const int32_t *__restrict__ col_a,
+                       const int32_t *__restrict__ col_b, const double *__restrict__ X, int32_t ldx, int32_t d,
+                       const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot, const int32_t *__restrict__ pos, int32_t C,
+                       int32_t k, int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt, int2 *__restrict__ work,
+                       int32_t *__restrict__ work_count)
+{
+    extern __shared__ __align__(16) unsigned char xs_raw[];
+    typedef unsigned long long u64;
+    const int dpad = (d + 1) & ~1;
+    double *xq_s = reinterpret_cast<double *>(xs_raw); // [XS_G][dpad]
+    u64 *key = reinterpret_cast<u64 *>(xq_s + XS_G * dpad); // 8-byte arrays first, then the 4-byte ones; all [XS_G][...]
+    u64 *tmk = key + XS_G * XS_CAP;
+    u64 *ck = tmk + XS_G * 64;
+    u64 *selk = ck + XS_G * XS_CAND;
+    int *idx = reinterpret_cast<int *>(selk + XS_G * XS_KEEP);
+    int *tmi = idx + XS_G * XS_CAP;
+    int *ci = tmi + XS_G * 64;
+    int *seli = ci + XS_G * XS_CAND;
+    __shared__ int s_n[XS_G], s_row[XS_G], s_p[XS_G], s_ti[XS_G];
+    __shared__ u64 s_tk[XS_G];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const u64 KMAX = ~0ull;
+    const int total = min(xs_off[C], cap_slots);
+    for (int g0 = blockIdx.x * XS_G; g0 < total; g0 += gridDim.x * XS_G) {
+        __syncthreads(); // the previous group's warps are done with the shared arrays
+        if (tid < XS_G) {
+            const int r = slots[g0 + tid].x; // -1: padding at the end of a bin's range
+            s_row[tid] = r;
+            s_n[tid] = 0;
+            s_p[tid] = r >= 0 ? pos[row_point[r]] : 0;
+        }
+        const int c = slots[g0].y; // the first slot of a group is always a real pair
+        __syncthreads();
+        for (int i = tid; i < XS_G * dpad; i += XS_THREADS) {
+            const int g = i / dpad, t = i - g * dpad;
+            const int r = s_row[g];
+            xq_s[i] = (r >= 0 && t < d) ? X[(int64_t)row_point[r] * ldx + t] : 0.0;
+        }
+        const int e0 = seg_off[c], e1 = e0 + bin_cnt[c];
+        for (int cs = e0; cs < e1; cs += XS_CHUNK) {
+            const int ce = min(cs + XS_CHUNK, e1);
+            __syncthreads(); // query rows staged / previous chunk's selection finished
+            // ---- distances of this chunk's members against the group's queries
+            for (int e = cs + tid; e < ce; e += XS_THREADS) {
+                const int pt = col_pt[e];
+                if (pt < 0) continue;
+                const int ca = col_a[e], cb = col_b[e];
+                double acc[XS_G];
+                group_distances(xq_s, dpad, X + (int64_t)pt * ldx, d, acc);
+#pragma unroll
+                for (int g = 0; g < XS_G; ++g) {
+                    if (s_row[g] < 0 || !((s_p[g] > ca) || (s_p[g] < cb))) continue; // member not visible to this query
+                    const int slot = atomicAdd(&s_n[g], 1);
+                    key[g * XS_CAP + slot] = (u64)__double_as_longlong(acc[g]);
+                    idx[g * XS_CAP + slot] = pt;
+                }
+            }
+            __syncthreads();
+            // ---- selection: warp w owns query w
+            const int N = s_n[w];
+            if (s_row[w] >= 0 && N > k) { // N <= k: all members so far (distance_matrix.py:58-59)
+                u64 *K = key + w * XS_CAP;
+                int *I = idx + w * XS_CAP;
+                u64 m0k = KMAX, m1k = KMAX;
+                int m0i = INT32_MAX, m1i = INT32_MAX;
+                for (int j = lane; j < N; j += 64) {
+                    if (comp_lt(K[j], I[j], m0k, m0i)) { m0k = K[j]; m0i = I[j]; }
+                    const int j2 = j + 32;
+                    if (j2 < N && comp_lt(K[j2], I[j2], m1k, m1i)) { m1k = K[j2]; m1i = I[j2]; }
+                }
+                tmk[w * 64 + lane] = m0k;
+                tmi[w * 64 + lane] = m0i;
+                tmk[w * 64 + 32 + lane] = m1k;
+                tmi[w * 64 + 32 + lane] = m1i;
+                __syncwarp();
+                // tau = k-th smallest of the 64 minima (empty strides hold the sentinel; the position breaks their ties)
+                int r0 = 0, r1 = 0;
+                for (int t = 0; t < 64; ++t) {
+                    const u64 ok = tmk[w * 64 + t];
+                    const int oi = tmi[w * 64 + t];
+                    r0 += (comp_lt(ok, oi, m0k, m0i) || (ok == m0k && oi == m0i && t < lane)) ? 1 : 0;
+                    r1 += (comp_lt(ok, oi, m1k, m1i) || (ok == m1k && oi == m1i && t < lane + 32)) ? 1 : 0;
+                }
+                if (r0 == k - 1) { s_tk[w] = m0k; s_ti[w] = m0i; }
+                if (r1 == k - 1) { s_tk[w] = m1k; s_ti[w] = m1i; }
+                __syncwarp();
+                const u64 tk = s_tk[w];
+                const int ti = s_ti[w];
+                // members <= tau (at least k of them), compacted in array order
+                int M = 0;
+                for (int base = 0; base < N; base += 32) {
+                    const int j = base + lane;
+                    const bool in = j < N && !comp_lt(tk, ti, K[j], I[j]);
+                    const unsigned b = __ballot_sync(CHB_FULL, in);
+                    if (in) {
+                        const int slot = M + __popc(b & ((1u << lane) - 1u));
+                        if (slot < XS_CAND) { ck[w * XS_CAND + slot] = K[j]; ci[w * XS_CAND + slot] = I[j]; }
+                    }
+                    M += __popc(b);
+                }
+                __syncwarp();
+                const bool compact = M <= XS_CAND; // otherwise (a sentinel tau: fewer than k strides saw a member) rank in place
+                const u64 *lk = compact ? ck + w * XS_CAND : K;
+                const int *li = compact ? ci + w * XS_CAND : I;
+                const int L = compact ? M : N;
+                for (int j = lane; j < L; j += 32) {
+                    const u64 a = lk[j];
+                    const int ai = li[j];
+                    if (!compact && comp_lt(tk, ti, a, ai)) continue;
+                    int rk = 0;
+                    for (int t = 0; t < L; ++t) rk += comp_lt(lk[t], li[t], a, ai) ? 1 : 0;
+                    if (rk < k) { selk[w * XS_KEEP + rk] = a; seli[w * XS_KEEP + rk] = ai; }
+                }
+                __syncwarp();
+                if (lane < k) { K[lane] = selk[w * XS_KEEP + lane]; I[lane] = seli[w * XS_KEEP + lane]; }
+                if (lane == 0) s_n[w] = k;
+            }
+        }
+        __syncthreads();
+        // ---- ascending index order (canonical), compare with the cache, list for the QP kernel if the set changed
+        if (s_row[w] >= 0) {
+            const int r = s_row[w];
+            const int m = s_n[w];
+            const int *I = idx + w * XS_CAP;
+            int *srt = seli + w * XS_KEEP;
+            const int my = lane < m ? I[lane] : INT32_MAX;
+            int rk = 0;
+            for (int t = 0; t < m; ++t) rk += I[t] < my ? 1 : 0;
+            __syncwarp();
+            if (lane < m) srt[rk] = my;
+            __syncwarp();
+            const int64_t pair = (int64_t)row_slot[r] * C + c;
+            const bool diff = lane < k && knn_idx[pair * k + lane] != (lane < m ? srt[lane] : -1);
+            const bool same = knn_cnt[pair] == m && !__any_sync(CHB_FULL, diff);
+            if (!same) {
+                if (lane < k) knn_idx[pair * k + lane] = lane < m ? srt[lane] : -1;
+                if (lane == 0) {
+                    knn_cnt[pair] = m;
+                    work[atomicAdd(work_count, 1)] = make_int2(row_slot[r], c);
+                }
             }
         }
     }
@@ -1616,7 +1845,7 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 bool chb_fused_supported(const chb_ctx *c)
 {
     const FusedGeom g = fused_geom(c->d);
-    return c->k <= 32 && g.nbox <= MAX_BOX && g.nstage >= 3;
+    return c->k <= XS_KEEP && g.nbox <= MAX_BOX && g.nstage >= 3;
 }
 
 void chb_fused_free(chb_ctx *c)
@@ -1722,8 +1951,9 @@ int chb_fused_setup(chb_ctx *c)
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_cand_key, &z, nown * C * KR * 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cand_idx, &z, nown * C * KR * 2)) return CHB_ENOMEM;
-        const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * std::min<int64_t>(C, 8), 1024), INT32_MAX);
-        z = 0; if (reserve(c, &c->f_fb_pairs, &z, fbc)) return CHB_ENOMEM;
+        const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * std::min<int64_t>(C, 8), 1024), INT32_MAX - 16 * (int64_t)C - 16);
+        // + XS_G * C: the large-k path pads every bin's range of the list to a multiple of XS_G (exact_group_kernel)
+        z = 0; if (reserve(c, &c->f_fb_pairs, &z, fbc + 8 * (int64_t)C + 8)) return CHB_ENOMEM;
         c->f_fb_cap = (int32_t)fbc;
         c->f_cap_cand = nown * C * KR * 2;
     }
@@ -1832,12 +2062,20 @@ int chb_round_fused(chb_ctx *c)
     if (k + 3 > 16) {
         // ---- 3'. large k: exact selection for every surviving pair (find_nearest_from_cluster on exact distances)
         chb_stage_timer t(c, CHB_ST_KNN);
-        all_pairs_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_nb, c->f_row_bins, nown, C, c->f_fb_pairs, c->f_fb_cap,
-                                                                 &c->counters[6]);
-        const size_t xs = sizeof(double) * (size_t)((c->d + 1) & ~1);
-        exact_pairs_kernel<32><<<c->sm_count * 8, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
-                                                                        c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
-                                                                        c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
+        // surviving pairs regrouped per bin (threshold_kernel counted them per bin), XS_G queries of a bin per CTA pass
+        int32_t *bin_surv = c->f_pair_meta, *xs_off = c->f_pair_meta + (C + 2), *xs_cur = c->f_pair_meta + 2 * (C + 2);
+        const int32_t cap_slots = (int32_t)std::min<int64_t>(((int64_t)c->f_fb_cap + (int64_t)XS_G * C) & ~(int64_t)(XS_G - 1), INT32_MAX & ~(XS_G - 1));
+        static bool attr_done = false;
+        if (!attr_done) {
+            CHB_CUDA(c, cudaFuncSetAttribute(exact_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_done = true;
+        }
+        CHB_CUDA(c, cudaMemsetAsync(c->f_fb_pairs, 0xFF, sizeof(int2) * (size_t)cap_slots, c->stream));
+        xs_plan_kernel<<<1, 32, 0, c->stream>>>(bin_surv, C, xs_off, &c->counters[6]);
+        xs_fill_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_nb, c->f_row_bins, nown, C, xs_off, xs_cur, c->f_fb_pairs, cap_slots);
+        exact_group_kernel<<<c->sm_count * 2, XS_THREADS, exact_group_smem(c->d), c->stream>>>(
+            c->f_fb_pairs, xs_off, cap_slots, c->f_seg_off, c->f_bin_cnt, c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
+            c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
         CHB_CUDA(c, cudaGetLastError());
         c->tm.rows_scanned += nown;
         return CHB_OK;

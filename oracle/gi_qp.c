@@ -101,11 +101,19 @@ int chb_oracle_gi_solve(int n, const double *G, const double *a, int q, const do
     int nact = 0, n_add = 0, n_drop = 0;
 
     /* --- Cholesky G = L L' (lower, stored column-major in R temporarily) --- */
+    /* A pivot at rounding level means G is singular to working precision (exact duplicate contigs among the neighbours make
+     * two rows of 2 V V' identical): whether such a pivot comes out as +1e-17 or -1e-17 is noise, and factoring through it
+     * returns garbage (1e32-size "solutions") with a success code.  The reference's designed route for a non-PD matrix is
+     * "ValueError -> fallback solver" (solve_qp.py:110-123); the restatement takes that route deterministically: a pivot
+     * below n * 64 * eps * max|diag| counts as not positive definite. */
     double *L = R;
+    double gmax = 0.0;
+    for (int j = 0; j < n; ++j) gmax = fmax(gmax, fabs(G[(size_t)j * n + j]));
+    const double ptol = (double)n * 64.0 * 2.220446049250313e-16 * gmax;
     for (int j = 0; j < n; ++j) {
         double dj = G[(size_t)j * n + j];
         for (int k = 0; k < j; ++k) dj -= L[(size_t)k * n + j] * L[(size_t)k * n + j];
-        if (!(dj > 0.0)) { rc = 2; goto done; }
+        if (!(dj > ptol)) { rc = 2; goto done; }
         dj = sqrt(dj);
         L[(size_t)j * n + j] = dj;
         for (int i = j + 1; i < n; ++i) {

@@ -498,7 +498,7 @@ def test_rng_contract_one_draw_per_executed_iteration(max_iterations):
 def test_large_neighbour_counts(k):
     """BASELINE config #5 sweeps AlgoNumNeighbors up to 32.  The fused kernel keeps k + 3 <= 16 candidates per list, so for
     k >= 14 distance mode 2 prunes bins and then selects the neighbours of every surviving (query, bin) pair on exact
-    distances (exact_pairs_kernel), followed by the general QP kernel -- same labels as the oracle, in mode 1 as well."""
+    distances (exact_group_kernel), followed by the general QP kernel -- same labels as the oracle, in mode 1 as well."""
     X, bins, _ = synth.make_contig_features(1400, 3, 2, 45, seed=16 + k, concentration=250.0)
     perms = oracle.draw_permutations(bins, 3, seed=0)
     ref = oracle.fit_cluster(X, 3, bins, None, k, 3, perms=perms, threads=4)
@@ -509,6 +509,22 @@ def test_large_neighbour_counts(k):
     np.random.seed(0)
     got1 = chbin_b200.fit_cluster(X, 3, bins, None, k, 3, distance_mode=1)
     assert np.array_equal(got1, ref)
+
+
+@pytest.mark.parametrize("k,n,C,n_seed", [(16, 7000, 3, 20), (24, 9000, 4, 12), (32, 5000, 2, 40)])
+def test_large_neighbour_counts_big_bins(k, n, C, n_seed):
+    """exact_group_kernel beyond one shared-memory pass (768 members per bin and pass): bins of 2-3 thousand members, bins that
+    start with fewer than k members (all-members rule, distance_matrix.py:58-59) and grow through k and through the pass
+    size within one iteration, exact duplicates (ties resolved by index)."""
+    X, bins, _ = synth.make_contig_features(n, C, 2, n_seed, seed=k, concentration=250.0)
+    X[1000:1040] = X[2000:2040]
+    X[3000:3003] = X[2000]
+    perms = oracle.draw_permutations(bins, 3, seed=0)
+    ref = oracle.fit_cluster(X, C, bins, None, k, 3, perms=perms, threads=4)
+    np.random.seed(0)
+    got, info = chbin_b200.fit_cluster(X, C, bins, None, k, 3, return_info=True)
+    assert np.array_equal(got, ref)
+    assert info["timers"]["launches_gram"] == 0
 
 
 def test_uncompacted_items_fallback(monkeypatch):

@@ -114,3 +114,24 @@ def test_duplicates_fall_back():
     d1, alpha, st = oracle.convex_hull_distance(x, V2, return_alpha=True)
     assert abs(d0 - d1) <= 1e-9 * d0
     assert abs(alpha.sum() - 1) < 1e-9 and alpha.min() >= -1e-12
+
+
+@pytest.mark.parametrize("m,ndup", [(24, 4), (32, 6), (16, 2), (8, 1)])
+def test_duplicates_never_factor_through_a_noise_pivot(m, ndup):
+    """Exact duplicate vertices make 2 V V' singular; whether the Cholesky pivot comes out as +1e-17 or -1e-17 is rounding
+    noise.  A factorisation that accepts the positive case returns garbage (distances of 1e32 were seen at m = 24) with a
+    success code, so the restatement treats rounding-level pivots as "not positive definite" and takes the reference's
+    designed route for that (ValueError -> fallback solver, solve_qp.py:110-123).  The distance is still the unique
+    projection distance: equal to the one on the de-duplicated vertex set."""
+    for seed in range(40):
+        rng = np.random.default_rng(1000 * m + seed)
+        V = rng.dirichlet(np.full(137, 8.0), size=m - ndup)
+        x = rng.dirichlet(np.full(137, 8.0))
+        src = rng.choice(m - ndup, ndup, replace=False)
+        order = rng.permutation(m)
+        V2 = np.vstack([V, V[src]])[order]
+        d0 = oracle.convex_hull_distance(x, V)
+        d1, alpha, st = oracle.convex_hull_distance(x, V2, return_alpha=True)
+        assert st == 1  # degenerate: handled by the fallback solver
+        assert abs(d0 - d1) <= 1e-9 * d0, (seed, d0, d1)
+        assert abs(alpha.sum() - 1) < 1e-9 and alpha.min() >= -1e-12
