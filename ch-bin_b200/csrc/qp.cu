@@ -95,8 +95,43 @@ __device__ __forceinline__ int affine_solve(const double *sG, double *sRow, unsi
     return bad;
 }
 
+// Principal pivot (Gauss-Jordan exchange) of the tableau on vertex kv; lane i holds row i.  Starting from M = G + s 11' and
+// exchanging the vertices of a corral S one by one leaves (M_SS)^-1 in the S block, whatever the order, and exchanging a
+// vertex again takes it out: moving a vertex in or out of the corral costs ONE rank-1 update of the rows instead of a fresh
+// factorisation of the corral.  The diagonal entry met when a vertex enters is its Schur complement (affine dependence shows
+// up there); when it leaves it is a diagonal entry of an SPD inverse.  Returns false if the pivot is not above min_piv.
 template <int KMAX>
-__global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
+__device__ __forceinline__ bool exchange(double (&A)[KMAX], double *sRow, int kv, int lane, double min_piv)
+{
+    if (lane == kv) {
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) sRow[c] = A[c];
+    }
+    __syncwarp();
+    const double piv = sRow[kv];
+    if (!(piv > min_piv)) {
+        __syncwarp();
+        return false;
+    }
+    const double rinv = 1.0 / piv;
+    if (lane == kv) {
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) A[c] = (c == kv) ? rinv : -A[c] * rinv;
+    } else {
+        double aik = 0.0;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c)
+            if (c == kv) aik = A[c];
+        const double f = aik * rinv;
+#pragma unroll
+        for (int c = 0; c < KMAX; ++c) A[c] = (c == kv) ? f : fma(-f, sRow[c], A[c]);
+    }
+    __syncwarp();
+    return true;
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fast)
 {
     __shared__ __align__(16) double sWall[QP_WARPS][KMAX * LDW];
     __shared__ __align__(16) double sRowAll[QP_WARPS][KMAX + 2];
@@ -131,12 +166,16 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
             const int t = t0 + lane;
             const bool tin = t < d;
             const double xv = tin ? xq[t] : 0.0;
+            // eight rows per batch, loads first: a load behind a per-row branch would expose one memory latency per row
+            const int tc = tin ? t : 0;
 #pragma unroll
-            for (int r = 0; r < KMAX; ++r) {
-                if (r < m) {
-                    const int ir = __shfl_sync(CHB_FULL, myidx, r);
-                    const double v = tin ? a.X[(int64_t)ir * ldx + t] : 0.0;
-                    sW[r * LDW + lane] = v - xv;
+            for (int r0 = 0; r0 < KMAX; r0 += 8) {
+                if (r0 < m) { // warp-uniform; lanes >= m hold index 0, a valid row
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = a.X[(int64_t)__shfl_sync(CHB_FULL, myidx, r0 + u) * ldx + tc];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) sW[(r0 + u) * LDW + lane] = tin ? v[u] - xv : 0.0;
                 }
             }
             __syncwarp();
@@ -188,64 +227,111 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
                 status = CHB_QP_DEGENERATE;
             }
         } else {
+            // Wolfe's method.  attempt 0 (fast, the main kernel for k > 10) keeps the exchanged tableau across iterations;
+            // if that runs into the iteration cap or meets a non-positive leaving pivot (drift on an ill-conditioned
+            // corral) attempt 1 redoes the pair with a fresh Gauss-Jordan solve per minor cycle, as the fallback launches do.
             const double tol = 1e-14 * scale;
-            double key = lane < m ? gii : DBL_MAX;
-            int start = lane;
-            warp_argmin(key, start);
-            alpha = (lane == start) ? 1.0 : 0.0;
-            unsigned smask = 1u << start, banned = 0u;
-            const int itmax = 3 * m + 8;
-            int it = 0;
-            for (; it < itmax; ++it) {
-                if (lane < KMAX) sAlpha[lane] = alpha;
-                __syncwarp();
-                double g = 0.0;
-                if (lane < m) {
+            for (int attempt = fast ? 0 : 1; attempt < 2; ++attempt) {
+                const bool tab = attempt == 0;
+                bool tab_fail = false;
+                status = CHB_QP_OK;
+                double key = lane < m ? gii : DBL_MAX;
+                int start = lane;
+                warp_argmin(key, start);
+                alpha = (lane == start) ? 1.0 : 0.0;
+                unsigned smask = 1u << start, banned = 0u;
+                double A[KMAX];
+                if (tab) {
 #pragma unroll
-                    for (int c = 0; c < KMAX; ++c)
-                        if (c < m) g = fma(sG[lane * LDW + c], sAlpha[c], g);
+                    for (int c = 0; c < KMAX; ++c) A[c] = (lane < m && c < m) ? sG[lane * LDW + c] + scale : ((c == lane) ? 1.0 : 0.0);
+                    exchange<KMAX>(A, sRow, start, lane, 0.0); // G_ss + scale >= scale > 0
                 }
-                const double f = warp_sum(alpha * g);
-                const bool cand = (lane < m) && !((smask >> lane) & 1u) && !((banned >> lane) & 1u) && (g < f - tol);
-                double gk = cand ? g : DBL_MAX;
-                int jn = lane;
-                warp_argmin(gk, jn);
-                if (gk == DBL_MAX) break; // optimal
-                smask |= 1u << jn;
-                for (int minor = 0; minor <= m; ++minor) {
+                const int itmax = 3 * m + 8;
+                int it = 0;
+                for (; it < itmax && !tab_fail; ++it) {
+                    if (lane < KMAX) sAlpha[lane] = alpha;
+                    __syncwarp();
+                    double g = 0.0;
+                    if (lane < m) {
+#pragma unroll
+                        for (int c = 0; c < KMAX; ++c)
+                            if (c < m) g = fma(sG[lane * LDW + c], sAlpha[c], g);
+                    }
+                    const double f = warp_sum(alpha * g);
+                    const bool cand = (lane < m) && !((smask >> lane) & 1u) && !((banned >> lane) & 1u) && (g < f - tol);
+                    double gk = cand ? g : DBL_MAX;
+                    int jn = lane;
+                    warp_argmin(gk, jn);
+                    if (gk == DBL_MAX) break; // optimal
+                    if (tab && !exchange<KMAX>(A, sRow, jn, lane, 1e-11 * (sG[jn * LDW + jn] + scale))) {
+                        banned |= 1u << jn; // affinely dependent on the corral: same hull without it
+                        status = CHB_QP_DEGENERATE;
+                        continue;
+                    }
+                    smask |= 1u << jn;
+                    for (int minor = 0; minor <= m; ++minor) {
+                        double y;
+                        if (tab) {
+                            y = 0.0;
+                            if ((smask >> lane) & 1u) {
+#pragma unroll
+                                for (int c = 0; c < KMAX; ++c)
+                                    if ((smask >> c) & 1u) y += A[c];
+                            }
+                        } else {
+                            const int bad = affine_solve<KMAX>(sG, sRow, smask, m, scale, lane, y);
+                            if (bad >= 0) {
+                                smask &= ~(1u << jn);
+                                banned |= 1u << jn;
+                                status = CHB_QP_DEGENERATE;
+                                break;
+                            }
+                        }
+                        const double beta = y / warp_sum(y);
+                        const bool in = (smask >> lane) & 1u;
+                        const bool neg = in && !(beta > 0.0);
+                        const unsigned negm = __ballot_sync(CHB_FULL, neg);
+                        if (!negm) {
+                            alpha = in ? beta : 0.0;
+                            break;
+                        }
+                        double th = DBL_MAX;
+                        if (neg) th = (alpha > 0.0) ? alpha / (alpha - beta) : 0.0;
+                        int lt = lane;
+                        warp_argmin(th, lt);
+                        th = fmin(fmax(th, 0.0), 1.0);
+                        alpha = in ? alpha + th * (beta - alpha) : 0.0;
+                        const bool drop = in && (lane == lt || !(alpha > 0.0));
+                        unsigned dropm = __ballot_sync(CHB_FULL, drop);
+                        smask &= ~dropm;
+                        if (drop) alpha = 0.0;
+                        if ((dropm >> jn) & 1u) banned |= 1u << jn; // the entering vertex bounced straight out
+                        const double sa = warp_sum(alpha);
+                        alpha = alpha / sa;
+                        if (tab) {
+                            while (dropm) { // take the dropped vertices out of the tableau again
+                                const int dv = __ffs(dropm) - 1;
+                                dropm &= dropm - 1;
+                                if (!exchange<KMAX>(A, sRow, dv, lane, 0.0)) { tab_fail = true; break; }
+                            }
+                            if (tab_fail) break;
+                        }
+                        if (!((smask >> jn) & 1u)) break;
+                    }
+                }
+                if (tab && (tab_fail || it >= itmax || !(warp_sum(alpha) > 0.5))) continue; // redo without the tableau
+                if (it >= itmax) status = CHB_QP_ITER_CAP;
+                if (tab) {
+                    // polish: one fresh solve on the final corral removes whatever rounding the exchanges accumulated
                     double y;
                     const int bad = affine_solve<KMAX>(sG, sRow, smask, m, scale, lane, y);
-                    if (bad >= 0) {
-                        smask &= ~(1u << jn);
-                        banned |= 1u << jn;
-                        status = CHB_QP_DEGENERATE;
-                        break;
-                    }
                     const double beta = y / warp_sum(y);
                     const bool in = (smask >> lane) & 1u;
-                    const bool neg = in && !(beta > 0.0);
-                    const unsigned negm = __ballot_sync(CHB_FULL, neg);
-                    if (!negm) {
-                        alpha = in ? beta : 0.0;
-                        break;
-                    }
-                    double th = DBL_MAX;
-                    if (neg) th = (alpha > 0.0) ? alpha / (alpha - beta) : 0.0;
-                    int lt = lane;
-                    warp_argmin(th, lt);
-                    th = fmin(fmax(th, 0.0), 1.0);
-                    alpha = in ? alpha + th * (beta - alpha) : 0.0;
-                    const bool drop = in && (lane == lt || !(alpha > 0.0));
-                    const unsigned dropm = __ballot_sync(CHB_FULL, drop);
-                    smask &= ~dropm;
-                    if (drop) alpha = 0.0;
-                    if ((dropm >> jn) & 1u) banned |= 1u << jn; // the entering vertex bounced straight out
-                    const double sa = warp_sum(alpha);
-                    alpha = alpha / sa;
-                    if (!((smask >> jn) & 1u)) break;
+                    const unsigned negm = __ballot_sync(CHB_FULL, in && !(beta > 0.0));
+                    if (bad < 0 && !negm) alpha = in ? beta : 0.0;
                 }
+                break;
             }
-            if (it >= itmax) status = CHB_QP_ITER_CAP;
         }
 
         // ---------------- phase 3: || alpha V - x ||  in d dimensions (hull_distance.py:34-35)
@@ -254,13 +340,15 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
             const int t = t0 + lane;
             const bool tin = t < d;
             double pr = 0.0;
+            const int tc = tin ? t : 0;
 #pragma unroll
-            for (int r = 0; r < KMAX; ++r) {
-                if (r < m) {
-                    const int ir = __shfl_sync(CHB_FULL, myidx, r);
-                    const double ar = __shfl_sync(CHB_FULL, alpha, r);
-                    const double v = tin ? a.X[(int64_t)ir * ldx + t] : 0.0;
-                    pr = fma(ar, v, pr);
+            for (int r0 = 0; r0 < KMAX; r0 += 8) {
+                if (r0 < m) { // alpha is 0 in the lanes >= m, whose index 0 is a valid row
+                    double v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = a.X[(int64_t)__shfl_sync(CHB_FULL, myidx, r0 + u) * ldx + tc];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) pr = fma(__shfl_sync(CHB_FULL, alpha, r0 + u), v[u], pr);
                 }
             }
             const double df = tin ? pr - xq[t] : 0.0;
@@ -277,7 +365,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a)
 }
 
 template <int KMAX>
-int launch(chb_ctx *ctx, const chb_qp_args &a, int blocks_per_sm = 16)
+int launch(chb_ctx *ctx, const chb_qp_args &a, int blocks_per_sm = 16, int fast = 0)
 {
     int64_t blocks = (a.n_work + QP_WARPS - 1) / QP_WARPS;
     const int64_t cap = (int64_t)ctx->sm_count * blocks_per_sm;
@@ -285,7 +373,7 @@ int launch(chb_ctx *ctx, const chb_qp_args &a, int blocks_per_sm = 16)
     if (blocks < 1) blocks = 1;
     {
         chb_stage_timer t(ctx, CHB_ST_QP);
-        qp_kernel<KMAX><<<(unsigned)blocks, QP_WARPS * 32, 0, ctx->stream>>>(a);
+        qp_kernel<KMAX><<<(unsigned)blocks, QP_WARPS * 32, 0, ctx->stream>>>(a, fast);
     }
     CHB_CUDA(ctx, cudaGetLastError());
     return CHB_OK;
@@ -341,7 +429,9 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
         b.work_count = &ctx->counters[3];
         return launch<16>(ctx, b, 1);
     }
-    if (a.k <= 8) return launch<8>(ctx, a);
-    if (a.k <= 16) return launch<16>(ctx, a);
-    return launch<32>(ctx, a);
+    // main kernel for these neighbour counts: the exchanged tableau is kept across the iterations of a pair
+    const int fast = a.metric == CHB_METRIC_CONVEX && !getenv("CHB_QP_NO_TABLEAU");
+    if (a.k <= 8) return launch<8>(ctx, a, 16, fast);
+    if (a.k <= 16) return launch<16>(ctx, a, 16, fast);
+    return launch<32>(ctx, a, 16, fast);
 }
