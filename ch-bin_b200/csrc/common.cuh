@@ -107,6 +107,7 @@ struct chb_ctx {
     int32_t *f_cand_idx = nullptr;
     int2 *f_fb_pairs = nullptr; // (row, bin) pairs to redo exactly this round
     int32_t f_fb_cap = 0;
+    int64_t f_fb_alloc = 0; // entries allocated behind f_fb_pairs (f_fb_cap pairs + per-bin padding of the large-k path)
     int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0, f_cap_thr = 0, f_cap_ldt = 0;
     float *f_thr = nullptr; // nown x C : largest FP32 key of the cached neighbour set (+inf: fewer than k members)
     float *f_t0 = nullptr;  // C x f_ldt : this round's admission threshold per (bin, owned slot)

@@ -1884,6 +1884,7 @@ void chb_fused_free(chb_ctx *c)
     c->f_col_nrm = c->f_bperm = c->f_cand_key = nullptr;
     c->f_cand_idx = nullptr;
     c->f_fb_pairs = nullptr;
+    c->f_fb_alloc = 0;
 }
 
 // Runs steps 1-3 of the header comment for ALL owned query slots against the current (pos, tent, old) labels.
@@ -1951,11 +1952,20 @@ int chb_fused_setup(chb_ctx *c)
         int64_t z = 0;
         z = 0; if (reserve(c, &c->f_cand_key, &z, nown * C * KR * 2)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_cand_idx, &z, nown * C * KR * 2)) return CHB_ENOMEM;
-        const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * std::min<int64_t>(C, 8), 1024), INT32_MAX - 16 * (int64_t)C - 16);
-        // + XS_G * C: the large-k path pads every bin's range of the list to a multiple of XS_G (exact_group_kernel)
-        z = 0; if (reserve(c, &c->f_fb_pairs, &z, fbc + 8 * (int64_t)C + 8)) return CHB_ENOMEM;
-        c->f_fb_cap = (int32_t)fbc;
         c->f_cap_cand = nown * C * KR * 2;
+    }
+    {
+        // pairs redone on exact distances: a few per row when they are the exception (k + 3 <= 16), every pair that survives
+        // the pruning otherwise -- possibly all of them; + XS_G * C: that path pads every bin's range of the list to a
+        // multiple of XS_G (exact_group_kernel)
+        const int64_t per_row = (c->k + 3 > 16) ? C : std::min<int64_t>(C, 8);
+        const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * per_row, 1024), INT32_MAX - 16 * (int64_t)C - 16);
+        if (c->f_fb_alloc < fbc + 8 * (int64_t)C + 8) {
+            int64_t z = 0;
+            if (reserve(c, &c->f_fb_pairs, &z, fbc + 8 * (int64_t)C + 8)) return CHB_ENOMEM;
+            c->f_fb_alloc = z;
+        }
+        c->f_fb_cap = (int32_t)fbc;
     }
     c->f_ldt = (nown + 127) & ~int64_t(127);
     if (c->f_cap_thr < c->f_ldt * C || c->f_cap_ldt < c->f_ldt) {

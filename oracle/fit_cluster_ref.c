@@ -122,7 +122,43 @@ static double hull_distance_impl(const double *query, const double *points, int3
     for (int32_t j = 1; j < q; ++j) bv[j] = 0.0;
     int rc = chb_oracle_gi_solve(m, P, qa, q, Cm, bv, 1, alpha, NULL, NULL, NULL, NULL, NULL);
     if (rc != 0) {
-        if (!with_ineq) { if (status) *status = 2; return NAN; }
+        if (!with_ineq) {
+            /* affine metrics with affinely dependent vertices (duplicate contigs): the affine hull is the same without
+             * them and the distance stays well defined -- hull_distance.py:64-87 gets it from an SVD basis
+             * (scipy.linalg.orth).  Restated rank-revealing: modified Gram-Schmidt over the edge vectors v_i - v_0,
+             * skipping the ones that are already in the span, then the residual of x - v_0. */
+            enum { DM = 1024 };
+            if (d > DM) { if (status) *status = 2; return NAN; }
+            static _Thread_local double Q[KM][DM];
+            double u[DM], r[DM];
+            int nb = 0;
+            for (int32_t i = 1; i < m; ++i) {
+                double un2 = 0.0, rn2 = 0.0;
+                for (int32_t t = 0; t < d; ++t) { u[t] = points[(size_t)i * d + t] - points[t]; un2 += u[t] * u[t]; }
+                for (int pass = 0; pass < 2; ++pass) /* twice is enough */
+                    for (int b = 0; b < nb; ++b) {
+                        double dot = 0.0;
+                        for (int32_t t = 0; t < d; ++t) dot += Q[b][t] * u[t];
+                        for (int32_t t = 0; t < d; ++t) u[t] -= dot * Q[b][t];
+                    }
+                for (int32_t t = 0; t < d; ++t) rn2 += u[t] * u[t];
+                if (!(rn2 > 1e-22 * un2)) continue;
+                const double inv = 1.0 / sqrt(rn2);
+                for (int32_t t = 0; t < d; ++t) Q[nb][t] = u[t] * inv;
+                ++nb;
+            }
+            for (int32_t t = 0; t < d; ++t) r[t] = query[t] - points[t];
+            for (int pass = 0; pass < 2; ++pass)
+                for (int b = 0; b < nb; ++b) {
+                    double dot = 0.0;
+                    for (int32_t t = 0; t < d; ++t) dot += Q[b][t] * r[t];
+                    for (int32_t t = 0; t < d; ++t) r[t] -= dot * Q[b][t];
+                }
+            double ss = 0.0;
+            for (int32_t t = 0; t < d; ++t) ss += r[t] * r[t];
+            if (status) *status = 1;
+            return sqrt(ss);
+        }
         double qv[KM];
         for (int32_t i = 0; i < m; ++i) qv[i] = -qa[i];
         chb_oracle_simplex_qp(m, P, qv, alpha);

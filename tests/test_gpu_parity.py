@@ -539,3 +539,18 @@ def test_uncompacted_items_fallback(monkeypatch):
         got, info = chbin_b200.fit_cluster(X, C, bins, None, k, 4, return_info=True, reuse_context=False)
         assert np.array_equal(got, ref), (n, C, k)
         assert info["timers"]["launches_gram"] > 0
+
+
+@pytest.mark.parametrize("seed", [4, 5, 36, 52, 77, 131])
+def test_soak_regressions(seed):
+    """Cases found by the randomised soak (tests/soak_parity.py).  5: k = 16 with NO pair pruned -- the exact-selection list
+    must hold every (row, bin) pair; 4, 36, 52: affine / affine-qp metrics with duplicate contigs among the neighbours
+    (affinely dependent vertices: same affine hull without them); 77, 131: two more random draws kept as a canary."""
+    from soak_parity import case
+
+    cfg, X, bins = case(seed)
+    perms = oracle.draw_permutations(bins, cfg["iters"], seed=0)
+    ref = oracle.fit_cluster(X, cfg["C"], bins, None, cfg["k"], cfg["iters"], metric=cfg["metric"], perms=perms, threads=4)
+    np.random.seed(0)
+    got = chbin_b200.fit_cluster(X, cfg["C"], bins, None, cfg["k"], cfg["iters"], metric=cfg["metric"], distance_mode=cfg["mode"])
+    assert np.array_equal(got, ref), cfg

@@ -135,3 +135,19 @@ def test_duplicates_never_factor_through_a_noise_pivot(m, ndup):
         assert st == 1  # degenerate: handled by the fallback solver
         assert abs(d0 - d1) <= 1e-9 * d0, (seed, d0, d1)
         assert abs(alpha.sum() - 1) < 1e-9 and alpha.min() >= -1e-12
+
+
+def test_affine_metrics_with_dependent_vertices():
+    """Duplicate contigs among the neighbours leave the affine hull unchanged; the QP form (hull_distance.py:38-61) is then
+    singular and the restatement falls back to a rank-revealing Gram-Schmidt -- same value as the SVD form
+    (hull_distance.py:64-87, restated in oracle.affine_hull_distance) and as the de-duplicated vertex set."""
+    for seed in range(30):
+        rng = np.random.default_rng(seed)
+        m = int(rng.integers(2, 12))
+        V = rng.dirichlet(np.full(137, 8.0), size=m)
+        x = rng.dirichlet(np.full(137, 8.0))
+        V2 = np.vstack([V, V[rng.integers(0, m, 3)]])[rng.permutation(m + 3)]
+        d0 = oracle.affine_hull_distance_qp(x, V)
+        d1 = oracle.affine_hull_distance_qp(x, V2)
+        d2 = oracle.affine_hull_distance(x, V2)
+        assert abs(d1 - d0) <= 1e-9 * d0 and abs(d2 - d0) <= 1e-9 * d0, (seed, d0, d1, d2)
