@@ -1513,7 +1513,7 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict
 //               k << |bin|, few more; those are compacted and ranked by counting; ranks < k are find_nearest_from_cluster's
 //               answer (distance_matrix.py:47-62, ties resolved by index as everywhere in this library).
 // Bins larger than one pass are walked in chunks: the k kept so far stay at the front of the query's array.
-constexpr int XS_G = 8, XS_THREADS = 32 * XS_G, XS_CHUNK = 3 * XS_THREADS, XS_KEEP = 32, XS_CAP = XS_CHUNK + XS_KEEP, XS_CAND = 128;
+constexpr int XS_G = 8, XS_THREADS = 32 * XS_G, XS_CHUNK = 4 * XS_THREADS, XS_KEEP = 32, XS_CAP = XS_CHUNK + XS_KEEP, XS_CAND = 128;
 // XS_KEEP = the largest k the fused mode accepts (chb_fused_supported)
 
 __device__ __forceinline__ bool comp_lt(unsigned long long ka, int ia, unsigned long long kb, int ib)
@@ -1554,49 +1554,66 @@ __global__ void xs_fill_kernel(const int32_t *__restrict__ row_nb, const int32_t
     }
 }
 
-// scipy's recipe (sequential sum of rounded squares, no FMA, then sqrt) for one member row against XS_G query rows
-__device__ __forceinline__ void group_distances(const double *__restrict__ xq_s, int dpad, const double *__restrict__ xi, int d,
-                                                double (&acc)[XS_G])
+// scipy's recipe (sequential sum of rounded squares, no FMA, then sqrt) for TWO member rows against XS_G query rows: every
+// query value read from shared memory (a broadcast load still costs its 16 bytes x 32 lanes of return bandwidth) feeds two
+// chains -- with one member per thread the kernel sat on the shared-memory pipe at 40 % FP64 utilisation (ncu)
+__device__ __forceinline__ void group_distances2(const double *__restrict__ xq_s, int dpad, const double *__restrict__ xa,
+                                                 const double *__restrict__ xb, int d, double (&accA)[XS_G], double (&accB)[XS_G])
 {
 #pragma unroll
-    for (int g = 0; g < XS_G; ++g) acc[g] = 0.0;
-    const int d8 = d & ~7;
-    double v[8];
-    if (d8 > 0) {
+    for (int g = 0; g < XS_G; ++g) accA[g] = accB[g] = 0.0;
+    const int d4 = d & ~3;
+    double va[4], vb[4];
+    if (d4 > 0) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = xi[u];
+        for (int u = 0; u < 4; ++u) { va[u] = xa[u]; vb[u] = xb[u]; }
     }
-    for (int t = 0; t < d8; t += 8) {
-        double w[8];
+    for (int t = 0; t < d4; t += 4) {
+        double wa[4], wb[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) w[u] = v[u];
-        if (t + 8 < d8) {
+        for (int u = 0; u < 4; ++u) { wa[u] = va[u]; wb[u] = vb[u]; }
+        if (t + 4 < d4) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = xi[t + 8 + u];
+            for (int u = 0; u < 4; ++u) { va[u] = xa[t + 4 + u]; vb[u] = xb[t + 4 + u]; }
         }
+        // the query values of group g + 1 are fetched from shared memory while group g is being consumed
+        double qn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qn[u] = xq_s[t + u];
 #pragma unroll
         for (int g = 0; g < XS_G; ++g) {
-            const double *q = xq_s + g * dpad + t;
+            double qc[4];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const double df = __dsub_rn(q[u], w[u]);
-                acc[g] = __dadd_rn(acc[g], __dmul_rn(df, df));
+            for (int u = 0; u < 4; ++u) qc[u] = qn[u];
+            if (g + 1 < XS_G) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) qn[u] = xq_s[(g + 1) * dpad + t + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const double da = __dsub_rn(qc[u], wa[u]);
+                const double db = __dsub_rn(qc[u], wb[u]);
+                accA[g] = __dadd_rn(accA[g], __dmul_rn(da, da));
+                accB[g] = __dadd_rn(accB[g], __dmul_rn(db, db));
             }
         }
     }
-    for (int t = d8; t < d; ++t) {
-        const double x = xi[t];
+    for (int t = d4; t < d; ++t) {
+        const double a = xa[t], b = xb[t];
 #pragma unroll
         for (int g = 0; g < XS_G; ++g) {
-            const double df = __dsub_rn(xq_s[g * dpad + t], x);
-            acc[g] = __dadd_rn(acc[g], __dmul_rn(df, df));
+            const double qv = xq_s[g * dpad + t];
+            const double da = __dsub_rn(qv, a);
+            const double db = __dsub_rn(qv, b);
+            accA[g] = __dadd_rn(accA[g], __dmul_rn(da, da));
+            accB[g] = __dadd_rn(accB[g], __dmul_rn(db, db));
         }
     }
 #pragma unroll
-    for (int g = 0; g < XS_G; ++g) acc[g] = __dsqrt_rn(acc[g]);
+    for (int g = 0; g < XS_G; ++g) { accA[g] = __dsqrt_rn(accA[g]); accB[g] = __dsqrt_rn(accB[g]); }
 }
 
-__global__ void __launch_bounds__(XS_THREADS, 2)
+__global__ void __launch_bounds__(XS_THREADS, 1)
     exact_group_kernel(const int2 *__restrict__ slots, const int32_t *__restrict__ xs_off, int32_t cap_slots, const int32_t *__restrict__ seg_off,
                        const int32_t *__restrict__ bin_cnt, const int32_t *__restrict__ col_pt, const int32_t *__restrict__ col_a,
                        const int32_t *__restrict__ col_b, const double *__restrict__ X, int32_t ldx, int32_t d,
@@ -1641,18 +1658,27 @@ __global__ void __launch_bounds__(XS_THREADS, 2)
             const int ce = min(cs + XS_CHUNK, e1);
             __syncthreads(); // query rows staged / previous chunk's selection finished
             // ---- distances of this chunk's members against the group's queries
-            for (int e = cs + tid; e < ce; e += XS_THREADS) {
-                const int pt = col_pt[e];
-                if (pt < 0) continue;
+            for (int e = cs + tid; e < ce; e += 2 * XS_THREADS) { // two members per thread and step
+                const int e2 = e + XS_THREADS;
+                const int pt = col_pt[e], pt2 = e2 < ce ? col_pt[e2] : -1; // -1: padding column
+                if (pt < 0 && pt2 < 0) continue;
                 const int ca = col_a[e], cb = col_b[e];
-                double acc[XS_G];
-                group_distances(xq_s, dpad, X + (int64_t)pt * ldx, d, acc);
+                const int ca2 = pt2 >= 0 ? col_a[e2] : 0, cb2 = pt2 >= 0 ? col_b[e2] : 0;
+                double acc[XS_G], acc2[XS_G];
+                group_distances2(xq_s, dpad, X + (int64_t)(pt >= 0 ? pt : pt2) * ldx, X + (int64_t)(pt2 >= 0 ? pt2 : pt) * ldx, d, acc, acc2);
 #pragma unroll
                 for (int g = 0; g < XS_G; ++g) {
-                    if (s_row[g] < 0 || !((s_p[g] > ca) || (s_p[g] < cb))) continue; // member not visible to this query
-                    const int slot = atomicAdd(&s_n[g], 1);
-                    key[g * XS_CAP + slot] = (u64)__double_as_longlong(acc[g]);
-                    idx[g * XS_CAP + slot] = pt;
+                    if (s_row[g] < 0) continue;
+                    if (pt >= 0 && ((s_p[g] > ca) || (s_p[g] < cb))) { // member visible to this query
+                        const int slot = atomicAdd(&s_n[g], 1);
+                        key[g * XS_CAP + slot] = (u64)__double_as_longlong(acc[g]);
+                        idx[g * XS_CAP + slot] = pt;
+                    }
+                    if (pt2 >= 0 && ((s_p[g] > ca2) || (s_p[g] < cb2))) {
+                        const int slot = atomicAdd(&s_n[g], 1);
+                        key[g * XS_CAP + slot] = (u64)__double_as_longlong(acc2[g]);
+                        idx[g * XS_CAP + slot] = pt2;
+                    }
                 }
             }
             __syncthreads();
@@ -2083,7 +2109,7 @@ int chb_round_fused(chb_ctx *c)
         CHB_CUDA(c, cudaMemsetAsync(c->f_fb_pairs, 0xFF, sizeof(int2) * (size_t)cap_slots, c->stream));
         xs_plan_kernel<<<1, 32, 0, c->stream>>>(bin_surv, C, xs_off, &c->counters[6]);
         xs_fill_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_nb, c->f_row_bins, nown, C, xs_off, xs_cur, c->f_fb_pairs, cap_slots);
-        exact_group_kernel<<<c->sm_count * 2, XS_THREADS, exact_group_smem(c->d), c->stream>>>(
+        exact_group_kernel<<<c->sm_count, XS_THREADS, exact_group_smem(c->d), c->stream>>>(
             c->f_fb_pairs, xs_off, cap_slots, c->f_seg_off, c->f_bin_cnt, c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
             c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
         CHB_CUDA(c, cudaGetLastError());

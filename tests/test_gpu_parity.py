@@ -513,7 +513,7 @@ def test_large_neighbour_counts(k):
 
 @pytest.mark.parametrize("k,n,C,n_seed", [(16, 7000, 3, 20), (24, 9000, 4, 12), (32, 5000, 2, 40)])
 def test_large_neighbour_counts_big_bins(k, n, C, n_seed):
-    """exact_group_kernel beyond one shared-memory pass (768 members per bin and pass): bins of 2-3 thousand members, bins that
+    """exact_group_kernel beyond one shared-memory pass (1024 members per bin and pass): bins of 2-3 thousand members, bins that
     start with fewer than k members (all-members rule, distance_matrix.py:58-59) and grow through k and through the pass
     size within one iteration, exact duplicates (ties resolved by index)."""
     X, bins, _ = synth.make_contig_features(n, C, 2, n_seed, seed=k, concentration=250.0)
