@@ -4,6 +4,11 @@ Randomised parity soak (GPU box): random small workloads -- sizes, bin counts, c
 counts 1..32, metrics, distance modes, injected duplicate contigs -- each compared label for label with the oracle's
 sequential fit_cluster.  Not collected by pytest (a failing random case must be reduced first); the cases it found live
 on as regular tests.  usage: python tests/soak_parity.py [first_seed] [count]
+
+Known benign differences (3 in seeds 0..759: 198, 657, 701; reduce with tests/soak_debug.py): a query that has an exact
+duplicate in TWO bins is at distance 0 from both hulls.  The library returns 0.0 for both and the strict comparison of
+algorithm.py:57 keeps the first bin; the oracle's (and quadprog's) solvers return 0.0 for one and 1e-16-size rounding noise
+for the other, so their choice is decided by that noise.
 """
 import os
 import sys
