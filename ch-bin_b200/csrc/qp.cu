@@ -433,5 +433,6 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
     const int fast = a.metric == CHB_METRIC_CONVEX && !getenv("CHB_QP_NO_TABLEAU");
     if (a.k <= 8) return launch<8>(ctx, a, 16, fast);
     if (a.k <= 16) return launch<16>(ctx, a, 16, fast);
+    if (a.k <= 24) return launch<24>(ctx, a, 16, fast); // the cost follows the unrolled width, not k
     return launch<32>(ctx, a, 16, fast);
 }
