@@ -464,15 +464,24 @@ __global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__
         nseed = seed_off[g + 1] - seed_off[g];
         int slot = 0;
         for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32, ++slot) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0; // independent chains: the loop is DFMA-latency bound otherwise
+            // eight loads in flight and eight independent chains: the loop is bound by the latency of the (L2-resident) seed
+            // tile and of DFMA otherwise
+            double acc[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc[u] = 0.0;
             int t = 0;
-            for (; t + 3 < d; t += 4) {
-                const double d0 = q_sm[w][t] - seedT[(int64_t)t * ns + i], d1 = q_sm[w][t + 1] - seedT[(int64_t)(t + 1) * ns + i];
-                const double d2 = q_sm[w][t + 2] - seedT[(int64_t)(t + 2) * ns + i], d3 = q_sm[w][t + 3] - seedT[(int64_t)(t + 3) * ns + i];
-                s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+            for (; t + 7 < d; t += 8) {
+                double sv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) sv[u] = seedT[(int64_t)(t + u) * ns + i];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double df = q_sm[w][t + u] - sv[u];
+                    acc[u] = fma(df, df, acc[u]);
+                }
             }
-            for (; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; s0 = fma(df, df, s0); }
-            const double s = (s0 + s1) + (s2 + s3);
+            for (; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; acc[0] = fma(df, df, acc[0]); }
+            const double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
             ub2 = fmin(ub2, s);
             if (slot == 0) v[0] = s; else if (slot == 1) v[1] = s; else if (slot == 2) v[2] = s; else if (slot == 3) v[3] = s;
         }
@@ -2101,11 +2110,8 @@ int chb_round_fused(chb_ctx *c)
         // surviving pairs regrouped per bin (threshold_kernel counted them per bin), XS_G queries of a bin per CTA pass
         int32_t *bin_surv = c->f_pair_meta, *xs_off = c->f_pair_meta + (C + 2), *xs_cur = c->f_pair_meta + 2 * (C + 2);
         const int32_t cap_slots = (int32_t)std::min<int64_t>(((int64_t)c->f_fb_cap + (int64_t)XS_G * C) & ~(int64_t)(XS_G - 1), INT32_MAX & ~(XS_G - 1));
-        static bool attr_done = false;
-        if (!attr_done) {
-            CHB_CUDA(c, cudaFuncSetAttribute(exact_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            attr_done = true;
-        }
+        // per device, not per process: set on every call (a context may live on any device of this process)
+        CHB_CUDA(c, cudaFuncSetAttribute(exact_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_group_smem(c->d)));
         CHB_CUDA(c, cudaMemsetAsync(c->f_fb_pairs, 0xFF, sizeof(int2) * (size_t)cap_slots, c->stream));
         xs_plan_kernel<<<1, 32, 0, c->stream>>>(bin_surv, C, xs_off, &c->counters[6]);
         xs_fill_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_nb, c->f_row_bins, nown, C, xs_off, xs_cur, c->f_fb_pairs, cap_slots);

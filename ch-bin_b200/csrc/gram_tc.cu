@@ -290,11 +290,8 @@ int chb_launch_gram_tc(chb_ctx *ctx, const float *a_split, const float *b_split,
     rc = make_map(ctx, &map_b, const_cast<float *>(b_split), ctx->n, Kp);
     if (rc != CHB_OK) return rc;
     const size_t smem = sizeof(SharedStorage) + 1024;
-    static bool configured = false;
-    if (!configured) {
-        CHB_CUDA(ctx, cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // a per-device attribute: set per call, a context may live on any device of this process
+    CHB_CUDA(ctx, cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((ctx->n + BN - 1) / BN), (unsigned)((nrows + BM - 1) / BM));
     CHB_CHECK(ctx, grid.y <= 65535u, CHB_EINVAL, "gram_tc: too many rows per launch (%lld)", (long long)nrows);
     {

@@ -556,11 +556,8 @@ int chb_launch_knn_scan(chb_ctx *ctx, const chb_knn_args &a)
     const size_t bytes = smem_layout(nullptr, a.C, KR, Wp, a.d, nullptr) + 16;
     CHB_CHECK(ctx, bytes <= 227 * 1024, CHB_EINVAL, "num_clusters*num_neighbors too large for the kNN kernel (%zu B smem)",
               bytes);
-    static size_t configured = 0;
-    if (bytes > configured) {
-        CHB_CUDA(ctx, cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
-    }
+    // a per-device attribute: set per call, a context may live on any device of this process
+    CHB_CUDA(ctx, cudaFuncSetAttribute(knn_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     {
         chb_stage_timer t(ctx, CHB_ST_KNN);
         knn_scan_kernel<<<(unsigned)a.n_items, NT, bytes, ctx->stream>>>(a);
