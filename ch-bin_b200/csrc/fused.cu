@@ -26,6 +26,8 @@
 //     recipe (sequential sum, no FMA) and are ranked by exact (distance, index).  A pair goes to the QP work list only
 //     if its neighbour SET changed.  Pairs whose kept lists could be incomplete (more than KR keys inside the window:
 //     duplicate contigs) are redone exactly on the device by exact_pairs_kernel.
+//  5. k + 3 > 16 (the register lists cannot hold the candidates): steps 3-4 are replaced by an exact selection over every pair
+//     that survived step 2, regrouped per bin so that eight queries share each member row (exact_group_kernel).
 //
 // Roofline of gram_select_kernel: tensor pipe, co-limited by the CUDA-core selection epilogue.
 #include <cuda.h>
