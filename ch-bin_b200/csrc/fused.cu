@@ -26,7 +26,7 @@
 //     recipe (sequential sum, no FMA) and are ranked by exact (distance, index).  A pair goes to the QP work list only
 //     if its neighbour SET changed.  Pairs whose kept lists could be incomplete (more than KR keys inside the window:
 //     duplicate contigs) are redone exactly on the device by exact_pairs_kernel.
-//  5. k + 3 > 16 (the register lists cannot hold the candidates): steps 3-4 are replaced by an exact selection over every pair
+//  5. k > 15 (a half-list of KR = 16 register entries must hold more than k candidates): steps 3-4 are replaced by an exact selection over every pair
 //     that survived step 2, regrouped per bin so that eight queries share each member row (exact_group_kernel).
 //
 // Roofline of gram_select_kernel: tensor pipe, co-limited by the CUDA-core selection epilogue.
@@ -1512,7 +1512,7 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Large neighbour counts (k + 3 > 16: the register lists of the fused kernel cannot hold the candidates): exact selection for
+// Large neighbour counts (k > 15: the 16-entry register lists of the fused kernel cannot hold k + 1 candidates): exact selection for
 // EVERY surviving (row, bin) pair.  With one pair per CTA every member row of the bin travels L2 -> SM once per pair and the
 // L2 fabric is the bound; here the surviving pairs are regrouped per bin and XS_G queries of one bin share every member row
 // they read (XS_G x fewer bytes, XS_G independent FP64 chains per thread), which leaves the FP64 pipe as the bound
@@ -1877,8 +1877,9 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 
 } // namespace
 
-// the resident query operand (2 * dp8 floats per row) fits MAX_BOX boxes with at least 3 ring stages left; k + 3 <= 16
-// candidates per half-list fit the register lists of the fused kernel, larger k uses pruning + exact selection only
+// the resident query operand (2 * dp8 floats per row) fits MAX_BOX boxes with at least 3 ring stages left; up to k = 15 the
+// k + 1 candidates the re-rank needs fit a 16-entry register half-list of the fused kernel, larger k uses pruning + exact
+// selection only (chb_round_fused)
 bool chb_fused_supported(const chb_ctx *c)
 {
     const FusedGeom g = fused_geom(c->d);
@@ -1992,10 +1993,10 @@ int chb_fused_setup(chb_ctx *c)
         c->f_cap_cand = nown * C * KR * 2;
     }
     {
-        // pairs redone on exact distances: a few per row when they are the exception (k + 3 <= 16), every pair that survives
+        // pairs redone on exact distances: a few per row when they are the exception (k <= 15), every pair that survives
         // the pruning otherwise -- possibly all of them; + XS_G * C: that path pads every bin's range of the list to a
         // multiple of XS_G (exact_group_kernel)
-        const int64_t per_row = (c->k + 3 > 16) ? C : std::min<int64_t>(C, 8);
+        const int64_t per_row = (c->k > 15) ? C : std::min<int64_t>(C, 8);
         const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * per_row, 1024), INT32_MAX - 16 * (int64_t)C - 16);
         if (c->f_fb_alloc < fbc + 8 * (int64_t)C + 8) {
             int64_t z = 0;
@@ -2106,7 +2107,10 @@ int chb_round_fused(chb_ctx *c)
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
         c->f_row_guess, eps_rel, nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins, c->f_pair_meta);
-    if (k + 3 > 16) {
+    // KR = 16 serves k <= 15: the re-rank needs the (k+1)-th key, and a half-list can only be full when more than k candidates
+    // exist, which is what arms its completeness test (k + 3 <= KR merely keeps that test from firing often; at k = 14, 15 it
+    // still fires only when nearly all of the k nearest fall into the same 64-column halves)
+    if (k > 15) {
         // ---- 3'. large k: exact selection for every surviving pair (find_nearest_from_cluster on exact distances)
         chb_stage_timer t(c, CHB_ST_KNN);
         // surviving pairs regrouped per bin (threshold_kernel counted them per bin), XS_G queries of a bin per CTA pass
@@ -2164,7 +2168,7 @@ int chb_round_fused(chb_ctx *c)
                                                               c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pos, C,
                                                               k, c->knn_idx, c->knn_cnt, c->work, c->counters);
         else
-            exact_pairs_kernel<13><<<64, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
+            exact_pairs_kernel<15><<<64, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
                                                                c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot,
                                                                c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
     }

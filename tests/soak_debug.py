@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Reduces a failing case of tests/soak_parity.py: finds the first query (in assignment order) whose label differs from the
 oracle's, rebuilds the label state at that step and prints, per bin, the oracle's neighbour set and hull distance (GI route
-and min-norm route) next to the library's (chb_knn_per_bin + chb_hull_distance_batch).  usage: python tests/soak_debug.py SEED"""
+and min-norm route) next to the library's (chb_knn_per_bin + chb_hull_distance_batch).  usage: python tests/soak_debug.py SEED   |   soak_debug.py K SEED (a soak_k case)"""
 import os
 import sys
 
@@ -14,8 +14,13 @@ import oracle  # noqa: E402
 from chbin_b200 import capi  # noqa: E402
 from soak_parity import case  # noqa: E402
 
-seed = int(sys.argv[1])
-cfg, X, bins = case(seed)
+if len(sys.argv) > 2:  # soak_k case: K SEED
+    import soak_k
+
+    cfg, X, bins = soak_k.case(int(sys.argv[1]), int(sys.argv[2]))
+else:
+    seed = int(sys.argv[1])
+    cfg, X, bins = case(seed)
 print(cfg)
 C, k, iters, metric = cfg["C"], cfg["k"], cfg["iters"], cfg["metric"]
 perms = oracle.draw_permutations(bins, iters, seed=0)
