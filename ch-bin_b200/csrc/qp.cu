@@ -158,7 +158,12 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fa
         const int myidx = lane < m ? a.knn_idx[pair * k + lane] : 0;
         const double *__restrict__ xq = a.X + (int64_t)jq * ldx;
 
-        // ---------------- phase 1: G = W W', lane i accumulates row i
+        // ---------------- phase 1: G = W W', lane i accumulates row i; with at most 16 rows both half-warps work: lane i and
+        // lane i + 16 take half of each tile's columns of row i
+        constexpr bool SPLIT = KMAX <= 16;
+        constexpr int TSPAN = SPLIT ? TC / 2 : TC;
+        const int grow = SPLIT ? (lane & 15) : lane;
+        const int tbeg = SPLIT ? (lane >> 4) * TSPAN : 0;
         double G[KMAX];
 #pragma unroll
         for (int c = 0; c < KMAX; ++c) G[c] = 0.0;
@@ -179,10 +184,10 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fa
                 }
             }
             __syncwarp();
-            if (lane < m) {
+            if (grow < m) {
 #pragma unroll 4
-                for (int tt = 0; tt < TC; tt += 2) {
-                    const double2 own = *reinterpret_cast<const double2 *>(&sW[lane * LDW + tt]);
+                for (int tt = tbeg; tt < tbeg + TSPAN; tt += 2) {
+                    const double2 own = *reinterpret_cast<const double2 *>(&sW[grow * LDW + tt]);
 #pragma unroll
                     for (int c = 0; c < KMAX; ++c) {
                         if (c < m) {
@@ -194,6 +199,10 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fa
                 }
             }
             __syncwarp();
+        }
+        if (SPLIT) { // the two half-warps each summed half of every tile's columns for row (lane & 15)
+#pragma unroll
+            for (int c = 0; c < KMAX; ++c) G[c] += __shfl_xor_sync(CHB_FULL, G[c], 16);
         }
         // G to shared memory (the tile buffer is free now): sG[i][c] at sW[i*LDW + c]
         double gii = 0.0;
