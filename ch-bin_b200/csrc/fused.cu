@@ -2182,6 +2182,7 @@ extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslot
     CHB_CHECK(c, c && key_out && idx_out && slack_out && kr_out, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->f_cand_key && c->f_slack && slot0 >= c->u0 && nslots >= 0 && slot0 + nslots <= c->u1, CHB_EINVAL,
               "slots not owned / no fused round has run yet");
+    CHB_CHECK(c, c->k <= 15, CHB_EINVAL, "no candidate lists exist for num_neighbors > 15 (exact selection, chb_round_fused)");
     CHB_CUDA(c, cudaSetDevice(c->device));
     const int KR = (c->k + 3 <= 8) ? 8 : 16;
     const int64_t nown = c->u1 - c->u0, s0 = slot0 - c->u0, per = (int64_t)c->C * 2 * KR;
