@@ -1168,8 +1168,10 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
     const int64_t r = i - (int64_t)c * nown;           // row (rows are the owned slots ordered by guessed bin)
     const float tq = tq_tab[(int64_t)c * ldt + r];
     // pruning (97-99 % of the pairs end here, so this test is all FP32 and touches nothing per pair but tq and t0):
-    // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test
-    {
+    // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test.
+    // Only the CONVEX hull of k members lies inside the ball around m_c: an affine hull is unbounded and may pass close to a
+    // query far from every member, so the affine metrics (hull_distance.py:38-87) keep every bin (prune == 0).
+    if (prune) {
         const float dq = __fsqrt_rd(tq), ym = __fmul_ru(__fsqrt_ru(ym2[c]), 1.000001f), ub = ub_row[r];
         const float scale = sq_row[r] + __fsqrt_ru(__uint_as_float(*nrm_max_bits));
         if (dq * 0.999999f - ym > ub + 1e-5f * (dq + ym + ub) + 4e-6f * scale) {
@@ -2106,7 +2108,7 @@ int chb_round_fused(chb_ctx *c)
     threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
         c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
         reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
-        c->f_row_guess, eps_rel, nown, C, k, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins, c->f_pair_meta);
+        c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins, c->f_pair_meta);
     // KR = 16 serves k <= 15: the re-rank needs the (k+1)-th key, and a half-list can only be full when more than k candidates
     // exist, which is what arms its completeness test (k + 3 <= KR merely keeps that test from firing often; at k = 14, 15 it
     // still fires only when nearly all of the k nearest fall into the same 64-column halves)

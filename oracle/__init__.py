@@ -33,7 +33,7 @@ _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
 
 def build(force: bool = False) -> str:
     """Compile oracle/*.c into oracle/liboracle.so (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("gi_qp.c", "minnorm.c", "fit_cluster_ref.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("gi_qp.c", "minnorm.c", "fit_cluster_ref.c", "verify.c", "oracle.h", "Makefile")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
@@ -74,6 +74,15 @@ def lib() -> ctypes.CDLL:
             _f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _i64p, ctypes.c_void_p, ctypes.c_int32,
             ctypes.c_int32, ctypes.c_int32, _i64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, _i64p,
             ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _i64p, ctypes.POINTER(ctypes.c_int64),
+        ]
+        L.chb_oracle_verify_positions.restype = ctypes.c_int64
+        L.chb_oracle_verify_positions.argtypes = [
+            _f64p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _i64p, _i64p, _i64p, ctypes.c_int64, _i64p, ctypes.c_int64,
+            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _i64p, _f64p, _f64p, ctypes.c_void_p,
+        ]
+        L.chb_oracle_hull_distance_batch.restype = None
+        L.chb_oracle_hull_distance_batch.argtypes = [
+            _f64p, ctypes.c_int32, _i64p, _i64p, _i32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _f64p, _i32p,
         ]
         _lib = L
     return _lib
@@ -194,6 +203,22 @@ def affine_hull_distance(query: np.ndarray, points: np.ndarray) -> float:
     return float(np.linalg.norm(dq - proj))
 
 
+def hull_distance_batch(samples: np.ndarray, queries: np.ndarray, idx: np.ndarray, m: np.ndarray, metric: str = "convex",
+                        threads: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """calculate_distance (hull_distance.py:90-108) for many (query, neighbour list) pairs at once: queries (P,) point
+    indices, idx (P, k) neighbour indices, m (P,) how many of them count.  Returns (distances (P,), status (P,))."""
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    queries = np.ascontiguousarray(queries, dtype=np.int64)
+    idx = np.ascontiguousarray(idx, dtype=np.int64)
+    m = np.ascontiguousarray(m, dtype=np.int32)
+    P, k = idx.shape
+    dist = np.empty(P)
+    status = np.empty(P, dtype=np.int32)
+    met = {"convex": 0, "affine-qp": 1, "affine": 1}[metric]
+    lib().chb_oracle_hull_distance_batch(samples, samples.shape[1], queries, idx, m, P, k, met, int(threads), dist, status)
+    return dist, status
+
+
 def calculate_distance(x: np.ndarray, mat_p: np.ndarray, qp_solver: str = "quadprog", metric: str = "convex") -> float:
     """hull_distance.py:90-108."""
     if metric == "convex":
@@ -266,6 +291,49 @@ def fit_cluster(
         return labels, dict(iterations=iters.value, converged=bool(conv.value),
                             changed=changed[: iters.value].copy(), qps=nqp.value)
     return labels
+
+
+def verify_iteration(
+    samples: np.ndarray,
+    num_clusters: int,
+    old_labels: np.ndarray,
+    new_labels: np.ndarray,
+    perm: np.ndarray,
+    num_neighbors: int,
+    positions: Optional[np.ndarray] = None,
+    metric: str = "convex",
+    threads: int = 0,
+    return_distances: bool = False,
+):
+    """Position-parallel check that `new_labels` is what ONE iteration of algorithm.py:46-60 makes of `old_labels` under
+    the permutation `perm` (oracle/verify.c): at every checked position p the oracle recomputes
+    assign(perm[p] | new labels of positions < p, old labels of positions > p and of the seeds) and compares.  All U
+    positions checked (positions=None) and none failing <=> new_labels is the sequential result.  Returns a dict:
+    mismatches (count), positions, labels (the oracle's), best / second (its two smallest hull distances per position:
+    best == second marks a tie the strict '<' of algorithm.py:57 decides)."""
+    samples = np.ascontiguousarray(samples, dtype=np.float64)
+    old_labels = np.ascontiguousarray(old_labels, dtype=np.int64)
+    new_labels = np.ascontiguousarray(new_labels, dtype=np.int64)
+    perm = np.ascontiguousarray(perm, dtype=np.int64)
+    n, d = samples.shape
+    if positions is None:
+        positions = np.arange(len(perm), dtype=np.int64)
+    positions = np.ascontiguousarray(positions, dtype=np.int64)
+    met = {"convex": 0, "affine-qp": 1, "affine": 1}[metric]
+    lab = np.empty(len(positions), dtype=np.int64)
+    best = np.empty(len(positions))
+    second = np.empty(len(positions))
+    dist = np.empty((len(positions), int(num_clusters))) if return_distances else None
+    rc = lib().chb_oracle_verify_positions(
+        samples, n, d, int(num_clusters), old_labels, new_labels, perm, len(perm), positions, len(positions),
+        int(num_neighbors), met, int(threads), lab, best, second, dist.ctypes.data if dist is not None else None,
+    )
+    if rc < 0:
+        raise ValueError(f"oracle verify_positions failed rc={rc}")
+    out = dict(mismatches=int(rc), positions=positions, labels=lab, best=best, second=second)
+    if dist is not None:
+        out["distances"] = dist
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -50,6 +50,24 @@ int chb_oracle_fit_cluster(const double *X, int64_t n, int32_t d, int32_t num_cl
                            const int64_t *perms, int64_t U, int32_t threads, int64_t max_steps, int64_t *labels_out,
                            int32_t *iters_run, int32_t *converged, int64_t *changed, int64_t *qps_solved);
 
+/* verify.c -- position-parallel check of ONE iteration of algorithm.py:46-60.  For each listed permutation position p
+ * (point j = perm[p]) evaluates assign(j | new_labels for positions < p, old_labels for positions > p and for seeds) with
+ * the arithmetic of chb_oracle_fit_cluster, and compares with new_labels[j].  `new_labels` is the sequential result iff the
+ * check passes at every position.  label_out / best_out / second_out (npos, optional): the oracle's label, its smallest
+ * and second smallest hull distance; dist_out (npos * C, optional): every hull distance.  Returns the number of
+ * positions whose label differs (negative: error). */
+int64_t chb_oracle_verify_positions(const double *X, int64_t n, int32_t d, int32_t C, const int64_t *old_labels,
+                                    const int64_t *new_labels, const int64_t *perm, int64_t U, const int64_t *positions,
+                                    int64_t npos, int32_t k, int32_t metric, int32_t threads, int64_t *label_out,
+                                    double *best_out, double *second_out, double *dist_out);
+
+/* verify.c -- calculate_distance (hull_distance.py:90-108) for npairs (query point, neighbour list) pairs: queries (npairs)
+ * point indices, idx (npairs * k) neighbour point indices of which the first m[p] count; metric 0 convex, 1 affine-qp.
+ * dist_out (npairs; +inf where m == 0), status_out (npairs, optional: 0 GI, 1 fallback solver, 3 empty). */
+void chb_oracle_hull_distance_batch(const double *X, int32_t d, const int64_t *queries, const int64_t *idx, const int32_t *m,
+                                    int64_t npairs, int32_t k, int32_t metric, int32_t threads, double *dist_out,
+                                    int32_t *status_out);
+
 #ifdef __cplusplus
 }
 #endif

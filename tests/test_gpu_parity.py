@@ -555,3 +555,73 @@ def test_soak_regressions(seed):
     np.random.seed(0)
     got = chbin_b200.fit_cluster(X, cfg["C"], bins, None, cfg["k"], cfg["iters"], metric=cfg["metric"], distance_mode=cfg["mode"])
     assert np.array_equal(got, ref), cfg
+
+
+@pytest.mark.parametrize("metric", ["affine-qp", "affine"])
+@pytest.mark.parametrize("k", [3, 5])
+def test_affine_metrics_never_prune_a_far_bin_whose_flat_passes_the_query(metric, k):
+    """The ball bound behind the bin pruning (LB = |x - mu_c| - max|y - mu_c|) holds for CONVEX hulls only: the affine hull
+    of k members is unbounded.  Bins 2 and 3 are far from every query (40 cluster radii) and tight, but their members lie
+    along a line that runs through one query each: its distance to that affine hull is ~0 while its home bin is at a
+    finite distance, so the reference assigns it to the far bin (hull_distance.py:38-87).  Labels must equal the
+    oracle's; under the convex metric the same far bins are (rightly) out of reach."""
+    X, bins, truth = synth.make_contig_features(900, 4, 1, 25, seed=41, concentration=2000.0)
+    rng = np.random.default_rng(41)
+    d = X.shape[1]
+    targets = []
+    for far_bin, home in ((2, 0), (3, 1)):
+        tq = np.where((bins == -1) & (truth == home))[0][3]
+        members = np.where(truth == far_bin)[0]
+        u = rng.normal(size=d)
+        u /= np.linalg.norm(u)
+        home_pts = X[truth == home]
+        spread = np.linalg.norm(home_pts - home_pts.mean(axis=0), axis=1).max()
+        t = 40.0 * spread + 2.0 * spread * rng.random(len(members))
+        X[members] = X[tq] + t[:, None] * u + 1e-5 * spread * rng.normal(size=(len(members), d))
+        targets.append((tq, far_bin))
+    perms = oracle.draw_permutations(bins, 3, seed=0)
+    ref = oracle.fit_cluster(X, 4, bins, None, k, 3, metric=metric, perms=perms, threads=4)
+    assert any(ref[t] == fb for t, fb in targets), "the construction must make a far bin win for its target query"
+    for mode in (2, 1):
+        np.random.seed(0)
+        got = chbin_b200.fit_cluster(X, 4, bins, None, k, 3, metric=metric, distance_mode=mode)
+        assert np.array_equal(got, ref), (metric, k, mode)
+    refc = oracle.fit_cluster(X, 4, bins, None, k, 3, metric="convex", perms=perms, threads=4)
+    np.random.seed(0)
+    gotc = chbin_b200.fit_cluster(X, 4, bins, None, k, 3, metric="convex")
+    assert np.array_equal(gotc, refc) and not any(refc[t] == fb for t, fb in targets)
+
+
+def test_query_duplicated_in_two_bins_keeps_the_lower_bin():
+    """A query with an exact duplicate among the members of TWO bins is at hull distance 0 from both.  The kernels return
+    exactly 0.0 for both (qp_small.cu: a vertex coincides with the query) and the strict '<' of algorithm.py:57 keeps the
+    LOWER bin.  (quadprog-style solvers return 0.0 and ~1e-16 of rounding noise and let the noise decide: the reference's
+    own answer is not reproducible there, so the pinned behaviour is the deterministic one.)  Every OTHER position must
+    still satisfy the sequential equation given these labels (oracle/verify.c)."""
+    X, bins, truth = synth.make_contig_features(700, 5, 1, 30, seed=43, concentration=1500.0)
+    q = np.where(bins == -1)[0][:6]
+    pairs = [(1, 3), (0, 4), (2, 3), (3, 4), (0, 1), (1, 4)]
+    for qi, (j, (lo, hi)) in enumerate(zip(q, pairs)):
+        X[np.where(bins == lo)[0][qi]] = X[j]
+        X[np.where(bins == hi)[0][8 + qi]] = X[j]
+    perms = oracle.draw_permutations(bins, 1, seed=0)
+    np.random.seed(0)
+    got, info = chbin_b200.fit_cluster(X, 5, bins, None, 5, 1, return_info=True)
+    for j, (lo, hi) in zip(q, pairs):
+        assert got[j] == lo, (j, lo, hi, got[j])
+    pos_of = np.full(len(X), -1)
+    pos_of[perms[0]] = np.arange(perms.shape[1])
+    others = np.setdiff1d(np.arange(perms.shape[1]), pos_of[q])
+    res = oracle.verify_iteration(X, 5, bins, got, perms[0], 5, positions=others, threads=4)
+    assert res["mismatches"] == 0
+    with capi.Context(0) as ctx:
+        ctx.set_features(X); ctx.set_labels(bins, 5); ctx.set_params(5, "convex")
+        idx = np.full((len(q), 5, 5), -1, dtype=np.int64)
+        m = np.zeros((len(q), 5), dtype=np.int32)
+        for qi, j in enumerate(q):
+            for c in range(5):
+                mem = np.where(bins == c)[0]
+                near = mem[np.argsort(np.linalg.norm(X[mem] - X[j], axis=1), kind="stable")[:5]]
+                idx[qi, c] = near; m[qi, c] = 5
+        dist, _ = ctx.hull_distance_batch(q, idx, m)
+    assert np.sum(dist == 0.0) == 2 * len(q), "both duplicated bins are at distance exactly 0.0"

@@ -1,0 +1,248 @@
+"""
+GPU parity at the sizes BASELINE.json names (configs #2-#5) and on overlapping ("hard") bins where the pruning bounds stop
+helping.  Every check goes through the C-ABI and is compared with the CPU oracle:
+
+  * sequential oracle (oracle/fit_cluster_ref.c, algorithm.py:12-76) where it finishes in seconds (20k);
+  * position-parallel oracle (oracle/verify.c) elsewhere: the labels an iteration produced are the sequential result iff
+        labels[perm[p]] == assign(perm[p] | new labels of positions < p, old labels of positions > p and of the seeds)
+    at every position p (algorithm.py:46-60; induction over p).  Checked at ALL positions for the 100k config and the
+    hard case, on a seeded sample of positions (always including the first and the last ones) for 200k / 1M;
+  * hull distances on >= 10^6 random (query, neighbour list) pairs per k with 1 % degenerate pairs injected
+    (duplicate neighbours, query among its neighbours, affinely dependent rows) -- SURVEY.md section 7 step 3.
+
+Bars: labels identical; hull distances within 1e-6 * d_ref + 1e-12 * |x|.
+"""
+import os
+import time
+
+import numpy as np
+import pytest
+
+import chbin_b200
+import oracle
+from chbin_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+THREADS = os.cpu_count() or 1
+
+
+def _gpu_iterations(X, bins, C, k, perms, max_iterations, metric="convex"):
+    """Labels after EVERY executed iteration (chb_fit_iteration), plus the change counts (algorithm.py:63-69)."""
+    out = []
+    with capi.Context(0) as ctx:
+        ctx.set_features(X)
+        ctx.set_labels(bins, C)
+        ctx.set_params(k, metric)
+        ctx.build_distance_matrix(True)
+        for it in range(max_iterations):
+            labels, nch = ctx.fit_iteration(perms[it])
+            out.append((labels, nch))
+            if nch == 0:
+                break
+        tm = ctx.timers()
+    return out, tm
+
+
+def _sample_positions(U, count, seed):
+    """first 256 and last 256 positions (smallest / fullest bins) plus a seeded random sample of the rest"""
+    rng = np.random.default_rng(seed)
+    edge = np.concatenate([np.arange(min(256, U)), np.arange(max(U - 256, 0), U)])
+    rest = rng.choice(U, min(count, U), replace=False)
+    return np.unique(np.concatenate([edge, rest])).astype(np.int64)
+
+
+def _assert_verified(res, what):
+    if res["mismatches"]:
+        bad = np.where(res["labels"] != res["expected"])[0][:5]
+        detail = [(int(res["positions"][i]), int(res["labels"][i]), int(res["expected"][i]), float(res["best"][i]),
+                   float(res["second"][i])) for i in bad]
+        raise AssertionError(f"{what}: {res['mismatches']} of {len(res['positions'])} positions differ from the oracle; "
+                             f"(position, oracle, gpu, best, second) = {detail}")
+
+
+def _verify(X, C, old, new, perm, k, positions=None, metric="convex"):
+    res = oracle.verify_iteration(X, C, old, new, perm, k, positions=positions, metric=metric, threads=THREADS)
+    res["expected"] = new[perm[res["positions"]]]
+    return res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_config2_20k_all_iterations_match_sequential_oracle():
+    """BASELINE config #2 in full: labels, iteration count and per-iteration change counts == the sequential oracle."""
+    X, bins, _, cfg = synth.make_config("20k")
+    C, k = cfg["C"], cfg["k"]
+    perms = oracle.draw_permutations(bins, 10, seed=0)
+    ref, rinfo = oracle.fit_cluster(X, C, bins, None, k, 10, perms=perms, threads=THREADS, return_info=True)
+    np.random.seed(0)
+    got, info = chbin_b200.fit_cluster(X, C, bins, None, k, 10, return_info=True)
+    assert np.array_equal(got, ref)
+    assert info["iterations"] == rinfo["iterations"] and info["converged"] == rinfo["converged"]
+    assert list(info["changed"]) == list(rinfo["changed"])
+    assert got.min() >= 0
+
+
+def test_config3_100k_k10_every_position_of_iteration_1():
+    """BASELINE config #3 (100k contigs, d = 146, C = 100, k = 10): iteration 1 checked at EVERY position, the later
+    iterations on a sample, the change counts against the label vectors themselves, and the first sequential steps
+    against the sequential oracle."""
+    X, bins, _, cfg = synth.make_config("100k")
+    C, k = cfg["C"], cfg["k"]
+    perms = oracle.draw_permutations(bins, 10, seed=0)
+    U = perms.shape[1]
+    its, tm = _gpu_iterations(X, bins, C, k, perms, 10)
+    assert its[-1][1] == 0, "the run must end on the reference's stop rule (algorithm.py:63-66)"
+    lab1 = its[0][0]
+    t0 = time.perf_counter()
+    _assert_verified(_verify(X, C, bins, lab1, perms[0], k), "100k iteration 1")
+    print(f"100k: {U} positions verified in {time.perf_counter() - t0:.1f} s on {THREADS} threads; "
+          f"device solved {tm['qps_solved']} of {tm['qps_reference']} reference QPs")
+    prev = bins
+    for it, (lab, nch) in enumerate(its):
+        assert nch == int(np.sum(lab != prev)), "n_changed must be sum(initial_bins != curr_bins) (algorithm.py:63,68)"
+        if it > 0:
+            _assert_verified(_verify(X, C, prev, lab, perms[it], k, _sample_positions(U, 4000, it)), f"100k iteration {it + 1}")
+        prev = lab
+    # the first steps through the sequential oracle itself
+    steps = 1500
+    seq = oracle.fit_cluster(X, C, bins, None, k, 1, perms=perms, threads=THREADS, max_steps=steps)
+    head = perms[0][:steps]
+    assert np.array_equal(seq[head], lab1[head])
+
+
+@pytest.mark.parametrize("k", [5, 12, 16, 32])
+def test_config5_200k_k_sweep(k):
+    """BASELINE config #5 (AlgoNumNeighbors sweep at 200k contigs): one iteration per k, every kernel family of the sweep
+    (qp_small / general QP kernel with fused selection / exact large-k selection), checked on sampled positions."""
+    X, bins, _, cfg = synth.make_config("200k")
+    C = cfg["C"]
+    perms = oracle.draw_permutations(bins, 1, seed=0)
+    U = perms.shape[1]
+    its, _ = _gpu_iterations(X, bins, C, k, perms, 1)
+    lab1, nch = its[0]
+    assert nch == int(np.sum(lab1 != bins)) and lab1.min() >= 0
+    _assert_verified(_verify(X, C, bins, lab1, perms[0], k, _sample_positions(U, 6000 if k <= 16 else 3000, k)), f"200k k={k}")
+
+
+def test_config4_1m_sampled_positions():
+    """BASELINE config #4 (1M contigs, d = 156, C = 500, k = 5) on ONE GPU: iteration 1 and 2 on sampled positions."""
+    X, bins, _, cfg = synth.make_config("1m")
+    C, k = cfg["C"], cfg["k"]
+    perms = oracle.draw_permutations(bins, 2, seed=0)
+    U = perms.shape[1]
+    its, _ = _gpu_iterations(X, bins, C, k, perms, 2)
+    prev = bins
+    for it, (lab, nch) in enumerate(its):
+        assert nch == int(np.sum(lab != prev))
+        _assert_verified(_verify(X, C, prev, lab, perms[it], k, _sample_positions(U, 1500, 40 + it)), f"1M iteration {it + 1}")
+        prev = lab
+
+
+def test_hard_overlapping_bins_20k_every_position_every_iteration():
+    """Overlapping genomes (Dirichlet concentration 60 instead of 4000): the pruning bounds keep most bins alive, the
+    speculation needs many repair rounds and the loop runs into the iteration limit -- the regime DESIGN 3b calls
+    "degrades to the unpruned path".  Every position of every iteration is checked."""
+    n, C, k = 20_000, 50, 5
+    X, bins, _ = synth.make_contig_features(n, C, 1, 50, seed=3, concentration=60.0)
+    max_it = 4
+    perms = oracle.draw_permutations(bins, max_it, seed=0)
+    its, tm = _gpu_iterations(X, bins, C, k, perms, max_it)
+    prev = bins
+    for it, (lab, nch) in enumerate(its):
+        assert nch == int(np.sum(lab != prev))
+        _assert_verified(_verify(X, C, prev, lab, perms[it], k), f"hard 20k iteration {it + 1}")
+        prev = lab
+    frac = tm["qps_solved"] / max(tm["qps_reference"], 1)
+    print(f"hard 20k: {len(its)} iterations, {tm['rounds']} rounds, device solved {frac:.2f} x the reference QP count")
+    assert its[0][1] > 0 and len(its) >= 2
+
+
+def test_hard_overlapping_bins_100k_k10_sampled():
+    n, C, k = 100_000, 100, 10
+    X, bins, _ = synth.make_contig_features(n, C, 10, 50, seed=4, concentration=120.0)
+    perms = oracle.draw_permutations(bins, 2, seed=0)
+    U = perms.shape[1]
+    its, _ = _gpu_iterations(X, bins, C, k, perms, 2)
+    prev = bins
+    for it, (lab, nch) in enumerate(its):
+        _assert_verified(_verify(X, C, prev, lab, perms[it], k, _sample_positions(U, 6000, 7 + it)), f"hard 100k iteration {it + 1}")
+        prev = lab
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def _pairs_with_degenerates(X, rng, nq, C, k):
+    """nq * C random (query, neighbour list) pairs; about 1 % are made degenerate:
+       A: a neighbour index repeated (two identical rows of V -> singular Gram matrix),
+       B: the query itself among its neighbours (distance exactly 0),
+       C: three neighbours a, b, (a + b) / 2 -- rows `mid` appended to X -- affinely dependent,
+       D: fewer than k neighbours (m < k), down to m = 1 and m = 0."""
+    n0 = len(X)
+    nmid = 512
+    a = rng.integers(0, n0, nmid)
+    b = rng.integers(0, n0, nmid)
+    Xe = np.concatenate([X, 0.5 * (X[a] + X[b])])
+    queries = rng.integers(0, n0, nq)
+    # regular pairs: k DISTINCT neighbours, none of them the query -- an arithmetic progression modulo n0 - 1 (distinct while
+    # step * k < n0 - 1), shifted past the query
+    base = rng.integers(0, n0 - 1, (nq, C, 1))
+    step = rng.integers(1, (n0 - 2) // k, (nq, C, 1))
+    v = (base + step * np.arange(k)[None, None, :]) % (n0 - 1)
+    idx = (queries[:, None, None] + 1 + v) % n0
+    m = np.full((nq, C), k, dtype=np.int32)
+    kind = np.zeros((nq, C), dtype=np.int8)
+    pick = rng.random((nq, C)) < 0.01
+    which = rng.integers(0, 4, (nq, C))
+    for qi, c in zip(*np.where(pick)):
+        w = which[qi, c]
+        if w == 0 and k >= 2:
+            idx[qi, c, 1] = idx[qi, c, 0]
+            kind[qi, c] = 1
+        elif w == 1:
+            idx[qi, c, rng.integers(0, k)] = queries[qi]
+            kind[qi, c] = 2
+        elif w == 2 and k >= 3:
+            t = rng.integers(0, nmid)
+            idx[qi, c, 0], idx[qi, c, 1], idx[qi, c, 2] = a[t], b[t], n0 + t
+            kind[qi, c] = 3
+        else:
+            m[qi, c] = rng.integers(0, k)
+            idx[qi, c, m[qi, c]:] = -1
+            kind[qi, c] = 4
+    return Xe, queries, idx, m, kind
+
+
+@pytest.mark.parametrize("k", [3, 5, 10, 16, 32])
+def test_hull_distance_million_pairs(k):
+    """>= 10^6 hull distances per k against the oracle (hull_distance.py:7-35 through the GI restatement)."""
+    nq, C = 10_000, 100
+    X, bins, _ = synth.make_contig_features(30_000, C, 1 if k <= 5 else 10, 20, seed=21)
+    rng = np.random.default_rng(500 + k)
+    Xe, queries, idx, m, kind = _pairs_with_degenerates(X, rng, nq, C, k)
+    bins_e = np.concatenate([bins, np.zeros(len(Xe) - len(X), dtype=np.int64)])
+    with capi.Context(0) as ctx:
+        ctx.set_features(Xe)
+        ctx.set_labels(bins_e, C)
+        ctx.set_params(k, "convex")
+        dist, status = ctx.hull_distance_batch(queries, idx, m)
+    ref, rst = oracle.hull_distance_batch(Xe, np.repeat(queries, C), np.where(idx < 0, 0, idx).reshape(nq * C, k), m.reshape(-1),
+                                          threads=THREADS)
+    ref = ref.reshape(nq, C)
+    assert nq * C >= 10 ** 6
+    empty = m == 0
+    assert np.all(np.isinf(dist[empty])) and np.all(status[empty] == 3)
+    xn = np.linalg.norm(Xe[queries], axis=1)[:, None]
+    err = np.abs(dist - ref)
+    regular = (kind == 0) | ((kind == 4) & ~empty)
+    tol = 1e-6 * ref + 1e-12 * xn
+    worst = np.max((err / tol)[regular])
+    assert worst <= 1.0, f"k={k}: regular pairs off by {worst:.3g} x the tolerance"
+    # degenerate pairs: the minimiser is not unique but the distance is; the oracle itself goes through its fallback solver
+    # there (solve_qp.py:126-129), so the bar is the tolerance plus 1e-7 of the scale of the data
+    deg = (kind >= 1) & (kind <= 3)
+    scale = xn + np.zeros_like(ref)
+    tol_d = 1e-6 * ref + 1e-7 * scale
+    worst_d = np.max((err / tol_d)[deg]) if deg.any() else 0.0
+    assert worst_d <= 1.0, f"k={k}: degenerate pairs off by {worst_d:.3g} x the tolerance"
+    assert np.all(dist[kind == 2] <= 1e-7 * scale[kind == 2]), "a query among its own neighbours is at distance 0"
+    print(f"k={k}: {nq * C} pairs, {int(deg.sum())} degenerate, worst regular {worst:.2e} x tol, worst degenerate {worst_d:.2e} x tol, "
+          f"oracle fallbacks {int((rst == 1).sum())}")
