@@ -16,6 +16,8 @@ There is no CPU fallback.
 from __future__ import annotations
 
 import logging
+import os
+import shutil
 from pathlib import Path
 from typing import Optional, Tuple
 
@@ -337,10 +339,25 @@ def perform_clustering(
     num_samples = len(samples)
 
     if not in_mem_dist_matrix:
-        # cli/clustering.py:60-63: the on-disk matrix is produced (or found) exactly where the reference keeps it; the
-        # assignment rounds below regenerate distances on the device and never read it back
-        logger.info(">> Creating a distance matrix of %s in-disk...", (num_samples, num_samples))
-        distance_cache.create_distance_matrix(samples, operating_dir)
+        # cli/clustering.py:60-63: the on-disk matrix is produced (or found) exactly where the reference keeps it, so that a
+        # later reference run can reuse it; the assignment rounds below regenerate distances on the device and never read
+        # it back.  The file is 8 n^2 bytes (320 GB at 200k contigs): beyond CHB_DISTANCE_MATRIX_MAX_GB (default 64) or
+        # the free space of the volume it is skipped -- InMemDistMatrix = no exists for inputs whose matrix does not fit,
+        # and this path does not need the matrix at all.
+        need = 8 * num_samples * num_samples
+        limit = float(os.environ.get("CHB_DISTANCE_MATRIX_MAX_GB", "64")) * (1 << 30)
+        existing = operating_dir / distance_cache.DISTANCE_MATRIX_NAME
+        if existing.exists():
+            logger.info("Reusing already existing distance matrix at %s.", existing)
+            if not distance_cache.validate_distance_matrix(existing, samples):
+                logger.warning("%s does not hold the distances of these features (stale cache); the b200 solver does not "
+                               "read it, a later reference run would.", existing)
+        elif need > limit or need > shutil.disk_usage(operating_dir).free:
+            logger.info(">> Skipping the in-disk distance matrix of %s (%.1f GB): not needed by the %s solver.",
+                        (num_samples, num_samples), need / (1 << 30), qp_solver)
+        else:
+            logger.info(">> Creating a distance matrix of %s in-disk...", (num_samples, num_samples))
+            distance_cache.create_distance_matrix(samples, operating_dir)
 
     logger.info(">> Performing binning using %s solver...", qp_solver)
     convex_labels = fit_cluster(

@@ -1159,7 +1159,7 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
                                  const float *__restrict__ ym2, const float *__restrict__ tcmax, const float *__restrict__ tq_tab,
                                  const float *__restrict__ ub_row, const float *__restrict__ sq_row,
                                  const float *__restrict__ ubk2_row, const int32_t *__restrict__ row_guess, double eps_rel, int64_t nown,
-                                 int32_t C, int32_t k, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
+                                 int32_t C, int32_t k, int32_t prune, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
                                  int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -80,3 +80,54 @@ def test_install_dispatches_on_solver(tmp_path, monkeypatch):
     assert fake.perform_clustering("c.fa", "f.csv", tmp_path, 5, 2, "convex", "quadprog", True) == "ref.csv"
     assert fake.perform_clustering("c.fa", "f.csv", tmp_path, 5, 2, "convex", "b200", True) == csv
     assert calls == [("reference", "quadprog"), ("b200", "b200"), ("dump_bins", str(tmp_path / "bins"))]
+
+
+def test_install_on_the_real_reference_module_through_the_ini_route(G, features_csv, tmp_path, monkeypatch):
+    """install() applied to the reference's OWN ch_bin.cli.clustering (imported unmodified from /root/reference; Biopython
+    and the two solver packages are stand-ins, oracle/ref_shim.py) and driven the way ch_bin/ch_bin.py:30 drives it:
+    run_perform_clustering(contigs, features.csv, dir, USER_CONFIG["PARAMETERS"]) (cli/clustering.py:102-127) with
+    `AlgoQpSolver = b200` in the INI.  The engine behind fit_cluster is the CPU oracle here (no GPU in this container); what
+    is under test is the dispatch: the b200 value reaches this package, every other value reaches the untouched original,
+    and both write the same binning-assignment.csv bytes as the reference's own run (tests/golden, section 5)."""
+    from configparser import ConfigParser
+
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("/root/reference is not mounted here (GPU box)")
+    mod = ref_shim.load_cli_clustering()
+    original = mod.perform_clustering
+    seen = []
+
+    def oracle_fit(**kw):
+        seen.append(kw["qp_solver"])
+        return _oracle_fit(kw["samples"], kw["num_clusters"], kw["initial_bins"], kw["num_neighbors"], kw["max_iterations"],
+                           kw["metric"], kw["qp_solver"], kw["in_mem_dist_matrix"])
+
+    monkeypatch.setattr(clustering, "fit_cluster", oracle_fit)
+    k, iters = (int(v) for v in G["pc_params"])
+    cfg = ConfigParser()
+    cfg.read(os.path.join(ref_shim.REFERENCE_ROOT, "config", "default.ini"))
+    cfg["PARAMETERS"]["AlgoNumNeighbors"] = str(k)
+    cfg["PARAMETERS"]["AlgoMaxIterations"] = str(iters)
+    try:
+        clustering.install(mod)
+        assert mod.perform_clustering is not original and mod.perform_clustering.__wrapped__ is original
+        cfg["PARAMETERS"]["AlgoQpSolver"] = "b200"
+        np.random.seed(0)  # ch_bin/ch_bin.py:22
+        out = mod.run_perform_clustering(tmp_path / "contigs.fasta", features_csv, tmp_path / "b200", cfg["PARAMETERS"])
+        assert seen == ["b200"]
+        assert out == tmp_path / "b200" / "binning-assignment.csv"
+        assert out.read_bytes() == G["pc_assignment_csv"].tobytes()
+        assert (tmp_path / "b200" / "bins").is_dir()  # step 05 was handed back to the reference's dump_bins
+        # any other solver value: the reference's own perform_clustering, untouched (quadprog stand-in behind it)
+        cfg["PARAMETERS"]["AlgoQpSolver"] = "quadprog"
+        np.random.seed(0)
+        out2 = mod.run_perform_clustering(tmp_path / "contigs.fasta", features_csv, tmp_path / "ref", cfg["PARAMETERS"])
+        assert seen == ["b200"]
+        assert out2.read_bytes() == G["pc_assignment_csv"].tobytes()
+        with pytest.raises(NotImplementedError):  # solve_qp.py:132 still answers for unknown values
+            cfg["PARAMETERS"]["AlgoQpSolver"] = "gurobi"
+            mod.run_perform_clustering(tmp_path / "contigs.fasta", features_csv, tmp_path / "bad", cfg["PARAMETERS"])
+    finally:
+        mod.perform_clustering = original
