@@ -24,8 +24,8 @@ EXPORTED_SYMBOLS = [
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
     "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
-    "chb_measure_fp64_tflops", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
-    "chb_get_fused_candidates", "chb_set_features_async", "chb_set_features_merged", "chb_get_features",
+    "chb_measure_fp64_tflops", "chb_measure_l2_gbs", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
+    "chb_get_fused_candidates", "chb_set_features_async", "chb_set_features_colmajor", "chb_set_features_merged", "chb_get_features",
 ]
 
 
@@ -38,6 +38,7 @@ class Timers(ctypes.Structure):
         ("qps_solved", ctypes.c_int64), ("qps_reference", ctypes.c_int64), ("rounds", ctypes.c_int64),
         ("rows_scanned", ctypes.c_int64),
         ("ms_gram", ctypes.c_double), ("launches_gram", ctypes.c_int64), ("gram_tiles", ctypes.c_int64),
+        ("gram_tiles_planned", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -79,6 +80,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_features.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_dev.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_async.argtypes = [_vp, _vp, _i64, _i32]
+    L.chb_set_features_colmajor.argtypes = [_vp, _vp, _i64, _i32, ctypes.c_int]
     L.chb_set_features_merged.argtypes = [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]
     L.chb_get_features.argtypes = [_vp, _vp]
     L.chb_set_labels.argtypes = [_vp, _vp, _i64, _i32, _i64, _i64]
@@ -103,6 +105,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_get_window.argtypes = [_vp]
     L.chb_get_window.restype = _i64
     L.chb_measure_fp64_tflops.argtypes = [_vp, ctypes.POINTER(_dbl)]
+    L.chb_measure_l2_gbs.argtypes = [_vp, ctypes.POINTER(_dbl)]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("chb_last_error", "chb_get_window"):
@@ -185,12 +188,20 @@ class Context:
 
     # -- set-up
     def set_features(self, samples: np.ndarray, asynchronous: bool = False):
-        """asynchronous=True: chb_set_features_async -- returns once the upload is enqueued; the array is kept alive
-        (and must stay unchanged) until build_distance_matrix() / synchronize()."""
-        x = np.ascontiguousarray(samples, dtype=np.float64)  # DataFrame.values arrives F-ordered
-        if x.ndim != 2:
+        """asynchronous=True: returns once the upload is enqueued; the array is kept alive (and must stay unchanged) until
+        build_distance_matrix() / synchronize().  An F-ordered float64 array -- what DataFrame.values hands over at
+        cli/clustering.py:53 -- is uploaded as it lies in memory and transposed on the device (chb_set_features_colmajor);
+        anything else goes through one C-contiguous float64 copy (a no-op for an array that already is one)."""
+        a = np.asarray(samples)
+        if a.ndim != 2:
             raise ValueError("samples must be a 2-D array")
-        self.n, self.d = x.shape
+        self.n, self.d = a.shape
+        if a.dtype == np.float64 and a.flags.f_contiguous and not a.flags.c_contiguous:
+            if asynchronous:
+                self._pending_features = a
+            self._check(self._lib.chb_set_features_colmajor(self._h, _ptr(a), a.shape[0], a.shape[1], int(bool(asynchronous))))
+            return
+        x = np.ascontiguousarray(a, dtype=np.float64)
         if asynchronous:
             self._pending_features = x
             self._check(self._lib.chb_set_features_async(self._h, _ptr(x), x.shape[0], x.shape[1]))
@@ -349,6 +360,11 @@ class Context:
     def measure_fp64_tflops(self) -> float:
         v = _dbl(0.0)
         self._check(self._lib.chb_measure_fp64_tflops(self._h, ctypes.byref(v)))
+        return float(v.value)
+
+    def measure_l2_gbs(self) -> float:
+        v = _dbl(0.0)
+        self._check(self._lib.chb_measure_l2_gbs(self._h, ctypes.byref(v)))
         return float(v.value)
 
     def iteration_end(self) -> int:

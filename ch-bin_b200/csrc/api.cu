@@ -124,6 +124,28 @@ __global__ void repack_features_kernel(const double *__restrict__ src, int64_t n
     dst[i] = t < d ? src[r * d + t] : 0.0;
 }
 
+// column-major n x d (the F-ordered DataFrame.values of cli/clustering.py:53: element (r, t) at src[t * n + r]) -> n x ldx
+// row-major, through 32 x 32 shared-memory tiles so that both the reads and the writes are coalesced
+__global__ void __launch_bounds__(256) repack_features_colmajor_kernel(const double *__restrict__ src, int64_t n, int32_t d,
+                                                                       int32_t ldx, double *__restrict__ dst)
+{
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int t0 = blockIdx.y * 32;
+    for (int i = ty; i < 32; i += 8) {
+        const int t = t0 + i;
+        const int64_t r = r0 + tx;
+        tile[i][tx] = (t < d && r < n) ? src[(int64_t)t * n + r] : 0.0;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int64_t r = r0 + i;
+        const int t = t0 + tx;
+        if (r < n && t < ldx) dst[r * ldx + t] = tile[tx][i];
+    }
+}
+
 __global__ void gather_rows_kernel(const int32_t *__restrict__ own_pos, const int32_t *__restrict__ perm_pt, int64_t cnt,
                                    int32_t *__restrict__ rows)
 {
@@ -267,12 +289,13 @@ int chb_create(chb_ctx **out, int device_id)
         return chb_fail(nullptr, CHB_ECUDA, "cudaStreamCreate failed");
     }
     c->stream = c->own_stream;
-    if (cudaMalloc(&c->counters, sizeof(int32_t) * 8) != cudaSuccess ||
-        cudaMallocHost(&c->counters_host, sizeof(int32_t) * 8) != cudaSuccess) {
+    if (cudaMalloc(&c->counters, sizeof(int32_t) * 16) != cudaSuccess ||
+        cudaMallocHost(&c->counters_host, sizeof(int32_t) * 16) != cudaSuccess) {
         delete c;
         return chb_fail(nullptr, CHB_ENOMEM, "counter allocation failed");
     }
-    cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * 8, c->stream);
+    cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * 16, c->stream);
+    memset(c->counters_host, 0, sizeof(int32_t) * 16);
     *out = c;
     return CHB_OK;
 }
@@ -398,7 +421,8 @@ static int features_finish(chb_ctx *c, bool defer_sync)
     return CHB_OK;
 }
 
-static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind, bool defer_sync = false)
+static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t d, cudaMemcpyKind kind, bool defer_sync = false,
+                               bool colmajor = false)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CHECK(c, src && n > 0 && d > 0, CHB_EINVAL, "samples must be a non-empty (n, d) float64 array");
@@ -412,7 +436,12 @@ static int set_features_common(chb_ctx *c, const double *src, int64_t n, int32_t
             CHB_CUDA(c, cudaMemcpyAsync(c->stage_X, src, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, c->stream));
             dsrc = c->stage_X;
         }
-        repack_features_kernel<<<nblk(n * c->ldx, 256), 256, 0, c->stream>>>(dsrc, n, d, c->ldx, c->X);
+        if (colmajor) {
+            dim3 grid(nblk(n, 32), nblk(c->ldx, 32));
+            repack_features_colmajor_kernel<<<grid, 256, 0, c->stream>>>(dsrc, n, d, c->ldx, c->X);
+        } else {
+            repack_features_kernel<<<nblk(n * c->ldx, 256), 256, 0, c->stream>>>(dsrc, n, d, c->ldx, c->X);
+        }
         ++c->tm.launches_other;
         CHB_CUDA(c, cudaGetLastError());
     }
@@ -630,6 +659,10 @@ int chb_set_features(chb_ctx *c, const double *x, int64_t n, int32_t d)
 int chb_set_features_async(chb_ctx *c, const double *x, int64_t n, int32_t d)
 {
     return set_features_common(c, x, n, d, cudaMemcpyHostToDevice, true);
+}
+int chb_set_features_colmajor(chb_ctx *c, const double *x, int64_t n, int32_t d, int asynchronous)
+{
+    return set_features_common(c, x, n, d, cudaMemcpyHostToDevice, asynchronous != 0, true);
 }
 int chb_set_features_dev(chb_ctx *c, const double *x_dev, int64_t n, int32_t d)
 {
@@ -1032,7 +1065,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         CHB_TRY(chb_round_fused(c)); // resets the work counter itself (round_reset_kernel)
         // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the
         // tile / redo counters travel with the commit's read-back
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         chb_qp_args q{};
         q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = nown * c->C;
         q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
@@ -1116,8 +1149,9 @@ int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev
     CHB_TRY(sync_stream(c));
     c->tm.qps_solved += c->counters_host[4];
     c->counters_host[4] = 0;
-    c->tm.gram_tiles += c->counters_host[7]; // tiles left after bin pruning (items_kernel), this round
-    c->counters_host[7] = 0;
+    c->tm.gram_tiles_planned += c->counters_host[7]; // tiles left after bin pruning (pairs_plan_kernel / items_kernel), this round
+    c->tm.gram_tiles += c->counters_host[8];         // tiles the MMA warps of gram_select_kernel actually issued
+    c->counters_host[7] = c->counters_host[8] = 0;
     if (c->f_fb_cap > 0 && c->counters_host[6] > c->f_fb_cap)
         return chb_fail(c, CHB_ECUDA, "exact-redo list overflow: %d pairs, capacity %d", c->counters_host[6], c->f_fb_cap);
     c->counters_host[6] = 0;

@@ -91,7 +91,8 @@ struct chb_ctx {
     // ---- work list of dirty (slot_local, bin) pairs
     int2 *work = nullptr;
     int64_t work_cap = 0;
-    int32_t *counters = nullptr;      // [0] work count, [1] first changed position, [2] n_changed, [3] scratch
+    int32_t *counters = nullptr;      // 16 ints: [0] work count, [1] first changed position, [2] n_changed, [3] QP fallback count,
+                                      // [5] max |x - mu|^2 bits, [6] exact-redo pairs, [7] planned tiles, [8] tiles issued by the MMA warps
     int32_t *counters_host = nullptr; // pinned mirror
 
     // capacities (elements) of the re-usable allocations above, so that repeated set-ups do not re-malloc

@@ -148,7 +148,7 @@ __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_c
     if (i < nown) row_nb[i] = 0;
     if (i < nmeta) pair_meta[i] = 0;
     if (i < cap_pairs) pair_row[i] = -1;
-    if (i == 0) { counters[0] = 0; counters[6] = 0; }
+    if (i == 0) { counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -819,7 +819,8 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                    const int32_t *__restrict__ col_a, const int32_t *__restrict__ col_b, const float *__restrict__ col_nrm,
                    const float *__restrict__ tq_tab, const int32_t *__restrict__ row_point, const int32_t *__restrict__ pos,
                    int64_t nrows, int32_t C, const float *__restrict__ t0_tab, int64_t ldt, const int4 *__restrict__ items,
-                   const int32_t *__restrict__ cta_begin, float *__restrict__ cand_key, int32_t *__restrict__ cand_idx)
+                   const int32_t *__restrict__ cta_begin, float *__restrict__ cand_key, int32_t *__restrict__ cand_idx,
+                   int32_t *__restrict__ tiles_issued)
 {
     // This CTA's work: items [cta_begin[b], cta_begin[b + 1]) of the list built by items_kernel, each one surviving
     // (row block, bin) = {row block, bin, first tile, #tiles}.  Pruned (row block, bin) pairs are not in the list: their
@@ -998,6 +999,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (elect_one_sync()) umma_commit(&S.tmem_full_bar[buf]);
                 }
             }
+            if (lane == 0 && tt > 0) atomicAdd(tiles_issued, (int32_t)tt); // measurement: tiles this CTA contracted
         }
     } else {
         // ---------------- epilogue warps 2..9: thread <-> (query row, column half).  The warps run decoupled: they
@@ -1837,7 +1839,7 @@ int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &map, cons
         chb_stage_timer t(c, CHB_ST_GRAM);
         gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
             ma, map, mb, c->f_mode, c->f_pair_row, g.nbox, g.nk, g.nstage, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq, c->f_row_pt, c->pos, nrows, c->C,
-            c->f_t0, c->f_ldt, c->f_items, c->f_cta_begin, c->f_cand_key, c->f_cand_idx);
+            c->f_t0, c->f_ldt, c->f_items, c->f_cta_begin, c->f_cand_key, c->f_cand_idx, &c->counters[8]);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;

@@ -1,5 +1,5 @@
-// peak.cu -- FP64 pipe peak microbenchmark (DFMA-saturating), used only by bench.py to obtain the measured
-// FP64 roofline denominator that MEASURED_PEAKS.json does not carry.
+// peak.cu -- FP64 pipe peak (DFMA-saturating) and L2 gather bandwidth microbenchmarks, used only by bench.py to obtain
+// the measured roofline denominators that MEASURED_PEAKS.json does not carry.
 #include "common.cuh"
 
 namespace {
@@ -14,7 +14,61 @@ __global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, doubl
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) out[0] = s; // never true: keeps the chain alive
 }
+// every thread streams 16-byte loads over a buffer that fits L2 (gathered 1104-byte "rows" like the QP kernels' neighbour
+// rows: consecutive lanes read consecutive 16-byte pieces of a row, consecutive warps jump to pseudo-random rows)
+__global__ void __launch_bounds__(256) l2_read_kernel(const double2 *__restrict__ buf, int64_t nrows, int row_vec, int iters, double *out)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    double2 acc = make_double2(0.0, 0.0);
+    uint64_t r = (uint64_t)gw * 2654435761u + 12345u;
+    for (int it = 0; it < iters; ++it) {
+        r = r * 6364136223846793005ull + 1442695040888963407ull;
+        const double2 *row = buf + (int64_t)((r >> 20) % (uint64_t)nrows) * row_vec;
+        for (int q = lane; q < row_vec; q += 32) {
+            const double2 v = __ldcg(row + q); // L2 only: what a gather with no reuse inside the SM sees
+            acc.x += v.x;
+            acc.y += v.y;
+        }
+    }
+    if (acc.x + acc.y == 123.456) out[0] = acc.x;
+}
 } // namespace
+
+extern "C" int chb_measure_l2_gbs(chb_ctx *c, double *gbs)
+{
+    CHB_CHECK(c, c && gbs, CHB_EINVAL, "NULL argument");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    const int row_vec = 69;          // 69 x 16 B = 1104 B: one 138-double feature row (d = 137, 16-byte pitch)
+    const int64_t nrows = 20000;     // 22 MB: the 20k-contig feature matrix, far inside the 126 MB L2
+    double2 *buf = nullptr;
+    double *d = nullptr;
+    CHB_CUDA(c, cudaMalloc(&buf, sizeof(double2) * (size_t)nrows * row_vec));
+    CHB_CUDA(c, cudaMalloc(&d, 8));
+    CHB_CUDA(c, cudaMemsetAsync(buf, 0, sizeof(double2) * (size_t)nrows * row_vec, c->stream));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 256, blocks = c->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        l2_read_kernel<<<blocks, 256, 0, c->stream>>>(buf, nrows, row_vec, iters, d);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = 16.0 * row_vec * (double)iters * (256.0 / 32.0) * blocks;
+        if (rep > 0) best = fmax(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(buf);
+    cudaFree(d);
+    CHB_CUDA(c, cudaGetLastError());
+    *gbs = best;
+    return CHB_OK;
+}
 
 extern "C" int chb_measure_fp64_tflops(chb_ctx *c, double *tflops)
 {

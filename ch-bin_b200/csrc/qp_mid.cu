@@ -4,10 +4,11 @@
 //  * phase 1 (as qp_small.cu): 8 lanes per (query, bin) pair split the feature columns with 16-byte loads, keep
 //    W = V - 1x' in registers and accumulate the 55 entries of G = W W' with DFMA; a transposed-halving reduction
 //    leaves 7 entries per lane, which go to shared memory.  A warp does this for 32 pairs (8 sub-steps of 4).
-//  * phase 2: ONE LANE PER PAIR runs Wolfe's finite active-set method on its own G (shared memory, conflict-free
-//    [entry][lane] layout): the affine minimiser on the current corral solves (G_SS + s 11') y = 1 by fully
-//    unrolled masked symmetric elimination in registers; vanishing pivots (affinely dependent neighbours) ban the
-//    entering vertex.  32 independent solves per warp instead of one warp-cooperative solve per pair (qp.cu).
+//  * phase 2: ONE LANE PER PAIR works on its own G (shared memory, conflict-free [entry][lane] layout): block principal
+//    pivoting from the full face (a handful of solves), and Wolfe's finite active-set method as the safety net.  The
+//    affine minimiser on a face solves (G_SS + s 11') y = 1 by fully unrolled masked symmetric elimination in
+//    registers; vanishing pivots (affinely dependent neighbours) ban the entering vertex.  32 independent solves per
+//    warp instead of one warp-cooperative solve per pair (qp.cu).
 //  * phase 3: distance = sqrt(a'Ga) when a'Ga > 1e-5 max G_ii, otherwise the pair is handed to qp.cu, which
 //    recomputes || aV - x || in d dimensions exactly as hull_distance.py:34-35.
 #include <cfloat>
@@ -22,6 +23,7 @@ constexpr int NPP = 56;          // padded to 7 per lane of an 8-lane group
 constexpr int GL = 8;
 constexpr int QPW = 4;           // pairs per warp and sub-step
 constexpr int WARPS = 3;          // 3 x 14 KB of Gram staging stays under the 48 KB static shared-memory limit
+constexpr int BPP_ITMAX = 12;
 
 __device__ __forceinline__ constexpr int pidx(int i, int j) { return i * M - (i * (i - 1)) / 2 + (j - i); } // i <= j
 
@@ -184,10 +186,57 @@ __global__ void __launch_bounds__(WARPS * 32) qp_mid_kernel(chb_qp_args a, int2 
             }
             if (scale > 0.0) {
                 const double tol = 1e-14 * scale;
+                // Block principal pivoting from the FULL face first: solve on S, take out every vertex with a negative weight,
+                // put back every excluded vertex with a negative multiplier, repeat.  It ends on the KKT conditions of the
+                // simplex problem after a handful of solves whatever m is, where Wolfe's method below adds one vertex per
+                // major cycle.  No feasibility is kept on the way, so it is only trusted when it ends by itself within the
+                // cap; otherwise (cycling, or a vanishing pivot: affinely dependent neighbours) Wolfe's method runs.
+                bool done = false;
+                {
+                    const unsigned full = (1u << m) - 1u;
+                    unsigned S = full;
+#pragma unroll 1
+                    for (int bit = 0; bit < BPP_ITMAX && !done; ++bit) {
+                        double beta[M];
+                        if (!affine_min(sg, S, scale, beta)) break;
+                        double gr[M];
 #pragma unroll
-                for (int i = 0; i < M; ++i) alpha[i] = (i == start) ? 1.0 : 0.0;
+                        for (int i = 0; i < M; ++i) gr[i] = 0.0;
+#pragma unroll
+                        for (int i = 0; i < M; ++i)
+#pragma unroll
+                            for (int j = i; j < M; ++j) {
+                                const double gij = sg[pidx(i, j) * 32];
+                                gr[i] = fma(gij, beta[j], gr[i]);
+                                if (j != i) gr[j] = fma(gij, beta[i], gr[j]);
+                            }
+                        double f = 0.0;
+#pragma unroll
+                        for (int i = 0; i < M; ++i) f = fma(beta[i], gr[i], f);
+                        unsigned neg = 0u, dual = 0u;
+#pragma unroll
+                        for (int i = 0; i < M; ++i) {
+                            if ((S >> i) & 1u) {
+                                if (beta[i] < 0.0) neg |= 1u << i;
+                            } else if (((full >> i) & 1u) && gr[i] < f - tol) {
+                                dual |= 1u << i;
+                            }
+                        }
+                        if (!neg && !dual) {
+#pragma unroll
+                            for (int i = 0; i < M; ++i) alpha[i] = beta[i];
+                            done = true;
+                        } else {
+                            S = (S & ~neg) | dual;
+                        }
+                    }
+                }
+                if (!done) {
+#pragma unroll
+                    for (int i = 0; i < M; ++i) alpha[i] = (i == start) ? 1.0 : 0.0;
+                }
                 unsigned smask = 1u << start, banned = 0u;
-                const int itmax = 3 * m + 8;
+                const int itmax = done ? 0 : 3 * m + 8;
                 int it = 0;
                 for (; it < itmax; ++it) {
                     // gradient g = G alpha, f = alpha' g
@@ -257,7 +306,7 @@ __global__ void __launch_bounds__(WARPS * 32) qp_mid_kernel(chb_qp_args a, int2 
                         if (!((smask >> jn) & 1u)) break;
                     }
                 }
-                if (it >= itmax) status = CHB_QP_ITER_CAP;
+                if (!done && it >= itmax) status = CHB_QP_ITER_CAP;
                 // objective at the final alpha
                 double o = 0.0;
 #pragma unroll

@@ -1,17 +1,21 @@
 // qp_small.cu -- hull-distance QPs with at most 5 neighbours (AlgoNumNeighbors <= 5, the reference's default,
-// /root/reference/config/default.ini:16), 8 lanes per (query, bin) pair, 4 pairs per warp (sm_100a).
+// /root/reference/config/default.ini:16) (sm_100a).
 //
 // Same contract as qp.cu (hull_distance.py:7-35 + solve_qp.py:18-51 + quadprog), different mapping:
-//  * phase 1: the 8 lanes of a group split the d feature columns (16-byte loads, one full 128-byte line per
-//    neighbour row and step), keep W = V - 1x' in registers and accumulate the 15 entries of G = W W' with
-//    DFMA; a transposed-halving reduction (28 SHFL per warp) plus one shared-memory broadcast gives every
-//    lane the whole G.
-//  * phase 2: the simplex-constrained minimum of a'Ga is attained on a face whose affine minimiser is
-//    non-negative (KKT).  With m <= 5 there are at most 31 faces: each lane takes 4 of them, solves
-//    (G_SS + s 11') y = 1 by fully unrolled masked elimination, normalises, rejects faces with a negative
-//    weight or a vanishing pivot (affinely dependent neighbours), and EVALUATES a'Ga directly -- every
-//    surviving candidate is a feasible point, so the minimum over candidates can never undershoot the true
-//    optimum, and the optimal face attains it.  No iteration, no divergence.
+//  * phase 1: 8 lanes per (query, bin) pair, 4 pairs per warp and sub-step.  The 8 lanes split the d feature columns
+//    (16-byte loads, one full 128-byte line per neighbour row and step), keep W = V - 1x' in registers and accumulate
+//    the 15 entries of G = W W' with DFMA; a transposed-halving reduction (28 SHFL per warp) leaves two entries per
+//    lane, which go to shared memory in an [entry][pair] layout.  A warp repeats this for up to 8 sub-steps (32 pairs);
+//    the number of sub-steps follows the size of the work list so that small lists still fill the machine.
+//  * phase 2: ONE LANE PER PAIR.  The simplex-constrained minimum of a'Ga is attained on the face S whose affine
+//    minimiser is non-negative and whose excluded vertices have non-negative multipliers (KKT).  Block principal
+//    pivoting from the full face: solve (G_SS + s 11') y = 1 by fully unrolled masked elimination, take out every
+//    vertex with a negative weight, put back every excluded vertex whose multiplier is negative, repeat.  On contig
+//    data the full face is already optimal for ~97 % of the pairs (high-dimensional noise keeps the projection inside
+//    the simplex), one more solve settles nearly all others.  Whatever the path, a'Ga is EVALUATED on a feasible point,
+//    so it can never undershoot the optimum.  If the pivoting does not settle within its cap, or meets a vanishing
+//    pivot (affinely dependent neighbours: duplicate contigs), the lane falls back to enumerating all <= 31 faces
+//    (each rejected if a pivot vanishes or a weight is negative) -- exact, no iteration.
 //  * phase 3: the distance is sqrt(a'Ga) when that is well conditioned (a'Ga > 1e-5 max G_ii, error ~1e-11
 //    relative); otherwise the pair is handed to the general kernel, which recomputes ||aV - x|| in d
 //    dimensions exactly as hull_distance.py:34-35.
@@ -21,16 +25,20 @@
 
 namespace {
 
-constexpr int GL = 8;        // lanes per QP
-constexpr int QPW = 32 / GL; // QPs per warp
+constexpr int GL = 8;        // lanes per QP in phase 1
+constexpr int QPW = 32 / GL; // QPs per warp and sub-step
+constexpr int MAXSUB = 8;    // sub-steps per warp batch: up to 32 pairs, one per lane in phase 2
 constexpr int WARPS = 4;
 constexpr int NCH = 3;                // double2 loads per row per chunk and lane
 constexpr int CHUNK_COLS = GL * 2 * NCH; // 48 columns per chunk
+constexpr int BPP_ITMAX = 8;
 
 __device__ __forceinline__ constexpr int pidx(int i, int j) { return i * 5 - (i * (i - 1)) / 2 + (j - i); } // i <= j
 
-// affine minimiser on the face `mask`, returns false if the face is rejected
-__device__ __forceinline__ bool eval_face(const double (&G)[15], unsigned mask, double shift, double (&beta)[5], double &obj)
+// affine minimiser on the face `mask`: beta (0 outside the face), obj = beta' G beta.  Returns false if a pivot vanishes
+// (affinely dependent vertices) or the solve breaks down; `feasible` says whether every weight is >= 0.
+__device__ __forceinline__ bool eval_face(const double (&G)[15], unsigned mask, double shift, double (&beta)[5], double &obj,
+                                          bool &feasible)
 {
     double A[15], rhs[5];
     bool in[5];
@@ -72,12 +80,13 @@ __device__ __forceinline__ bool eval_face(const double (&G)[15], unsigned mask, 
     const double sy = y[0] + y[1] + y[2] + y[3] + y[4];
     const double isy = 1.0 / sy;
     ok = ok && (sy > 0.0);
+    feasible = true;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
         beta[i] = in[i] ? y[i] * isy : 0.0;
-        ok = ok && (beta[i] >= 0.0);
+        feasible = feasible && (beta[i] >= 0.0);
     }
-    // objective evaluated on the feasible point itself
+    // objective evaluated on the point itself
     double o = 0.0;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
@@ -93,147 +102,182 @@ __device__ __forceinline__ bool eval_face(const double (&G)[15], unsigned mask, 
 __global__ void __launch_bounds__(WARPS * 32) qp_small_kernel(chb_qp_args a, int2 *__restrict__ fallback,
                                                                int32_t *__restrict__ fallback_count)
 {
-    __shared__ __align__(16) double sG[WARPS][QPW][16];
+    __shared__ __align__(16) double sG[WARPS][16 * 32]; // [entry][pair of the warp batch]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & (GL - 1), grp = lane / GL;
     const int64_t n_work = a.work_count ? (int64_t)*a.work_count : a.n_work;
     const int ldx = a.ldx, k = a.k, C = a.C;
-    const int64_t stride = (int64_t)gridDim.x * WARPS * QPW;
+    double *sg_w = sG[warp];
+    // pairs per warp batch: as many sub-steps as keep every warp of the grid busy (phase 2 then runs on 4 * nsub lanes)
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    int nsub = (int)((n_work + nwarps * QPW - 1) / (nwarps * QPW));
+    nsub = nsub < 1 ? 1 : (nsub >= MAXSUB ? MAXSUB : (nsub >= 4 ? 4 : (nsub >= 2 ? 2 : 1)));
+    const int per_batch = nsub * QPW;
+    const int64_t stride = nwarps * per_batch;
 
-    for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * QPW; base < n_work; base += stride) {
-        const int64_t item = base + grp;
-        const bool valid = item < n_work;
-        int2 wk = make_int2(0, 0);
-        int m = 0;
-        int64_t pair = 0;
-        if (valid) {
-            wk = a.work[item];
-            pair = (int64_t)wk.x * C + wk.y;
-            m = a.knn_cnt[pair];
-        }
-        const double *rows[5];
-        const double *xq = a.X;
-        if (m > 0) xq = a.X + (int64_t)a.row_point[wk.x] * ldx;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) rows[r] = (r < m) ? a.X + (int64_t)a.knn_idx[pair * k + r] * ldx : a.X;
-
-        // ---------------- phase 1
-        double acc[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) acc[i] = 0.0;
-        for (int c0 = 0; c0 < ldx; c0 += CHUNK_COLS) {
-            double2 xv[NCH], w[5][NCH];
-#pragma unroll
-            for (int i = 0; i < NCH; ++i) {
-                const int col = c0 + i * (2 * GL) + 2 * g;
-                const bool inb = (col < ldx) && (m > 0);
-                xv[i] = inb ? __ldg(reinterpret_cast<const double2 *>(xq + col)) : make_double2(0.0, 0.0);
-#pragma unroll
-                for (int r = 0; r < 5; ++r)
-                    w[r][i] = (inb && r < m) ? __ldg(reinterpret_cast<const double2 *>(rows[r] + col)) : xv[i];
-            }
-#pragma unroll
-            for (int i = 0; i < NCH; ++i)
-#pragma unroll
-                for (int r = 0; r < 5; ++r) {
-                    w[r][i].x -= xv[i].x;
-                    w[r][i].y -= xv[i].y;
-                }
-#pragma unroll
-            for (int i = 0; i < NCH; ++i)
-#pragma unroll
-                for (int p = 0; p < 5; ++p)
-#pragma unroll
-                    for (int q = p; q < 5; ++q) {
-                        acc[pidx(p, q)] = fma(w[p][i].x, w[q][i].x, acc[pidx(p, q)]);
-                        acc[pidx(p, q)] = fma(w[p][i].y, w[q][i].y, acc[pidx(p, q)]);
-                    }
-        }
-        // transposed halving reduction inside the 8-lane group: lane g ends with entries 2g, 2g+1
-        double v8[8], v4[4], v2[2];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool hi = g & 4;
-            const double send = hi ? acc[i] : acc[i + 8];
-            const double keep = hi ? acc[i + 8] : acc[i];
-            v8[i] = keep + __shfl_xor_sync(CHB_FULL, send, 4);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const bool hi = g & 2;
-            const double send = hi ? v8[i] : v8[i + 4];
-            const double keep = hi ? v8[i + 4] : v8[i];
-            v4[i] = keep + __shfl_xor_sync(CHB_FULL, send, 2);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const bool hi = g & 1;
-            const double send = hi ? v4[i] : v4[i + 2];
-            const double keep = hi ? v4[i + 2] : v4[i];
-            v2[i] = keep + __shfl_xor_sync(CHB_FULL, send, 1);
-        }
-        *reinterpret_cast<double2 *>(&sG[warp][grp][2 * g]) = make_double2(v2[0], v2[1]);
-        __syncwarp();
-        double G[15];
-#pragma unroll
-        for (int i = 0; i < 14; i += 2) {
-            const double2 t = *reinterpret_cast<const double2 *>(&sG[warp][grp][i]);
-            G[i] = t.x;
-            G[i + 1] = t.y;
-        }
-        G[14] = sG[warp][grp][14];
-        __syncwarp();
-
-        // ---------------- phase 2: faces g+1, g+9, g+17, g+25 (< 2^m)
-        double scale = 0.0;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) scale = fmax(scale, G[pidx(i, i)]);
-        double best = DBL_MAX, bbeta[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-        const unsigned nfaces = 1u << m;
-        if (scale > 0.0) {
+    for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * per_batch; base < n_work; base += stride) {
+        // ---------------- phase 1: Gram matrices of 4 * nsub pairs, 4 at a time
 #pragma unroll 1
-            for (unsigned mask = g + 1; mask < nfaces; mask += GL) {
-                double beta[5], obj;
-                if (eval_face(G, mask, scale, beta, obj) && obj < best) {
-                    best = obj;
-#pragma unroll
-                    for (int i = 0; i < 5; ++i) bbeta[i] = beta[i];
-                }
+        for (int sub = 0; sub < nsub; ++sub) {
+            if (base + (int64_t)sub * QPW >= n_work) break; // warp-uniform
+            const int64_t item = base + sub * QPW + grp;
+            const bool valid = item < n_work;
+            int m = 0;
+            int64_t pair = 0;
+            int2 wk = make_int2(0, 0);
+            if (valid) {
+                wk = a.work[item];
+                pair = (int64_t)wk.x * C + wk.y;
+                m = a.knn_cnt[pair];
             }
-        } else if (m > 0 && g == 0) {
-            best = 0.0; // every neighbour coincides with the query
-            bbeta[0] = 1.0;
-        }
-        // group argmin (lowest lane wins ties)
-        double bv = best;
-        int bl = g;
+            const double *rows[5];
+            const double *xq = a.X;
+            if (m > 0) xq = a.X + (int64_t)a.row_point[wk.x] * ldx;
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(CHB_FULL, bv, o);
-            const int ol = __shfl_xor_sync(CHB_FULL, bl, o);
-            if (ov < bv || (ov == bv && ol < bl)) { bv = ov; bl = ol; }
+            for (int r = 0; r < 5; ++r) rows[r] = (r < m) ? a.X + (int64_t)a.knn_idx[pair * k + r] * ldx : a.X;
+
+            double acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.0;
+            for (int c0 = 0; c0 < ldx; c0 += CHUNK_COLS) {
+                double2 xv[NCH], w[5][NCH];
+#pragma unroll
+                for (int i = 0; i < NCH; ++i) {
+                    const int col = c0 + i * (2 * GL) + 2 * g;
+                    const bool inb = (col < ldx) && (m > 0);
+                    xv[i] = inb ? __ldg(reinterpret_cast<const double2 *>(xq + col)) : make_double2(0.0, 0.0);
+#pragma unroll
+                    for (int r = 0; r < 5; ++r)
+                        w[r][i] = (inb && r < m) ? __ldg(reinterpret_cast<const double2 *>(rows[r] + col)) : xv[i];
+                }
+#pragma unroll
+                for (int i = 0; i < NCH; ++i)
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) {
+                        w[r][i].x -= xv[i].x;
+                        w[r][i].y -= xv[i].y;
+                    }
+#pragma unroll
+                for (int i = 0; i < NCH; ++i)
+#pragma unroll
+                    for (int p = 0; p < 5; ++p)
+#pragma unroll
+                        for (int q = p; q < 5; ++q) {
+                            acc[pidx(p, q)] = fma(w[p][i].x, w[q][i].x, acc[pidx(p, q)]);
+                            acc[pidx(p, q)] = fma(w[p][i].y, w[q][i].y, acc[pidx(p, q)]);
+                        }
+            }
+            // transposed halving reduction inside the 8-lane group: lane g ends with entries 2g, 2g+1
+            double v8[8], v4[4], v2[2];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const bool hi = g & 4;
+                const double send = hi ? acc[i] : acc[i + 8];
+                const double keep = hi ? acc[i + 8] : acc[i];
+                v8[i] = keep + __shfl_xor_sync(CHB_FULL, send, 4);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const bool hi = g & 2;
+                const double send = hi ? v8[i] : v8[i + 4];
+                const double keep = hi ? v8[i + 4] : v8[i];
+                v4[i] = keep + __shfl_xor_sync(CHB_FULL, send, 2);
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const bool hi = g & 1;
+                const double send = hi ? v4[i] : v4[i + 2];
+                const double keep = hi ? v4[i + 2] : v4[i];
+                v2[i] = keep + __shfl_xor_sync(CHB_FULL, send, 1);
+            }
+            const int slot = sub * QPW + grp; // pair index inside the warp batch = the lane that solves it
+            sg_w[(2 * g) * 32 + slot] = v2[0];
+            sg_w[(2 * g + 1) * 32 + slot] = v2[1];
         }
-        if (!valid) continue;
-        if (m <= 0) {
-            if (g == 0) {
+        __syncwarp();
+
+        // ---------------- phase 2: one lane per pair
+        const int64_t item = base + lane;
+        const bool valid = lane < per_batch && item < n_work;
+        if (valid) {
+            const int2 wk = a.work[item];
+            const int64_t pair = (int64_t)wk.x * C + wk.y;
+            const int m = a.knn_cnt[pair];
+            if (m <= 0) {
                 a.dist[pair] = INFINITY;
                 if (a.status) a.status[pair] = CHB_QP_EMPTY_BIN;
-            }
-            continue;
-        }
-        const bool exact_needed = !(bv < DBL_MAX) || (scale > 0.0 && !(bv > 1e-5 * scale));
-        if (g == bl) {
-            if (exact_needed && bv != 0.0) {
-                const int w = atomicAdd(fallback_count, 1);
-                fallback[w] = wk;
             } else {
-                a.dist[pair] = sqrt(fmax(bv, 0.0));
-                if (a.status) a.status[pair] = CHB_QP_OK;
-                if (a.alpha) {
-                    for (int i = 0; i < k; ++i) a.alpha[pair * k + i] = i < 5 ? bbeta[i] : 0.0;
+                double G[15];
+#pragma unroll
+                for (int i = 0; i < 15; ++i) G[i] = sg_w[i * 32 + lane];
+                double scale = 0.0;
+#pragma unroll
+                for (int i = 0; i < 5; ++i) scale = fmax(scale, G[pidx(i, i)]);
+                double best = DBL_MAX, bbeta[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+                if (scale > 0.0) {
+                    const unsigned full = (1u << m) - 1u;
+                    const double tol = 1e-14 * scale;
+                    // block principal pivoting from the full face
+                    unsigned S = full;
+                    bool done = false;
+#pragma unroll 1
+                    for (int it = 0; it < BPP_ITMAX && !done; ++it) {
+                        double beta[5], obj;
+                        bool feas;
+                        if (!eval_face(G, S, scale, beta, obj, feas)) break; // vanishing pivot: enumerate
+                        unsigned neg = 0u, dual = 0u;
+                        // multipliers of the excluded vertices: (G beta)_i - beta' G beta >= 0
+#pragma unroll
+                        for (int i = 0; i < 5; ++i) {
+                            if ((S >> i) & 1u) {
+                                if (beta[i] < 0.0) neg |= 1u << i;
+                            } else if ((full >> i) & 1u) {
+                                double gi = 0.0;
+#pragma unroll
+                                for (int j = 0; j < 5; ++j) gi = fma(G[i <= j ? pidx(i, j) : pidx(j, i)], beta[j], gi);
+                                if (gi < obj - tol) dual |= 1u << i;
+                            }
+                        }
+                        if (!neg && !dual) {
+                            best = obj;
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) bbeta[i] = beta[i];
+                            done = true;
+                        } else {
+                            S = (S & ~neg) | dual;
+                        }
+                    }
+                    if (!done) {
+                        // exact fallback: every face; feasible candidates can only overshoot, the optimal face attains
+#pragma unroll 1
+                        for (unsigned mask = 1; mask <= full; ++mask) {
+                            double beta[5], obj;
+                            bool feas;
+                            if (eval_face(G, mask, scale, beta, obj, feas) && feas && obj < best) {
+                                best = obj;
+#pragma unroll
+                                for (int i = 0; i < 5; ++i) bbeta[i] = beta[i];
+                            }
+                        }
+                    }
+                } else {
+                    best = 0.0; // every neighbour coincides with the query
+                    bbeta[0] = 1.0;
+                }
+                const bool exact_needed = !(best < DBL_MAX) || (scale > 0.0 && !(best > 1e-5 * scale));
+                if (exact_needed && best != 0.0) {
+                    const int w = atomicAdd(fallback_count, 1);
+                    fallback[w] = wk;
+                } else {
+                    a.dist[pair] = sqrt(fmax(best, 0.0));
+                    if (a.status) a.status[pair] = CHB_QP_OK;
+                    if (a.alpha) {
+                        for (int i = 0; i < k; ++i) a.alpha[pair * k + i] = i < 5 ? bbeta[i] : 0.0;
+                    }
                 }
             }
         }
+        __syncwarp();
     }
 }
 

@@ -67,7 +67,9 @@ typedef struct chb_timers {
      * then holds the re-rank (and the rare exact-path scans) only */
     double ms_gram;
     int64_t launches_gram;
-    int64_t gram_tiles;     /* 128 x 128 (query, column) tiles contracted: 2*128*128*3*dp8 flop each, dp8 = d rounded up to 8 */
+    int64_t gram_tiles;     /* 128 x 128 (query, column) tiles contracted, counted by the MMA-issuing warps themselves:
+                             * 2*128*128*3*dp8 flop each, dp8 = d rounded up to 8 */
+    int64_t gram_tiles_planned; /* the same count as the work-list planner predicted it (must agree) */
 } chb_timers;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
@@ -98,6 +100,11 @@ int chb_set_features_dev(chb_ctx *ctx, const double *x_rowmajor_dev, int64_t n, 
  * pointer is retained": x_rowmajor must stay valid and unchanged until chb_build_distance_matrix (or chb_synchronize)
  * returns.  Pageable memory is staged before the call returns, as with chb_set_features. */
 int chb_set_features_async(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
+/* `samples` exactly as the reference holds it: cli/clustering.py:53 takes DataFrame.values of a single float64 block, an
+ * F-ordered (n, d) array -- element (r, t) at x_colmajor[t * n + r].  The block is uploaded as it lies in host memory and
+ * transposed into the device layout on the device (no host-side np.ascontiguousarray pass).  asynchronous != 0: returns
+ * once the upload is enqueued, with chb_set_features_async's lifetime rule for x_colmajor. */
+int chb_set_features_colmajor(chb_ctx *ctx, const double *x_colmajor, int64_t n, int32_t d, int asynchronous);
 /* Builds `samples` on the device from its two sources instead of from features.csv:
  *   kmer      (n, dk)  normalised k-mer profiles of the sub-contigs (seq2vec output, cli/features.py:84-93), row-major;
  *   cov_raw   (P, S)   RAW per-sample coverages of the P parent contigs as read from the abundance file
@@ -200,6 +207,9 @@ int64_t chb_get_window(chb_ctx *ctx);
 /* ---- measurement aid (bench.py only) ------------------------------------------------------------------ */
 /* DFMA-saturating microbenchmark: measured FP64 pipe peak of this device in TFLOP/s (FMA = 2 flop). */
 int chb_measure_fp64_tflops(chb_ctx *ctx, double *tflops);
+/* L2 -> SM gather bandwidth in GB/s: 1104-byte rows (one d = 137 feature row) read at random from a 22 MB buffer with
+ * 16-byte L2-only loads -- the ceiling of the QP kernels' neighbour-row gather while the feature matrix is L2-resident. */
+int chb_measure_l2_gbs(chb_ctx *ctx, double *gbs);
 
 #ifdef __cplusplus
 }
