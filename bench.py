@@ -9,8 +9,10 @@ REFERENCE-EQUIVALENT QPs: sum over executed iterations of U*C (one (query, bin) 
 norm).  Speculative re-solves the GPU path performs on top of that are NOT counted.
 
   value : QPs/s with the feature matrix already resident in HBM when the timed region starts.
-  e2e   : the same metric through the public API chbin_b200.fit_cluster() with HOST (pinned) buffers -- context
-          creation, H2D of features/labels, D2H of the final labels all inside the timed region.
+  e2e   : the same metric through the public API chbin_b200.fit_cluster() with HOST (pinned) buffers -- H2D of the
+          features / labels / permutations and D2H of the final labels all inside the timed region (the library context
+          of the device is created once per process and reused, like a BLAS handle).  `e2e_pageable_f_order` repeats
+          it from the reference's own boundary layout: a pageable, F-ordered `samples` array.
   roofline     : the dominant kernel of the timed region, timed live with CUDA events on the launch stream.
   cpu_baseline : the oracle port (oracle/*.c) on the host cores, bounded sample, rank 0 at N=1 only.
 
@@ -49,6 +51,9 @@ def parse_args():
     ap.add_argument("--window", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-qp-isolated", action="store_true")
+    ap.add_argument("--scale-workloads", default="100k,1m",
+                    help="other BASELINE workloads timed briefly at this N (stage ms in `scale_workloads`); '' to skip")
     return ap.parse_args()
 
 
@@ -180,7 +185,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-def cpu_sample(X, bins, cfg, seconds, threads):
+def cpu_sample(X, bins, cfg, seconds, threads, return_labels=False):
     """Oracle port on `threads` host threads over a bounded prefix of iteration 1 (rows computed on the fly)."""
     import oracle
 
@@ -193,9 +198,49 @@ def cpu_sample(X, bins, cfg, seconds, threads):
     per_step = (time.perf_counter() - t0) / probe
     steps = int(max(probe, min(U, seconds / max(per_step, 1e-9))))
     t0 = time.perf_counter()
-    _, info = oracle.fit_cluster(X, C, bins, None, k, 1, perms=perms, threads=threads, max_steps=steps, return_info=True)
+    labels, info = oracle.fit_cluster(X, C, bins, None, k, 1, perms=perms, threads=threads, max_steps=steps, return_info=True)
     dt = time.perf_counter() - t0
+    if return_labels:
+        return info["qps"] / dt, steps, dt, labels, perms[0]
     return info["qps"] / dt, steps, dt
+
+
+def cpu_extras(X, bins, cfg, seconds=3.0):
+    """BASELINE.md section 3 beside the all-threads port: the port on ONE thread (QP/s per core), scipy's cdist (B3) on a
+    bounded block of rows, and what the image offers of the reference's own solvers."""
+    out = {}
+    try:
+        v, steps, dt = cpu_sample(X, bins, cfg, seconds, 1)
+        out["single_thread"] = {"value": v, "unit": "QP/s", "cores": 1, "kind": "port",
+                                "sample": f"first {steps} sequential steps of iteration 1 ({dt:.1f} s)"}
+    except Exception as e:  # noqa: BLE001
+        out["single_thread"] = {"error": repr(e)}
+    try:
+        from scipy.spatial.distance import cdist
+
+        rows = max(64, min(len(X), int(2.5e8 / (len(X) * X.shape[1]))))
+        t0 = time.perf_counter()
+        cdist(X[:rows], X, "euclidean")
+        dt = time.perf_counter() - t0
+        out["b3_cdist"] = {"value": rows * len(X) / dt, "unit": "pairs/s", "cores": 1, "kind": "reference (scipy)",
+                           "sample": f"cdist of the first {rows} rows against all {len(X)} (distance_matrix.py:41), {dt:.2f} s"}
+    except Exception as e:  # noqa: BLE001
+        out["b3_cdist"] = {"error": repr(e)}
+    for mod in ("quadprog", "cvxopt"):
+        try:
+            __import__(mod)
+            out[mod] = "importable (not timed: the reference flow around it needs /root/reference)"
+        except Exception:
+            out[mod] = "unavailable in image"
+    p = os.path.join(ROOT, "profiles", "r2_baseline_b1_b3_container.json")
+    if os.path.exists(p):
+        try:
+            j = json.load(open(p))
+            out["b1_reference_verbatim"] = dict(j["b1_reference_verbatim"], where="build container (the reference tree does not "
+                                                "travel to the GPU box), tools/baseline_b1.py", solver=j.get("quadprog"), file="profiles/r2_baseline_b1_b3_container.json")
+        except Exception:
+            pass
+    return out
 
 
 def run_reference(args):
@@ -236,11 +281,88 @@ def config_dict(args, cfg, U):
 
 
 # ----------------------------------------------------------------------------------------------------------
+class StageRunner:
+    """One resident feature matrix in one library context; run() = one clustering stage (label set-up, distance structure,
+    every iteration to the reference's stop rule) -- through chb_fit on one GPU, through the round protocol + NCCL
+    all-reduce when the query slots are sharded over ranks."""
+
+    def __init__(self, torch, dist, rank, world, local_rank, stream, X, bins, cfg, window):
+        from chbin_b200 import capi, clustering
+
+        self.torch, self.dist, self.rank, self.world, self.clustering = torch, dist, rank, world, clustering
+        self.bins, self.C, self.k = bins, cfg["C"], cfg["k"]
+        self.U = int(np.sum(bins == -1))
+        self.perms = clustering.draw_permutations(bins, MAX_ITERATIONS, seed=0)  # the host RNG contract (algorithm.py:45)
+        self.ctx = capi.Context(local_rank)
+        self.ctx.set_stream(stream.cuda_stream)
+        dev = torch.device("cuda", local_rank)
+        n, d = X.shape
+        if world > 1:
+            # SURVEY 8(e): the feature matrix is uploaded by rank 0 only and replicated with ONE NCCL broadcast over NVLink
+            Xd = torch.empty((n, d), dtype=torch.float64, device=dev)
+            if rank == 0:
+                Xd.copy_(torch.from_numpy(X))
+            dist.broadcast(Xd, src=0)
+        else:
+            Xd = torch.from_numpy(X).to(dev)
+        self.ctx.set_features_dev(Xd.data_ptr(), n, d)
+        del Xd
+        self.ctx.set_params(self.k, "convex")
+        self.ctx.set_window(window)
+        self.u0, self.u1 = clustering.owned_slots(self.U, rank, world)
+        self.engine = self.comm = None
+        self.local_rank, self.stream = local_rank, stream
+
+    def run(self):
+        ctx = self.ctx
+        ctx.set_labels(self.bins, self.C, self.u0, self.u1)
+        ctx.build_distance_matrix(True)
+        if self.world == 1:
+            labels, iters, conv, changed = ctx.fit(self.perms, MAX_ITERATIONS)
+            return labels, iters
+        if self.engine is None:
+            self.engine = self.clustering.GpuEngine(ctx, self.local_rank, self.stream)
+            self.comm = self.clustering.TorchComm()
+        self.clustering.exchange_guess(self.engine, self.comm, self.U)  # every rank guesses for its own slots only
+        iters = 0
+        with self.engine.stream_context():
+            for it in range(MAX_ITERATIONS):
+                nch, _ = self.clustering.run_iteration(self.engine, self.perms[it], self.comm)
+                iters += 1
+                if nch == 0:
+                    break
+        return ctx.get_labels(), iters
+
+    def timed(self, steps, flush, barrier, stream):
+        """K stages, each bracketed by CUDA events on the launch stream, L2 flushed in between; returns total ms (max over
+        ranks), iterations executed and the labels of the last stage."""
+        torch = self.torch
+        events, total_iters, labels = [], 0, None
+        barrier()
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            labels, iters = self.run()
+            e1.record(stream)
+            events.append((e0, e1))
+            total_iters += iters
+        barrier()
+        ms = float(sum(a.elapsed_time(b) for a, b in events))
+        t = torch.tensor([ms], dtype=torch.float64, device=flush.device)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()), total_iters, labels
+
+    def close(self):
+        self.ctx.close()
+
+
 def run_b200(args):
     import torch
 
     import chbin_b200
-    from chbin_b200 import capi, clustering
+    from chbin_b200 import capi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -248,211 +370,326 @@ def run_b200(args):
     dist = None
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
-        import torch.distributed as dist
-
         import datetime
 
+        import torch.distributed as dist
+
         torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=180))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=300))
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
-
-    X, bins, cfg, U = workload(args)
-    n, d = X.shape
-    C, k = cfg["C"], cfg["k"]
-    perms = clustering.draw_permutations(bins, MAX_ITERATIONS, seed=0)  # the host RNG contract (algorithm.py:45)
-
-    # ---------------- value arm: features resident in HBM, one context reused ----------------
-    ctx = capi.Context(local_rank)
     stream = torch.cuda.Stream(dev)  # the library's kernels, torch events and NCCL collectives all run on this stream
     torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    Xd = torch.from_numpy(X).to(dev)
-    ctx.set_features_dev(Xd.data_ptr(), n, d)
-    ctx.set_params(k, "convex")
-    ctx.set_window(args.window)
-    u0, u1 = clustering.owned_slots(U, rank, world)
-    engine = comm = None
-
-    def one_stage():
-        nonlocal engine, comm
-        ctx.set_labels(bins, C, u0, u1)
-        ctx.build_distance_matrix(True)
-        if world == 1:
-            labels, iters, conv, changed = ctx.fit(perms, MAX_ITERATIONS)
-            return labels, iters
-        if engine is None:
-            engine = clustering.GpuEngine(ctx, local_rank, stream)
-            comm = clustering.TorchComm()
-        iters = 0
-        with engine.stream_context():
-            for it in range(MAX_ITERATIONS):
-                nch, _ = clustering.run_iteration(engine, perms[it], comm)
-                iters += 1
-                if nch == 0:
-                    break
-        return ctx.get_labels(), iters
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    X, bins, cfg, U = workload(args)
+    n, d = X.shape
+    C, k = cfg["C"], cfg["k"]
+    # L2 policy: a 256 MB memset (2x the 126 MB L2) runs between steps, outside the per-step event brackets, so that no
+    # step starts with the previous step's feature rows or candidate lists in cache
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---------------- value arm: features resident in HBM, one context reused ----------------
+    R = StageRunner(torch, dist, rank, world, local_rank, stream, X, bins, cfg, args.window)
+    ctx = R.ctx
     for _ in range(args.warmup):
-        labels_w, iters_w = one_stage()
-    barrier()
+        R.run()
+    # pass A (the headline): per-kernel event timers OFF, nothing but the stage itself between the step's two events
+    ctx.enable_timers(False)
     ctx.reset_timers()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # L2 policy: a 256 MB memset (2x the 126 MB L2) runs between steps, outside the per-step event brackets, so that no
-    # step starts with the previous step's feature rows or candidate lists in cache
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    events = []
-    barrier()
-    total_iters = 0
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        labels_v, iters = one_stage()
-        e1.record(stream)
-        events.append((e0, e1))
-        total_iters += iters
-    barrier()
-    elapsed_ms = float(sum(a.elapsed_time(b) for a, b in events))
+    elapsed_ms, total_iters, labels_v = R.timed(args.steps, flush, barrier, stream)
     clocks = sampler.stop() if rank == 0 else None
+    tmA = ctx.timers()
+    # pass B (explains it): the same K steps again with a CUDA-event pair around every timed kernel launch -> live durations
+    # for the roofline records; its own step time is reported next to the headline
+    ctx.enable_timers(True)
+    ctx.reset_timers()
+    elapsed_ms_b, _, _ = R.timed(args.steps, flush, barrier, stream)
     tm = ctx.timers()
-    t_el = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_el, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t_el.item())
     qps_ref_total = total_iters * U * C
     value = qps_ref_total / (elapsed_ms * 1e-3)
-    fp64_peak = ctx.measure_fp64_tflops() if rank == 0 else 0.0
-    ctx.close()  # the end-to-end arm below builds its own context through the public API: release this one's HBM first
 
-    # ---------------- e2e arm: public API, host (pinned) buffers ----------------
+    # iteration-1 labels of the device, for the oracle check below
+    lab1 = None
+    if world == 1:
+        ctx.set_labels(bins, C, 0, -1)
+        ctx.build_distance_matrix(True)
+        lab1, _ = ctx.fit_iteration(R.perms[0])
+    fp64_peak = ctx.measure_fp64_tflops() if rank == 0 else 0.0
+    l2_gbs = ctx.measure_l2_gbs() if rank == 0 else 0.0
+    qp_iso = qp_isolated(ctx, X, bins, cfg) if (rank == 0 and world == 1 and not args.no_qp_isolated) else None
+    R.close()  # the end-to-end arm below builds its own context through the public API: release this one's HBM first
+
+    # ---------------- e2e arm: public API, host buffers, H2D of features/labels and D2H of the labels inside ----------------
+    def e2e_arm(Xh, bh, steps):
+        iters = 0
+        for _ in range(max(1, min(args.warmup, 2))):
+            np.random.seed(0)
+            chbin_b200.fit_cluster(Xh, C, bh, None, k, MAX_ITERATIONS, device=local_rank, window=args.window)
+        barrier()
+        secs, lab = 0.0, None
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize(dev)
+            np.random.seed(0)
+            t0 = time.perf_counter()
+            lab, info = chbin_b200.fit_cluster(Xh, C, bh, None, k, MAX_ITERATIONS, device=local_rank, window=args.window,
+                                               return_info=True)
+            secs += time.perf_counter() - t0
+            iters += info["iterations"]
+        barrier()
+        t = torch.tensor([secs], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), iters, lab
+
     Xp = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
     Xp.copy_(torch.from_numpy(X))
-    Xh = Xp.numpy()
     bp = torch.empty((n,), dtype=torch.int64, pin_memory=True)
     bp.copy_(torch.from_numpy(bins))
-    bh = bp.numpy()
-    e2e_iters = 0
-    for i in range(max(1, min(args.warmup, 2))):
-        np.random.seed(0)
-        chbin_b200.fit_cluster(Xh, C, bh, None, k, MAX_ITERATIONS, device=local_rank, window=args.window)
-    barrier()
-    e2e_s = 0.0
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize(dev)
-        np.random.seed(0)
-        t0 = time.perf_counter()
-        lab_e, info_e = chbin_b200.fit_cluster(Xh, C, bh, None, k, MAX_ITERATIONS, device=local_rank, window=args.window,
-                                               return_info=True)
-        e2e_s += time.perf_counter() - t0
-        e2e_iters += info_e["iterations"]
-    barrier()
-    t_e = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_s = float(t_e.item())
+    e2e_s, e2e_iters, lab_e = e2e_arm(Xp.numpy(), bp.numpy(), args.steps)
     e2e_value = e2e_iters * U * C / e2e_s
     same = bool(np.array_equal(lab_e, labels_v))
+    # the reference's own boundary: `samples` is DataFrame.values of one float block -- a PAGEABLE, F-ORDERED
+    # (n, d) array -- and `initial_bins` a pageable int64 copy
+    Xf = np.asfortranarray(X)
+    pg_s, pg_iters, lab_pg = e2e_arm(Xf, bins.copy(), args.steps)
+    e2e_pageable = {"value": pg_iters * U * C / pg_s, "unit": "QP/s", "ms_per_step": pg_s * 1e3 / args.steps,
+                    "buffers": "pageable, F-ordered float64 samples (DataFrame.values, cli/clustering.py:53) + pageable int64 bins; "
+                               "transposed on the device",
+                    "labels_equal_value_arm": bool(np.array_equal(lab_pg, labels_v))}
+    del Xp, Xf
+
+    # ---------------- the other BASELINE workloads, one short measurement each (scaling record) ----------------
+    scale = {}
+    for name in [w for w in args.scale_workloads.split(",") if w and w != args.workload]:
+        try:
+            scale[name] = scale_workload(torch, dist, rank, world, local_rank, stream, flush, barrier, name, args.window)
+        except Exception as e:  # noqa: BLE001
+            scale[name] = {"error": repr(e)[:300]}
 
     if rank == 0:
-        hbm_peak, hbm_src = measured_peaks()
-        ms = {"distance": tm["ms_distance"], "gram": tm["ms_gram"], "knn": tm["ms_knn"], "qp": tm["ms_qp"],
-              "commit": tm["ms_commit"]}
-        ln = {"distance": tm["launches_distance"], "gram": tm["launches_gram"], "knn": tm["launches_knn"],
-              "qp": tm["launches_qp"], "commit": tm["launches_commit"]}
-        dom = None  # chosen below among the stages that ran and have a roofline
-        traffic_all = {}
-        tp = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tp):
-            try:
-                traffic_all = json.load(open(tp))
-            except Exception:
-                traffic_all = {}
-        nown = u1 - u0
-        try:
-            tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
-            tf32_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"
-        except Exception:
-            tf32_peak, tf32_src = 1590.0 / 2.0, "fallback (B200_PROFILING.md bf16 figure / 2)"
-        stages = {}
-        if ln["gram"]:
-            # fused tcgen05 Gram + per-bin selection (distance mode 2): TF32 3-term split, K = 3 * dp8 per 128x128 tile
-            dp8 = (d + 7) // 8 * 8
-            fl = tm["gram_tiles"] * 2.0 * 128 * 128 * 3 * dp8
-            stages["gram"] = {"kernel": "gram_select_kernel", "bound": "tensor", "achieved": fl / (ms["gram"] * 1e-3) / 1e12,
-                              "peak": tf32_peak, "unit": "TFLOP/s", "ms_total": ms["gram"], "launches": ln["gram"],
-                              "flops_per_launch": fl / ln["gram"], "tiles_128x128": tm["gram_tiles"], "peak_source": tf32_src}
-        if ln["knn"]:
-            if ln["gram"]:
-                # re-rank of the surviving (query, bin) pairs: issue/latency bound set-up work, no bandwidth roofline
-                stages["knn"] = {"kernel": "rerank_kernel", "bound": "issue", "achieved": None, "peak": None, "unit": None,
-                                 "ms_total": ms["knn"], "launches": ln["knn"]}
-            else:
-                b = tm["rows_scanned"] * n * 4.0  # kNN scan: one row of FP32 candidate values (4n bytes) per item
-                stages["knn"] = {"kernel": "knn_scan_kernel", "bound": "hbm", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": hbm_peak,
-                                 "unit": "GB/s", "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"],
-                                 "peak_source": hbm_src}
-        if ln["qp"]:
-            b = tm["qps_solved"] * bytes_per_qp(k, d, C)
-            f = tm["qps_solved"] * flops_per_qp(k, d)
-            stages["qp"] = {"kernel": "qp_small_kernel" if k <= 5 else ("qp_mid_kernel" if k <= 10 else "qp_kernel"),
-                            "bound": "hbm", "achieved": b / (ms["qp"] * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "ms_total": ms["qp"], "launches": ln["qp"], "bytes_per_launch": b / ln["qp"],
-                            "qps_solved": tm["qps_solved"], "qps_per_s": tm["qps_solved"] / (ms["qp"] * 1e-3),
-                            "fp64_tflops": f / (ms["qp"] * 1e-3) / 1e12, "fp64_peak_tflops": fp64_peak,
-                            "fp64_frac": (f / (ms["qp"] * 1e-3) / 1e12 / fp64_peak) if fp64_peak else None,
-                            "peak_source": hbm_src,
-                            "note": "algorithmic bytes B(k,d) per QP (SURVEY 8d); the gathered rows are L2-resident at this n"}
-        if ln["distance"]:
-            # candidate-distance Gram of distance mode 1 / the exact-path fallback rows (gram_tc.cu)
-            stages["distance"] = {"kernel": "gram_tc_kernel", "bound": "tensor", "achieved": None, "peak": tf32_peak,
-                                  "unit": "TFLOP/s", "ms_total": ms["distance"], "launches": ln["distance"],
-                                  "peak_source": tf32_src}
-        for s in stages.values():
-            s["frac"] = (s["achieved"] / s["peak"]) if (s["peak"] and s["achieved"] is not None) else None
-            s["share_of_step"] = s["ms_total"] / elapsed_ms
-        # dominant kernel = the longest-running stage with a defined roofline (the re-rank and the set-up kernels are
-        # issue / latency bound bookkeeping; their shares are reported in `stages` and `launches_by_stage`)
-        dom = max((s for s in stages if stages[s].get("achieved") is not None), key=lambda s: ms[s])
-        roof = dict(stages[dom])
-        roof["traffic"] = traffic_all.get(roof["kernel"])
-        roof["avg_launch_ms"] = roof["ms_total"] / roof["launches"]
-
-        cpu = None
-        if world == 1 and not args.no_cpu_baseline:
-            threads = os.cpu_count() or 1
-            v, steps_used, dt = cpu_sample(X, bins, cfg, args.cpu_seconds, threads)
-            cpu = {"value": v, "unit": "QP/s", "cores": threads, "kind": "port",
-                   "sample": f"oracle port, first {steps_used} sequential steps of iteration 1 ({steps_used * C} QPs, {dt:.1f} s), "
-                             f"rows recomputed on the fly"}
-        line = {
-            "metric": "point-to-hull QP distances/sec", "value": value, "unit": "QP/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": config_dict(args, cfg, U),
-            "clustering_stage_ms": elapsed_ms / args.steps, "iterations_per_step": total_iters / args.steps,
-            "qps_reference_per_step": qps_ref_total / args.steps,
-            "qps_solved_per_step": tm["qps_solved"] / args.steps, "rounds_per_step": tm["rounds"] / args.steps,
-            "roofline": roof, "stages": stages, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": int(n * d * 8 + n * 8 + e2e_iters / args.steps * U * 8),
-                    "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_s * 1e3 / args.steps,
-                    "labels_equal_value_arm": same},
-            "gpu_launches": int(sum(ln.values()) + tm["launches_other"]),
-            "launches_by_stage": dict(ln, other=tm["launches_other"]),
-            "clocks": clocks,
-        }
+        line = report(args, cfg, X, bins, U, world, elapsed_ms, elapsed_ms_b, total_iters, tmA, tm, fp64_peak, l2_gbs, clocks, value,
+                      qps_ref_total, e2e_value, e2e_s, e2e_iters, same, e2e_pageable, scale, lab1, labels_v, R.perms, qp_iso, torch)
         _emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def scale_workload(torch, dist, rank, world, local_rank, stream, flush, barrier, name, window, steps=2, warmup=1):
+    """Stage time of another BASELINE workload (config #3: 100k / k = 10, config #4: 1M / C = 500) at this N, features
+    resident, so that every `--gpus N` line carries the sizes BASELINE.json asks to scale beside the 20k headline."""
+    from chbin_b200 import synth
+
+    X, bins, truth, cfg = synth.make_config(name, seed=0)
+    R = StageRunner(torch, dist, rank, world, local_rank, stream, X, bins, cfg, window)
+    try:
+        for _ in range(warmup):
+            R.run()
+        R.ctx.enable_timers(False)
+        R.ctx.reset_timers()
+        ms, iters, labels = R.timed(steps, flush, barrier, stream)
+        tm = R.ctx.timers()
+        U = R.U
+        out = {"n": cfg["n"], "d": X.shape[1], "C": cfg["C"], "k": cfg["k"], "U": U, "steps": steps,
+               "stage_ms": ms / steps, "iterations_per_stage": iters / steps,
+               "value_qps": iters * U * cfg["C"] / (ms * 1e-3), "qps_solved_per_stage_this_rank": tm["qps_solved"] / steps,
+               "rounds_per_stage": tm["rounds"] / steps, "labels_equal_ground_truth": bool(np.array_equal(labels, truth))}
+        if rank == 0:
+            try:  # a seeded sample of positions of iteration-1-equivalent state against the position-parallel oracle
+                import oracle
+
+                if iters / steps == 2:  # converged after one changing iteration: the final labels ARE iteration 1's result
+                    pos = np.sort(np.random.default_rng(5).choice(U, min(U, 1024), replace=False)).astype(np.int64)
+                    res = oracle.verify_iteration(X, cfg["C"], bins, labels, R.perms[0], cfg["k"], positions=pos, threads=os.cpu_count() or 1)
+                    out["oracle_sampled_positions"] = int(len(pos))
+                    out["oracle_mismatches"] = int(res["mismatches"])
+            except Exception as e:  # noqa: BLE001
+                out["oracle_error"] = repr(e)[:200]
+        return out
+    finally:
+        R.close()
+
+
+def qp_isolated(ctx, X, bins, cfg):
+    """The QP kernel on a FULL batch, isolated (north_star: 'QP kernel as a fraction of the FP64 roofline'): every
+    (query, bin) pair of the workload with fixed, precomputed neighbour lists (chb_knn_per_bin on the generator's labels),
+    timed by the library's CUDA-event pair around the kernel launch."""
+    from chbin_b200 import synth
+
+    C, k = cfg["C"], cfg["k"]
+    _, _, truth = synth.make_contig_features(cfg["n"], C, cfg["S"], cfg["n_seed"], seed=0)
+    queries = np.where(bins == -1)[0][:20000].astype(np.int64)
+    ctx.set_labels(bins, C, 0, -1)
+    ctx.build_distance_matrix(True)
+    idx, m = ctx.knn_per_bin(truth, queries)
+    best = None
+    for _ in range(3):
+        ctx.reset_timers()
+        dist, status = ctx.hull_distance_batch(queries, idx, m)
+        t = ctx.timers()
+        if best is None or t["ms_qp"] < best:
+            best = t["ms_qp"]
+    return {"pairs": int(dist.size), "ms": best, "qps_per_s": dist.size / (best * 1e-3)}
+
+
+def report(args, cfg, X, bins, U, world, elapsed_ms, elapsed_ms_b, total_iters, tmA, tm, fp64_peak, l2_gbs, clocks, value,
+           qps_ref_total, e2e_value, e2e_s, e2e_iters, same, e2e_pageable, scale, lab1, labels_v, perms, qp_iso, torch):
+    n, d = X.shape
+    C, k = cfg["C"], cfg["k"]
+    hbm_peak, hbm_src = measured_peaks()
+    l2_bytes = int(torch.cuda.get_device_properties(0).L2_cache_size)
+    ms = {"distance": tm["ms_distance"], "gram": tm["ms_gram"], "knn": tm["ms_knn"], "qp": tm["ms_qp"], "commit": tm["ms_commit"]}
+    ln = {"distance": tm["launches_distance"], "gram": tm["launches_gram"], "knn": tm["launches_knn"],
+          "qp": tm["launches_qp"], "commit": tm["launches_commit"]}
+    traffic_all = {}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic_all = json.load(open(tp))
+        except Exception:
+            traffic_all = {}
+    try:
+        tf32_peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"]) / 2.0
+        tf32_src = "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 runs at half the bf16 rate)"
+    except Exception:
+        tf32_peak, tf32_src = 1590.0 / 2.0, "fallback (B200_PROFILING.md bf16 figure / 2)"
+    x_bytes = n * ((d + 1) // 2 * 2) * 8
+    x_in_l2 = x_bytes < 0.5 * l2_bytes
+    ai = flops_per_qp(k, d) / bytes_per_qp(k, d, C)
+
+    def qp_ceilings():
+        """min over the ceilings that APPLY: the FP64 pipe always; the neighbour-row gather through the L2 fabric
+        while the feature matrix is L2-resident, through HBM once it is not."""
+        c = {"fp64": fp64_peak}
+        if x_in_l2:
+            c["l2_gather"] = ai * l2_gbs / 1e3
+        else:
+            c["hbm"] = ai * hbm_peak / 1e3
+        bind = min(c, key=lambda kk: c[kk])
+        return c, bind
+
+    stages = {}
+    if ln["gram"]:
+        # fused tcgen05 Gram + per-bin selection (distance mode 2): TF32 3-term split, K = 3 * dp8 per 128x128 tile; tiles are
+        # counted by the MMA-issuing warps (gram_tiles) and must equal the planner's count (gram_tiles_planned)
+        dp8 = (d + 7) // 8 * 8
+        fl = tm["gram_tiles"] * 2.0 * 128 * 128 * 3 * dp8
+        fl_alg = tm["gram_tiles"] * 2.0 * 128 * 128 * d
+        t = ms["gram"] * 1e-3
+        stages["gram"] = {"kernel": "gram_select_kernel", "bound": "tensor", "achieved": fl / t / 1e12, "peak": tf32_peak,
+                          "unit": "TFLOP/s", "ms_total": ms["gram"], "launches": ln["gram"], "flops_per_launch": fl / ln["gram"],
+                          "tiles_128x128": tm["gram_tiles"], "tiles_planned": tm["gram_tiles_planned"], "peak_source": tf32_src,
+                          "achieved_algorithmic": fl_alg / t / 1e12, "frac_algorithmic": fl_alg / t / 1e12 / tf32_peak,
+                          "note": "achieved/frac count the executed MMA work (3-term TF32 split, d padded to a multiple of 8); "
+                                  "*_algorithmic count SURVEY 8(d)'s 2*d flop per (query, column)"}
+    if ln["knn"]:
+        if ln["gram"]:
+            # re-rank: per surviving (query, bin) pair reads the two kept half-lists (keys + indices) and writes k indices;
+            # algorithmic bytes against the L2 gather bandwidth (the lists were just written by the fused kernel)
+            KR = 8 if k + 3 <= 8 else 16
+            b = tm["qps_solved"] * (2 * KR * 8 + 4 * k + 8.0)
+            stages["knn"] = {"kernel": "rerank_kernel", "bound": "l2", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": l2_gbs,
+                             "unit": "GB/s", "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"],
+                             "peak_source": "chb_measure_l2_gbs (live)",
+                             "note": "latency/issue-bound bookkeeping kernel: a few KB per surviving pair; bytes counted for the pairs "
+                                     "whose neighbour set changed (a lower bound of the pairs re-ranked)"}
+        else:
+            b = tm["rows_scanned"] * n * 4.0  # kNN scan: one row of FP32 candidate values (4n bytes) per item
+            stages["knn"] = {"kernel": "knn_scan_kernel", "bound": "hbm", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": hbm_peak,
+                             "unit": "GB/s", "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"],
+                             "peak_source": hbm_src}
+    qp_name = "qp_small_kernel" if k <= 5 else ("qp_mid_kernel" if k <= 10 else "qp_kernel")
+    ceil, bind = qp_ceilings()
+    if ln["qp"]:
+        f = tm["qps_solved"] * flops_per_qp(k, d)
+        ach = f / (ms["qp"] * 1e-3) / 1e12
+        stages["qp"] = {"kernel": qp_name, "bound": bind, "achieved": ach, "peak": ceil[bind], "unit": "TFLOP/s",
+                        "ms_total": ms["qp"], "launches": ln["qp"], "flops_per_launch": f / ln["qp"],
+                        "qps_solved": tm["qps_solved"], "qps_per_s": tm["qps_solved"] / (ms["qp"] * 1e-3),
+                        "ceilings_tflops": ceil, "fp64_frac": ach / fp64_peak if fp64_peak else None,
+                        "features_l2_resident": x_in_l2, "peak_source": "live: chb_measure_fp64_tflops, chb_measure_l2_gbs; "
+                        + hbm_src + " for HBM",
+                        "note": "algorithmic flops F(k,d) per QP (SURVEY 8d) over the small post-pruning batches of this workload "
+                                "(launch-latency dominated); the full-batch rate is in qp_isolated"}
+    if ln["distance"]:
+        stages["distance"] = {"kernel": "gram_tc_kernel", "bound": "tensor", "achieved": None, "peak": tf32_peak,
+                              "unit": "TFLOP/s", "ms_total": ms["distance"], "launches": ln["distance"], "peak_source": tf32_src}
+    for s in stages.values():
+        s["frac"] = (s["achieved"] / s["peak"]) if (s["peak"] and s["achieved"] is not None) else None
+        s["share_of_step"] = s["ms_total"] / elapsed_ms_b
+        s["avg_launch_ms"] = s["ms_total"] / max(s["launches"], 1)
+    dom = max(stages, key=lambda s: ms[s])  # the longest-running timed kernel family of the step
+    roof = dict(stages[dom])
+    roof["traffic"] = traffic_all.get(roof["kernel"])
+    if qp_iso:
+        f = qp_iso["pairs"] * flops_per_qp(k, d)
+        ach = f / (qp_iso["ms"] * 1e-3) / 1e12
+        qp_iso.update({"kernel": qp_name, "achieved": ach, "unit": "TFLOP/s", "ceilings_tflops": ceil, "bound": bind, "peak": ceil[bind],
+                       "frac": ach / ceil[bind], "fp64_frac": ach / fp64_peak if fp64_peak else None,
+                       "l2_gather_gbs": l2_gbs, "gathered_gbs": qp_iso["pairs"] * bytes_per_qp(k, d, C) / (qp_iso["ms"] * 1e-3) / 1e9})
+
+    cpu = oracle_check = None
+    if not args.no_cpu_baseline:
+        import oracle
+
+        threads = os.cpu_count() or 1
+        if world == 1:
+            v, steps_used, dt, seq_labels, perm0 = cpu_sample(X, bins, cfg, args.cpu_seconds, threads, return_labels=True)
+            cpu = {"value": v, "unit": "QP/s", "cores": threads, "kind": "port",
+                   "sample": f"oracle port, first {steps_used} sequential steps of iteration 1 ({steps_used * C} QPs, {dt:.1f} s), "
+                             f"rows recomputed on the fly"}
+            cpu.update(cpu_extras(X, bins, cfg))
+            head = perm0[:steps_used]
+            oracle_check = {"kind": "sequential oracle, iteration 1", "positions": int(steps_used), "of": int(U),
+                            "equal": bool(np.array_equal(seq_labels[head], lab1[head]))}
+        # any N: the final labels against the position-parallel oracle on a seeded sample (valid when the run converged after
+        # one changing iteration, i.e. the final labels are iteration 1's result)
+        if total_iters / args.steps == 2:
+            pos = np.sort(np.random.default_rng(11).choice(U, min(U, 2048), replace=False)).astype(np.int64)
+            res = oracle.verify_iteration(X, C, bins, labels_v, perms[0], k, positions=pos, threads=threads)
+            oracle_check = dict(oracle_check or {}, sampled_positions=int(len(pos)), sampled_mismatches=int(res["mismatches"]))
+    labels_equal_oracle = None
+    if oracle_check is not None:
+        labels_equal_oracle = bool(oracle_check.get("equal", True) and oracle_check.get("sampled_mismatches", 0) == 0)
+
+    kernel_ms = sum(ms.values())
+    launches_step = (sum(tmA[f] for f in ("launches_distance", "launches_gram", "launches_knn", "launches_qp", "launches_commit",
+                                           "launches_other"))) / args.steps
+    return {
+        "metric": "point-to-hull QP distances/sec", "value": value, "unit": "QP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(args, cfg, U),
+        "clustering_stage_ms": elapsed_ms / args.steps, "iterations_per_step": total_iters / args.steps,
+        "qps_reference_per_step": qps_ref_total / args.steps,
+        "qps_solved_per_step": tmA["qps_solved"] / args.steps, "rounds_per_step": tmA["rounds"] / args.steps,
+        "labels_equal_oracle": labels_equal_oracle, "oracle_check": oracle_check,
+        "roofline": roof, "stages": stages, "qp_isolated": qp_iso,
+        "latency": {"ms_per_step": elapsed_ms / args.steps, "ms_per_step_with_stage_timers": elapsed_ms_b / args.steps,
+                    "timed_kernels_ms_per_step": kernel_ms / args.steps, "launches_per_step": launches_step,
+                    "note": "timed kernels = gram_select, rerank (+exact redo), QP, argmin/commit; the rest of the step is the "
+                            "per-label-set and per-round set-up kernels and host round trips"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": int(n * d * 8 + n * 8 + e2e_iters / args.steps * U * 8),
+                "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_s * 1e3 / args.steps,
+                "buffers": "pinned, C-contiguous", "labels_equal_value_arm": same},
+        "e2e_pageable_f_order": e2e_pageable,
+        "scale_workloads": scale,
+        "gpu_launches": int(launches_step * args.steps),
+        "launches_by_stage": {"distance": tmA["launches_distance"], "gram": tmA["launches_gram"], "knn": tmA["launches_knn"],
+                              "qp": tmA["launches_qp"], "commit": tmA["launches_commit"], "other": tmA["launches_other"]},
+        "peaks": {"fp64_tflops": fp64_peak, "l2_gather_gbs": l2_gbs, "hbm_gbs": hbm_peak, "tf32_tflops": tf32_peak, "l2_bytes": l2_bytes},
+        "clocks": clocks,
+    }
 
 
 def _emit(line: dict):

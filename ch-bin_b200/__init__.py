@@ -17,6 +17,7 @@ from .clustering import (  # noqa: F401
     GpuEngine,
     TorchComm,
     draw_permutations,
+    exchange_guess,
     fit_cluster,
     install,
     owned_slots,
@@ -26,6 +27,6 @@ from .clustering import (  # noqa: F401
 )
 
 __all__ = [
-    "B200_SOLVER", "GpuEngine", "TorchComm", "draw_permutations", "fit_cluster", "install", "owned_slots", "perform_clustering",
+    "B200_SOLVER", "GpuEngine", "TorchComm", "draw_permutations", "exchange_guess", "fit_cluster", "install", "owned_slots", "perform_clustering",
     "run_iteration", "shutdown", "build", "capi", "distance_cache", "features", "synth",
 ]

@@ -22,9 +22,9 @@ EXPORTED_SYMBOLS = [
     "chb_abi_version", "chb_create", "chb_destroy", "chb_last_error", "chb_set_stream", "chb_synchronize",
     "chb_get_timers", "chb_reset_timers", "chb_enable_timers", "chb_set_features", "chb_set_features_dev",
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
-    "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin",
-    "chb_round_run", "chb_round_commit", "chb_iteration_end", "chb_set_window", "chb_get_window",
-    "chb_measure_fp64_tflops", "chb_measure_l2_gbs", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
+    "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin", "chb_iteration_begin_dev",
+    "chb_round_run", "chb_round_commit", "chb_round_commit_end", "chb_iteration_end", "chb_set_window", "chb_get_window",
+    "chb_measure_fp64_tflops", "chb_measure_l2_gbs", "chb_guess_export", "chb_guess_import", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
     "chb_get_fused_candidates", "chb_set_features_async", "chb_set_features_colmajor", "chb_set_features_merged", "chb_get_features",
 ]
 
@@ -98,14 +98,18 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_fit.argtypes = [_vp, _vp, _i64, _i32, _vp, ctypes.POINTER(_i32), ctypes.POINTER(_i32), _vp]
     L.chb_get_labels.argtypes = [_vp, _vp]
     L.chb_iteration_begin.argtypes = [_vp, _vp, _i64]
+    L.chb_iteration_begin_dev.argtypes = [_vp, _vp, _i64]
     L.chb_round_run.argtypes = [_vp, _i64, _i64, _vp]
     L.chb_round_commit.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_i64)]
     L.chb_iteration_end.argtypes = [_vp, ctypes.POINTER(_i64)]
+    L.chb_round_commit_end.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_i64), ctypes.POINTER(_i64), ctypes.POINTER(_i32)]
     L.chb_set_window.argtypes = [_vp, _i64]
     L.chb_get_window.argtypes = [_vp]
     L.chb_get_window.restype = _i64
     L.chb_measure_fp64_tflops.argtypes = [_vp, ctypes.POINTER(_dbl)]
     L.chb_measure_l2_gbs.argtypes = [_vp, ctypes.POINTER(_dbl)]
+    L.chb_guess_export.argtypes = [_vp, _vp, ctypes.POINTER(_i32)]
+    L.chb_guess_import.argtypes = [_vp, _vp]
     for name in EXPORTED_SYMBOLS:
         fn = getattr(L, name)
         if name not in ("chb_last_error", "chb_get_window"):
@@ -348,6 +352,19 @@ class Context:
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         self._check(self._lib.chb_iteration_begin(self._h, _ptr(perm), len(perm)))
 
+    def guess_export(self, guess_dev_ptr: int) -> bool:
+        """chb_guess_export: the owned slots' speculation start into a device buffer of U int32; False = nothing to exchange."""
+        active = _i32(0)
+        self._check(self._lib.chb_guess_export(self._h, _vp(guess_dev_ptr), ctypes.byref(active)))
+        return bool(active.value)
+
+    def guess_import(self, guess_dev_ptr: int):
+        self._check(self._lib.chb_guess_import(self._h, _vp(guess_dev_ptr)))
+
+    def iteration_begin_dev(self, perm_dev_ptr: int, U: int):
+        """chb_iteration_begin_dev: the permutation (int64, U entries) already lies in device memory."""
+        self._check(self._lib.chb_iteration_begin_dev(self._h, _vp(perm_dev_ptr), int(U)))
+
     def round_run(self, lo: int, hi: int, tent_dev_ptr: Optional[int] = None):
         """Enqueues one speculate round (asynchronous).  tent_dev_ptr None: the library's own tentative buffer."""
         self._check(self._lib.chb_round_run(self._h, lo, hi, _vp(tent_dev_ptr)))
@@ -356,6 +373,14 @@ class Context:
         first = _i64(-1)
         self._check(self._lib.chb_round_commit(self._h, lo, hi, _vp(tent_dev_ptr), ctypes.byref(first)))
         return int(first.value)
+
+    def round_commit_end(self, lo: int, hi: int, tent_dev_ptr: Optional[int] = None):
+        """chb_round_commit_end: (first_changed, iteration_done, n_changed) -- one synchronisation for the commit and, when
+        the round settled the iteration, its end."""
+        first, nch, done = _i64(-1), _i64(0), _i32(0)
+        self._check(self._lib.chb_round_commit_end(self._h, lo, hi, _vp(tent_dev_ptr), ctypes.byref(first), ctypes.byref(nch),
+                                                   ctypes.byref(done)))
+        return int(first.value), bool(done.value), int(nch.value)
 
     def measure_fp64_tflops(self) -> float:
         v = _dbl(0.0)

@@ -59,25 +59,33 @@ def owned_slots(U: int, rank: int, world: int) -> Tuple[int, int]:
     return (U * rank) // world, (U * (rank + 1)) // world
 
 
-def run_iteration(engine, perm: np.ndarray, comm=None) -> Tuple[int, int]:
+def run_iteration(engine, perm, comm=None) -> Tuple[int, int]:
     """One iteration of algorithm.py:43-72 as speculate/repair rounds (csrc/api.cu header).
 
     engine: iteration_begin(perm), round_run(lo, hi) -> tent, round_commit(lo, hi, tent) -> first_changed (-1 = none),
-            iteration_end() -> n_changed, window() -> int.
+            iteration_end() -> n_changed, window() -> int; optionally round_commit_end(lo, hi, tent) ->
+            (first_changed, iteration_done, n_changed), which ends the iteration in the same call when the round settled it.
     comm:   None, or an object with all_reduce_max(tent) -> tent merging the ranks' tentative labels.
     Returns (n_changed, rounds)."""
     U = len(perm)
     engine.iteration_begin(perm)
     W = engine.window() or U
+    merged = getattr(engine, "round_commit_end", None)
     lo, rounds = 0, 0
     while lo < U:
         hi = min(U, lo + W)
         tent = engine.round_run(lo, hi)
         if comm is not None:
             tent = comm.all_reduce_max(tent)
-        first = engine.round_commit(lo, hi, tent)
+        if merged is not None:
+            first, done, n_changed = merged(lo, hi, tent)
+            rounds += 1
+            if done:
+                return n_changed, rounds
+        else:
+            first = engine.round_commit(lo, hi, tent)
+            rounds += 1
         lo = hi if first < 0 else first + 1
-        rounds += 1
     return engine.iteration_end(), rounds
 
 
@@ -104,7 +112,23 @@ class GpuEngine:
         return self.ctx.get_window()
 
     def iteration_begin(self, perm):
+        if isinstance(perm, self.torch.Tensor):  # rank 0's draw, broadcast over NCCL: stays on the device
+            try:
+                self.ctx.iteration_begin_dev(perm.data_ptr(), perm.numel())
+                return
+            except ValueError:  # not distance mode 2 (wide features, ...): the library wants the permutation on the host
+                perm = perm.cpu().numpy()
         self.ctx.iteration_begin(perm)
+
+    def round_commit_end(self, lo, hi, tent):
+        return self.ctx.round_commit_end(lo, hi, tent.data_ptr())
+
+    def guess_export(self, U):
+        g = self.torch.empty(max(U, 1), dtype=self.torch.int32, device=self.device)[:U]
+        return g if self.ctx.guess_export(g.data_ptr()) else None
+
+    def guess_import(self, g):
+        self.ctx.guess_import(g.data_ptr())
 
     def round_run(self, lo, hi):
         n = hi - lo
@@ -136,6 +160,21 @@ class TorchComm:
         return tent
 
 
+def exchange_guess(engine, comm, U: int) -> bool:
+    """Sharded contexts: every rank computes the first iteration's speculation start (nearest seed centroid) for its OWN query
+    slots and the ranks merge them with one all-reduce(MAX) of U int32 labels (un-owned entries are INT32_MIN) -- instead of
+    every rank repeating the U x C x d contraction.  No-op for engines without the export/import pair."""
+    if not hasattr(engine, "guess_export"):
+        return False
+    with engine.stream_context():
+        g = engine.guess_export(U)
+        if g is None:
+            return False
+        g = comm.all_reduce_max(g)
+        engine.guess_import(g)
+    return True
+
+
 def _dist_state():
     try:
         import torch.distributed as dist
@@ -157,16 +196,24 @@ def draw_permutations(initial_bins: np.ndarray, max_iterations: int, seed: Optio
     return np.stack([np.random.permutation(pts) for _ in range(max_iterations)]).astype(np.int64).reshape(max_iterations, len(pts))
 
 
-def _draw_permutation(points_to_assign: np.ndarray, dist_mod, device_index: int) -> np.ndarray:
+def _draw_permutation(points_to_assign: np.ndarray, dist_mod, device_index: int, keep_on_device: bool = False):
     """algorithm.py:45.  Every rank draws from its own global RNG (so the stream advances exactly as in the
-    reference); rank 0's draw is authoritative and broadcast so that differently-seeded ranks cannot diverge."""
+    reference); rank 0's draw is authoritative and broadcast so that differently-seeded ranks cannot diverge.  With NCCL
+    and keep_on_device the broadcast permutation is returned as a device tensor (it goes straight into
+    chb_iteration_begin_dev: no device -> host -> device round trip); otherwise as a numpy array."""
     perm = np.random.permutation(points_to_assign).astype(np.int64)
     if dist_mod is not None and dist_mod.get_world_size() > 1:
         import torch
 
-        dev = torch.device("cuda", device_index) if dist_mod.get_backend() == "nccl" else torch.device("cpu")
-        t = torch.from_numpy(perm).to(dev)
+        nccl = dist_mod.get_backend() == "nccl"
+        dev = torch.device("cuda", device_index) if nccl else torch.device("cpu")
+        if nccl and dist_mod.get_rank() != 0:
+            t = torch.empty(len(perm), dtype=torch.int64, device=dev)  # the receivers need no upload of their own draw
+        else:
+            t = torch.from_numpy(perm).to(dev)
         dist_mod.broadcast(t, src=0)
+        if nccl and keep_on_device:
+            return t
         perm = t.cpu().numpy()
     return perm
 
@@ -230,8 +277,27 @@ def fit_cluster(
     try:
         ctx.set_stream(capi.OWN_STREAM)
         ctx.reset_timers()
-        ctx.set_features(samples, asynchronous=True)  # the upload overlaps the label set-up and the first permutation draw
+        engine = comm = None
         u0, u1 = owned_slots(num_points_to_assign, rank, world)
+        if world > 1:
+            engine = GpuEngine(ctx, device)
+            comm = TorchComm()
+        if world > 1 and dist_mod.get_backend() == "nccl":
+            # the (small) feature matrix is replicated with ONE NCCL broadcast over NVLink -- rank 0 uploads its
+            # host array once, the other ranks receive it device to device instead of pushing the same bytes over PCIe
+            import torch
+
+            with engine.stream_context():
+                n_, d_ = np.shape(samples)
+                Xd = torch.empty((n_, d_), dtype=torch.float64, device=engine.device)
+                if rank == 0:
+                    Xd.copy_(torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)), non_blocking=True)
+                dist_mod.broadcast(Xd, src=0)
+                ctx.set_features_dev(Xd.data_ptr(), n_, d_)
+                engine.stream.synchronize()
+            del Xd
+        else:
+            ctx.set_features(samples, asynchronous=True)  # the upload overlaps the label set-up and the first permutation draw
         ctx.set_labels(curr, int(num_clusters), u0, u1)
         ctx.set_params(int(num_neighbors), metric)
         ctx.set_window(int(window))
@@ -242,16 +308,15 @@ def fit_cluster(
             spec_perm = _draw_permutation(points_to_assign, dist_mod, device)  # iteration 1 always executes
         ctx.build_distance_matrix(bool(in_mem_dist_matrix))
         ctx._pending_features = None
-        engine = comm = None
-        if world > 1:
-            engine = GpuEngine(ctx, device)
-            comm = TorchComm()
+        on_device = world > 1 and dist_mod.get_backend() == "nccl" and int(distance_mode) == 2 and np.shape(samples)[1] <= 160
+        if world > 1 and num_points_to_assign > 0 and max_iterations > 0:
+            exchange_guess(engine, comm, num_points_to_assign)
 
         iterations, converged, rounds_total, changed = 0, False, 0, []
         for i_iter in range(max_iterations):
             if world > 1:
                 with engine.stream_context():
-                    sample_perm = _draw_permutation(points_to_assign, dist_mod, device)
+                    sample_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
                     change_count, rounds = run_iteration(engine, sample_perm, comm)
             else:
                 # Single context: chb_round_run only enqueues, chb_round_commit synchronises.  The next iteration's
@@ -263,16 +328,18 @@ def fit_cluster(
                 ctx.iteration_begin(sample_perm)
                 U, W = len(sample_perm), ctx.get_window()
                 lo = rounds = 0
+                done, change_count = False, 0
                 while lo < U:
                     hi = min(U, lo + (W or U))
                     ctx.round_run(lo, hi)
                     if spec_state is None and i_iter + 1 < max_iterations:
                         spec_state = np.random.get_state()
                         spec_perm = _draw_permutation(points_to_assign, dist_mod, device)
-                    first = ctx.round_commit(lo, hi)
+                    first, done, change_count = ctx.round_commit_end(lo, hi)
                     lo = hi if first < 0 else first + 1
                     rounds += 1
-                change_count = ctx.iteration_end()
+                if not done:
+                    change_count = ctx.iteration_end()
                 if (change_count == 0 or i_iter + 1 == max_iterations) and spec_state is not None:
                     np.random.set_state(spec_state)  # the speculative draw never happened
                     spec_perm = spec_state = None

@@ -193,6 +193,54 @@ __global__ void commit_kernel(const int32_t *__restrict__ tent, int64_t lo, int6
     }
 }
 
+// Device path of chb_iteration_begin: the caller's int64 permutation becomes perm_pt / pos / own_pos in one pass, and is
+// validated on the way (out of range: counters[9], not a query point: counters[10]; repeats are found by
+// check_perm_kernel once the scatter is complete: counters[11]) -- the first offending position of each kind, reported
+// by the next commit.  An offending entry is replaced by a valid query point so that the round stays memory-safe.
+__global__ void begin_perm_kernel(const int64_t *__restrict__ perm64, int64_t U, int64_t n, const int32_t *__restrict__ qslot,
+                                  const int32_t *__restrict__ qpoint, int64_t u0, int64_t u1, int32_t *__restrict__ perm_pt,
+                                  int32_t *__restrict__ pos, int32_t *__restrict__ own_pos, int32_t *__restrict__ counters)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= U) return;
+    int64_t pt = perm64[p];
+    if (pt < 0 || pt >= n) {
+        atomicMin(&counters[9], (int32_t)p);
+        pt = qpoint[p];
+    } else if (qslot[pt] < 0) {
+        atomicMin(&counters[10], (int32_t)p);
+        pt = qpoint[p];
+    }
+    perm_pt[p] = (int32_t)pt;
+    pos[pt] = (int32_t)p;
+    const int64_t slot = qslot[pt];
+    if (slot >= u0 && slot < u1) own_pos[slot - u0] = (int32_t)p;
+}
+
+__global__ void check_perm_kernel(const int32_t *__restrict__ perm_pt, int64_t U, const int32_t *__restrict__ pos,
+                                  int32_t *__restrict__ counters)
+{
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < U && pos[perm_pt[p]] != (int32_t)p) atomicMin(&counters[11], (int32_t)p);
+}
+
+// algorithm.py:63-72 on the device, taken only when the round just committed changed nothing (counters[1] still holds the
+// "none" pattern): the iteration is over -- count sum(initial_bins != curr_bins) and make the new labels the old ones.
+__global__ void end_if_done_kernel(int32_t *__restrict__ old_label, const int32_t *__restrict__ tent_pt, int64_t n,
+                                   int32_t *__restrict__ counters)
+{
+    if (counters[1] != 0x7f7f7f7f) return;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool ch = false;
+    if (i < n) {
+        const int32_t t = tent_pt[i];
+        ch = old_label[i] != t;
+        if (ch) old_label[i] = t;
+    }
+    const unsigned m = __ballot_sync(CHB_FULL, ch);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], __popc(m));
+}
+
 __global__ void count_changed_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t n,
                                      int32_t *__restrict__ counters)
 {
@@ -308,7 +356,7 @@ int chb_destroy(chb_ctx *c)
     chb_resolve_timers(c);
     for (auto &p : c->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     dev_free(&c->X); dev_free(&c->old_label); dev_free(&c->tent_pt); dev_free(&c->pos); dev_free(&c->qslot);
-    dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
+    dev_free(&c->perm64); dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
     dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
@@ -692,26 +740,40 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     int32_t *lab = c->pin_i32, *qs = lab + n, *qp = qs + n, *seed_idx = qp + n, *seed_off = seed_idx + n;
     c->h_qslot = qs; // host mirror used by chb_iteration_begin
     for (int32_t b = 0; b <= C; ++b) seed_off[b] = 0;
-    int64_t U = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        const int64_t b = bins[i];
-        CHB_CHECK(c, b >= -1 && b < C, CHB_EINVAL, "initial_bins[%lld] = %lld outside [-1, %d)", (long long)i, (long long)b, C);
-        lab[i] = (int32_t)b;
-        if (b == -1) {
-            qs[i] = (int32_t)U;
-            qp[U++] = (int32_t)i;
-        } else {
-            qs[i] = -1;
-            ++seed_off[b + 1];
+    int64_t U = 0, ns = 0;
+    int32_t *seed_tmp = seed_idx; // seeds in index order first (compact), grouped by bin below
+    {
+        // one pass over n: labels to int32, query slots, the compact seed list; range check folded into a min / max
+        int64_t mn = 0, mx = -1;
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t b = bins[i];
+            mn = b < mn ? b : mn;
+            mx = b > mx ? b : mx;
+            lab[i] = (int32_t)b;
+            if (b == -1) {
+                qs[i] = (int32_t)U;
+                qp[U++] = (int32_t)i;
+            } else {
+                qs[i] = -1;
+                seed_tmp[ns++] = (int32_t)i;
+            }
+        }
+        if (mn < -1 || mx >= C) {
+            for (int64_t i = 0; i < n; ++i)
+                CHB_CHECK(c, bins[i] >= -1 && bins[i] < C, CHB_EINVAL, "initial_bins[%lld] = %lld outside [-1, %d)", (long long)i,
+                          (long long)bins[i], C);
         }
     }
-    // seed contigs sorted by (bin, index): the bin reference points are summed in this fixed order on every rank
+    // seed contigs sorted by (bin, index): the bin reference points are summed in this fixed order on every rank.  Stable
+    // counting sort over the ns seeds only (the permuted copy goes through qp's tail, free beyond U, and back).
+    for (int64_t s = 0; s < ns; ++s) ++seed_off[lab[seed_tmp[s]] + 1];
     for (int32_t b = 0; b < C; ++b) seed_off[b + 1] += seed_off[b];
     {
-        std::vector<int32_t> &cur = c->h_lab; // scratch: write cursor per bin
+        std::vector<int32_t> &cur = c->h_lab; // scratch: write cursor per bin, then the grouped list
         cur.assign(seed_off, seed_off + C);
-        for (int64_t i = 0; i < n; ++i)
-            if (lab[i] >= 0) seed_idx[cur[(size_t)lab[i]]++] = (int32_t)i;
+        int32_t *grouped = qp + U; // qp has n entries, of which U are used: n - U = ns are free
+        for (int64_t s = 0; s < ns; ++s) grouped[cur[(size_t)lab[seed_tmp[s]]]++] = seed_tmp[s];
+        memcpy(seed_idx, grouped, sizeof(int32_t) * (size_t)ns);
     }
     if (slot_end < 0) slot_end = U;
     CHB_CHECK(c, 0 <= slot_begin && slot_begin <= slot_end && slot_end <= U, CHB_EINVAL, "owned slot range [%lld,%lld) invalid for U=%lld",
@@ -753,6 +815,8 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     ++c->tm.launches_other;
     c->labels_set = true;
     c->guess_pending = true;
+    c->guess_shared = false; // the caller opts in again with chb_guess_export after every chb_set_labels
+    c->guess_imported = false;
     c->in_iteration = false;
     c->dist_ready = false;
     c->f_asplit_ready = false;
@@ -968,7 +1032,18 @@ int chb_set_window(chb_ctx *c, int64_t window)
 }
 int64_t chb_get_window(chb_ctx *c) { return c ? (c->window > 0 ? c->window : c->U) : 0; }
 
-int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
+static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bool perm_on_device);
+
+int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U) { return iteration_begin_common(c, perm, U, false); }
+
+int chb_iteration_begin_dev(chb_ctx *c, const int64_t *perm_dev, int64_t U)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, use_fused(c) || U == 0, CHB_EINVAL, "chb_iteration_begin_dev needs distance mode 2 (d <= 160); pass a host permutation otherwise");
+    return iteration_begin_common(c, perm_dev, U, true);
+}
+
+static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bool perm_on_device)
 {
     CHB_CHECK(c, c && (perm || U == 0), CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->labels_set && c->dist_ready, CHB_EINVAL, "iteration_begin: labels / distance matrix not set up");
@@ -976,6 +1051,23 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
               (long long)c->U);
     CHB_CUDA(c, cudaSetDevice(c->device));
     CHB_TRY(ensure_caches(c));
+    c->own_pos_by_slot = false;
+    if (use_fused(c) && U > 0) {
+        // Device path (distance mode 2): the permutation is uploaded as it is and turned into perm_pt / pos / own_pos by
+        // one kernel; its validation travels with the next commit's read-back (no host pass over U, no host mirror).
+        CHB_TRY(dev_reserve(c, &c->perm64, &c->cap_perm64, U));
+        CHB_CUDA(c, cudaMemcpyAsync(c->perm64, perm, sizeof(int64_t) * (size_t)U,
+                                    perm_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        CHB_CUDA(c, cudaMemsetAsync(&c->counters[9], 0x7f, 3 * sizeof(int32_t), c->stream));
+        begin_perm_kernel<<<nblk(U, 256), 256, 0, c->stream>>>(c->perm64, U, c->n, c->qslot, c->qpoint, c->u0, c->u1, c->perm_pt, c->pos,
+                                                             c->own_pos, c->counters);
+        check_perm_kernel<<<nblk(U, 256), 256, 0, c->stream>>>(c->perm_pt, U, c->pos, c->counters);
+        CHB_CUDA(c, cudaGetLastError());
+        c->tm.launches_other += 2;
+        c->n_own_pos = c->u1 - c->u0;
+        c->own_pos_by_slot = true;
+        c->perm_check_pending = true;
+    } else {
     // positions this context owns, ascending (a context owns the queries of slots [u0, u1)); host mirrors of
     // qslot / the permutation scratch are kept in the context so that nothing is allocated or read back per iteration
     std::vector<int32_t> &p32 = c->h_perm32;
@@ -1009,12 +1101,15 @@ int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U)
         CHB_CUDA(c, cudaGetLastError());
         ++c->tm.launches_other;
     }
+    }
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     if (c->guess_pending && use_fused(c) && U > 0) {
         // First iteration: every query still carries -1.  Any starting vector T0 leads the speculate/repair rounds to
         // the same fixed point (position p is final once positions < p are, whatever it started from), so start from
         // the bin of the nearest seed centroid instead of "unassigned": when that guess is right the first round already
         // reproduces itself and the seed-only round (a full batch of QPs that the second round re-solves) is saved.
+        CHB_CHECK(c, !c->guess_shared || c->guess_imported, CHB_EINVAL,
+                  "iteration_begin: chb_guess_export was called without chb_guess_import (the other ranks' guesses are missing)");
         CHB_TRY(chb_fused_setup(c));
         CHB_TRY(chb_fused_guess(c));
     }
@@ -1043,9 +1138,12 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     CHB_CHECK(c, 0 <= lo && lo < hi && hi <= c->U, CHB_EINVAL, "round window [%lld,%lld) invalid", (long long)lo, (long long)hi);
     CHB_CUDA(c, cudaSetDevice(c->device));
     if (!tent_dev) CHB_TRY(own_tent(c, hi - lo, &tent_dev));
-    const int64_t *ob = c->own_pos_host, *oe = c->own_pos_host + c->n_own_pos;
-    const int64_t b = std::lower_bound(ob, oe, lo) - ob, e = std::lower_bound(ob, oe, hi) - ob;
-    const int64_t cnt = e - b;
+    int64_t b = 0, cnt = c->n_own_pos; // device path: every owned position, the kernels skip those outside [lo, hi)
+    if (!c->own_pos_by_slot) {
+        const int64_t *ob = c->own_pos_host, *oe = c->own_pos_host + c->n_own_pos;
+        b = std::lower_bound(ob, oe, lo) - ob;
+        cnt = (std::lower_bound(ob, oe, hi) - ob) - b;
+    }
     if (c->n_own_pos < c->U) { // positions of other ranks' queries stay CHB_UNOWNED; a context that owns them all skips the fill
         fill_i32_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, hi - lo, CHB_UNOWNED);
         CHB_CUDA(c, cudaGetLastError());
@@ -1072,7 +1170,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
         CHB_TRY(chb_launch_qp(c, q));
         cudaMemcpyAsync(&c->counters_host[4], c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-        CHB_TRY(chb_fused_argmin(c, c->own_pos + b, cnt, lo, tent_dev));
+        CHB_TRY(chb_fused_argmin(c, c->own_pos + b, cnt, lo, hi, tent_dev));
         return CHB_OK;
     }
     CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));
@@ -1129,7 +1227,28 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
     return CHB_OK;
 }
 
-int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed)
+// chb_iteration_begin's device-side validation of the permutation (the rounds ran on a sanitised copy): the caller has
+// copied counters[9..11] to the host and synchronised
+static int resolve_perm_check(chb_ctx *c)
+{
+    if (!c->perm_check_pending) return CHB_OK;
+    c->perm_check_pending = false;
+    const int32_t none = 0x7f7f7f7f;
+    const int32_t bad = std::min(std::min(c->counters_host[9], c->counters_host[10]), c->counters_host[11]);
+    if (bad == none) return CHB_OK;
+    int64_t pt = -1;
+    cudaMemcpy(&pt, c->perm64 + bad, sizeof(int64_t), cudaMemcpyDeviceToHost);
+    c->in_iteration = false; // the iteration is abandoned; the next chb_iteration_begin starts from the old labels again
+    if (c->counters_host[9] == bad) return chb_fail(c, CHB_EINVAL, "permutation entry %lld out of range", (long long)pt);
+    if (c->counters_host[10] == bad) return chb_fail(c, CHB_EINVAL, "permutation entry %lld is not an un-assigned point", (long long)pt);
+    return chb_fail(c, CHB_EINVAL, "permutation repeats point %lld", (long long)pt);
+}
+
+// Commit of one round; with n_changed != NULL also the end of the iteration when the round changed nothing and its window
+// reached the last position -- decided on the device, so that the common "one round settles the iteration" case costs ONE
+// host synchronisation instead of two.
+static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed, int64_t *n_changed,
+                         int32_t *iteration_done)
 {
     CHB_CHECK(c, c && first_changed, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->in_iteration, CHB_EINVAL, "round_commit outside chb_iteration_begin/end");
@@ -1139,24 +1258,51 @@ int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev
         CHB_CHECK(c, c->tent_win && c->tent_win_cap >= hi - lo, CHB_EINVAL, "round_commit(NULL) without a preceding round_run(NULL)");
         tent_dev = c->tent_win;
     }
+    const bool may_end = n_changed != nullptr && hi == c->U;
     CHB_CUDA(c, cudaMemsetAsync(&c->counters[1], 0x7f, sizeof(int32_t), c->stream)); // 0x7f7f7f7f: above any position
+    if (may_end) CHB_CUDA(c, cudaMemsetAsync(&c->counters[2], 0, sizeof(int32_t), c->stream));
     {
         chb_stage_timer t(c, CHB_ST_COMMIT);
         commit_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters);
     }
+    if (may_end) {
+        end_if_done_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->old_label, c->tent_pt, c->n, c->counters);
+        ++c->tm.launches_other;
+    }
     CHB_CUDA(c, cudaGetLastError());
-    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[1], &c->counters[1], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[1], &c->counters[1], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (c->perm_check_pending)
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[9], &c->counters[9], 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CHB_TRY(sync_stream(c));
     c->tm.qps_solved += c->counters_host[4];
     c->counters_host[4] = 0;
     c->tm.gram_tiles_planned += c->counters_host[7]; // tiles left after bin pruning (pairs_plan_kernel / items_kernel), this round
     c->tm.gram_tiles += c->counters_host[8];         // tiles the MMA warps of gram_select_kernel actually issued
     c->counters_host[7] = c->counters_host[8] = 0;
+    CHB_TRY(resolve_perm_check(c));
     if (c->f_fb_cap > 0 && c->counters_host[6] > c->f_fb_cap)
         return chb_fail(c, CHB_ECUDA, "exact-redo list overflow: %d pairs, capacity %d", c->counters_host[6], c->f_fb_cap);
     c->counters_host[6] = 0;
     *first_changed = (c->counters_host[1] == 0x7f7f7f7f) ? -1 : (int64_t)c->counters_host[1];
+    if (iteration_done) *iteration_done = 0;
+    if (may_end && *first_changed < 0) {
+        *n_changed = c->counters_host[2];
+        if (iteration_done) *iteration_done = 1;
+        c->in_iteration = false;
+    }
     return CHB_OK;
+}
+
+int chb_round_commit(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed)
+{
+    return commit_common(c, lo, hi, tent_dev, first_changed, nullptr, nullptr);
+}
+
+int chb_round_commit_end(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed, int64_t *n_changed,
+                         int32_t *iteration_done)
+{
+    CHB_CHECK(c, c && n_changed && iteration_done, CHB_EINVAL, "NULL argument");
+    return commit_common(c, lo, hi, tent_dev, first_changed, n_changed, iteration_done);
 }
 
 int chb_iteration_end(chb_ctx *c, int64_t *n_changed)
@@ -1169,6 +1315,11 @@ int chb_iteration_end(chb_ctx *c, int64_t *n_changed)
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
     CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[2], &c->counters[2], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    if (c->perm_check_pending) {
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[9], &c->counters[9], 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_TRY(sync_stream(c));
+        CHB_TRY(resolve_perm_check(c)); // an invalid permutation: the labels stay as they were
+    }
     CHB_CUDA(c, cudaMemcpyAsync(c->old_label, c->tent_pt, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     CHB_TRY(sync_stream(c));
     if (n_changed) *n_changed = c->counters_host[2];
@@ -1201,16 +1352,23 @@ int chb_fit_iteration(chb_ctx *c, const int64_t *perm, int64_t U, int64_t *label
             CHB_TRY(dev_alloc(c, &c->tent_win, W));
             c->tent_win_cap = W;
         }
-        int64_t lo = 0;
+        int64_t lo = 0, nch = 0;
+        int32_t done = 0;
         while (lo < U) {
             const int64_t hi = std::min(U, lo + W);
             CHB_TRY(chb_round_run(c, lo, hi, c->tent_win));
             int64_t first = -1;
-            CHB_TRY(chb_round_commit(c, lo, hi, c->tent_win, &first));
+            CHB_TRY(chb_round_commit_end(c, lo, hi, c->tent_win, &first, &nch, &done));
             lo = (first < 0) ? hi : first + 1;
         }
+        if (done) {
+            if (n_changed) *n_changed = nch;
+        } else {
+            CHB_TRY(chb_iteration_end(c, n_changed));
+        }
+    } else {
+        CHB_TRY(chb_iteration_end(c, n_changed));
     }
-    CHB_TRY(chb_iteration_end(c, n_changed));
     if (labels_out) CHB_TRY(chb_get_labels(c, labels_out));
     return CHB_OK;
 }

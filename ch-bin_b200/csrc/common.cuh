@@ -34,6 +34,9 @@ struct chb_ctx {
     int32_t *seed_off = nullptr, *seed_idx = nullptr; // C + 1 offsets / seed points (initial label >= 0) sorted by (bin, index)
     int64_t cap_seed_off = 0, cap_seed_idx = 0;
     bool guess_pending = false; // first iteration after chb_set_labels: speculation starts from the nearest seed centroid
+    bool guess_shared = false;  // sharded contexts exchange the speculation start (chb_guess_export / chb_guess_import): each
+                                // computes the centroid terms of its OWN slots only
+    bool guess_imported = false; // f_guess_all holds every slot's guess (after chb_guess_import)
     int32_t ldf = 0;
     int dist_mode = 2;    // 2: fused tensor-core Gram + selection (default); 1: FP32 candidate matrix + scan; 0: exact FP64 rows
     int gram_engine = 1;  // filter mode: 1 = tcgen05 TF32x3 tensor-core Gram (gram_tc.cu), 0 = FFMA Gram (approx.cu)
@@ -56,6 +59,10 @@ struct chb_ctx {
     int32_t *own_pos = nullptr;    // n_own: ascending positions whose query this context owns
     int64_t n_own_pos = 0;
     int64_t *own_pos_host = nullptr;
+    int64_t *perm64 = nullptr;     // U : this iteration's permutation as the caller passed it (device path of chb_iteration_begin)
+    int64_t cap_perm64 = 0;
+    bool perm_check_pending = false; // the device-side validation of this iteration's permutation has not been read back yet
+    bool own_pos_by_slot = false;  // own_pos is indexed by owned slot (device path) instead of ascending by position (host path)
     bool labels_set = false, in_iteration = false;
     std::vector<int32_t> h_lab, h_perm32, h_own32; // per-call scratch
     int32_t *pin_i32 = nullptr; // page-locked staging block of chb_set_labels
@@ -229,7 +236,7 @@ bool chb_fused_supported(const chb_ctx *c);
 int chb_round_fused(chb_ctx *c);
 int chb_fused_setup(chb_ctx *c);  // allocations + once-per-label-set operands (idempotent)
 int chb_fused_guess(chb_ctx *c);
-int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int32_t *tent_dev); // argmin over surviving bins
+int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int64_t hi, int32_t *tent_dev); // argmin over surviving bins, positions in [lo, hi)
 int chb_fused_mask_pair_cache(chb_ctx *c, int64_t slot0, int64_t nslots, int32_t *cnt_out, double *dist_out); // test aid  // tent_pt of every query point := bin of the nearest seed centroid
 void chb_fused_free(chb_ctx *c);
 

@@ -14,7 +14,8 @@
 //     to a multiple of 128; column_gather_kernel writes the per-bin-centred TF32 [hi | lo] operand rows in that order.
 //  2. threshold_kernel: per (row, bin) the pruning test (bin cannot be the argmin: admission threshold -inf, nothing
 //     else happens for the pair), else the key error bound E and the admission threshold T0 from the cached set;
-//     skip_kernel / items_kernel turn the surviving (row block, bin) pairs into a balanced work list.
+//     the same kernel flags the (row block, bin) pairs none of whose rows survived; pairs_plan_kernel / items_kernel turn
+//     the survivors into a balanced work list.
 //  3. gram_select_kernel: one persistent CTA per SM walking its work items.  TMA: the row block's query operand is
 //     loaded once and stays resident, the column operand streams through a 3-4-stage ring -> tcgen05.mma kind::tf32
 //     (3-term hi/lo split, see gram_tc.cu) -> FP32 accumulators double-buffered in TMEM.  Eight decoupled epilogue
@@ -544,25 +545,6 @@ __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const in
     row_guess[r] = guess_own[sl];
     slot_row[sl] = (int32_t)r;
     sq_row[r] = __fmul_ru(__fsqrt_ru(nrm[pt]), 1.000001f); // >= |a_q|
-}
-
-// one warp per (row block, bin): skip = every row of the block pruned the bin (t0 == -inf) or lies beyond nrows
-__global__ void __launch_bounds__(256) skip_kernel(const float *__restrict__ t0_tab, int64_t ldt, int64_t nrows, int32_t C,
-                                                   uint8_t *__restrict__ skip)
-{
-    const int lane = threadIdx.x & 31;
-    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int64_t nrb = (nrows + BM - 1) / BM;
-    if (w >= nrb * C) return;
-    const int64_t rb = w / C;
-    const int c = (int)(w - rb * C);
-    bool all = true;
-    for (int i = lane; i < BM; i += 32) {
-        const int64_t r = rb * BM + i;
-        if (r < nrows && !(t0_tab[(int64_t)c * ldt + r] == -INFINITY)) all = false;
-    }
-    all = __all_sync(CHB_FULL, all);
-    if (lane == 0) skip[rb * C + c] = all ? 1 : 0;
 }
 
 // one warp per column entry: y = fl32(x_i - mu_c) split into the [hi | lo] operand row, the column term
@@ -1154,7 +1136,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // Columns above T0 are skipped by the fused kernel without touching the per-thread lists.  T0 = +inf when there is no
 // usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
 // ---------------------------------------------------------------------------------------------------------
-__global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
+__global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
                                  const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
                                  const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
                                  const float *__restrict__ nrm, const unsigned int *__restrict__ nrm_max_bits,
@@ -1162,51 +1144,68 @@ __global__ void threshold_kernel(const int32_t *__restrict__ knn_idx, const int3
                                  const float *__restrict__ ub_row, const float *__restrict__ sq_row,
                                  const float *__restrict__ ubk2_row, const int32_t *__restrict__ row_guess, double eps_rel, int64_t nown,
                                  int32_t C, int32_t k, int32_t prune, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
-                                 int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv)
+                                 int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv,
+                                 uint8_t *__restrict__ skip)
 {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nown * C) return;
-    const int c = (int)(i / nown);
-    const int64_t r = i - (int64_t)c * nown;           // row (rows are the owned slots ordered by guessed bin)
-    const float tq = tq_tab[(int64_t)c * ldt + r];
-    // pruning (97-99 % of the pairs end here, so this test is all FP32 and touches nothing per pair but tq and t0):
-    // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test.
-    // Only the CONVEX hull of k members lies inside the ball around m_c: an affine hull is unbounded and may pass close to a
-    // query far from every member, so the affine metrics (hull_distance.py:38-87) keep every bin (prune == 0).
-    if (prune) {
-        const float dq = __fsqrt_rd(tq), ym = __fmul_ru(__fsqrt_ru(ym2[c]), 1.000001f), ub = ub_row[r];
-        const float scale = sq_row[r] + __fsqrt_ru(__uint_as_float(*nrm_max_bits));
-        if (dq * 0.999999f - ym > ub + 1e-5f * (dq + ym + ub) + 4e-6f * scale) {
-            t0_tab[(int64_t)c * ldt + r] = -INFINITY; // no candidates, no re-rank, no QP; argmin never looks at the pair
-            return;
-        }
-    }
-    row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
-    atomicAdd(&bin_surv[c], 1);
-    const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
-    const int jq = row_point[r];
-    const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
-    slack_tab[(int64_t)c * ldt + r] = E;
-    float out = INFINITY;
-    if (knn_cnt[pair] == k) {
-        const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
-        if (ub < INFINITY) {
-            const int p = pos[jq];
-            bool ok = true;
-            for (int s = 0; s < k; ++s) {
-                const int j = knn_idx[pair * k + s];
-                const int ps = pos[j];
-                const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
-                ok = ok && (lab == c);
+    // grid: x = chunks of 256 rows (two 128-row blocks of the fused kernel), y = bin.  Besides the per-pair tables the block
+    // leaves skip[row block][bin] = "every row of the block pruned the bin": the (row block, bin) work items of the
+    // uncompacted path, without a second pass over the threshold table.
+    __shared__ int s_alive[2];
+    const int c = blockIdx.y;
+    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; // row (rows are the owned slots ordered by guessed bin)
+    if (threadIdx.x < 2) s_alive[threadIdx.x] = 0;
+    __syncthreads();
+    bool alive = false;
+    if (r < nown) {
+        const float tq = tq_tab[(int64_t)c * ldt + r];
+        alive = true;
+        // pruning (97-99 % of the pairs end here, so this test is all FP32 and touches nothing per pair but tq and t0):
+        // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test.
+        // Only the CONVEX hull of k members lies inside the ball around m_c: an affine hull is unbounded and may pass close to a
+        // query far from every member, so the affine metrics (hull_distance.py:38-87) keep every bin (prune == 0).
+        if (prune) {
+            const float dq = __fsqrt_rd(tq), ym = __fmul_ru(__fsqrt_ru(ym2[c]), 1.000001f), ub = ub_row[r];
+            const float scale = sq_row[r] + __fsqrt_ru(__uint_as_float(*nrm_max_bits));
+            if (dq * 0.999999f - ym > ub + 1e-5f * (dq + ym + ub) + 4e-6f * scale) {
+                t0_tab[(int64_t)c * ldt + r] = -INFINITY; // no candidates, no re-rank, no QP; argmin never looks at the pair
+                alive = false;
             }
-            // this round's keys of the cached neighbours are <= ub + E, so is the k-th smallest key a_k, and the re-rank
-            // looks no further than a_k + 2E
-            if (ok) out = __fadd_ru(ub, __fmul_ru(3.f, E));
+        }
+        if (alive) {
+            row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
+            atomicAdd(&bin_surv[c], 1);
+            const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
+            const int jq = row_point[r];
+            const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
+            slack_tab[(int64_t)c * ldt + r] = E;
+            float out = INFINITY;
+            if (knn_cnt[pair] == k) {
+                const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
+                if (ub < INFINITY) {
+                    const int p = pos[jq];
+                    bool ok = true;
+                    for (int s = 0; s < k; ++s) {
+                        const int j = knn_idx[pair * k + s];
+                        const int ps = pos[j];
+                        const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
+                        ok = ok && (lab == c);
+                    }
+                    // this round's keys of the cached neighbours are <= ub + E, so is the k-th smallest key a_k, and the
+                    // re-rank looks no further than a_k + 2E
+                    if (ok) out = __fadd_ru(ub, __fmul_ru(3.f, E));
+                }
+            }
+            // no usable cache: in the query's guessed bin the k-th nearest SEED bounds the k-th smallest squared distance
+            if (out == INFINITY && c == row_guess[r] && ubk2_row[r] < INFINITY) out = __fadd_ru(ubk2_row[r], __fmul_ru(3.f, E));
+            t0_tab[(int64_t)c * ldt + r] = out;
+            s_alive[threadIdx.x >> 7] = 1;
         }
     }
-    // no usable cache: in the query's guessed bin the k-th nearest SEED bounds the k-th smallest squared distance
-    if (out == INFINITY && c == row_guess[r] && ubk2_row[r] < INFINITY) out = __fadd_ru(ubk2_row[r], __fmul_ru(3.f, E));
-    t0_tab[(int64_t)c * ldt + r] = out;
+    __syncthreads();
+    if ((threadIdx.x & 127) == 0) {
+        const int64_t rb = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
+        if (rb * BM < nown) skip[rb * C + c] = s_alive[threadIdx.x >> 7] ? 0 : 1;
+    }
 }
 
 // algorithm.py:47-48,57-58,60 over the surviving bins of each query: strict '<' so the lowest bin wins ties; a query
@@ -1215,12 +1214,13 @@ __global__ void argmin_rows_kernel(const int32_t *__restrict__ own_pos, int64_t 
                                    const int32_t *__restrict__ qslot, int64_t u0, const int32_t *__restrict__ slot_row,
                                    const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins,
                                    const double *__restrict__ pair_dist, int32_t C, const int32_t *__restrict__ old_label,
-                                   int64_t lo, int32_t *__restrict__ tent)
+                                   int64_t lo, int64_t hi, int32_t *__restrict__ tent)
 {
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= cnt) return;
     const int p = own_pos[w];
+    if (p < lo || p >= hi) return; // outside this round's window (own_pos may list every owned position)
     const int j = perm_pt[p];
     const int64_t sl = (int64_t)qslot[j] - u0;
     const int64_t r = slot_row[sl];
@@ -1932,13 +1932,13 @@ void chb_fused_free(chb_ctx *c)
 // Runs steps 1-3 of the header comment for ALL owned query slots against the current (pos, tent, old) labels.
 // Appends changed (slot_local, bin) pairs to ctx->work (count in counters[0]); queries needing the exact fallback are
 // redone exactly on the device (exact_pairs_kernel; their count stays in counters[6]).
-int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int32_t *tent_dev)
+int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int64_t hi, int32_t *tent_dev)
 {
     if (cnt <= 0) return CHB_OK;
     {
         chb_stage_timer t(c, CHB_ST_COMMIT);
         argmin_rows_kernel<<<nblk(cnt * 32, 256), 256, 0, c->stream>>>(own_pos_dev, cnt, c->perm_pt, c->qslot, c->u0, c->f_slot_row, c->f_row_nb,
-                                                                       c->f_row_bins, c->pair_dist, c->C, c->old_label, lo, tent_dev);
+                                                                       c->f_row_bins, c->pair_dist, c->C, c->old_label, lo, hi, tent_dev);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
@@ -1950,6 +1950,46 @@ int chb_fused_guess(chb_ctx *c)
     guess_scatter_kernel<<<nblk(c->U, 256), 256, 0, c->stream>>>(c->qpoint, c->f_guess_all, c->U, c->C, c->tent_pt);
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
+    return CHB_OK;
+}
+
+namespace {
+__global__ void guess_export_kernel(const int32_t *__restrict__ guess_all, int64_t U, int64_t u0, int64_t u1, int32_t *__restrict__ out)
+{
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < U) out[u] = (u >= u0 && u < u1) ? guess_all[u] : CHB_UNOWNED;
+}
+} // namespace
+
+// Sharded contexts: every rank derives the speculation start of its OWN query slots (centroid terms = an U_own x C x d FP64
+// contraction instead of U x C x d on every rank) and the ranks merge them with one all-reduce(MAX) over U int32 values.
+extern "C" int chb_guess_export(chb_ctx *c, int32_t *guess_dev, int32_t *active)
+{
+    CHB_CHECK(c, c && guess_dev && active, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->labels_set && c->dist_ready, CHB_EINVAL, "guess_export: labels / distance structure not set up");
+    *active = 0;
+    if (!(c->dist_mode == 2 && c->filter_ok && chb_fused_supported(c)) || c->U <= 0 || !c->guess_pending) return CHB_OK;
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    if (!c->guess_shared) { c->guess_shared = true; c->f_asplit_ready = false; }
+    c->guess_imported = false;
+    {
+        const int rc = chb_fused_setup(c);
+        if (rc != CHB_OK) return rc;
+    }
+    guess_export_kernel<<<nblk(c->U, 256), 256, 0, c->stream>>>(c->f_guess_all, c->U, c->u0, c->u1, guess_dev);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    *active = 1;
+    return CHB_OK;
+}
+
+extern "C" int chb_guess_import(chb_ctx *c, const int32_t *guess_dev)
+{
+    CHB_CHECK(c, c && guess_dev, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->guess_shared && c->f_guess_all, CHB_EINVAL, "guess_import without a preceding guess_export");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_CUDA(c, cudaMemcpyAsync(c->f_guess_all, guess_dev, sizeof(int32_t) * (size_t)c->U, cudaMemcpyDeviceToDevice, c->stream));
+    c->guess_imported = true;
     return CHB_OK;
 }
 
@@ -2044,11 +2084,14 @@ int chb_fused_setup(chb_ctx *c)
         centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2,
                                                                  c->f_mcT, Cp);
         c->tm.launches_other += 2;
-        if (c->U > 0) {
-            if (reserve(c, &c->f_tqs, &c->f_cap_tqs, c->U * (int64_t)Cp)) return CHB_ENOMEM;
-            dim3 gt((unsigned)((c->U + 63) / 64), (unsigned)((C + 63) / 64));
-            centroid_terms_kernel<<<gt, 256, 0, c->stream>>>(c->qpoint, c->U, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2, C, c->f_tqs);
-            guess_from_terms_kernel<<<nblk(c->U * 32, 256), 256, 0, c->stream>>>(c->f_tqs, c->U, Cp, C, c->f_mcnt, c->f_guess_all);
+        // centroid terms |a_u - m_c|^2 and the nearest-centroid guess: for every slot, or -- when the ranks exchange their guesses
+        // (chb_guess_export / chb_guess_import) -- for the owned slots only; f_tqs then starts at slot u0
+        const int64_t t_first = c->guess_shared ? c->u0 : 0, t_cnt = c->guess_shared ? nown : c->U;
+        if (t_cnt > 0) {
+            if (reserve(c, &c->f_tqs, &c->f_cap_tqs, t_cnt * (int64_t)Cp)) return CHB_ENOMEM;
+            dim3 gt((unsigned)((t_cnt + 63) / 64), (unsigned)((C + 63) / 64));
+            centroid_terms_kernel<<<gt, 256, 0, c->stream>>>(c->qpoint + t_first, t_cnt, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2, C, c->f_tqs);
+            guess_from_terms_kernel<<<nblk(t_cnt * 32, 256), 256, 0, c->stream>>>(c->f_tqs, t_cnt, Cp, C, c->f_mcnt, c->f_guess_all + t_first);
             c->tm.launches_other += 2;
         }
         if (nown > 0) {
@@ -2068,7 +2111,7 @@ int chb_fused_setup(chb_ctx *c)
             split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
             dim3 gq((unsigned)((nown + 31) / 32), (unsigned)((C + 31) / 32));
-            query_terms_gather_kernel<<<gq, 256, 0, c->stream>>>(c->f_tqs, Cp, c->u0, c->f_row_slot, nown, C, c->f_ldt, c->f_tq);
+            query_terms_gather_kernel<<<gq, 256, 0, c->stream>>>(c->f_tqs, Cp, c->u0 - t_first, c->f_row_slot, nown, C, c->f_ldt, c->f_tq);
             c->tm.launches_other += 4;
         }
         CHB_CUDA(c, cudaGetLastError());
@@ -2107,10 +2150,14 @@ int chb_round_fused(chb_ctx *c)
 
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
-    threshold_kernel<<<nblk(nown * C, 256), 256, 0, c->stream>>>(
-        c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
-        reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
-        c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb, c->f_row_bins, c->f_pair_meta);
+    {
+        dim3 tg(nblk(nown, 256), (unsigned)C);
+        threshold_kernel<<<tg, 256, 0, c->stream>>>(
+            c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
+            reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
+            c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb,
+            c->f_row_bins, c->f_pair_meta, c->f_skip);
+    }
     // KR = 16 serves k <= 15: the re-rank needs the (k+1)-th key, and a half-list can only be full when more than k candidates
     // exist, which is what arms its completeness test (k + 3 <= KR merely keeps that test from firing often; at k = 14, 15 it
     // still fires only when nearly all of the k nearest fall into the same 64-column halves)
@@ -2134,7 +2181,6 @@ int chb_round_fused(chb_ctx *c)
     }
     const int64_t nrb = (nown + BM - 1) / BM;
     int32_t *bin_surv = c->f_pair_meta, *pair_off = c->f_pair_meta + (C + 2), *pair_cur = c->f_pair_meta + 2 * (C + 2);
-    skip_kernel<<<nblk(nrb * C * 32, 256), 256, 0, c->stream>>>(c->f_t0, c->f_ldt, nown, C, c->f_skip);
     // test aid: CHB_FUSED_NO_COMPACT forces the (row block, bin) items that are otherwise only used when the compact buffer
     // would overflow
     const int64_t plan_cap = getenv("CHB_FUSED_NO_COMPACT") ? -1 : c->f_cap_pairs;
@@ -2145,7 +2191,7 @@ int chb_round_fused(chb_ctx *c)
     pairs_fill_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
                                                                    c->f_pair_row, c->f_a2, g.Kp2, c->f_ap);
     CHB_CUDA(c, cudaGetLastError());
-    c->tm.launches_other += 5;
+    c->tm.launches_other += 4;
     CUtensorMap ma, mb, map;
     int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
     if (rc != CHB_OK) return rc;
@@ -2167,12 +2213,15 @@ int chb_round_fused(chb_ctx *c)
         // pairs the re-rank could not settle from the kept lists (rare): exact redo, no host round trip -- the grid is
         // fixed and walks the device-side list
         const size_t xs = sizeof(double) * (size_t)((c->d + 1) & ~1);
+        // one CTA per listed pair at a time (grid-stride over the device-side list): a handful at 20k contigs, tens of thousands
+        // at 1M -- the grid follows the number of rows, up to eight resident CTAs per SM
+        const unsigned xgrid = (unsigned)std::min<int64_t>((int64_t)c->sm_count * 8, std::max<int64_t>(64, nown / 256));
         if (KR == 8)
-            exact_pairs_kernel<5><<<64, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt, c->f_col_pt,
+            exact_pairs_kernel<5><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt, c->f_col_pt,
                                                               c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pos, C,
                                                               k, c->knn_idx, c->knn_cnt, c->work, c->counters);
         else
-            exact_pairs_kernel<15><<<64, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
+            exact_pairs_kernel<15><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
                                                                c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot,
                                                                c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
     }

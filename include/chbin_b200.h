@@ -197,12 +197,32 @@ int chb_get_labels(chb_ctx *ctx, int64_t *labels_out);
  * window: suggested hi-lo (chb_get_window).  A single context that owns every slot may pass tent_dev = NULL to both calls
  * (the library keeps the tentative labels itself); chb_round_run only ENQUEUES work, chb_round_commit is the sync point,
  * so the host can overlap its own work (drawing the next permutation) with a round. */
+/* In distance mode 2 the permutation is validated on the device: an entry that is out of range, not an un-assigned point
+ * or repeated is reported (CHB_EINVAL, same messages) by the first chb_round_commit / chb_iteration_end that follows; the
+ * iteration is then abandoned and the labels stay as they were before chb_iteration_begin. */
 int chb_iteration_begin(chb_ctx *ctx, const int64_t *perm, int64_t U);
+/* The same with the permutation already in DEVICE memory (e.g. rank 0's draw after an NCCL broadcast): distance mode 2 only. */
+int chb_iteration_begin_dev(chb_ctx *ctx, const int64_t *perm_dev, int64_t U);
 int chb_round_run(chb_ctx *ctx, int64_t lo, int64_t hi, int32_t *tent_dev);
 int chb_round_commit(chb_ctx *ctx, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed);
 int chb_iteration_end(chb_ctx *ctx, int64_t *n_changed);
+/* chb_round_commit and -- when the round changed nothing and hi is the last position -- chb_iteration_end in ONE call and
+ * ONE host synchronisation (the "is the iteration over" decision is taken on the device): *iteration_done = 1 and
+ * *n_changed = sum(initial_bins != curr_bins) (algorithm.py:63,68) in that case, else *iteration_done = 0 and the caller
+ * continues with the next round as after chb_round_commit. */
+int chb_round_commit_end(chb_ctx *ctx, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed,
+                         int64_t *n_changed, int32_t *iteration_done);
 int chb_set_window(chb_ctx *ctx, int64_t window); /* 0 = whole iteration */
 int64_t chb_get_window(chb_ctx *ctx);
+
+/* Sharded contexts (distance mode 2), optional, between chb_build_distance_matrix and the FIRST chb_iteration_begin after
+ * chb_set_labels: the speculation of the first iteration starts from every query's nearest seed centroid (any start leads to
+ * the same result, algorithm.py:46-60; a good one saves a round).  chb_guess_export computes that start for the OWNED slots
+ * only and writes it to guess_dev (U int32, slot order; un-owned entries INT32_MIN); the caller merges the ranks' vectors
+ * (all-reduce MAX) and hands the result back with chb_guess_import.  *active = 0: nothing to exchange (other distance mode,
+ * no queries) -- skip the collective and the import.  Without this pair every context computes all U guesses itself. */
+int chb_guess_export(chb_ctx *ctx, int32_t *guess_dev, int32_t *active);
+int chb_guess_import(chb_ctx *ctx, const int32_t *guess_dev);
 
 /* ---- measurement aid (bench.py only) ------------------------------------------------------------------ */
 /* DFMA-saturating microbenchmark: measured FP64 pipe peak of this device in TFLOP/s (FMA = 2 flop). */

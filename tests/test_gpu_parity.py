@@ -309,8 +309,9 @@ def test_cached_neighbour_sets_match_each_querys_view(path):
     ctx.close()
 
 
+@pytest.mark.parametrize("share_guess", [False, True])
 @pytest.mark.parametrize("cuts", [(0.5,), (0.1, 0.1, 0.73)])
-def test_sharded_contexts_exchange_labels(cuts):
+def test_sharded_contexts_exchange_labels(cuts, share_guess):
     """The multi-GPU form on one device: several contexts, each owning a slice of the query slots (one of them may be
     empty), run the round protocol of include/chbin_b200.h and exchange tentative labels by element-wise MAX -- what the
     NCCL all-reduce does between ranks.  Labels must equal the sequential oracle after every iteration."""
@@ -331,6 +332,14 @@ def test_sharded_contexts_exchange_labels(cuts):
         ctxs.append(ctx)
     cur = bins.copy()
     with torch.cuda.stream(stream):
+        if share_guess:
+            # chb_guess_export / chb_guess_import: every context guesses for its own slots, the vectors are merged by MAX
+            gs = [torch.empty(U, dtype=torch.int32, device=dev) for _ in ctxs]
+            assert all(ctx.guess_export(g.data_ptr()) for ctx, g in zip(ctxs, gs))
+            merged_g = torch.stack(gs).max(dim=0).values.contiguous()
+            assert int(merged_g.min()) >= 0
+            for ctx in ctxs:
+                ctx.guess_import(merged_g.data_ptr())
         for it in range(4):
             for ctx in ctxs:
                 ctx.iteration_begin(perms[it])
@@ -460,15 +469,30 @@ def test_abi_argument_validation():
     ctx.build_distance_matrix(True)
     with pytest.raises(ValueError, match="permutation length"):
         ctx.iteration_begin(perm[:-1])
+    # the entries themselves are validated on the device (distance mode 2): the error surfaces at the first commit that
+    # follows, the iteration is abandoned and the labels stay as they were
+    def refused(bad, pattern):
+        ctx.iteration_begin(bad)
+        ctx.round_run(0, len(bad))
+        with pytest.raises(ValueError, match=pattern):
+            ctx.round_commit(0, len(bad))
+        assert np.array_equal(ctx.get_labels(), bins)
+
+    bad = perm.copy(); bad[3] = bad[4]
+    refused(bad, "repeats")
+    bad = perm.copy(); bad[0] = int(np.where(bins >= 0)[0][0])    # a seed contig is not a query
+    refused(bad, "not an un-assigned")
+    bad = perm.copy(); bad[0] = len(X)
+    refused(bad, "out of range")
+    bad = perm.copy(); bad[5] = -7
+    with pytest.raises(ValueError, match="out of range"):
+        ctx.fit_iteration(bad)
+    # distance mode 1 validates on the host, at once
+    ctx.set_distance_mode(1); ctx.build_distance_matrix(True)
     bad = perm.copy(); bad[3] = bad[4]
     with pytest.raises(ValueError, match="repeats"):
         ctx.iteration_begin(bad)
-    bad = perm.copy(); bad[0] = int(np.where(bins >= 0)[0][0])    # a seed contig is not a query
-    with pytest.raises(ValueError, match="not an un-assigned"):
-        ctx.iteration_begin(bad)
-    bad = perm.copy(); bad[0] = len(X)
-    with pytest.raises(ValueError, match="out of range"):
-        ctx.iteration_begin(bad)
+    ctx.set_distance_mode(2); ctx.build_distance_matrix(True)
     # the context is still usable after the refused calls
     ref = oracle.fit_cluster(X, 3, bins, None, 5, 1, perms=perm[None, :])
     lab, _ = ctx.fit_iteration(perm)
