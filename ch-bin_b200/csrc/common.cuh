@@ -129,7 +129,7 @@ struct chb_ctx {
     int64_t f_cap_guess = 0, f_cap_mcT = 0, f_cap_seedT = 0;
     float *f_tqs = nullptr;         // U x Cp : |a_u - m_c|^2 of every query slot (slot order)
     int64_t f_cap_tqs = 0;
-    double *f_seedT = nullptr;      // d x (#seeds) : seed contigs transposed, (bin, index) order
+    float *f_seedT = nullptr;       // d x (#seeds) : centred FP32 seed contigs transposed, (bin, index) order
     int32_t *f_slot_row = nullptr;  // owned slot -> row
     float *f_sq_row = nullptr;      // per row: >= |a_q|
     int32_t *f_row_nb = nullptr, *f_row_bins = nullptr; // per row: number / list of the bins that survived pruning this round

@@ -292,40 +292,49 @@ __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__r
 
 constexpr int DMAX_F = 160; // fused mode: d <= 160
 
-// |a_u - m_c|^2 for every query slot u and every bin c, once per label set: an FP64 GEMM (U x C x d) in 64 x 64 tiles, 4 x 4
-// outputs per thread, 16 features per shared-memory stage.  tqs[u][c] = fl32( |a_u|^2 - 2 a_u.m_c + |m_c|^2 ), a_u = the FP32
-// centred feature row the tensor core contracts.  Both the speculation start (argmin over bins, all U slots -- every rank
-// must derive the same vector, and the summation order here is fixed) and the query terms of the owned rows come from it.
+// |a_u - m_c|^2 for every query slot u and every bin c, once per label set: an FP64 GEMM (U x C x d) in 128 x 64 tiles, 8 x 4
+// outputs per thread (16-byte shared-memory reads: 6 per 32 DFMA), 16 features per shared-memory stage.
+// tqs[u][c] = fl32( |a_u|^2 - 2 a_u.m_c + |m_c|^2 ), a_u = the FP32 centred feature row the tensor core contracts.  Both the
+// speculation start (argmin over bins -- every rank must derive the same vector, and the summation order here is fixed) and
+// the query terms of the owned rows come from it.
+constexpr int CT_M = 128, CT_N = 64, CT_K = 16;
 __global__ void __launch_bounds__(256) centroid_terms_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
                                                              int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
                                                              const double *__restrict__ mc2, int32_t C, float *__restrict__ tqs)
 {
-    __shared__ __align__(16) double As[16][64 + 2];
-    __shared__ __align__(16) double Bs[16][64 + 2];
-    __shared__ double aa_s[64];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int64_t u0 = (int64_t)blockIdx.x * 64;
-    const int c0 = blockIdx.y * 64;
-    // loader roles: A: query lq, features 4*lk..4*lk+3 of the stage; B: feature bk, bins 4*bc..4*bc+3
+    __shared__ __align__(16) double As[CT_K][CT_M + 2];
+    __shared__ __align__(16) double Bs[CT_K][CT_N + 2];
+    __shared__ double aa_s[CT_M];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // rows 8 ty .. 8 ty + 7, bins 4 tx .. 4 tx + 3
+    const int64_t u0 = (int64_t)blockIdx.x * CT_M;
+    const int c0 = blockIdx.y * CT_N;
+    // loader roles: A: query lq (two per thread: lq, lq + 64), features 4 lk .. 4 lk + 3 of the stage; B: feature bk, bins 4 bc ..
     const int lq = tid >> 2, lk = tid & 3;
     const int bk = tid >> 4, bc = tid & 15;
-    const int64_t uq = u0 + lq;
-    const float *xrow = uq < U ? Xf + (int64_t)qpoint[uq] * ldf : nullptr;
-    double acc[4][4];
+    const float *xrow[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int h = 0; h < 2; ++h) {
+        const int64_t uq = u0 + lq + 64 * h;
+        xrow[h] = uq < U ? Xf + (int64_t)qpoint[uq] * ldf : nullptr;
+    }
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    double aa[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k0 = 0; k0 < d; k0 += 16) {
+    double aa[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int k0 = 0; k0 < d; k0 += CT_K) {
         {
             const int t = k0 + 4 * lk;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (xrow && t < ldf) v = *reinterpret_cast<const float4 *>(xrow + t); // pads beyond d are zero (prep_f32_kernel)
-            As[4 * lk + 0][lq] = t + 0 < d ? (double)v.x : 0.0;
-            As[4 * lk + 1][lq] = t + 1 < d ? (double)v.y : 0.0;
-            As[4 * lk + 2][lq] = t + 2 < d ? (double)v.z : 0.0;
-            As[4 * lk + 3][lq] = t + 3 < d ? (double)v.w : 0.0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (xrow[h] && t < ldf) v = *reinterpret_cast<const float4 *>(xrow[h] + t); // pads beyond d are zero (prep_f32_kernel)
+                As[4 * lk + 0][lq + 64 * h] = t + 0 < d ? (double)v.x : 0.0;
+                As[4 * lk + 1][lq + 64 * h] = t + 1 < d ? (double)v.y : 0.0;
+                As[4 * lk + 2][lq + 64 * h] = t + 2 < d ? (double)v.z : 0.0;
+                As[4 * lk + 3][lq + 64 * h] = t + 3 < d ? (double)v.w : 0.0;
+            }
             const int tb = k0 + bk;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -335,14 +344,22 @@ __global__ void __launch_bounds__(256) centroid_terms_kernel(const int32_t *__re
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            double av[4], bv[4];
+        for (int k = 0; k < CT_K; ++k) {
+            double av[8], bv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) av[i] = As[k][4 * ty + i];
+            for (int i = 0; i < 8; i += 2) {
+                const double2 t2 = *reinterpret_cast<const double2 *>(&As[k][8 * ty + i]);
+                av[i] = t2.x;
+                av[i + 1] = t2.y;
+            }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bv[j] = Bs[k][4 * tx + j];
+            for (int j = 0; j < 4; j += 2) {
+                const double2 t2 = *reinterpret_cast<const double2 *>(&Bs[k][4 * tx + j]);
+                bv[j] = t2.x;
+                bv[j + 1] = t2.y;
+            }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
+            for (int i = 0; i < 8; ++i) {
                 if (tx == 0) aa[i] = fma(av[i], av[i], aa[i]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
@@ -352,14 +369,14 @@ __global__ void __launch_bounds__(256) centroid_terms_kernel(const int32_t *__re
     }
     if (tx == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) aa_s[4 * ty + i] = aa[i];
+        for (int i = 0; i < 8; ++i) aa_s[8 * ty + i] = aa[i];
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t u = u0 + 4 * ty + i;
+    for (int i = 0; i < 8; ++i) {
+        const int64_t u = u0 + 8 * ty + i;
         if (u >= U) continue;
-        const double au = aa_s[4 * ty + i];
+        const double au = aa_s[8 * ty + i];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int c = c0 + 4 * tx + j;
@@ -432,83 +449,170 @@ __global__ void guess_scatter_kernel(const int32_t *__restrict__ qpoint, const i
 // pruned: admission threshold -inf, no candidates, no QP, hull distance +inf.  Rows are ordered by guessed bin so that
 // whole 128-query row blocks prune the same bins and their tiles are skipped by the fused kernel.
 // ---------------------------------------------------------------------------------------------------------
-// seed contigs transposed, [feature][seed] in (bin, index) order: lanes that each take one seed read consecutive addresses
-__global__ void seed_transpose_kernel(const double *__restrict__ X, int32_t ldx, int32_t d, const int32_t *__restrict__ seed_idx,
-                                      int64_t ns, double *__restrict__ seedT)
+// seed contigs transposed, [feature][seed] in (bin, index) order, as the centred FP32 values fl32(x - mu) (prep_f32_kernel)
+__global__ void seed_transpose_kernel(const float *__restrict__ Xf, int32_t ldf, int32_t d, const int32_t *__restrict__ seed_idx,
+                                      int64_t ns, float *__restrict__ seedT)
 {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns * d) return;
     const int64_t sidx = i / d;
     const int t = (int)(i - sidx * d);
-    seedT[(int64_t)t * ns + sidx] = X[(int64_t)seed_idx[sidx] * ldx + t];
+    seedT[(int64_t)t * ns + sidx] = Xf[(int64_t)seed_idx[sidx] * ldf + t];
 }
 
-// one warp per row: UB = distance to the nearest seed of the guessed bin, and the squared distance to its k-th nearest
-// seed (an admission threshold for the first round, when there is no cached neighbour set yet: all seeds are visible
-// members of the bin, so the bin's k-th smallest squared distance cannot exceed it).  One lane per seed; rows come in
-// guessed-bin order, so the warps of a CTA read the same seed tile.
-__global__ void __launch_bounds__(256) row_ub_kernel(const int32_t *__restrict__ row_pt, const int32_t *__restrict__ row_guess,
-                                                     int64_t nown, const double *__restrict__ X, int32_t ldx, int32_t d, int32_t C,
-                                                     int32_t k, const int32_t *__restrict__ seed_off, const double *__restrict__ seedT,
-                                                     int64_t ns, float *__restrict__ ub_out, float *__restrict__ ubk2_out)
+// UB = an upper bound of the distance to the nearest seed of the guessed bin, and of the squared distance to its k-th nearest
+// seed (an admission threshold for the first round, when there is no cached neighbour set yet: all seeds are visible members
+// of the bin, so the bin's k-th smallest squared distance cannot exceed it).
+//
+// Both are BOUNDS, not distances, so they are evaluated in FP32 on the centred features a = fl32(x - mu) the tensor core
+// contracts as well, and inflated rigorously: with D = x_q - x_s and D~ = a_q - a_s (exact difference of the stored floats),
+//   | D~ - D |_2 <= 2^-24 (|x_q - mu| + |x_s - mu|)            (one rounding per stored coordinate)
+//   S~ = fl32 sum of fl32(a_q,t - a_s,t)^2  >=  |D~|^2 (1 - (d + 3) 2^-24)   (all terms non-negative)
+// hence  |D| <= sqrt(S~) (1 + 1e-5) + 6e-8 (|a_q| + max_i |a_i|)  for d <= 160, every operation rounded upwards.  The pruning test
+// (threshold_kernel) keeps margins a hundred times wider than what this adds.
+//
+// Rows come grouped by guessed bin (row_end[c] = end of bin c's group), so a CTA takes 64 rows of ONE bin against that bin's
+// seeds: a register-tiled squared-distance "GEMM" -- 4 rows x 4 seeds per thread, operands staged through shared memory in
+// 32-feature slices -- then per row the minimum and k rounds of minimum extraction over the row's values (kept in shared
+// memory, up to RU_MAXSEED seeds per bin; beyond that only the minimum, ubk2 = +inf).
+constexpr int RU_ROWS = 64, RU_SEEDS = 32, RU_TK = 32, RU_THREADS = 128, RU_MAXSEED = 128;
+constexpr int RU_QP = RU_ROWS + 4, RU_DP = RU_MAXSEED + 1;
+__device__ __forceinline__ float ru_bound(float s2, float scale)
 {
-    __shared__ double q_sm[8][DMAX_F];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (r >= nown) return;
-    const double *xq = X + (int64_t)row_pt[r] * ldx;
-    for (int t = lane; t < d; t += 32) q_sm[w][t] = xq[t];
-    __syncwarp();
-    const int g = row_guess[r];
-    double v[4] = {INFINITY, INFINITY, INFINITY, INFINITY}; // this lane's seeds (up to 128 per bin)
-    double ub2 = INFINITY;
-    int nseed = 0;
-    if (g < C) {
-        nseed = seed_off[g + 1] - seed_off[g];
-        int slot = 0;
-        for (int i = seed_off[g] + lane; i < seed_off[g + 1]; i += 32, ++slot) {
-            // eight loads in flight and eight independent chains: the loop is bound by the latency of the (L2-resident) seed
-            // tile and of DFMA otherwise
-            double acc[8];
+    return __fadd_ru(__fmul_ru(__fsqrt_ru(s2), 1.00001f), __fmul_ru(6e-8f, scale));
+}
+__global__ void __launch_bounds__(RU_THREADS) row_ub_kernel(const int32_t *__restrict__ row_pt, int64_t nown, const float *__restrict__ Xf,
+                                                            int32_t ldf, int32_t d, int32_t C, int32_t k, const int32_t *__restrict__ seed_off,
+                                                            const float *__restrict__ seedT, int64_t ns, const int32_t *__restrict__ row_end,
+                                                            const float *__restrict__ sq_row, const unsigned int *__restrict__ nrm_max_bits,
+                                                            float *__restrict__ ub_out, float *__restrict__ ubk2_out)
+{
+    __shared__ float dist[RU_ROWS * RU_DP];                 // 33 KB
+    __shared__ __align__(16) float qs[RU_TK * RU_QP];       // feature-major slice of the 64 query rows
+    __shared__ __align__(16) float ss[RU_TK * RU_SEEDS];
+    __shared__ int s_bin, s_r0, s_nr;
+    __shared__ unsigned int s_min[RU_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // which (bin, 64-row chunk) is this CTA?  bins 0..C (C = "no seeded bin": rows without any bound).  Warp 0 scans the chunk
+    // counts 32 bins at a time.
+    if (warp == 0) {
+        int acc = 0, found = -1, r0 = 0, nr = 0;
+        for (int cb = 0; cb <= C && found < 0; cb += 32) {
+            const int c = cb + lane;
+            const int beg = (c <= C && c > 0) ? row_end[c - 1] : 0, end = c <= C ? row_end[c] : beg;
+            const int nch = c <= C ? (end - beg + RU_ROWS - 1) / RU_ROWS : 0;
+            int incl = nch;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) acc[u] = 0.0;
-            int t = 0;
-            for (; t + 7 < d; t += 8) {
-                double sv[8];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(CHB_FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int excl = acc + incl - nch;
+            const bool mine = (int)blockIdx.x >= excl && (int)blockIdx.x < excl + nch;
+            const unsigned who = __ballot_sync(CHB_FULL, mine);
+            if (who) {
+                const int src = __ffs(who) - 1;
+                found = __shfl_sync(CHB_FULL, c, src);
+                const int b0 = __shfl_sync(CHB_FULL, beg, src), e0 = __shfl_sync(CHB_FULL, end, src), x0 = __shfl_sync(CHB_FULL, excl, src);
+                r0 = b0 + ((int)blockIdx.x - x0) * RU_ROWS;
+                nr = min(RU_ROWS, e0 - r0);
+            }
+            acc += __shfl_sync(CHB_FULL, incl, 31);
+        }
+        if (lane == 0) { s_bin = found; s_r0 = r0; s_nr = nr; }
+    }
+    if (tid < RU_ROWS) s_min[tid] = 0x7f800000u; // +inf
+    __syncthreads();
+    const int c = s_bin, r0 = s_r0, nr = s_nr;
+    if (c < 0) return;
+    const int sbeg = c < C ? seed_off[c] : 0, nseed = c < C ? seed_off[c + 1] - seed_off[c] : 0;
+    const int ty = tid >> 3, tx = tid & 7; // rows 4 ty .. 4 ty + 3, seeds 4 tx .. 4 tx + 3 of the tile
+    // loader roles: query slice element e = tid + 128 i -> (row e >> 5, feature e & 31): 16 per thread; seed slice: 8 per thread
+    const float *qrow[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) sv[u] = seedT[(int64_t)(t + u) * ns + i];
+    for (int i = 0; i < 16; ++i) {
+        const int rr = (tid + RU_THREADS * i) >> 5;
+        qrow[i] = rr < nr ? Xf + (int64_t)row_pt[r0 + rr] * ldf : nullptr;
+    }
+    for (int sb = 0; sb < nseed; sb += RU_SEEDS) {
+        float acc[4][4];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const double df = q_sm[w][t + u] - sv[u];
-                    acc[u] = fma(df, df, acc[u]);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+        for (int t0 = 0; t0 < d; t0 += RU_TK) {
+            float qv_[16], sv_[8];
+            const int tq = t0 + lane; // this thread's feature of the query slice (tid & 31 == lane)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qv_[i] = (qrow[i] && tq < d) ? __ldg(qrow[i] + tq) : 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = tid + RU_THREADS * i, t = e >> 5, sidx = e & 31;
+                sv_[i] = (sb + sidx < nseed && t0 + t < d) ? __ldg(seedT + (int64_t)(t0 + t) * ns + sbeg + sb + sidx) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) qs[lane * RU_QP + ((tid + RU_THREADS * i) >> 5)] = qv_[i];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ss[tid + RU_THREADS * i] = sv_[i];
+            __syncthreads();
+#pragma unroll 8
+            for (int t = 0; t < RU_TK; ++t) {
+                const float4 q4 = *reinterpret_cast<const float4 *>(&qs[t * RU_QP + 4 * ty]);
+                const float4 s4 = *reinterpret_cast<const float4 *>(&ss[t * RU_SEEDS + 4 * tx]);
+                const float qv[4] = {q4.x, q4.y, q4.z, q4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float df = qv[i] - sv[j]; // pad features are 0 - 0
+                        acc[i][j] = fmaf(df, df, acc[i][j]);
+                    }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rr = 4 * ty + i;
+            float mn = INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int sidx = sb + 4 * tx + j;
+                if (sidx < nseed) {
+                    mn = fminf(mn, acc[i][j]);
+                    if (sidx < RU_MAXSEED) dist[rr * RU_DP + sidx] = acc[i][j];
                 }
             }
-            for (; t < d; ++t) { const double df = q_sm[w][t] - seedT[(int64_t)t * ns + i]; acc[0] = fma(df, df, acc[0]); }
-            const double s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-            ub2 = fmin(ub2, s);
-            if (slot == 0) v[0] = s; else if (slot == 1) v[1] = s; else if (slot == 2) v[2] = s; else if (slot == 3) v[3] = s;
+            if (mn < INFINITY) atomicMin(&s_min[rr], __float_as_uint(mn)); // non-negative floats order like their bits
         }
     }
+    __syncthreads();
+    // per row: warp w takes rows w, w + 4, ...; k-th smallest by k rounds of "extract the minimum" (as many lanes as seeds)
+    const float amax = __fsqrt_ru(__uint_as_float(*nrm_max_bits));
+    for (int rr = warp; rr < nr; rr += RU_THREADS / 32) {
+        const float mn2 = __uint_as_float(s_min[rr]);
+        float kth = INFINITY;
+        if (nseed >= k && nseed <= RU_MAXSEED) {
+            float v[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ub2 = fmin(ub2, __shfl_xor_sync(CHB_FULL, ub2, o));
-    // k-th smallest over the warp: k rounds of "extract the minimum"
-    double kth = INFINITY;
-    if (nseed >= k && nseed <= 128) {
-        for (int round = 0; round < k; ++round) {
-            const double mine = fmin(fmin(v[0], v[1]), fmin(v[2], v[3]));
-            double m = mine;
+            for (int u = 0; u < 4; ++u) v[u] = (lane + 32 * u < nseed) ? dist[rr * RU_DP + lane + 32 * u] : INFINITY;
+            for (int round = 0; round < k; ++round) {
+                const float mine = fminf(fminf(v[0], v[1]), fminf(v[2], v[3]));
+                float m = mine;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(CHB_FULL, m, o));
-            kth = m;
-            const unsigned owners = __ballot_sync(CHB_FULL, mine == m);
-            if (lane == __ffs(owners) - 1) { // remove one copy of the minimum
-                if (v[0] == m) v[0] = INFINITY; else if (v[1] == m) v[1] = INFINITY; else if (v[2] == m) v[2] = INFINITY; else v[3] = INFINITY;
+                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(CHB_FULL, m, o));
+                kth = m;
+                const unsigned owners = __ballot_sync(CHB_FULL, mine == m);
+                if (lane == __ffs(owners) - 1) { // remove one copy of the minimum
+                    if (v[0] == m) v[0] = INFINITY; else if (v[1] == m) v[1] = INFINITY; else if (v[2] == m) v[2] = INFINITY; else v[3] = INFINITY;
+                }
             }
         }
-    }
-    if (lane == 0) {
-        ub_out[r] = ub2 < INFINITY ? __double2float_ru(sqrt(ub2) * (1.0 + 1e-9)) : INFINITY;
-        ubk2_out[r] = kth < INFINITY ? __double2float_ru(kth * (1.0 + 1e-9)) : INFINITY;
+        if (lane == 0) {
+            const float scale = __fadd_ru(sq_row[r0 + rr], amax);
+            ub_out[r0 + rr] = mn2 < INFINITY ? ru_bound(mn2, scale) : INFINITY;
+            const float bk = kth < INFINITY ? ru_bound(kth, scale) : INFINITY;
+            ubk2_out[r0 + rr] = bk < INFINITY ? __fmul_ru(bk, bk) : INFINITY;
+        }
     }
 }
 
@@ -2089,7 +2193,7 @@ int chb_fused_setup(chb_ctx *c)
         const int64_t t_first = c->guess_shared ? c->u0 : 0, t_cnt = c->guess_shared ? nown : c->U;
         if (t_cnt > 0) {
             if (reserve(c, &c->f_tqs, &c->f_cap_tqs, t_cnt * (int64_t)Cp)) return CHB_ENOMEM;
-            dim3 gt((unsigned)((t_cnt + 63) / 64), (unsigned)((C + 63) / 64));
+            dim3 gt((unsigned)((t_cnt + CT_M - 1) / CT_M), (unsigned)((C + CT_N - 1) / CT_N));
             centroid_terms_kernel<<<gt, 256, 0, c->stream>>>(c->qpoint + t_first, t_cnt, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2, C, c->f_tqs);
             guess_from_terms_kernel<<<nblk(t_cnt * 32, 256), 256, 0, c->stream>>>(c->f_tqs, t_cnt, Cp, C, c->f_mcnt, c->f_guess_all + t_first);
             c->tm.launches_other += 2;
@@ -2098,15 +2202,16 @@ int chb_fused_setup(chb_ctx *c)
             // rows = owned slots grouped by guessed bin, so that a 128-row block prunes the same bins
             const int64_t ns = std::max<int64_t>(n - c->U, 1);
             if (reserve(c, &c->f_seedT, &c->f_cap_seedT, ns * c->d)) return CHB_ENOMEM;
-            seed_transpose_kernel<<<nblk(ns * c->d, 256), 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_idx, n - c->U, c->f_seedT);
+            seed_transpose_kernel<<<nblk(ns * c->d, 256), 256, 0, c->stream>>>(c->Xf, c->ldf, c->d, c->seed_idx, n - c->U, c->f_seedT);
             CHB_CUDA(c, cudaMemsetAsync(c->f_rhist, 0, sizeof(int32_t) * (size_t)(C + 2), c->stream));
             row_hist_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_guess_all + c->u0, nown, c->f_rhist);
             row_scan_kernel<<<1, 32, 0, c->stream>>>(c->f_rhist, C + 1, c->f_rhist + C + 2);
             row_scatter_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_guess_all + c->u0, nown, c->f_rhist + C + 2, c->f_row_slot);
             row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_guess_all + c->u0, c->nrm, nown,
                                                                       c->f_row_pt, c->f_row_guess, c->f_slot_row, c->f_sq_row);
-            row_ub_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_row_pt, c->f_row_guess, nown, c->X, c->ldx, c->d, C, k,
-                                                                      c->seed_off, c->f_seedT, n - c->U, c->f_ub, c->f_ubk2);
+            row_ub_kernel<<<(unsigned)(nown / RU_ROWS + C + 2), RU_THREADS, 0, c->stream>>>(
+                c->f_row_pt, nown, c->Xf, c->ldf, c->d, C, k, c->seed_off, c->f_seedT, n - c->U, c->f_rhist + C + 2, c->f_sq_row,
+                reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ub, c->f_ubk2);
             c->tm.launches_other += 2;
             split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
