@@ -10,8 +10,9 @@
 //
 // Method.  With W = V - 1 x' the objective is alpha' G alpha, G = W W' (m x m, PSD): the minimum-norm point of
 // the hull of the rows of W.  Phase 1 forms G in FP64 (lane i accumulates row i from a shared-memory tile of W);
-// phase 2 runs Wolfe's finite active-set method on G -- lane i owns vertex i; the affine minimiser on the
-// current corral S solves (G_SS + s 11') y = 1 by Gauss-Jordan with rows distributed over lanes; affinely
+// phase 2 finds the optimal face -- lane i owns vertex i -- by block principal pivoting on an exchanged tableau of
+// M = G + s 11' (main launches) with Wolfe's finite active-set method as the safety net (and as the method of the
+// fallback launches): the affine minimiser on a face S solves (M_SS) y = 1, rows distributed over lanes; affinely
 // dependent vertices (duplicate contigs) show up as a vanishing pivot and are banned, which leaves the distance
 // unchanged; phase 3 evaluates the residual norm in d dimensions from global memory.
 // The QP is strictly convex on the affine hull, so its distance is unique: any exact solver agrees with
@@ -236,11 +237,107 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fa
                 status = CHB_QP_DEGENERATE;
             }
         } else {
-            // Wolfe's method.  attempt 0 (fast, the main kernel for k > 10) keeps the exchanged tableau across iterations;
-            // if that runs into the iteration cap or meets a non-positive leaving pivot (drift on an ill-conditioned
-            // corral) attempt 1 redoes the pair with a fresh Gauss-Jordan solve per minor cycle, as the fallback launches do.
+            // attempt 0 (fast, the main kernel for k > 10): block principal pivoting on an exchanged tableau of M = G + s 11'
+            // (principal pivots on the vertices of a face S leave (M_SS)^-1 in the S block).  Per sweep,
+            // beta = (M_SS)^-1 1 / (1' (M_SS)^-1 1) is read off the tableau's row sums, every vertex with a negative weight is
+            // pivoted OUT and every excluded vertex with a negative multiplier (g_i < beta' G beta) is pivoted IN -- all at once.
+            // A sweep costs one pivot per vertex that moves; the whole solve needs about (size of the optimal face + wrong
+            // guesses) pivots and a handful of sweeps, where Wolfe's method spends a sweep per vertex.  The sweeps keep no
+            // feasibility, so the result only counts if they END on the KKT conditions and a fresh solve on the final face
+            // confirms it; otherwise (cycling, drift, a vanishing pivot on the way out) attempt 1 runs Wolfe's method with a
+            // fresh Gauss-Jordan solve per minor cycle, as the fallback launches do.
             const double tol = 1e-14 * scale;
-            for (int attempt = fast ? 0 : 1; attempt < 2; ++attempt) {
+            bool solved = false;
+            if (fast == 1) {
+                double A[KMAX];
+#pragma unroll
+                for (int c = 0; c < KMAX; ++c) A[c] = (lane < m && c < m) ? sG[lane * LDW + c] + scale : ((c == lane) ? 1.0 : 0.0);
+                unsigned S = 0u, banned = 0u;
+                int st = CHB_QP_OK;
+                {
+                    // start from the vertex nearest to the query (as Wolfe's method does): for a query far from the bin the
+                    // optimal face has one or two vertices and the first sweeps find it; a query inside the cloud gets most
+                    // vertices added by the first sweep, all at once
+                    double key = lane < m ? gii : DBL_MAX;
+                    int start = lane;
+                    warp_argmin(key, start);
+                    exchange<KMAX>(A, sRow, start, lane, 0.0); // G_ss + scale >= scale > 0
+                    S = 1u << start;
+                }
+                bool ended = false, broke = false;
+                double beta = 0.0;
+                for (int sweep = 0; sweep < 2 * m + 8 && !ended && !broke; ++sweep) {
+                    const bool in = (S >> lane) & 1u;
+                    double y = 0.0;
+                    if (in) {
+#pragma unroll
+                        for (int c = 0; c < KMAX; ++c)
+                            if ((S >> c) & 1u) y += A[c];
+                    }
+                    beta = y / warp_sum(y);
+                    if (lane < KMAX) sAlpha[lane] = in ? beta : 0.0;
+                    __syncwarp();
+                    double g = 0.0;
+                    if (lane < m) {
+#pragma unroll
+                        for (int c = 0; c < KMAX; ++c)
+                            if (c < m) g = fma(sG[lane * LDW + c], sAlpha[c], g);
+                    }
+                    const double f = warp_sum(in ? beta * g : 0.0);
+                    __syncwarp();
+                    const unsigned neg = __ballot_sync(CHB_FULL, in && beta < 0.0);
+                    const unsigned dual = __ballot_sync(CHB_FULL, lane < m && !in && !((banned >> lane) & 1u) && g < f - tol);
+                    if (!neg && !dual) { ended = true; break; }
+                    unsigned flip = neg | dual;
+                    while (flip) {
+                        const int v = __ffs(flip) - 1;
+                        flip &= flip - 1;
+                        const bool entering = (dual >> v) & 1u;
+                        if (exchange<KMAX>(A, sRow, v, lane, entering ? 1e-11 * (sG[v * LDW + v] + scale) : 0.0)) {
+                            S ^= 1u << v;
+                            if (!entering) banned = 0u; // the face shrank: a vertex that depended on it may be independent now
+                        } else if (entering) {
+                            banned |= 1u << v;
+                            st = CHB_QP_DEGENERATE;
+                        } else {
+                            broke = true; // a diagonal entry of an SPD inverse came out non-positive: drift
+                            break;
+                        }
+                    }
+                }
+                if (ended) {
+                    // confirm on a fresh solve of the final face (removes whatever rounding the pivots accumulated)
+                    double y;
+                    const int bad = affine_solve<KMAX>(sG, sRow, S, m, scale, lane, y);
+                    const double b2 = y / warp_sum(y);
+                    const bool in = (S >> lane) & 1u;
+                    const unsigned negm = __ballot_sync(CHB_FULL, in && !(b2 >= 0.0));
+                    if (bad < 0 && !negm) {
+                        // ... and the multipliers of EVERY excluded vertex (banned ones included) on that fresh solution: the
+                        // result is accepted only as a verified KKT point, whatever the tableau drifted to on the way
+                        if (lane < KMAX) sAlpha[lane] = in ? b2 : 0.0;
+                        __syncwarp();
+                        double g = 0.0;
+                        if (lane < m) {
+#pragma unroll
+                            for (int c = 0; c < KMAX; ++c)
+                                if (c < m) g = fma(sG[lane * LDW + c], sAlpha[c], g);
+                        }
+                        const double f = warp_sum(in ? b2 * g : 0.0);
+                        __syncwarp();
+                        const unsigned viol = __ballot_sync(CHB_FULL, lane < m && !in && g < f - tol);
+                        if (!viol) {
+                            alpha = in ? b2 : 0.0;
+                            status = st;
+                            solved = true;
+                        }
+                    }
+                }
+            }
+            // Wolfe's method: the main path for 25..32 neighbours (fast == 2: exchanged tableau kept across its iterations -- there
+            // the block pivoting above moves too many vertices the wrong way to pay off), and the safety net of the block pivoting
+            // (a fresh Gauss-Jordan solve per minor cycle, as in the fallback launches)
+            for (int attempt = (fast == 2) ? 0 : 1; attempt < 2 && !solved; ++attempt) {
                 const bool tab = attempt == 0;
                 bool tab_fail = false;
                 status = CHB_QP_OK;
@@ -439,9 +536,11 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
         return launch<16>(ctx, b, 1);
     }
     // main kernel for these neighbour counts: the exchanged tableau is kept across the iterations of a pair
+    // fast: 0 = Wolfe with a fresh solve per minor cycle (test aid CHB_QP_NO_TABLEAU), 1 = block principal pivoting on the
+    // exchanged tableau (<= 24 neighbours), 2 = Wolfe on the exchanged tableau (25..32 neighbours)
     const int fast = a.metric == CHB_METRIC_CONVEX && !getenv("CHB_QP_NO_TABLEAU");
     if (a.k <= 8) return launch<8>(ctx, a, 16, fast);
     if (a.k <= 16) return launch<16>(ctx, a, 16, fast);
     if (a.k <= 24) return launch<24>(ctx, a, 16, fast); // the cost follows the unrolled width, not k
-    return launch<32>(ctx, a, 16, fast);
+    return launch<32>(ctx, a, 16, fast ? 2 : 0);
 }
