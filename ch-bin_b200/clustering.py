@@ -18,6 +18,7 @@ from __future__ import annotations
 import logging
 import os
 import shutil
+import time
 from pathlib import Path
 from typing import Optional, Tuple
 
@@ -32,6 +33,9 @@ B200_SOLVER = "b200"
 # One library context per device is kept alive between fit_cluster calls of a process (like a BLAS handle): creating
 # a context, its stream and its multi-GB device buffers costs ~10 ms, comparable to the whole 20k-contig stage.
 _CTX_CACHE = {}
+# ... and one torch stream per device for the sharded path: torch's caching allocator keeps its pools per stream, so a fresh
+# stream per call would turn every torch.empty into a cudaMalloc (tens of milliseconds)
+_STREAM_CACHE = {}
 
 
 def _get_context(device: int, reuse: bool) -> "capi.Context":
@@ -145,6 +149,30 @@ class GpuEngine:
         return self.ctx.iteration_end()
 
 
+class _ContextEngine:
+    """The round interface over a context that owns every query slot (no exchange: the library keeps the tentative labels
+    itself, nothing of torch is touched)."""
+
+    def __init__(self, ctx: capi.Context):
+        self.ctx = ctx
+
+    def window(self):
+        return self.ctx.get_window()
+
+    def iteration_begin(self, perm):
+        self.ctx.iteration_begin(perm)
+
+    def round_run(self, lo, hi):
+        self.ctx.round_run(lo, hi)
+        return None
+
+    def round_commit_end(self, lo, hi, tent):
+        return self.ctx.round_commit_end(lo, hi)
+
+    def iteration_end(self):
+        return self.ctx.iteration_end()
+
+
 class TorchComm:
     """Label exchange between ranks: one all-reduce(MAX) of a window of int32 labels per round (un-owned
     positions hold INT32_MIN).  NCCL over NVLink on the GPU box, gloo in the CPU tests."""
@@ -160,17 +188,20 @@ class TorchComm:
         return tent
 
 
-def exchange_guess(engine, comm, U: int) -> bool:
+def exchange_guess(engine, comm, U: int, mark=None) -> bool:
     """Sharded contexts: every rank computes the first iteration's speculation start (nearest seed centroid) for its OWN query
     slots and the ranks merge them with one all-reduce(MAX) of U int32 labels (un-owned entries are INT32_MIN) -- instead of
     every rank repeating the U x C x d contraction.  No-op for engines without the export/import pair."""
     if not hasattr(engine, "guess_export"):
         return False
+    mark = mark or (lambda label: None)
     with engine.stream_context():
         g = engine.guess_export(U)
+        mark("  guess exported")
         if g is None:
             return False
         g = comm.all_reduce_max(g)
+        mark("  guess all-reduced")
         engine.guess_import(g)
     return True
 
@@ -273,6 +304,13 @@ def fit_cluster(
     num_points_to_assign = len(points_to_assign)
     logger.debug("Assigning %s points.", num_points_to_assign)
 
+    marks = [] if os.environ.get("CHB_PROFILE_FIT") else None  # wall-clock marks of the host driver (tools/e2e_multi.py)
+
+    def mark(label):
+        if marks is not None:
+            marks.append((label, time.perf_counter()))
+
+    mark("start")
     ctx = _get_context(device, reuse_context)
     try:
         ctx.set_stream(capi.OWN_STREAM)
@@ -280,22 +318,33 @@ def fit_cluster(
         engine = comm = None
         u0, u1 = owned_slots(num_points_to_assign, rank, world)
         if world > 1:
-            engine = GpuEngine(ctx, device)
+            import torch
+
+            stream = _STREAM_CACHE.get(device)
+            if stream is None:
+                stream = _STREAM_CACHE[device] = torch.cuda.Stream(torch.device("cuda", device))
+            engine = GpuEngine(ctx, device, stream)
             comm = TorchComm()
         if world > 1 and dist_mod.get_backend() == "nccl":
             # the (small) feature matrix is replicated with ONE NCCL broadcast over NVLink -- rank 0 uploads its
             # host array once, the other ranks receive it device to device instead of pushing the same bytes over PCIe
             import torch
 
+            mark("engine created")
             with engine.stream_context():
                 n_, d_ = np.shape(samples)
                 Xd = torch.empty((n_, d_), dtype=torch.float64, device=engine.device)
+                mark("Xd allocated")
                 if rank == 0:
                     Xd.copy_(torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)), non_blocking=True)
+                mark("X copy enqueued")
                 dist_mod.broadcast(Xd, src=0)
-                ctx.set_features_dev(Xd.data_ptr(), n_, d_)
-                engine.stream.synchronize()
+                mark("broadcast X enqueued")
+                # enqueued behind the broadcast on the same stream; Xd goes back to torch's stream-ordered allocator, which
+                # hands it out again only to work enqueued on this stream after the repack
+                ctx.set_features_dev(Xd.data_ptr(), n_, d_, asynchronous=True)
             del Xd
+            mark("features set")
         else:
             ctx.set_features(samples, asynchronous=True)  # the upload overlaps the label set-up and the first permutation draw
         ctx.set_labels(curr, int(num_clusters), u0, u1)
@@ -304,60 +353,79 @@ def fit_cluster(
         ctx.set_distance_mode(int(distance_mode))
         ctx.set_gram_engine(int(gram_engine))
         spec_perm = spec_state = None  # a permutation drawn ahead of the iteration that will use it
-        if world == 1 and max_iterations > 0:
-            spec_perm = _draw_permutation(points_to_assign, dist_mod, device)  # iteration 1 always executes
-        ctx.build_distance_matrix(bool(in_mem_dist_matrix))
-        ctx._pending_features = None
         on_device = world > 1 and dist_mod.get_backend() == "nccl" and int(distance_mode) == 2 and np.shape(samples)[1] <= 160
-        if world > 1 and num_points_to_assign > 0 and max_iterations > 0:
-            exchange_guess(engine, comm, num_points_to_assign)
-
-        iterations, converged, rounds_total, changed = 0, False, 0, []
-        for i_iter in range(max_iterations):
+        if max_iterations > 0:  # iteration 1 always executes: its permutation is drawn while the features are still in flight
             if world > 1:
                 with engine.stream_context():
-                    sample_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
-                    change_count, rounds = run_iteration(engine, sample_perm, comm)
+                    spec_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
             else:
-                # Single context: chb_round_run only enqueues, chb_round_commit synchronises.  The next iteration's
-                # np.random.permutation (algorithm.py:45) is drawn while the first round runs on the device; if the loop
-                # then stops (algorithm.py:63-66, or the iteration limit) the global RNG is put back, so that exactly one
-                # draw per EXECUTED iteration remains visible -- the reference's RNG contract.
-                sample_perm = spec_perm if spec_perm is not None else _draw_permutation(points_to_assign, dist_mod, device)
-                spec_perm = spec_state = None
-                ctx.iteration_begin(sample_perm)
-                U, W = len(sample_perm), ctx.get_window()
+                spec_perm = _draw_permutation(points_to_assign, dist_mod, device)
+        mark("labels/params set")
+        ctx.build_distance_matrix(bool(in_mem_dist_matrix))
+        ctx._pending_features = None
+        mark("distance structure")
+        if world > 1 and num_points_to_assign > 0 and max_iterations > 0:
+            exchange_guess(engine, comm, num_points_to_assign, mark)
+            mark("guess exchanged")
+
+        iterations, converged, rounds_total, changed = 0, False, 0, []
+        # One loop for one context and for sharded contexts.  chb_round_run only enqueues, the commit synchronises: the NEXT
+        # iteration's np.random.permutation (algorithm.py:45) is drawn -- and, between ranks, broadcast -- while the first
+        # round runs on the device; if the loop then stops (algorithm.py:63-66, or the iteration limit) the global RNG is put
+        # back, so that exactly one draw per EXECUTED iteration remains visible: the reference's RNG contract.
+        import contextlib
+
+        eng = engine if world > 1 else _ContextEngine(ctx)
+        stream_ctx = engine.stream_context() if world > 1 else contextlib.nullcontext()
+        with stream_ctx:
+            if spec_perm is None and max_iterations > 0:
+                spec_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
+            for i_iter in range(max_iterations):
+                sample_perm, spec_perm, spec_state = spec_perm, None, None
+                U = num_points_to_assign
+                eng.iteration_begin(sample_perm)
+                mark(f"it{i_iter + 1} begun")
+                W = eng.window() or U
                 lo = rounds = 0
                 done, change_count = False, 0
                 while lo < U:
-                    hi = min(U, lo + (W or U))
-                    ctx.round_run(lo, hi)
+                    hi = min(U, lo + W)
+                    tent = eng.round_run(lo, hi)
+                    if comm is not None:
+                        tent = comm.all_reduce_max(tent)
                     if spec_state is None and i_iter + 1 < max_iterations:
                         spec_state = np.random.get_state()
-                        spec_perm = _draw_permutation(points_to_assign, dist_mod, device)
-                    first, done, change_count = ctx.round_commit_end(lo, hi)
+                        spec_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
+                    first, done, change_count = eng.round_commit_end(lo, hi, tent)
                     lo = hi if first < 0 else first + 1
                     rounds += 1
                 if not done:
-                    change_count = ctx.iteration_end()
-                if (change_count == 0 or i_iter + 1 == max_iterations) and spec_state is not None:
+                    change_count = eng.iteration_end()
+                mark(f"it{i_iter + 1} rounds done ({rounds})")
+                stop = change_count == 0 or i_iter + 1 == max_iterations
+                if stop and spec_state is not None:
                     np.random.set_state(spec_state)  # the speculative draw never happened
                     spec_perm = spec_state = None
-            rounds_total += rounds
-            iterations += 1
-            changed.append(change_count)
-            # If the assignments did not change, break  (algorithm.py:63-66)
-            if change_count == 0:
-                logger.info("Iteration %s: No changes with previous iteration... Stopping...", i_iter + 1)
-                converged = True
-                break
-            change_avg = change_count / len(curr)
-            logger.info("Iteration %s: Points changed clusters. avg=%s, count=%s", i_iter + 1, change_avg, change_count)
-        else:
-            logger.info("Exit due to max iteration limit.")
+                rounds_total += rounds
+                iterations += 1
+                changed.append(change_count)
+                # If the assignments did not change, break  (algorithm.py:63-66)
+                if change_count == 0:
+                    logger.info("Iteration %s: No changes with previous iteration... Stopping...", i_iter + 1)
+                    converged = True
+                    break
+                change_avg = change_count / len(curr)
+                logger.info("Iteration %s: Points changed clusters. avg=%s, count=%s", i_iter + 1, change_avg, change_count)
+                if spec_perm is None and not stop:
+                    spec_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
+            else:
+                logger.info("Exit due to max iteration limit.")
         labels = ctx.get_labels()
+        mark("labels read back")
         info = dict(iterations=iterations, converged=converged, changed=changed, timers=ctx.timers(), rank=rank,
                     world=world, owned_slots=(u0, u1))
+        if marks is not None:
+            info["marks_ms"] = [(lab, (t - marks[0][1]) * 1e3) for lab, t in marks]
     except BaseException:
         _CTX_CACHE.pop(device, None)  # never reuse a context after a failure
         ctx.close()

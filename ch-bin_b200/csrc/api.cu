@@ -716,6 +716,10 @@ int chb_set_features_dev(chb_ctx *c, const double *x_dev, int64_t n, int32_t d)
 {
     return set_features_common(c, x_dev, n, d, cudaMemcpyDeviceToDevice);
 }
+int chb_set_features_dev_async(chb_ctx *c, const double *x_dev, int64_t n, int32_t d)
+{
+    return set_features_common(c, x_dev, n, d, cudaMemcpyDeviceToDevice, true);
+}
 
 int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_t slot_begin, int64_t slot_end)
 {

@@ -95,6 +95,10 @@ int chb_enable_timers(chb_ctx *ctx, int enable);
  * F-ordered DataFrame.values of cli/clustering.py:53).  Copied to the device in a 16-byte-pitched layout. */
 int chb_set_features(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
 int chb_set_features_dev(chb_ctx *ctx, const double *x_rowmajor_dev, int64_t n, int32_t d);
+/* The same, returning as soon as the repack is ENQUEUED on the context's stream: x_rowmajor_dev may be released once work
+ * enqueued on that stream after this call would be ordered behind it (e.g. a stream-ordered allocator on the same stream, or
+ * after chb_build_distance_matrix / chb_synchronize).  For a buffer that an NCCL broadcast on the same stream just filled. */
+int chb_set_features_dev_async(chb_ctx *ctx, const double *x_rowmajor_dev, int64_t n, int32_t d);
 /* Same as chb_set_features, but returns as soon as the upload is ENQUEUED: when x_rowmajor is page-locked memory the
  * copy overlaps the caller's next host work (reading labels, drawing the first permutation).  The one exception to "no
  * pointer is retained": x_rowmajor must stay valid and unchanged until chb_build_distance_matrix (or chb_synchronize)
