@@ -20,7 +20,7 @@ OWN_STREAM = 2**64 - 1  # CHB_OWN_STREAM: (void*)-1
 
 EXPORTED_SYMBOLS = [
     "chb_abi_version", "chb_create", "chb_destroy", "chb_last_error", "chb_set_stream", "chb_synchronize",
-    "chb_get_timers", "chb_reset_timers", "chb_enable_timers", "chb_set_features", "chb_set_features_dev", "chb_set_features_dev_async",
+    "chb_get_timers", "chb_reset_timers", "chb_enable_timers", "chb_set_features", "chb_set_features_dev", "chb_set_features_dev_async", "chb_features_buffer", "chb_features_commit",
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
     "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin", "chb_iteration_begin_dev",
     "chb_round_run", "chb_round_commit", "chb_round_commit_end", "chb_iteration_end", "chb_set_window", "chb_get_window",
@@ -80,6 +80,8 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_set_features.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_dev.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_dev_async.argtypes = [_vp, _vp, _i64, _i32]
+    L.chb_features_buffer.argtypes = [_vp, _i64, _i32, ctypes.POINTER(_vp), ctypes.POINTER(_i64)]
+    L.chb_features_commit.argtypes = [_vp, ctypes.c_int]
     L.chb_set_features_async.argtypes = [_vp, _vp, _i64, _i32]
     L.chb_set_features_colmajor.argtypes = [_vp, _vp, _i64, _i32, ctypes.c_int]
     L.chb_set_features_merged.argtypes = [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _vp]
@@ -244,6 +246,16 @@ class Context:
         self.n, self.d = int(n), int(d)
         fn = self._lib.chb_set_features_dev_async if asynchronous else self._lib.chb_set_features_dev
         self._check(fn(self._h, _vp(dev_ptr), n, d))
+
+    def features_buffer(self, n: int, d: int):
+        """(device address, number of float64 elements) of the context's feature matrix, allocated for (n, d)."""
+        ptr, cnt = _vp(), _i64(0)
+        self._check(self._lib.chb_features_buffer(self._h, int(n), int(d), ctypes.byref(ptr), ctypes.byref(cnt)))
+        self.n, self.d = int(n), int(d)
+        return int(ptr.value), int(cnt.value)
+
+    def features_commit(self, asynchronous: bool = False):
+        self._check(self._lib.chb_features_commit(self._h, int(bool(asynchronous))))
 
     def set_labels(self, initial_bins: np.ndarray, num_clusters: int, slot_begin: int = 0, slot_end: int = -1):
         b = np.ascontiguousarray(initial_bins, dtype=np.int64)

@@ -188,6 +188,17 @@ class TorchComm:
         return tent
 
 
+class _CudaArray:
+    """Minimal __cuda_array_interface__ carrier: lets torch wrap device memory the library owns (no copy, no ownership)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def _device_view(torch, ptr: int, count: int, device):
+    return torch.as_tensor(_CudaArray(ptr, count), device=device)
+
+
 def exchange_guess(engine, comm, U: int, mark=None) -> bool:
     """Sharded contexts: every rank computes the first iteration's speculation start (nearest seed centroid) for its OWN query
     slots and the ranks merge them with one all-reduce(MAX) of U int32 labels (un-owned entries are INT32_MIN) -- instead of
@@ -330,19 +341,17 @@ def fit_cluster(
             # host array once, the other ranks receive it device to device instead of pushing the same bytes over PCIe
             import torch
 
-            mark("engine created")
             with engine.stream_context():
                 n_, d_ = np.shape(samples)
-                Xd = torch.empty((n_, d_), dtype=torch.float64, device=engine.device)
-                mark("Xd allocated")
-                if rank == 0:
-                    Xd.copy_(torch.from_numpy(np.ascontiguousarray(samples, dtype=np.float64)), non_blocking=True)
-                mark("X copy enqueued")
+                if rank == 0:  # exactly the single-GPU upload: pinned or pageable, C- or F-ordered (transposed on the device)
+                    ctx.set_features(samples, asynchronous=True)
+                ptr, count = ctx.features_buffer(n_, d_)
+                Xd = _device_view(torch, ptr, count, engine.device)  # the library's own matrix: no copy on either side
+                mark("X upload enqueued")
                 dist_mod.broadcast(Xd, src=0)
                 mark("broadcast X enqueued")
-                # enqueued behind the broadcast on the same stream; Xd goes back to torch's stream-ordered allocator, which
-                # hands it out again only to work enqueued on this stream after the repack
-                ctx.set_features_dev(Xd.data_ptr(), n_, d_, asynchronous=True)
+                if rank != 0:
+                    ctx.features_commit(asynchronous=True)
             del Xd
             mark("features set")
         else:

@@ -193,6 +193,85 @@ __global__ void commit_kernel(const int32_t *__restrict__ tent, int64_t lo, int6
     }
 }
 
+// Query slots on the device (chb_set_labels): slot of point i = number of un-assigned points before it (algorithm.py:38:
+// points_to_assign is ascending) -- an exclusive scan over n flags in three small kernels (tile counts, scan of the tile
+// counts, per-tile scan + scatter) instead of a host pass that writes three arrays of n entries.
+constexpr int SLOT_TILE = 1024; // 256 threads x 4 points
+__device__ __forceinline__ int block_exclusive_scan_256(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(CHB_FULL, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[w] = incl;
+    __syncthreads();
+    int woff = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int t = s_warp[i];
+        if (i < w) woff += t;
+        tot += t;
+    }
+    __syncthreads();
+    total = tot;
+    return woff + incl - v;
+}
+__global__ void __launch_bounds__(256) slots_count_kernel(const int32_t *__restrict__ lab, int64_t n, int32_t *__restrict__ tile_cnt)
+{
+    __shared__ int s_warp[8];
+    const int64_t base = (int64_t)blockIdx.x * SLOT_TILE + threadIdx.x * 4;
+    int v = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v += (base + u < n && lab[base + u] == -1) ? 1 : 0;
+    int total;
+    block_exclusive_scan_256(v, s_warp, total);
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(256) slots_tile_scan_kernel(int32_t *__restrict__ tile_cnt, int32_t ntiles)
+{
+    __shared__ int s_warp[8];
+    int carry = 0;
+    for (int32_t t0 = 0; t0 < ntiles; t0 += 256) {
+        const int32_t t = t0 + threadIdx.x;
+        const int v = t < ntiles ? tile_cnt[t] : 0;
+        int total;
+        const int ex = block_exclusive_scan_256(v, s_warp, total);
+        if (t < ntiles) tile_cnt[t] = carry + ex;
+        carry += total;
+    }
+}
+__global__ void __launch_bounds__(256) slots_fill_kernel(const int32_t *__restrict__ lab, int64_t n, const int32_t *__restrict__ tile_off,
+                                                         int32_t *__restrict__ qslot, int32_t *__restrict__ qpoint, int32_t *__restrict__ pos)
+{
+    __shared__ int s_warp[8];
+    const int64_t base = (int64_t)blockIdx.x * SLOT_TILE + threadIdx.x * 4;
+    bool f[4];
+    int v = 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        f[u] = base + u < n && lab[base + u] == -1;
+        v += f[u] ? 1 : 0;
+    }
+    int total;
+    int slot = tile_off[blockIdx.x] + block_exclusive_scan_256(v, s_warp, total);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int64_t i = base + u;
+        if (i >= n) break;
+        pos[i] = -1; // no permutation position yet (seeds keep -1 for good)
+        if (f[u]) {
+            qslot[i] = slot;
+            qpoint[slot] = (int32_t)i;
+            ++slot;
+        } else {
+            qslot[i] = -1;
+        }
+    }
+}
+
 // Device path of chb_iteration_begin: the caller's int64 permutation becomes perm_pt / pos / own_pos in one pass, and is
 // validated on the way (out of range: counters[9], not a query point: counters[10]; repeats are found by
 // check_perm_kernel once the scatter is complete: counters[11]) -- the first offending position of each kind, reported
@@ -239,6 +318,12 @@ __global__ void end_if_done_kernel(int32_t *__restrict__ old_label, const int32_
     }
     const unsigned m = __ballot_sync(CHB_FULL, ch);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], __popc(m));
+}
+
+__global__ void widen_labels_kernel(const int32_t *__restrict__ lab, int64_t n, int64_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = lab[i];
 }
 
 __global__ void count_changed_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int64_t n,
@@ -356,13 +441,14 @@ int chb_destroy(chb_ctx *c)
     chb_resolve_timers(c);
     for (auto &p : c->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     dev_free(&c->X); dev_free(&c->old_label); dev_free(&c->tent_pt); dev_free(&c->pos); dev_free(&c->qslot);
-    dev_free(&c->perm64); dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
+    dev_free(&c->perm64); dev_free(&c->lab64); dev_free(&c->slot_tiles); dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback);
     dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
     chb_fused_free(c); dev_free(&c->Aq); dev_free(&c->Ascratch); dev_free(&c->knn_dist);
     if (c->counters_host) cudaFreeHost(c->counters_host);
     if (c->pin_i32) cudaFreeHost(c->pin_i32);
+    if (c->pin_lab64) cudaFreeHost(c->pin_lab64);
     delete[] c->own_pos_host;
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -720,6 +806,24 @@ int chb_set_features_dev_async(chb_ctx *c, const double *x_dev, int64_t n, int32
 {
     return set_features_common(c, x_dev, n, d, cudaMemcpyDeviceToDevice, true);
 }
+// The device feature matrix itself (n x ldx, 16-byte row pitch): allocated for (n, d) if need be.  One rank fills it with any
+// chb_set_features* call, broadcasts `count` doubles from *x_dev over NCCL, and the receivers call chb_features_commit.
+int chb_features_buffer(chb_ctx *c, int64_t n, int32_t d, double **x_dev, int64_t *count)
+{
+    CHB_CHECK(c, c && x_dev && count, CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, n > 0 && d > 0, CHB_EINVAL, "samples must be a non-empty (n, d) float64 array");
+    CHB_TRY(features_begin(c, n, d));
+    *x_dev = c->X;
+    *count = n * (int64_t)c->ldx;
+    return CHB_OK;
+}
+int chb_features_commit(chb_ctx *c, int asynchronous)
+{
+    CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
+    CHB_CHECK(c, c->X && c->n > 0, CHB_EINVAL, "features_commit: call chb_features_buffer first");
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    return features_finish(c, asynchronous != 0);
+}
 
 int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_t slot_begin, int64_t slot_end)
 {
@@ -742,25 +846,21 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
         }
     }
     int32_t *lab = c->pin_i32, *qs = lab + n, *qp = qs + n, *seed_idx = qp + n, *seed_off = seed_idx + n;
-    c->h_qslot = qs; // host mirror used by chb_iteration_begin
+    c->h_qslot = qs;          // host mirror of the slots: only the host path of chb_iteration_begin reads it ...
+    c->h_qslot_valid = false; // ... and builds it on first use (ensure_host_slots)
     for (int32_t b = 0; b <= C; ++b) seed_off[b] = 0;
-    int64_t U = 0, ns = 0;
-    int32_t *seed_tmp = seed_idx; // seeds in index order first (compact), grouped by bin below
+    int64_t ns = 0;
+    int32_t *seed_tmp = qp; // seeds in index order first (compact), grouped by bin into seed_idx below
     {
-        // one pass over n: labels to int32, query slots, the compact seed list; range check folded into a min / max
+        // one pass over n: labels to int32 and the compact seed list (a rarely taken branch); range check folded into a
+        // min / max.  The query slots themselves are derived on the device (slots_*_kernel).
         int64_t mn = 0, mx = -1;
         for (int64_t i = 0; i < n; ++i) {
             const int64_t b = bins[i];
             mn = b < mn ? b : mn;
             mx = b > mx ? b : mx;
             lab[i] = (int32_t)b;
-            if (b == -1) {
-                qs[i] = (int32_t)U;
-                qp[U++] = (int32_t)i;
-            } else {
-                qs[i] = -1;
-                seed_tmp[ns++] = (int32_t)i;
-            }
+            if (b != -1) seed_tmp[ns++] = (int32_t)i;
         }
         if (mn < -1 || mx >= C) {
             for (int64_t i = 0; i < n; ++i)
@@ -768,16 +868,15 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
                           (long long)bins[i], C);
         }
     }
+    const int64_t U = n - ns;
     // seed contigs sorted by (bin, index): the bin reference points are summed in this fixed order on every rank.  Stable
-    // counting sort over the ns seeds only (the permuted copy goes through qp's tail, free beyond U, and back).
+    // counting sort over the ns seeds only.
     for (int64_t s = 0; s < ns; ++s) ++seed_off[lab[seed_tmp[s]] + 1];
     for (int32_t b = 0; b < C; ++b) seed_off[b + 1] += seed_off[b];
     {
-        std::vector<int32_t> &cur = c->h_lab; // scratch: write cursor per bin, then the grouped list
+        std::vector<int32_t> &cur = c->h_lab; // scratch: write cursor per bin
         cur.assign(seed_off, seed_off + C);
-        int32_t *grouped = qp + U; // qp has n entries, of which U are used: n - U = ns are free
-        for (int64_t s = 0; s < ns; ++s) grouped[cur[(size_t)lab[seed_tmp[s]]]++] = seed_tmp[s];
-        memcpy(seed_idx, grouped, sizeof(int32_t) * (size_t)ns);
+        for (int64_t s = 0; s < ns; ++s) seed_idx[cur[(size_t)lab[seed_tmp[s]]]++] = seed_tmp[s];
     }
     if (slot_end < 0) slot_end = U;
     CHB_CHECK(c, 0 <= slot_begin && slot_begin <= slot_end && slot_end <= U, CHB_EINVAL, "owned slot range [%lld,%lld) invalid for U=%lld",
@@ -812,11 +911,15 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
         CHB_CUDA(c, cudaMemcpyAsync(c->seed_idx, seed_idx, sizeof(int32_t) * (size_t)(n - U), cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->old_label, lab, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
     CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToDevice, c->stream));
-    CHB_CUDA(c, cudaMemcpyAsync(c->qslot, qs, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    if (U) CHB_CUDA(c, cudaMemcpyAsync(c->qpoint, qp, sizeof(int32_t) * (size_t)U, cudaMemcpyHostToDevice, c->stream));
-    fill_i32_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->pos, n, -1);
-    CHB_CUDA(c, cudaGetLastError());
-    ++c->tm.launches_other;
+    {
+        const int32_t ntiles = (int32_t)((n + SLOT_TILE - 1) / SLOT_TILE);
+        CHB_TRY(dev_reserve(c, &c->slot_tiles, &c->cap_slot_tiles, (int64_t)ntiles));
+        slots_count_kernel<<<(unsigned)ntiles, 256, 0, c->stream>>>(c->old_label, n, c->slot_tiles);
+        slots_tile_scan_kernel<<<1, 256, 0, c->stream>>>(c->slot_tiles, ntiles);
+        slots_fill_kernel<<<(unsigned)ntiles, 256, 0, c->stream>>>(c->old_label, n, c->slot_tiles, c->qslot, c->qpoint, c->pos);
+        CHB_CUDA(c, cudaGetLastError());
+        c->tm.launches_other += 3;
+    }
     c->labels_set = true;
     c->guess_pending = true;
     c->guess_shared = false; // the caller opts in again with chb_guess_export after every chb_set_labels
@@ -1072,6 +1175,12 @@ static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bo
         c->own_pos_by_slot = true;
         c->perm_check_pending = true;
     } else {
+    if (!c->h_qslot_valid) { // host mirror of the query slots (the device derives its own copy in chb_set_labels)
+        int32_t *lab = c->pin_i32, *qs = lab + c->n;
+        int32_t u = 0;
+        for (int64_t i = 0; i < c->n; ++i) qs[i] = (lab[i] == -1) ? u++ : -1;
+        c->h_qslot_valid = true;
+    }
     // positions this context owns, ascending (a context owns the queries of slots [u0, u1)); host mirrors of
     // qslot / the permutation scratch are kept in the context so that nothing is allocated or read back per iteration
     std::vector<int32_t> &p32 = c->h_perm32;
@@ -1336,11 +1445,22 @@ int chb_get_labels(chb_ctx *c, int64_t *labels_out)
     CHB_CHECK(c, c && labels_out, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->labels_set, CHB_EINVAL, "labels not set");
     CHB_CUDA(c, cudaSetDevice(c->device));
-    std::vector<int32_t> lab((size_t)c->n);
-    CHB_CUDA(c, cudaMemcpyAsync(lab.data(), c->in_iteration ? c->tent_pt : c->old_label, sizeof(int32_t) * (size_t)c->n,
-                                cudaMemcpyDeviceToHost, c->stream));
+    // widened to the caller's int64 on the device, then one copy straight into labels_out (no host pass over n)
+    CHB_TRY(dev_reserve(c, &c->lab64, &c->cap_lab64, c->n));
+    widen_labels_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->in_iteration ? c->tent_pt : c->old_label, c->n, c->lab64);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    // through a page-locked staging block (full PCIe rate), then one memcpy into the caller's pageable array
+    if (c->pin_lab_cap < c->n) {
+        if (c->pin_lab64) cudaFreeHost(c->pin_lab64);
+        c->pin_lab64 = nullptr;
+        c->pin_lab_cap = 0;
+        CHB_CUDA(c, cudaMallocHost(reinterpret_cast<void **>(&c->pin_lab64), sizeof(int64_t) * (size_t)c->n));
+        c->pin_lab_cap = c->n;
+    }
+    CHB_CUDA(c, cudaMemcpyAsync(c->pin_lab64, c->lab64, sizeof(int64_t) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     CHB_TRY(sync_stream(c));
-    for (int64_t i = 0; i < c->n; ++i) labels_out[i] = lab[(size_t)i];
+    memcpy(labels_out, c->pin_lab64, sizeof(int64_t) * (size_t)c->n);
     return CHB_OK;
 }
 

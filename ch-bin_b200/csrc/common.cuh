@@ -67,7 +67,14 @@ struct chb_ctx {
     std::vector<int32_t> h_lab, h_perm32, h_own32; // per-call scratch
     int32_t *pin_i32 = nullptr; // page-locked staging block of chb_set_labels
     int64_t pin_cap = 0;
-    const int32_t *h_qslot = nullptr; // host mirror of qslot (inside pin_i32)
+    int32_t *h_qslot = nullptr; // host mirror of qslot (inside pin_i32), built on demand
+    bool h_qslot_valid = false;
+    int64_t *lab64 = nullptr; // n : labels widened to int64 for chb_get_labels
+    int64_t cap_lab64 = 0;
+    int64_t *pin_lab64 = nullptr; // page-locked staging block of chb_get_labels
+    int64_t pin_lab_cap = 0;
+    int32_t *slot_tiles = nullptr; // per-1024-point tile counts / offsets of the slot scan
+    int64_t cap_slot_tiles = 0;
     std::vector<uint8_t> h_seen;
 
     // ---- parameters

@@ -104,6 +104,14 @@ int chb_set_features_dev_async(chb_ctx *ctx, const double *x_rowmajor_dev, int64
  * pointer is retained": x_rowmajor must stay valid and unchanged until chb_build_distance_matrix (or chb_synchronize)
  * returns.  Pageable memory is staged before the call returns, as with chb_set_features. */
 int chb_set_features_async(chb_ctx *ctx, const double *x_rowmajor, int64_t n, int32_t d);
+/* Replication across GPUs ("the small feature matrix replicated via NCCL broadcast over NVLink").  The context's
+ * device feature matrix is n x ldx doubles (ldx = d rounded up to 2, pad columns zero).  chb_features_buffer makes sure it is
+ * allocated for (n, d) and returns its device address and length.  The rank that holds the host array fills it with any
+ * chb_set_features* call; every rank then takes part in ONE broadcast of *count doubles at *x_dev (ordered on the context's
+ * stream, see chb_set_stream); the receiving ranks finish with chb_features_commit, which derives the FP32 copy / norms the
+ * set_features calls derive (asynchronous as for chb_set_features_async). */
+int chb_features_buffer(chb_ctx *ctx, int64_t n, int32_t d, double **x_dev, int64_t *count);
+int chb_features_commit(chb_ctx *ctx, int asynchronous);
 /* `samples` exactly as the reference holds it: cli/clustering.py:53 takes DataFrame.values of a single float64 block, an
  * F-ordered (n, d) array -- element (r, t) at x_colmajor[t * n + r].  The block is uploaded as it lies in host memory and
  * transposed into the device layout on the device (no host-side np.ascontiguousarray pass).  asynchronous != 0: returns
