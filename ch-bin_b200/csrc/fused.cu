@@ -27,7 +27,7 @@
 //     recipe (sequential sum, no FMA) and are ranked by exact (distance, index).  A pair goes to the QP work list only
 //     if its neighbour SET changed.  Pairs whose kept lists could be incomplete (more than KR keys inside the window:
 //     duplicate contigs) are redone exactly on the device by exact_pairs_kernel.
-//  5. k > 15 (a half-list of KR = 16 register entries must hold more than k candidates): steps 3-4 are replaced by an exact selection over every pair
+//  5. k > 24 (one of the two 16-entry half-lists would overflow for most pairs): steps 3-4 are replaced by an exact selection over every pair
 //     that survived step 2, regrouped per bin so that eight queries share each member row (exact_group_kernel).
 //
 // Roofline of gram_select_kernel: tensor pipe, co-limited by the CUDA-core selection epilogue.
@@ -252,7 +252,9 @@ __global__ void split2_gather_kernel(const int32_t *__restrict__ idx, const int3
 // and the contraction error is bounded by eps |a_q| max_i |y_i| -- the column vectors are now in-bin offsets.
 // The brackets are evaluated in FP64 from the FP32 operand values actually contracted and rounded once.
 // ---------------------------------------------------------------------------------------------------------
-// one block per bin: sum of its seed contigs (initial labels), in index order -- the same bits on every rank
+// one block per bin: sum of its seed contigs (initial labels) in a FIXED order -- eight interleaved partial sums over the
+// (bin, index)-ordered seed list, combined pairwise -- so that every rank gets the same bits; eight independent loads are
+// in flight per thread instead of one dependent chain of gathers
 __global__ void __launch_bounds__(256) centre_sum_kernel(const double *__restrict__ X, int32_t ldx, int32_t d,
                                                          const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
                                                          double *__restrict__ sum, int32_t *__restrict__ cnt)
@@ -260,9 +262,17 @@ __global__ void __launch_bounds__(256) centre_sum_kernel(const double *__restric
     const int c = blockIdx.x;
     const int b = seed_off[c], e = seed_off[c + 1];
     for (int t = threadIdx.x; t < d; t += blockDim.x) {
-        double s = 0.0;
-        for (int i = b; i < e; ++i) s += X[(int64_t)seed_idx[i] * ldx + t];
-        sum[(int64_t)c * d + t] = s;
+        double s[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        int i = b;
+        for (; i + 8 <= e; i += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = X[(int64_t)seed_idx[i + u] * ldx + t];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s[u] += v[u];
+        }
+        for (int u = 0; i < e; ++i, ++u) s[u] += X[(int64_t)seed_idx[i] * ldx + t];
+        sum[(int64_t)c * d + t] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
     }
     if (threadIdx.x == 0) cnt[c] = e - b;
 }
@@ -724,19 +734,23 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
                                                           int32_t *__restrict__ mode)
 {
     __shared__ int s_mode, s_ti, s_tt;
+    constexpr int PLAN_SMEM_BINS = 2048;
+    __shared__ int s_nb[PLAN_SMEM_BINS], s_w[PLAN_SMEM_BINS];
     int32_t *item_off = scratch, *tile_cum = scratch + C + 1;
     const int tid = threadIdx.x;
+    const bool in_smem = C <= PLAN_SMEM_BINS; // the serial prefix below then walks shared memory instead of L2
     // per-bin block and tile counts first (all threads, coalesced), then one thread runs the three prefix sums over them
     for (int c = tid; c < C; c += 1024) {
-        item_off[c] = (bin_surv[c] + BM - 1) / BM;
-        tile_cum[c] = (seg_off[c + 1] - seg_off[c]) / BN;
+        const int nb = (bin_surv[c] + BM - 1) / BM, w = (seg_off[c + 1] - seg_off[c]) / BN;
+        if (in_smem) { s_nb[c] = nb; s_w[c] = w; }
+        else { item_off[c] = nb; tile_cum[c] = w; }
     }
     __syncthreads();
     if (tid == 0) {
         int64_t po = 0;
         int io = 0, tc = 0;
         for (int c = 0; c < C; ++c) {
-            const int nb = item_off[c], w = tile_cum[c];
+            const int nb = in_smem ? s_nb[c] : item_off[c], w = in_smem ? s_w[c] : tile_cum[c];
             pair_off[c] = (int32_t)po;
             item_off[c] = io;
             tile_cum[c] = tc;
@@ -1458,6 +1472,11 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
             // a half-list that is full and entirely inside the slack may have dropped a closer point
             const unsigned lo_half = (1u << KR) - 1u;
             if (hi > t0v || __popc(cm & lo_half) == KR || __popc(cm >> KR) == KR) ovf = true;
+        } else if (k >= KR) {
+            // "at most k candidates" only means "the bin has at most k visible members" if no half-list is full: with k >= KR
+            // a full half-list may have dropped members (k < KR: nc <= k < KR, no half-list can be full)
+            const unsigned lo_half = (1u << KR) - 1u;
+            if (__popc(vm & lo_half) == KR || __popc(vm >> KR) == KR) ovf = true;
         }
         // ambiguous candidates: exact scipy-recipe distance, rank by (distance, index)
         const bool amb = big && __popc(cm) != k && could && !sure;
@@ -1620,7 +1639,7 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Large neighbour counts (k > 15: the 16-entry register lists of the fused kernel cannot hold k + 1 candidates): exact selection for
+// Large neighbour counts (k > FUSED_KMAX: the 16-entry register half-lists of the fused kernel overflow for most pairs): exact selection for
 // EVERY surviving (row, bin) pair.  With one pair per CTA every member row of the bin travels L2 -> SM once per pair and the
 // L2 fabric is the bound; here the surviving pairs are regrouped per bin and XS_G queries of one bin share every member row
 // they read (XS_G x fewer bytes, XS_G independent FP64 chains per thread), which leaves the FP64 pipe as the bound
@@ -1633,6 +1652,11 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict
 //               answer (distance_matrix.py:47-62, ties resolved by index as everywhere in this library).
 // Bins larger than one pass are walked in chunks: the k kept so far stay at the front of the query's array.
 constexpr int XS_G = 8, XS_THREADS = 32 * XS_G, XS_CHUNK = 4 * XS_THREADS, XS_KEEP = 32, XS_CAP = XS_CHUNK + XS_KEEP, XS_CAND = 128;
+// largest k that goes through the fused tensor-core kernel's two 16-entry half-lists: the k + 1 smallest keys must all be kept,
+// which holds unless one 64-column half holds 16 or more of them (the re-rank detects that and has the pair redone exactly).
+// The members of a bin fall into the halves at random, so up to k = 24 that is the exception (a few per cent of the pairs at
+// k = 20, about one in six at k = 24); beyond it is the rule and the exact selection below takes every pair.
+constexpr int FUSED_KMAX = 24;
 // XS_KEEP = the largest k the fused mode accepts (chb_fused_supported)
 
 __device__ __forceinline__ bool comp_lt(unsigned long long ka, int ia, unsigned long long kb, int ib)
@@ -2144,7 +2168,7 @@ int chb_fused_setup(chb_ctx *c)
         // pairs redone on exact distances: a few per row when they are the exception (k <= 15), every pair that survives
         // the pruning otherwise -- possibly all of them; + XS_G * C: that path pads every bin's range of the list to a
         // multiple of XS_G (exact_group_kernel)
-        const int64_t per_row = (c->k > 15) ? C : std::min<int64_t>(C, 8);
+        const int64_t per_row = (c->k > FUSED_KMAX) ? C : std::min<int64_t>(C, c->k > 15 ? 16 : 8);
         const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * per_row, 1024), INT32_MAX - 16 * (int64_t)C - 16);
         if (c->f_fb_alloc < fbc + 8 * (int64_t)C + 8) {
             int64_t z = 0;
@@ -2263,10 +2287,10 @@ int chb_round_fused(chb_ctx *c)
             c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb,
             c->f_row_bins, c->f_pair_meta, c->f_skip);
     }
-    // KR = 16 serves k <= 15: the re-rank needs the (k+1)-th key, and a half-list can only be full when more than k candidates
-    // exist, which is what arms its completeness test (k + 3 <= KR merely keeps that test from firing often; at k = 14, 15 it
-    // still fires only when nearly all of the k nearest fall into the same 64-column halves)
-    if (k > 15) {
+    // KR = 16 serves k <= FUSED_KMAX: the re-rank needs the k + 1 smallest keys of the pair; they are all among the kept 2 x 16
+    // unless one 64-column half holds 16 or more of them, which the re-rank's completeness tests detect (exact redo).  k + 3 <= KR
+    // merely keeps those tests from firing often for small k.
+    if (k > FUSED_KMAX) {
         // ---- 3'. large k: exact selection for every surviving pair (find_nearest_from_cluster on exact distances)
         chb_stage_timer t(c, CHB_ST_KNN);
         // surviving pairs regrouped per bin (threshold_kernel counted them per bin), XS_G queries of a bin per CTA pass
@@ -2325,10 +2349,14 @@ int chb_round_fused(chb_ctx *c)
             exact_pairs_kernel<5><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt, c->f_col_pt,
                                                               c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pos, C,
                                                               k, c->knn_idx, c->knn_cnt, c->work, c->counters);
-        else
+        else if (k <= 15)
             exact_pairs_kernel<15><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
                                                                c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot,
                                                                c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
+        else
+            exact_pairs_kernel<FUSED_KMAX><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
+                                                                       c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
+                                                                       c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;
@@ -2340,7 +2368,7 @@ extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslot
     CHB_CHECK(c, c && key_out && idx_out && slack_out && kr_out, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->f_cand_key && c->f_slack && slot0 >= c->u0 && nslots >= 0 && slot0 + nslots <= c->u1, CHB_EINVAL,
               "slots not owned / no fused round has run yet");
-    CHB_CHECK(c, c->k <= 15, CHB_EINVAL, "no candidate lists exist for num_neighbors > 15 (exact selection, chb_round_fused)");
+    CHB_CHECK(c, c->k <= FUSED_KMAX, CHB_EINVAL, "no candidate lists exist for num_neighbors > 24 (exact selection, chb_round_fused)");
     CHB_CUDA(c, cudaSetDevice(c->device));
     const int KR = (c->k + 3 <= 8) ? 8 : 16;
     const int64_t nown = c->u1 - c->u0, s0 = slot0 - c->u0, per = (int64_t)c->C * 2 * KR;

@@ -14,10 +14,11 @@ __global__ void __launch_bounds__(256) dfma_kernel(double *out, int iters, doubl
     const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
     if (s == 123.456) out[0] = s; // never true: keeps the chain alive
 }
-// A warp gathers ROWS_IN_FLIGHT pseudo-random 1104-byte "rows" at a time (consecutive lanes read consecutive 16-byte pieces
-// of a row: the access pattern of the QP kernels' neighbour-row gather), all loads of the batch issued before any is
-// consumed, with L2-only loads (ld.global.cg): what a gather with no reuse inside the SM can get from the L2 fabric.
-constexpr int ROWS_IN_FLIGHT = 8;
+// A warp gathers RIF pseudo-random 1104-byte "rows" at a time (consecutive lanes read consecutive 16-byte pieces of a row:
+// the access pattern of the QP kernels' neighbour-row gather), all loads of the batch issued before any is consumed.  The
+// buffer (22 MB) is far larger than an SM's L1 and far smaller than L2, and rows are drawn at random: what a gather with no
+// reuse inside the SM can get from the L2 fabric.  NC = 1: ld.global.nc (the QP kernels' __ldg), 0: ld.global.cg.
+template <int RIF, int NC>
 __global__ void __launch_bounds__(256) l2_read_kernel(const double2 *__restrict__ buf, int64_t nrows, int row_vec, int iters, double *out)
 {
     const int lane = threadIdx.x & 31;
@@ -25,22 +26,22 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const double2 *__restrict_
     double2 acc = make_double2(0.0, 0.0);
     uint64_t r = (uint64_t)gw * 2654435761u + 12345u;
     for (int it = 0; it < iters; ++it) {
-        const double2 *row[ROWS_IN_FLIGHT];
+        const double2 *row[RIF];
 #pragma unroll
-        for (int u = 0; u < ROWS_IN_FLIGHT; ++u) {
+        for (int u = 0; u < RIF; ++u) {
             r = r * 6364136223846793005ull + 1442695040888963407ull;
             row[u] = buf + (int64_t)((r >> 20) % (uint64_t)nrows) * row_vec;
         }
-        double2 v[ROWS_IN_FLIGHT][3]; // row_vec <= 96: at most three 16-byte pieces per lane and row
+        double2 v[RIF][3]; // row_vec <= 96: at most three 16-byte pieces per lane and row
 #pragma unroll
-        for (int u = 0; u < ROWS_IN_FLIGHT; ++u)
+        for (int u = 0; u < RIF; ++u)
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const int e = lane + 32 * q;
-                v[u][q] = e < row_vec ? __ldcg(row[u] + e) : make_double2(0.0, 0.0);
+                v[u][q] = e < row_vec ? (NC ? __ldg(row[u] + e) : __ldcg(row[u] + e)) : make_double2(0.0, 0.0);
             }
 #pragma unroll
-        for (int u = 0; u < ROWS_IN_FLIGHT; ++u)
+        for (int u = 0; u < RIF; ++u)
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 acc.x += v[u][q].x;
@@ -48,6 +49,24 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const double2 *__restrict_
             }
     }
     if (acc.x + acc.y == 123.456) out[0] = acc.x;
+}
+
+template <int RIF, int NC>
+double run_l2_variant(chb_ctx *c, const double2 *buf, int64_t nrows, int row_vec, double *d, cudaEvent_t e0, cudaEvent_t e1)
+{
+    const int iters = 512 / RIF, blocks = c->sm_count * 8;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        l2_read_kernel<RIF, NC><<<blocks, 256, 0, c->stream>>>(buf, nrows, row_vec, iters, d);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double bytes = 16.0 * row_vec * (double)RIF * (double)iters * (256.0 / 32.0) * blocks;
+        if (rep > 0) best = fmax(best, bytes / (ms * 1e-3) / 1e9);
+    }
+    return best;
 }
 } // namespace
 
@@ -65,18 +84,13 @@ extern "C" int chb_measure_l2_gbs(chb_ctx *c, double *gbs)
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    const int iters = 64, blocks = c->sm_count * 8;
+    // the best of a few shapes of the same gather (batch depth, load flavour): the ceiling is what the fabric can deliver
     double best = 0.0;
-    for (int rep = 0; rep < 5; ++rep) {
-        cudaEventRecord(e0, c->stream);
-        l2_read_kernel<<<blocks, 256, 0, c->stream>>>(buf, nrows, row_vec, iters, d);
-        cudaEventRecord(e1, c->stream);
-        cudaEventSynchronize(e1);
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        const double bytes = 16.0 * row_vec * (double)ROWS_IN_FLIGHT * (double)iters * (256.0 / 32.0) * blocks;
-        if (rep > 0) best = fmax(best, bytes / (ms * 1e-3) / 1e9);
-    }
+    best = fmax(best, run_l2_variant<2, 1>(c, buf, nrows, row_vec, d, e0, e1));
+    best = fmax(best, run_l2_variant<4, 1>(c, buf, nrows, row_vec, d, e0, e1));
+    best = fmax(best, run_l2_variant<8, 1>(c, buf, nrows, row_vec, d, e0, e1));
+    best = fmax(best, run_l2_variant<4, 0>(c, buf, nrows, row_vec, d, e0, e1));
+    best = fmax(best, run_l2_variant<8, 0>(c, buf, nrows, row_vec, d, e0, e1));
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     cudaFree(buf);
