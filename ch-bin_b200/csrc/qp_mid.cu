@@ -79,6 +79,7 @@ __global__ void __launch_bounds__(WARPS * 32) qp_mid_kernel(chb_qp_args a, int2 
                                                              int32_t *__restrict__ fallback_count)
 {
     __shared__ __align__(16) double sG[WARPS][NPP * 32]; // [entry][pair-in-warp-batch]
+    __shared__ int sI[WARPS][32][12];                     // per pair of the batch: m, query point, up to 10 neighbour points
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & (GL - 1), grp = lane / GL;
     const int64_t n_work = a.work_count ? (int64_t)*a.work_count : a.n_work;
@@ -87,35 +88,51 @@ __global__ void __launch_bounds__(WARPS * 32) qp_mid_kernel(chb_qp_args a, int2 
     double *sg_w = sG[warp];
 
     for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * 32; base < n_work; base += stride) {
+        // ---------------- phase 0: lane l fetches the indices of pair l of the batch (work item -> neighbour count ->
+        // neighbour points: three dependent loads, paid once per batch instead of once per sub-step) and keeps what phase 2
+        // needs in its own registers
+        const int64_t my_item = base + lane;
+        const bool my_valid = my_item < n_work;
+        int2 my_wk = make_int2(0, 0);
+        int64_t my_pair = 0;
+        int my_m = 0;
+        {
+            int qpt = 0;
+            if (my_valid) {
+                my_wk = a.work[my_item];
+                my_pair = (int64_t)my_wk.x * C + my_wk.y;
+                my_m = a.knn_cnt[my_pair];
+                qpt = a.row_point[my_wk.x];
+            }
+            sI[warp][lane][0] = my_m;
+            sI[warp][lane][1] = qpt;
+#pragma unroll
+            for (int r = 0; r < M; ++r) sI[warp][lane][2 + r] = (my_valid && r < my_m) ? a.knn_idx[my_pair * k + r] : qpt; // r >= m: W row = 0
+        }
+        __syncwarp();
         // ---------------- phase 1: Gram matrices of 32 pairs, 4 at a time
 #pragma unroll 1
         for (int sub = 0; sub < 8; ++sub) {
-            const int64_t item = base + sub * QPW + grp;
-            const bool valid = item < n_work;
-            int m = 0;
-            int64_t pair = 0;
-            int2 wk = make_int2(0, 0);
-            if (valid) {
-                wk = a.work[item];
-                pair = (int64_t)wk.x * C + wk.y;
-                m = a.knn_cnt[pair];
-            }
+            if (base + (int64_t)sub * QPW >= n_work) break; // warp-uniform
+            const int slot = sub * QPW + grp; // pair index inside the warp batch = the lane that will solve it
+            const int m = sI[warp][slot][0];
+            const double *xq = a.X + (int64_t)sI[warp][slot][1] * ldx;
             const double *rows[M];
-            const double *xq = a.X;
-            if (m > 0) xq = a.X + (int64_t)a.row_point[wk.x] * ldx;
 #pragma unroll
-            for (int r = 0; r < M; ++r) rows[r] = (r < m) ? a.X + (int64_t)a.knn_idx[pair * k + r] * ldx : a.X;
+            for (int r = 0; r < M; ++r) rows[r] = a.X + (int64_t)sI[warp][slot][2 + r] * ldx;
             double acc[NPP];
 #pragma unroll
             for (int i = 0; i < NPP; ++i) acc[i] = 0.0;
             for (int c0 = 0; c0 < ldx; c0 += 2 * GL) {
+                // a column beyond the row is replaced by column 0 of the QUERY row for every row: w - x = 0 there, exactly as
+                // for the rows r >= m, which point at the query row altogether
                 const int col = c0 + 2 * g;
-                const bool inb = (col < ldx) && (m > 0);
-                const double2 xv = inb ? __ldg(reinterpret_cast<const double2 *>(xq + col)) : make_double2(0.0, 0.0);
+                const bool inb = col < ldx;
+                const double2 xv = __ldg(reinterpret_cast<const double2 *>(xq + (inb ? col : 0)));
                 double2 w[M];
 #pragma unroll
                 for (int r = 0; r < M; ++r) {
-                    w[r] = (inb && r < m) ? __ldg(reinterpret_cast<const double2 *>(rows[r] + col)) : xv;
+                    w[r] = __ldg(reinterpret_cast<const double2 *>((inb ? rows[r] : xq) + (inb ? col : 0)));
                     w[r].x -= xv.x;
                     w[r].y -= xv.y;
                 }
@@ -150,23 +167,16 @@ __global__ void __launch_bounds__(WARPS * 32) qp_mid_kernel(chb_qp_args a, int2 
                 const double keep = hi ? v14[i + 7] : v14[i];
                 v7[i] = keep + __shfl_xor_sync(CHB_FULL, send, 1);
             }
-            const int slot = sub * QPW + grp; // pair index inside the warp batch = the lane that will solve it
 #pragma unroll
             for (int i = 0; i < 7; ++i) sg_w[(7 * g + i) * 32 + slot] = v7[i];
         }
         __syncwarp();
 
         // ---------------- phase 2: one lane per pair
-        const int64_t item = base + lane;
-        const bool valid = item < n_work;
-        int m = 0;
-        int64_t pair = 0;
-        int2 wk = make_int2(0, 0);
-        if (valid) {
-            wk = a.work[item];
-            pair = (int64_t)wk.x * C + wk.y;
-            m = a.knn_cnt[pair];
-        }
+        const bool valid = my_valid;
+        const int m = my_m;
+        const int64_t pair = my_pair;
+        const int2 wk = my_wk;
         const double *sg = sg_w + lane;
         double alpha[M];
 #pragma unroll

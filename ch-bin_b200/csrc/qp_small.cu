@@ -99,10 +99,11 @@ __device__ __forceinline__ bool eval_face(const double (&G)[15], unsigned mask, 
     return ok && (obj == obj);
 }
 
-__global__ void __launch_bounds__(WARPS * 32) qp_small_kernel(chb_qp_args a, int2 *__restrict__ fallback,
+__global__ void __launch_bounds__(WARPS * 32, 4) qp_small_kernel(chb_qp_args a, int2 *__restrict__ fallback,
                                                                int32_t *__restrict__ fallback_count)
 {
     __shared__ __align__(16) double sG[WARPS][16 * 32]; // [entry][pair of the warp batch]
+    __shared__ int sI[WARPS][32][8];                     // per pair of the batch: m, query point, 5 neighbour points
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane & (GL - 1), grp = lane / GL;
     const int64_t n_work = a.work_count ? (int64_t)*a.work_count : a.n_work;
@@ -116,25 +117,40 @@ __global__ void __launch_bounds__(WARPS * 32) qp_small_kernel(chb_qp_args a, int
     const int64_t stride = nwarps * per_batch;
 
     for (int64_t base = ((int64_t)blockIdx.x * WARPS + warp) * per_batch; base < n_work; base += stride) {
+        // ---------------- phase 0: lane l fetches the indices of pair l of the batch (work item -> neighbour count ->
+        // neighbour points: three dependent loads, paid once per batch instead of once per sub-step) and keeps what phase 2
+        // needs in its own registers
+        const int64_t my_item = base + lane;
+        const bool my_valid = lane < per_batch && my_item < n_work;
+        int2 my_wk = make_int2(0, 0);
+        int64_t my_pair = 0;
+        int my_m = 0;
+        {
+            int qpt = 0, nb[5] = {0, 0, 0, 0, 0};
+            if (my_valid) {
+                my_wk = a.work[my_item];
+                my_pair = (int64_t)my_wk.x * C + my_wk.y;
+                my_m = a.knn_cnt[my_pair];
+                qpt = a.row_point[my_wk.x];
+#pragma unroll
+                for (int r = 0; r < 5; ++r) nb[r] = (r < my_m) ? a.knn_idx[my_pair * k + r] : qpt; // r >= m: the query itself, W row = 0
+            }
+            sI[warp][lane][0] = my_m;
+            sI[warp][lane][1] = qpt;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) sI[warp][lane][2 + r] = nb[r];
+        }
+        __syncwarp();
         // ---------------- phase 1: Gram matrices of 4 * nsub pairs, 4 at a time
 #pragma unroll 1
         for (int sub = 0; sub < nsub; ++sub) {
             if (base + (int64_t)sub * QPW >= n_work) break; // warp-uniform
-            const int64_t item = base + sub * QPW + grp;
-            const bool valid = item < n_work;
-            int m = 0;
-            int64_t pair = 0;
-            int2 wk = make_int2(0, 0);
-            if (valid) {
-                wk = a.work[item];
-                pair = (int64_t)wk.x * C + wk.y;
-                m = a.knn_cnt[pair];
-            }
+            const int slot = sub * QPW + grp; // pair index inside the warp batch = the lane that solves it
+            const int m = sI[warp][slot][0];
+            const double *xq = a.X + (int64_t)sI[warp][slot][1] * ldx;
             const double *rows[5];
-            const double *xq = a.X;
-            if (m > 0) xq = a.X + (int64_t)a.row_point[wk.x] * ldx;
 #pragma unroll
-            for (int r = 0; r < 5; ++r) rows[r] = (r < m) ? a.X + (int64_t)a.knn_idx[pair * k + r] * ldx : a.X;
+            for (int r = 0; r < 5; ++r) rows[r] = a.X + (int64_t)sI[warp][slot][2 + r] * ldx;
 
             double acc[16];
 #pragma unroll
@@ -143,12 +159,13 @@ __global__ void __launch_bounds__(WARPS * 32) qp_small_kernel(chb_qp_args a, int
                 double2 xv[NCH], w[5][NCH];
 #pragma unroll
                 for (int i = 0; i < NCH; ++i) {
+                    // a column beyond the row (last chunk) is replaced by column 0 of the QUERY row for every row: w - x = 0
+                    // there, exactly as for the rows r >= m, which point at the query row altogether
                     const int col = c0 + i * (2 * GL) + 2 * g;
-                    const bool inb = (col < ldx) && (m > 0);
-                    xv[i] = inb ? __ldg(reinterpret_cast<const double2 *>(xq + col)) : make_double2(0.0, 0.0);
+                    const bool inb = col < ldx;
+                    xv[i] = __ldg(reinterpret_cast<const double2 *>(xq + (inb ? col : 0)));
 #pragma unroll
-                    for (int r = 0; r < 5; ++r)
-                        w[r][i] = (inb && r < m) ? __ldg(reinterpret_cast<const double2 *>(rows[r] + col)) : xv[i];
+                    for (int r = 0; r < 5; ++r) w[r][i] = __ldg(reinterpret_cast<const double2 *>((inb ? rows[r] : xq) + (inb ? col : 0)));
                 }
 #pragma unroll
                 for (int i = 0; i < NCH; ++i)
@@ -190,19 +207,16 @@ __global__ void __launch_bounds__(WARPS * 32) qp_small_kernel(chb_qp_args a, int
                 const double keep = hi ? v4[i + 2] : v4[i];
                 v2[i] = keep + __shfl_xor_sync(CHB_FULL, send, 1);
             }
-            const int slot = sub * QPW + grp; // pair index inside the warp batch = the lane that solves it
             sg_w[(2 * g) * 32 + slot] = v2[0];
             sg_w[(2 * g + 1) * 32 + slot] = v2[1];
         }
         __syncwarp();
 
         // ---------------- phase 2: one lane per pair
-        const int64_t item = base + lane;
-        const bool valid = lane < per_batch && item < n_work;
-        if (valid) {
-            const int2 wk = a.work[item];
-            const int64_t pair = (int64_t)wk.x * C + wk.y;
-            const int m = a.knn_cnt[pair];
+        if (my_valid) {
+            const int2 wk = my_wk;
+            const int64_t pair = my_pair;
+            const int m = my_m;
             if (m <= 0) {
                 a.dist[pair] = INFINITY;
                 if (a.status) a.status[pair] = CHB_QP_EMPTY_BIN;
