@@ -832,6 +832,7 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     CHB_CHECK(c, bins && C >= 1, CHB_EINVAL, "initial_bins is NULL or num_clusters < 1");
     CHB_CUDA(c, cudaSetDevice(c->device));
     c->labels_set = false; // the staging block (and with it the host mirror of the slots) is rewritten below
+    c->labels_staged = false;
     // Host staging in ONE page-locked block: lab[n] | qslot[n] | qpoint[n] | seed_idx[n] | seed_off[C + 1].  Copies from
     // page-locked memory neither stage nor wait for earlier work on the stream, so they (and the host loops here) overlap a
     // feature upload still in flight (chb_set_features_async).  The block is rewritten by the next chb_set_labels only.
@@ -967,6 +968,8 @@ int chb_build_distance_matrix(chb_ctx *c, int materialise)
         CHB_TRY(dev_reserve(c, &c->Ascratch, &c->cap_Ascratch, srows * c->lda));
         c->scratch_rows = srows;
         c->materialise = false;
+        c->dist_ready = true; // nothing was enqueued: no synchronisation either (the label set-up keeps running underneath)
+        return CHB_OK;
     } else if (filt) {
         dev_free(&c->Dq); c->cap_Dq = 0;
         dev_free(&c->Dscratch); c->cap_scratch = 0;
@@ -1159,6 +1162,7 @@ static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bo
     CHB_CUDA(c, cudaSetDevice(c->device));
     CHB_TRY(ensure_caches(c));
     c->own_pos_by_slot = false;
+    c->labels_staged = false;
     if (use_fused(c) && U > 0) {
         // Device path (distance mode 2): the permutation is uploaded as it is and turned into perm_pt / pos / own_pos by
         // one kernel; its validation travels with the next commit's read-back (no host pass over U, no host mirror).
@@ -1357,6 +1361,26 @@ static int resolve_perm_check(chb_ctx *c)
     return chb_fail(c, CHB_EINVAL, "permutation repeats point %lld", (long long)pt);
 }
 
+// Labels widened to the caller's int64 on the device and copied into the page-locked staging block (enqueued only)
+constexpr int64_t LABEL_STAGE_MAX = 1 << 18;
+static int stage_labels(chb_ctx *c, const int32_t *lab_dev)
+{
+    CHB_TRY(dev_reserve(c, &c->lab64, &c->cap_lab64, c->n));
+    if (c->pin_lab_cap < c->n) {
+        CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (c->pin_lab64) cudaFreeHost(c->pin_lab64);
+        c->pin_lab64 = nullptr;
+        c->pin_lab_cap = 0;
+        CHB_CUDA(c, cudaMallocHost(reinterpret_cast<void **>(&c->pin_lab64), sizeof(int64_t) * (size_t)c->n));
+        c->pin_lab_cap = c->n;
+    }
+    widen_labels_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(lab_dev, c->n, c->lab64);
+    CHB_CUDA(c, cudaGetLastError());
+    ++c->tm.launches_other;
+    CHB_CUDA(c, cudaMemcpyAsync(c->pin_lab64, c->lab64, sizeof(int64_t) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
+    return CHB_OK;
+}
+
 // Commit of one round; with n_changed != NULL also the end of the iteration when the round changed nothing and its window
 // reached the last position -- decided on the device, so that the common "one round settles the iteration" case costs ONE
 // host synchronisation instead of two.
@@ -1378,9 +1402,16 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
         chb_stage_timer t(c, CHB_ST_COMMIT);
         commit_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters);
     }
+    bool staged = false;
     if (may_end) {
         end_if_done_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->old_label, c->tent_pt, c->n, c->counters);
         ++c->tm.launches_other;
+        if (c->n <= LABEL_STAGE_MAX) {
+            // if this commit ends the iteration the caller may well ask for the labels next: they travel with the counters
+            // (old_label holds them once end_if_done_kernel has run; if the iteration goes on the copy is simply not used)
+            CHB_TRY(stage_labels(c, c->old_label));
+            staged = true;
+        }
     }
     CHB_CUDA(c, cudaGetLastError());
     CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[1], &c->counters[1], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
@@ -1402,6 +1433,7 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
         *n_changed = c->counters_host[2];
         if (iteration_done) *iteration_done = 1;
         c->in_iteration = false;
+        c->labels_staged = staged;
     }
     return CHB_OK;
 }
@@ -1445,21 +1477,10 @@ int chb_get_labels(chb_ctx *c, int64_t *labels_out)
     CHB_CHECK(c, c && labels_out, CHB_EINVAL, "NULL argument");
     CHB_CHECK(c, c->labels_set, CHB_EINVAL, "labels not set");
     CHB_CUDA(c, cudaSetDevice(c->device));
-    // widened to the caller's int64 on the device, then one copy straight into labels_out (no host pass over n)
-    CHB_TRY(dev_reserve(c, &c->lab64, &c->cap_lab64, c->n));
-    widen_labels_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->in_iteration ? c->tent_pt : c->old_label, c->n, c->lab64);
-    CHB_CUDA(c, cudaGetLastError());
-    ++c->tm.launches_other;
-    // through a page-locked staging block (full PCIe rate), then one memcpy into the caller's pageable array
-    if (c->pin_lab_cap < c->n) {
-        if (c->pin_lab64) cudaFreeHost(c->pin_lab64);
-        c->pin_lab64 = nullptr;
-        c->pin_lab_cap = 0;
-        CHB_CUDA(c, cudaMallocHost(reinterpret_cast<void **>(&c->pin_lab64), sizeof(int64_t) * (size_t)c->n));
-        c->pin_lab_cap = c->n;
+    if (!(c->labels_staged && !c->in_iteration)) { // else: they came back with the commit that ended the last iteration
+        CHB_TRY(stage_labels(c, c->in_iteration ? c->tent_pt : c->old_label));
+        CHB_TRY(sync_stream(c));
     }
-    CHB_CUDA(c, cudaMemcpyAsync(c->pin_lab64, c->lab64, sizeof(int64_t) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
-    CHB_TRY(sync_stream(c));
     memcpy(labels_out, c->pin_lab64, sizeof(int64_t) * (size_t)c->n);
     return CHB_OK;
 }

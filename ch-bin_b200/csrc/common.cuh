@@ -73,6 +73,7 @@ struct chb_ctx {
     int64_t cap_lab64 = 0;
     int64_t *pin_lab64 = nullptr; // page-locked staging block of chb_get_labels
     int64_t pin_lab_cap = 0;
+    bool labels_staged = false; // pin_lab64 holds the current labels (they travelled with the commit that ended the iteration)
     int32_t *slot_tiles = nullptr; // per-1024-point tile counts / offsets of the slot scan
     int64_t cap_slot_tiles = 0;
     std::vector<uint8_t> h_seen;

@@ -1254,6 +1254,10 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // Columns above T0 are skipped by the fused kernel without touching the per-thread lists.  T0 = +inf when there is no
 // usable cache (first round, fewer than k members, a member left the bin, exact-path fallback row).
 // ---------------------------------------------------------------------------------------------------------
+// THR_ROWS rows per thread: 4 (16-byte loads of the per-row tables, 16-byte stores of the pruned thresholds) when the pair
+// table is large and nearly everything is pruned -- the kernel is then a stream over 8 bytes per pair; 1 when it is small and
+// the surviving pairs' work (serial per thread) sets the time
+template <int THR_ROWS>
 __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
                                  const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
                                  const int32_t *__restrict__ pos, const int32_t *__restrict__ tent, const int32_t *__restrict__ old,
@@ -1265,64 +1269,101 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
                                  int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv,
                                  uint8_t *__restrict__ skip)
 {
-    // grid: x = chunks of 256 rows (two 128-row blocks of the fused kernel), y = bin.  Besides the per-pair tables the block
-    // leaves skip[row block][bin] = "every row of the block pruned the bin": the (row block, bin) work items of the
-    // uncompacted path, without a second pass over the threshold table.
-    __shared__ int s_alive[2];
+    // grid: x = chunks of 1024 rows (eight 128-row blocks of the fused kernel; a thread takes 4 consecutive rows, a warp one
+    // 128-row block), y = bin.  Besides the per-pair tables the block leaves skip[row block][bin] = "every row of the block
+    // pruned the bin": the (row block, bin) work items of the uncompacted path, without a second pass over the thresholds.
     const int c = blockIdx.y;
-    const int64_t r = (int64_t)blockIdx.x * 256 + threadIdx.x; // row (rows are the owned slots ordered by guessed bin)
-    if (threadIdx.x < 2) s_alive[threadIdx.x] = 0;
-    __syncthreads();
-    bool alive = false;
-    if (r < nown) {
-        const float tq = tq_tab[(int64_t)c * ldt + r];
-        alive = true;
-        // pruning (97-99 % of the pairs end here, so this test is all FP32 and touches nothing per pair but tq and t0):
-        // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test.
-        // Only the CONVEX hull of k members lies inside the ball around m_c: an affine hull is unbounded and may pass close to a
-        // query far from every member, so the affine metrics (hull_distance.py:38-87) keep every bin (prune == 0).
-        if (prune) {
-            const float dq = __fsqrt_rd(tq), ym = __fmul_ru(__fsqrt_ru(ym2[c]), 1.000001f), ub = ub_row[r];
-            const float scale = sq_row[r] + __fsqrt_ru(__uint_as_float(*nrm_max_bits));
-            if (dq * 0.999999f - ym > ub + 1e-5f * (dq + ym + ub) + 4e-6f * scale) {
-                t0_tab[(int64_t)c * ldt + r] = -INFINITY; // no candidates, no re-rank, no QP; argmin never looks at the pair
-                alive = false;
-            }
+    const int lane = threadIdx.x & 31;
+    const int64_t r0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * THR_ROWS; // first row (rows = owned slots ordered by guessed bin)
+    bool any_alive = false;
+    if (r0 < nown) { // ldt is a multiple of 128 and the tables are allocated up to it: whole float4s may be touched
+        float tqv[4], ubv[4], sqv[4];
+        if (THR_ROWS == 4) {
+            const float4 tq4 = *reinterpret_cast<const float4 *>(tq_tab + (int64_t)c * ldt + r0);
+            const float4 ub4 = *reinterpret_cast<const float4 *>(ub_row + r0);
+            const float4 sq4 = *reinterpret_cast<const float4 *>(sq_row + r0);
+            tqv[0] = tq4.x; tqv[1] = tq4.y; tqv[2] = tq4.z; tqv[3] = tq4.w;
+            ubv[0] = ub4.x; ubv[1] = ub4.y; ubv[2] = ub4.z; ubv[3] = ub4.w;
+            sqv[0] = sq4.x; sqv[1] = sq4.y; sqv[2] = sq4.z; sqv[3] = sq4.w;
+        } else {
+            tqv[0] = tq_tab[(int64_t)c * ldt + r0];
+            ubv[0] = ub_row[r0];
+            sqv[0] = sq_row[r0];
         }
-        if (alive) {
-            row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
-            atomicAdd(&bin_surv[c], 1);
-            const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
-            const int jq = row_point[r];
-            const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
-            slack_tab[(int64_t)c * ldt + r] = E;
-            float out = INFINITY;
-            if (knn_cnt[pair] == k) {
-                const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
-                if (ub < INFINITY) {
-                    const int p = pos[jq];
-                    bool ok = true;
-                    for (int s = 0; s < k; ++s) {
-                        const int j = knn_idx[pair * k + s];
-                        const int ps = pos[j];
-                        const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
-                        ok = ok && (lab == c);
+        const float ym = __fmul_ru(__fsqrt_ru(ym2[c]), 1.000001f), amax = __fsqrt_ru(__uint_as_float(*nrm_max_bits));
+        float t0v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        bool alive[4] = {false, false, false, false};
+#pragma unroll
+        for (int u = 0; u < THR_ROWS; ++u) {
+            alive[u] = r0 + u < nown;
+            t0v[u] = -INFINITY;
+            // pruning (97-99 % of the pairs end here, so this test is all FP32 and touches nothing per pair but tq and t0):
+            // LB = |a_q - m_c| - max|y| > UB, with a margin far above the FP32 roundings of the operands and of this test.
+            // Only the CONVEX hull of k members lies inside the ball around m_c: an affine hull is unbounded and may pass close
+            // to a query far from every member, so the affine metrics (hull_distance.py:38-87) keep every bin (prune == 0).
+            if (alive[u] && prune) {
+                const float dq = __fsqrt_rd(tqv[u]), ub = ubv[u];
+                const float scale = sqv[u] + amax;
+                if (dq * 0.999999f - ym > ub + 1e-5f * (dq + ym + ub) + 4e-6f * scale) alive[u] = false;
+            }
+            any_alive = any_alive || alive[u];
+        }
+        if (any_alive) {
+#pragma unroll
+            for (int u = 0; u < THR_ROWS; ++u) {
+                if (!alive[u]) continue;
+                const int64_t r = r0 + u;
+                const float tq = tqv[u];
+                row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
+                atomicAdd(&bin_surv[c], 1);
+                const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
+                const int jq = row_point[r];
+                const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
+                slack_tab[(int64_t)c * ldt + r] = E;
+                float out = INFINITY;
+                if (knn_cnt[pair] == k) {
+                    const float ub = thr[pair]; // upper bound on the true squared distance of every cached neighbour (re-rank)
+                    if (ub < INFINITY) {
+                        const int p = pos[jq];
+                        bool ok = true;
+                        for (int s = 0; s < k; ++s) {
+                            const int j = knn_idx[pair * k + s];
+                            const int ps = pos[j];
+                            const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
+                            ok = ok && (lab == c);
+                        }
+                        // this round's keys of the cached neighbours are <= ub + E, so is the k-th smallest key a_k, and the
+                        // re-rank looks no further than a_k + 2E
+                        if (ok) out = __fadd_ru(ub, __fmul_ru(3.f, E));
                     }
-                    // this round's keys of the cached neighbours are <= ub + E, so is the k-th smallest key a_k, and the
-                    // re-rank looks no further than a_k + 2E
-                    if (ok) out = __fadd_ru(ub, __fmul_ru(3.f, E));
                 }
+                // no usable cache: in the query's guessed bin the k-th nearest SEED bounds the k-th smallest squared distance
+                if (out == INFINITY && c == row_guess[r] && ubk2_row[r] < INFINITY) out = __fadd_ru(ubk2_row[r], __fmul_ru(3.f, E));
+                t0v[u] = out;
             }
-            // no usable cache: in the query's guessed bin the k-th nearest SEED bounds the k-th smallest squared distance
-            if (out == INFINITY && c == row_guess[r] && ubk2_row[r] < INFINITY) out = __fadd_ru(ubk2_row[r], __fmul_ru(3.f, E));
-            t0_tab[(int64_t)c * ldt + r] = out;
-            s_alive[threadIdx.x >> 7] = 1;
         }
+        // rows beyond nown inside the last float4 hold -inf as well (never read)
+        if (THR_ROWS == 4) *reinterpret_cast<float4 *>(t0_tab + (int64_t)c * ldt + r0) = make_float4(t0v[0], t0v[1], t0v[2], t0v[3]);
+        else t0_tab[(int64_t)c * ldt + r0] = t0v[0];
     }
-    __syncthreads();
-    if ((threadIdx.x & 127) == 0) {
-        const int64_t rb = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
-        if (rb * BM < nown) skip[rb * C + c] = s_alive[threadIdx.x >> 7] ? 0 : 1;
+    if (THR_ROWS == 4) {
+        // a warp covers exactly one 128-row block
+        const bool warp_alive = __any_sync(CHB_FULL, any_alive);
+        if (lane == 0) {
+            const int64_t rb = ((int64_t)blockIdx.x * 256 + threadIdx.x) * THR_ROWS / BM;
+            if (rb * BM < nown) skip[rb * C + c] = warp_alive ? 0 : 1;
+        }
+    } else {
+        // 256 threads = two 128-row blocks
+        __shared__ int s_alive[2];
+        if (threadIdx.x < 2) s_alive[threadIdx.x] = 0;
+        __syncthreads();
+        if (any_alive) s_alive[threadIdx.x >> 7] = 1;
+        __syncthreads();
+        if ((threadIdx.x & 127) == 0) {
+            const int64_t rb = (int64_t)blockIdx.x * 2 + (threadIdx.x >> 7);
+            if (rb * BM < nown) skip[rb * C + c] = s_alive[threadIdx.x >> 7] ? 0 : 1;
+        }
     }
 }
 
@@ -2280,8 +2321,10 @@ int chb_round_fused(chb_ctx *c)
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
     {
-        dim3 tg(nblk(nown, 256), (unsigned)C);
-        threshold_kernel<<<tg, 256, 0, c->stream>>>(
+        const bool wide = nown * (int64_t)C >= (int64_t)1 << 24; // 16 M pairs and more: a stream over the pair table
+        dim3 tg(nblk(nown, wide ? 1024 : 256), (unsigned)C);
+        auto tk = wide ? threshold_kernel<4> : threshold_kernel<1>;
+        tk<<<tg, 256, 0, c->stream>>>(
             c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
             reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
             c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb,
