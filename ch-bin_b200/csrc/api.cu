@@ -1280,7 +1280,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         CHB_TRY(chb_round_fused(c)); // resets the work counter itself (round_reset_kernel)
         // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the
         // tile / redo counters travel with the commit's read-back
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 7 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
         chb_qp_args q{};
         q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = nown * c->C;
         q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
@@ -1424,6 +1424,13 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
     c->tm.gram_tiles += c->counters_host[8];         // tiles the MMA warps of gram_select_kernel actually issued
     c->counters_host[7] = c->counters_host[8] = 0;
     CHB_TRY(resolve_perm_check(c));
+    if (c->counters_host[12]) {
+        c->counters_host[12] = 0;
+        c->in_iteration = false;
+        return chb_fail(c, CHB_ENOMEM, "the pruning bounds left more (query, bin) pairs than the compact buffers hold and the per-pair candidate "
+                                       "table (%lld x %d pairs) is beyond CHB_DENSE_LIST_GB: raise it or use distance mode 1",
+                        (long long)(c->u1 - c->u0), c->C);
+    }
     if (c->f_fb_cap > 0 && c->counters_host[6] > c->f_fb_cap)
         return chb_fail(c, CHB_ECUDA, "exact-redo list overflow: %d pairs, capacity %d", c->counters_host[6], c->f_fb_cap);
     c->counters_host[6] = 0;

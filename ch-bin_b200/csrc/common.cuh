@@ -141,6 +141,8 @@ struct chb_ctx {
     int32_t *f_slot_row = nullptr;  // owned slot -> row
     float *f_sq_row = nullptr;      // per row: >= |a_q|
     int32_t *f_row_nb = nullptr, *f_row_bins = nullptr; // per row: number / list of the bins that survived pruning this round
+    int32_t *f_row_pid = nullptr;   // per (row, j-th surviving bin): compact pair id of this round (compacted rounds)
+    bool f_cand_dense = true;       // the candidate lists have a slot per (row, bin); false: per compact pair id only
     int64_t f_cap_mc = 0;
     float *f_tq = nullptr, *f_slack = nullptr; // C x f_ldt : |a_q - m_c|^2 and the key error bound per (bin, owned slot)
     int4 *f_items = nullptr;                   // surviving (row block, bin) work items of the fused kernel, row-block order

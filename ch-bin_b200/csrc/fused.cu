@@ -149,7 +149,7 @@ __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_c
     if (i < nown) row_nb[i] = 0;
     if (i < nmeta) pair_meta[i] = 0;
     if (i < cap_pairs) pair_row[i] = -1;
-    if (i == 0) { counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; }
+    if (i == 0) { counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; counters[12] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
                                                           int32_t C, int64_t cap_pairs, int32_t G, int32_t *__restrict__ pair_off,
                                                           int32_t *__restrict__ scratch /* 2 (C + 1) */, int4 *__restrict__ items,
                                                           int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
-                                                          int32_t *__restrict__ mode)
+                                                          int32_t *__restrict__ mode, int32_t dense_ok)
 {
     __shared__ int s_mode, s_ti, s_tt;
     constexpr int PLAN_SMEM_BINS = 2048;
@@ -761,11 +761,25 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
         item_off[C] = io;
         tile_cum[C] = tc;
         s_mode = po <= cap_pairs ? 1 : 0;
+        if (!s_mode && !dense_ok) {
+            // the survivors do not fit the compact buffers and there is no per-(row, bin) list table to fall back on (it
+            // was beyond the memory budget, chb_fused_setup): the round is refused -- no items, nothing filled, nothing
+            // re-ranked -- and the commit reports CHB_ENOMEM
+            s_mode = 2;
+            totals[5] = 1; // counters[12]
+            io = 0;
+            tc = 0;
+        }
         s_ti = io;
         s_tt = tc;
         *mode = s_mode;
     }
     __syncthreads();
+    if (s_mode == 2) {
+        for (int b = tid; b <= G; b += 1024) cta_begin[b] = 0;
+        if (tid == 0) totals[0] = 0;
+        return;
+    }
     if (!s_mode) return; // items_kernel builds the (row block, bin) list instead
     for (int b = tid; b <= G; b += 1024) cta_begin[b] = INT32_MAX;
     __syncthreads();
@@ -795,10 +809,10 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
 __global__ void __launch_bounds__(256) pairs_fill_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ row_nb,
                                                          const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
                                                          const int32_t *__restrict__ pair_off, int32_t *__restrict__ pair_cur,
-                                                         int32_t *__restrict__ pair_row, const float *__restrict__ a2, int32_t Kp2,
-                                                         float *__restrict__ ap)
+                                                         int32_t *__restrict__ pair_row, int32_t *__restrict__ row_pid,
+                                                         const float *__restrict__ a2, int32_t Kp2, float *__restrict__ ap)
 {
-    if (!*mode) return;
+    if (*mode != 1) return;
     const int lane = threadIdx.x & 31;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= nown) return;
@@ -810,6 +824,7 @@ __global__ void __launch_bounds__(256) pairs_fill_kernel(const int32_t *__restri
             const int c = row_bins[r * C + j];
             id = pair_off[c] + atomicAdd(&pair_cur[c], 1);
             pair_row[id] = (int32_t)r;
+            row_pid[r * C + j] = id; // the re-rank finds this pair's candidate lists under its compact id
         }
         id = __shfl_sync(CHB_FULL, id, 0);
         float4 *dst = reinterpret_cast<float4 *>(ap + (int64_t)id * Kp2);
@@ -1228,8 +1243,10 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #undef SCREEN_STEP
             }
             if (rvalid && !wskip) { // the item's (half-)list is complete (pruned rows' lists are never read)
-                float4 *ok = reinterpret_cast<float4 *>(cand_key + ((gr * C + cur_bin) * 2 + half) * KR);
-                int4 *oi = reinterpret_cast<int4 *>(cand_idx + ((gr * C + cur_bin) * 2 + half) * KR);
+                // compacted rounds: one list slot per compact pair id (what this thread's accumulator row is); otherwise per (row, bin)
+                const int64_t lslot = mode ? gid : gr * C + cur_bin;
+                float4 *ok = reinterpret_cast<float4 *>(cand_key + (lslot * 2 + half) * KR);
+                int4 *oi = reinterpret_cast<int4 *>(cand_idx + (lslot * 2 + half) * KR);
 #pragma unroll
                 for (int s = 0; s < KR; s += 4) {
                     ok[s >> 2] = make_float4(L.key[s], L.key[s + 1], L.key[s + 2], L.key[s + 3]);
@@ -1448,8 +1465,11 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
                                                      int2 *__restrict__ work, int32_t *__restrict__ work_count,
                                                      int2 *__restrict__ fb_pairs, int32_t fb_cap, int32_t *__restrict__ fb_count,
                                                      const float *__restrict__ t0_tab, int64_t ldt, float *__restrict__ thr_out,
-                                                     const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins)
+                                                     const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins,
+                                                     const int32_t *__restrict__ row_pid, const int32_t *__restrict__ mode_p)
 {
+    const int mode = *mode_p; // 1: the fused kernel worked on compact (row, bin) pairs and filed the lists under their ids
+    if (mode == 2) return;    // refused round (pairs_plan_kernel): there are no lists
     constexpr int NG = 32 / G;
     constexpr unsigned GM = G == 32 ? 0xffffffffu : ((1u << (G & 31)) - 1u);
     const int lane = threadIdx.x & 31;
@@ -1468,7 +1488,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
         const bool act = j < nb;
         const int c = act ? row_bins[r * C + j] : 0;
         const int64_t pair = sl * C + c;
-        const int64_t rpair = r * C + c;
+        const int64_t rpair = (act && mode) ? (int64_t)row_pid[r * C + j] : r * C + c;
         const float t0v = act ? t0_tab[(int64_t)c * ldt + r] : INFINITY;
         const int mo = act ? knn_cnt[pair] : 0;
         float ka = INFINITY;
@@ -2067,11 +2087,11 @@ void chb_fused_free(chb_ctx *c)
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_pair_row); cudaFree(c->f_pair_meta); cudaFree(c->f_ap); cudaFree(c->f_mode); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
     cudaFree(c->f_ub); cudaFree(c->f_ubk2); cudaFree(c->f_row_guess); cudaFree(c->f_rhist); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
     c->f_tqs = nullptr;
-    c->f_cap_tqs = 0; cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
+    c->f_cap_tqs = 0; cudaFree(c->f_seedT); cudaFree(c->f_row_nb); cudaFree(c->f_row_bins); cudaFree(c->f_row_pid); cudaFree(c->f_slot_row); cudaFree(c->f_sq_row);
     c->f_slot_row = nullptr;
     c->f_sq_row = nullptr;
     c->f_seedT = nullptr;
-    c->f_row_nb = c->f_row_bins = nullptr;
+    c->f_row_nb = c->f_row_bins = c->f_row_pid = nullptr;
     c->f_cap_seedT = 0;
     c->f_mcT = nullptr;
     c->f_guess_all = nullptr;
@@ -2199,11 +2219,25 @@ int chb_fused_setup(chb_ctx *c)
         c->f_cap_cols = ncol_max;
     }
     if (reserve(c, &c->f_bperm, &c->f_cap_bperm, ncol_max * g.Kp2)) return CHB_ENOMEM;
-    if (c->f_cap_cand < nown * C * KR * 2) {
-        int64_t z = 0;
-        z = 0; if (reserve(c, &c->f_cand_key, &z, nown * C * KR * 2)) return CHB_ENOMEM;
-        z = 0; if (reserve(c, &c->f_cand_idx, &z, nown * C * KR * 2)) return CHB_ENOMEM;
-        c->f_cap_cand = nown * C * KR * 2;
+    {
+        // Candidate lists (2 x KR keys + points per pair).  A slot per (row, bin) serves both kinds of round; at 1M contigs x
+        // 500 bins that table alone is 61 GB for the 0.4 % of the pairs that survive the pruning, so beyond a budget
+        // (CHB_DENSE_LIST_GB, default 8) only the compact pair ids get a slot -- rounds whose survivors do not fit the
+        // compact buffers (hardly any pruning at that size) are then refused (pairs_plan_kernel -> CHB_ENOMEM at the commit).
+        const int64_t per = (int64_t)KR * 2;
+        const char *env = getenv("CHB_DENSE_LIST_GB");
+        const double budget = (env ? atof(env) : 8.0) * (double)(1 << 30);
+        const int64_t cap_pairs_now = ((4 * std::max<int64_t>(nown, 1) + (int64_t)BM * C + BM - 1) / BM) * BM;
+        const bool dense = c->k > FUSED_KMAX ? false : (double)(nown * C * per) * 8.0 <= budget;
+        // compacted rounds file the lists under compact pair ids (< cap_pairs, which exceeds nown * C when C < 4 + padding)
+        const int64_t need = c->k > FUSED_KMAX ? 0 : (dense ? std::max<int64_t>(nown * C, cap_pairs_now) : cap_pairs_now) * per;
+        if (c->f_cap_cand < need) {
+            int64_t z = 0;
+            z = 0; if (reserve(c, &c->f_cand_key, &z, need)) return CHB_ENOMEM;
+            z = 0; if (reserve(c, &c->f_cand_idx, &z, need)) return CHB_ENOMEM;
+            c->f_cap_cand = need;
+        }
+        c->f_cand_dense = dense;
     }
     {
         // pairs redone on exact distances: a few per row when they are the exception (k <= 15), every pair that survives
@@ -2238,6 +2272,7 @@ int chb_fused_setup(chb_ctx *c)
         z = 0; if (reserve(c, &c->f_slot_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_sq_row, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_bins, &z, c->f_ldt * C)) return CHB_ENOMEM;
+        z = 0; if (reserve(c, &c->f_row_pid, &z, c->f_ldt * C)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_ubk2, &z, c->f_ldt)) return CHB_ENOMEM;
         z = 0; if (reserve(c, &c->f_row_guess, &z, c->f_ldt)) return CHB_ENOMEM;
         c->f_cap_thr = c->f_ldt * C;
@@ -2357,11 +2392,12 @@ int chb_round_fused(chb_ctx *c)
     // would overflow
     const int64_t plan_cap = getenv("CHB_FUSED_NO_COMPACT") ? -1 : c->f_cap_pairs;
     pairs_plan_kernel<<<1, 1024, 0, c->stream>>>(bin_surv, c->f_seg_off, C, plan_cap, c->sm_count, pair_off,
-                                                 c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode);
+                                                 c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode,
+                                                 c->f_cand_dense ? 1 : 0);
     items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
                                             c->f_mode);
     pairs_fill_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
-                                                                   c->f_pair_row, c->f_a2, g.Kp2, c->f_ap);
+                                                                   c->f_pair_row, c->f_row_pid, c->f_a2, g.Kp2, c->f_ap);
     CHB_CUDA(c, cudaGetLastError());
     c->tm.launches_other += 4;
     CUtensorMap ma, mb, map;
@@ -2381,7 +2417,7 @@ int chb_round_fused(chb_ctx *c)
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
         kern<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(
             nown, c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->f_slack, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
-            c->f_fb_pairs, c->f_fb_cap, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins);
+            c->f_fb_pairs, c->f_fb_cap, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins, c->f_row_pid, c->f_mode);
         // pairs the re-rank could not settle from the kept lists (rare): exact redo, no host round trip -- the grid is
         // fixed and walks the device-side list
         const size_t xs = sizeof(double) * (size_t)((c->d + 1) & ~1);
@@ -2416,20 +2452,37 @@ extern "C" int chb_get_fused_candidates(chb_ctx *c, int64_t slot0, int64_t nslot
     const int KR = (c->k + 3 <= 8) ? 8 : 16;
     const int64_t nown = c->u1 - c->u0, s0 = slot0 - c->u0, per = (int64_t)c->C * 2 * KR;
     *kr_out = KR;
-    // the kernels keep these tables per ROW (owned slots ordered by guessed bin): translate back to slots
-    std::vector<int32_t> row_slot((size_t)std::max<int64_t>(nown, 1));
+    // the kernels keep these tables per ROW (owned slots ordered by guessed bin) and, in compacted rounds, the lists per
+    // compact pair id: translate back to (slot, bin); bins the bounds ruled out have no list (keys +inf)
+    const int32_t C = c->C;
+    std::vector<int32_t> row_slot((size_t)std::max<int64_t>(nown, 1)), nb((size_t)std::max<int64_t>(nown, 1)), bins((size_t)C), pid((size_t)C);
+    int32_t mode = 0;
     CHB_CUDA(c, cudaMemcpyAsync(row_slot.data(), c->f_row_slot, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(nb.data(), c->f_row_nb, sizeof(int32_t) * (size_t)nown, cudaMemcpyDeviceToHost, c->stream));
+    CHB_CUDA(c, cudaMemcpyAsync(&mode, c->f_mode, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     CHB_CUDA(c, cudaStreamSynchronize(c->stream));
-    std::vector<float> srow((size_t)c->C);
+    std::vector<float> srow((size_t)C);
     for (int64_t r = 0; r < nown; ++r) {
         const int64_t sl = row_slot[(size_t)r] - s0;
         if (sl < 0 || sl >= nslots) continue;
-        CHB_CUDA(c, cudaMemcpyAsync(key_out + sl * per, c->f_cand_key + r * per, sizeof(float) * (size_t)per, cudaMemcpyDeviceToHost, c->stream));
-        CHB_CUDA(c, cudaMemcpyAsync(idx_out + sl * per, c->f_cand_idx + r * per, sizeof(int32_t) * (size_t)per, cudaMemcpyDeviceToHost, c->stream));
+        for (int64_t e = 0; e < per; ++e) { key_out[sl * per + e] = INFINITY; idx_out[sl * per + e] = -1; }
+        const int32_t n_b = nb[(size_t)r];
+        CHB_CUDA(c, cudaMemcpyAsync(bins.data(), c->f_row_bins + r * C, sizeof(int32_t) * (size_t)n_b, cudaMemcpyDeviceToHost, c->stream));
+        if (mode == 1)
+            CHB_CUDA(c, cudaMemcpyAsync(pid.data(), c->f_row_pid + r * C, sizeof(int32_t) * (size_t)n_b, cudaMemcpyDeviceToHost, c->stream));
         CHB_CUDA(c, cudaMemcpy2DAsync(srow.data(), sizeof(float), c->f_slack + r, sizeof(float) * (size_t)c->f_ldt, sizeof(float),
-                                      (size_t)c->C, cudaMemcpyDeviceToHost, c->stream));
+                                      (size_t)C, cudaMemcpyDeviceToHost, c->stream));
         CHB_CUDA(c, cudaStreamSynchronize(c->stream));
-        for (int32_t b = 0; b < c->C; ++b) slack_out[(int64_t)b * nslots + sl] = srow[(size_t)b];
+        for (int32_t jb = 0; jb < n_b; ++jb) {
+            const int32_t b = bins[(size_t)jb];
+            const int64_t lslot = mode == 1 ? (int64_t)pid[(size_t)jb] : r * C + b;
+            CHB_CUDA(c, cudaMemcpyAsync(key_out + sl * per + (int64_t)b * 2 * KR, c->f_cand_key + lslot * 2 * KR, sizeof(float) * 2 * KR,
+                                        cudaMemcpyDeviceToHost, c->stream));
+            CHB_CUDA(c, cudaMemcpyAsync(idx_out + sl * per + (int64_t)b * 2 * KR, c->f_cand_idx + lslot * 2 * KR, sizeof(int32_t) * 2 * KR,
+                                        cudaMemcpyDeviceToHost, c->stream));
+        }
+        CHB_CUDA(c, cudaStreamSynchronize(c->stream));
+        for (int32_t b = 0; b < C; ++b) slack_out[(int64_t)b * nslots + sl] = srow[(size_t)b];
     }
     CHB_CUDA(c, cudaStreamSynchronize(c->stream));
     return CHB_OK;

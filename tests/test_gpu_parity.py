@@ -651,3 +651,22 @@ def test_query_duplicated_in_two_bins_keeps_the_lower_bin():
                 idx[qi, c] = near; m[qi, c] = 5
         dist, _ = ctx.hull_distance_batch(q, idx, m)
     assert np.sum(dist == 0.0) == 2 * len(q), "both duplicated bins are at distance exactly 0.0"
+
+
+def test_candidate_lists_by_compact_pair_id_only(monkeypatch):
+    """Beyond a memory budget (CHB_DENSE_LIST_GB; 1M contigs x 500 bins would need 61 GB) the candidate lists exist per
+    COMPACT pair id only.  Forced here with a zero budget: binnable data runs compacted rounds and must give the same labels;
+    overlapping bins leave more pairs than the compact buffers hold -- that round is refused with MemoryError instead of
+    writing outside the lists, and the context is discarded."""
+    monkeypatch.setenv("CHB_DENSE_LIST_GB", "0")
+    for (n, C, S, n_seed, k, conc) in [(5000, 20, 1, 20, 5, 4000.0), (3000, 12, 10, 25, 10, 4000.0), (2500, 10, 1, 30, 16, 4000.0)]:
+        X, bins, _ = synth.make_contig_features(n, C, S, n_seed, seed=33, concentration=conc)
+        perms = oracle.draw_permutations(bins, 4, seed=0)
+        ref = oracle.fit_cluster(X, C, bins, None, k, 4, perms=perms, threads=4)
+        np.random.seed(0)
+        got, info = chbin_b200.fit_cluster(X, C, bins, None, k, 4, return_info=True, reuse_context=False)
+        assert np.array_equal(got, ref), (n, C, k)
+        assert info["timers"]["launches_gram"] > 0
+    X, bins, _ = synth.make_contig_features(1500, 8, 1, 30, seed=7, concentration=60.0)
+    with pytest.raises(MemoryError, match="CHB_DENSE_LIST_GB"):
+        chbin_b200.fit_cluster(X, 8, bins, None, 5, 10, reuse_context=False)
