@@ -5,8 +5,8 @@
 // these very doubles, so the kernel reproduces scipy's arithmetic bit for bit:
 //     s = 0;  for t in 0..d-1:  diff = a[t] - b[t];  s = s + diff*diff   (separate multiply and add, no FMA)
 //     D = sqrt(s)                                                         (IEEE round-to-nearest)
-// (tests/test_oracle_knn.py pins that recipe against scipy itself; tests/test_gpu_knn.py pins this kernel
-// against the oracle.)  The sum MUST run in ascending t per output, so the contraction is register-tiled over
+// (tests/test_oracle_golden.py pins that recipe against scipy itself; tests/test_gpu_parity.py::test_distance_rows_bit_exact
+// pins this kernel against the oracle.)  The sum MUST run in ascending t per output, so the contraction is register-tiled over
 // outputs (4x4 per thread) and streamed over t -- it cannot be re-associated into tensor-core MMAs.
 //
 // Roofline: FP64 pipe.  3 dependent-free FP64 instructions per (row, column, t): DADD(sub), DMUL, DADD.

@@ -8,7 +8,7 @@
  *   chb_oracle_fit_cluster      <- algorithm.py:12-76
  *
  * Build with -ffp-contract=off: the cdist recipe is "subtract, multiply, add, left to right, then sqrt"
- * with no fused multiply-add (checked bit-for-bit against scipy in tests/test_oracle_knn.py).
+ * with no fused multiply-add (checked bit-for-bit against scipy in tests/test_oracle_golden.py).
  *
  * Deviations from the reference, all documented in DESIGN.md:
  *  - nearest_positive_definite (positive_def.py:25-48) is not applied: it perturbs a well-conditioned Gram
