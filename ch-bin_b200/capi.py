@@ -38,7 +38,7 @@ class Timers(ctypes.Structure):
         ("qps_solved", ctypes.c_int64), ("qps_reference", ctypes.c_int64), ("rounds", ctypes.c_int64),
         ("rows_scanned", ctypes.c_int64),
         ("ms_gram", ctypes.c_double), ("launches_gram", ctypes.c_int64), ("gram_tiles", ctypes.c_int64),
-        ("gram_tiles_planned", ctypes.c_int64),
+        ("gram_tiles_planned", ctypes.c_int64), ("qp_iter_cap", ctypes.c_int64),
     ]
 
     def as_dict(self):

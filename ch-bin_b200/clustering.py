@@ -29,6 +29,7 @@ from . import capi, distance_cache
 logger = logging.getLogger(__name__)
 
 B200_SOLVER = "b200"
+ROUND_AGAIN = -2  # CHB_ROUND_AGAIN (include/chbin_b200.h)
 
 # One library context per device is kept alive between fit_cluster calls of a process (like a BLAS handle): creating
 # a context, its stream and its multi-GB device buffers costs ~10 ms, comparable to the whole 20k-contig stage.
@@ -89,6 +90,8 @@ def run_iteration(engine, perm, comm=None) -> Tuple[int, int]:
         else:
             first = engine.round_commit(lo, hi, tent)
             rounds += 1
+        if first == ROUND_AGAIN:
+            continue  # the library enlarged its exact-redo list: the same window runs again
         lo = hi if first < 0 else first + 1
     return engine.iteration_end(), rounds
 
@@ -406,8 +409,10 @@ def fit_cluster(
                         spec_state = np.random.get_state()
                         spec_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
                     first, done, change_count = eng.round_commit_end(lo, hi, tent)
-                    lo = hi if first < 0 else first + 1
                     rounds += 1
+                    if first == ROUND_AGAIN:
+                        continue  # the library enlarged its exact-redo list: the same window runs again
+                    lo = hi if first < 0 else first + 1
                 if not done:
                     change_count = eng.iteration_end()
                 mark(f"it{i_iter + 1} rounds done ({rounds})")
@@ -431,7 +436,11 @@ def fit_cluster(
                 logger.info("Exit due to max iteration limit.")
         labels = ctx.get_labels()
         mark("labels read back")
-        info = dict(iterations=iterations, converged=converged, changed=changed, timers=ctx.timers(), rank=rank,
+        tm_end = ctx.timers()
+        if tm_end.get("qp_iter_cap", 0):
+            logger.warning("%s hull-distance QPs stopped on the iteration cap of the active-set method (feasible, possibly not "
+                           "optimal); the reference would have fallen back to cvxopt there.", tm_end["qp_iter_cap"])
+        info = dict(iterations=iterations, converged=converged, changed=changed, timers=tm_end, rank=rank,
                     world=world, owned_slots=(u0, u1))
         if marks is not None:
             info["marks_ms"] = [(lab, (t - marks[0][1]) * 1e3) for lab, t in marks]

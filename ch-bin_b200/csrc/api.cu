@@ -181,10 +181,16 @@ __global__ void argmin_kernel(const int32_t *__restrict__ own_pos, int64_t cnt, 
 }
 
 __global__ void commit_kernel(const int32_t *__restrict__ tent, int64_t lo, int64_t hi, const int32_t *__restrict__ perm_pt,
-                              int32_t *__restrict__ tent_pt, int32_t *__restrict__ counters)
+                              int32_t *__restrict__ tent_pt, int32_t *__restrict__ counters, int32_t fb_cap)
 {
     const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= hi) return;
+    // more pairs needed the exact redo than its list holds: this round's tentative labels are incomplete and must not be
+    // committed -- the host grows the list and the caller runs the same window again (chb_round_commit)
+    if (fb_cap > 0 && counters[6] > fb_cap) {
+        if (p == lo) counters[1] = (int32_t)lo; // not the "nothing changed" pattern: end_if_done_kernel must not end the iteration
+        return;
+    }
     const int32_t v = tent[p - lo];
     const int j = perm_pt[p];
     if (v != tent_pt[j]) {
@@ -1285,8 +1291,10 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = nown * c->C;
         q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
         q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
+        q.cap_count = &c->counters[14];
         CHB_TRY(chb_launch_qp(c, q));
         cudaMemcpyAsync(&c->counters_host[4], c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(&c->counters_host[14], &c->counters[14], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
         CHB_TRY(chb_fused_argmin(c, c->own_pos + b, cnt, lo, hi, tent_dev));
         return CHB_OK;
     }
@@ -1400,7 +1408,8 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
     if (may_end) CHB_CUDA(c, cudaMemsetAsync(&c->counters[2], 0, sizeof(int32_t), c->stream));
     {
         chb_stage_timer t(c, CHB_ST_COMMIT);
-        commit_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters);
+        commit_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters,
+                                                                  (use_fused(c) && c->u1 - c->u0 == c->U) ? c->f_fb_cap : 0);
     }
     bool staged = false;
     if (may_end) {
@@ -1420,6 +1429,8 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
     CHB_TRY(sync_stream(c));
     c->tm.qps_solved += c->counters_host[4];
     c->counters_host[4] = 0;
+    c->tm.qp_iter_cap += c->counters_host[14];
+    c->counters_host[14] = 0;
     c->tm.gram_tiles_planned += c->counters_host[7]; // tiles left after bin pruning (pairs_plan_kernel / items_kernel), this round
     c->tm.gram_tiles += c->counters_host[8];         // tiles the MMA warps of gram_select_kernel actually issued
     c->counters_host[7] = c->counters_host[8] = 0;
@@ -1431,8 +1442,19 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
                                        "table (%lld x %d pairs) is beyond CHB_DENSE_LIST_GB: raise it or use distance mode 1",
                         (long long)(c->u1 - c->u0), c->C);
     }
-    if (c->f_fb_cap > 0 && c->counters_host[6] > c->f_fb_cap)
-        return chb_fail(c, CHB_ECUDA, "exact-redo list overflow: %d pairs, capacity %d", c->counters_host[6], c->f_fb_cap);
+    if (use_fused(c) && c->f_fb_cap > 0 && c->counters_host[6] > c->f_fb_cap) {
+        const int32_t wanted = c->counters_host[6];
+        c->counters_host[6] = 0;
+        // a sharded context cannot take the round back on its own (its tentative labels are already merged with the other
+        // ranks'): the fit fails there; a context that owns every slot committed nothing (commit_kernel saw the same
+        // counter), grows the list to its worst case -- every (row, bin) pair -- and asks for the window again
+        if (c->u1 - c->u0 != c->U)
+            return chb_fail(c, CHB_ECUDA, "exact-redo list overflow: %d pairs, capacity %d", wanted, c->f_fb_cap);
+        CHB_TRY(chb_fused_grow_redo_list(c));
+        *first_changed = CHB_ROUND_AGAIN;
+        if (iteration_done) *iteration_done = 0;
+        return CHB_OK;
+    }
     c->counters_host[6] = 0;
     *first_changed = (c->counters_host[1] == 0x7f7f7f7f) ? -1 : (int64_t)c->counters_host[1];
     if (iteration_done) *iteration_done = 0;
@@ -1511,6 +1533,7 @@ int chb_fit_iteration(chb_ctx *c, const int64_t *perm, int64_t U, int64_t *label
             CHB_TRY(chb_round_run(c, lo, hi, c->tent_win));
             int64_t first = -1;
             CHB_TRY(chb_round_commit_end(c, lo, hi, c->tent_win, &first, &nch, &done));
+            if (first == CHB_ROUND_AGAIN) continue; // the exact-redo list was too small and has grown: same window again
             lo = (first < 0) ? hi : first + 1;
         }
         if (done) {

@@ -122,7 +122,10 @@ struct chb_ctx {
     float *f_col_nrm = nullptr, *f_bperm = nullptr, *f_cand_key = nullptr;
     int32_t *f_cand_idx = nullptr;
     int2 *f_fb_pairs = nullptr; // (row, bin) pairs to redo exactly this round
+    int2 *f_xs_slots = nullptr; // the same pairs regrouped per bin (16 <= k <= 24: exact_group_kernel redoes them)
+    int64_t f_xs_cap = 0;
     int32_t f_fb_cap = 0;
+    bool f_fb_worst = false; // the exact-redo list was grown to every (row, bin) pair after an overflow
     int64_t f_fb_alloc = 0; // entries allocated behind f_fb_pairs (f_fb_cap pairs + per-bin padding of the large-k path)
     int64_t f_cap_bins = 0, f_cap_cols = 0, f_cap_cand = 0, f_cap_thr = 0, f_cap_ldt = 0;
     float *f_thr = nullptr; // nown x C : largest FP32 key of the cached neighbour set (+inf: fewer than k members)
@@ -245,6 +248,7 @@ int chb_launch_gram_tc(chb_ctx *ctx, const float *a_split, const float *b_split,
 bool chb_fused_supported(const chb_ctx *c);
 int chb_round_fused(chb_ctx *c);
 int chb_fused_setup(chb_ctx *c);  // allocations + once-per-label-set operands (idempotent)
+int chb_fused_grow_redo_list(chb_ctx *c); // exact-redo list to its worst-case size (every (row, bin) pair)
 int chb_fused_guess(chb_ctx *c);
 int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_t lo, int64_t hi, int32_t *tent_dev); // argmin over surviving bins, positions in [lo, hi)
 int chb_fused_mask_pair_cache(chb_ctx *c, int64_t slot0, int64_t nslots, int32_t *cnt_out, double *dist_out); // test aid  // tent_pt of every query point := bin of the nearest seed centroid
@@ -290,6 +294,7 @@ struct chb_qp_args {
     double *dist;
     int32_t *status;
     double *alpha; // optional rows x C x k
+    int32_t *cap_count; // optional device counter: pairs whose active-set method ended on its iteration cap (CHB_QP_ITER_CAP)
 };
 int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a);
 // qp_small.cu : k <= 5 fast path; ill-conditioned pairs are appended to `fallback`

@@ -149,7 +149,7 @@ __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_c
     if (i < nown) row_nb[i] = 0;
     if (i < nmeta) pair_meta[i] = 0;
     if (i < cap_pairs) pair_row[i] = -1;
-    if (i == 0) { counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; counters[12] = 0; }
+    if (i == 0) { counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; counters[12] = 0; counters[14] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1745,6 +1745,26 @@ __global__ void xs_plan_kernel(const int32_t *__restrict__ bin_surv, int32_t C, 
     *npairs = np; // chb_round_commit reports an error if this exceeds the pair capacity
 }
 
+// the pairs the re-rank could not settle (16 < k <= FUSED_KMAX: overflowing half-lists are common), regrouped per bin so
+// that exact_group_kernel can share each member row among eight of them
+__global__ void fb_hist_kernel(const int2 *__restrict__ fb_pairs, const int32_t *__restrict__ fb_count, int32_t fb_cap,
+                               int32_t *__restrict__ bin_cnt)
+{
+    const int n = min(*fb_count, fb_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&bin_cnt[fb_pairs[i].y], 1);
+}
+__global__ void fb_scatter_kernel(const int2 *__restrict__ fb_pairs, const int32_t *__restrict__ fb_count, int32_t fb_cap,
+                                  const int32_t *__restrict__ xs_off, int32_t *__restrict__ xs_cur, int2 *__restrict__ slots,
+                                  int32_t cap_slots)
+{
+    const int n = min(*fb_count, fb_cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int2 pr = fb_pairs[i];
+        const int sidx = xs_off[pr.y] + atomicAdd(&xs_cur[pr.y], 1);
+        if (sidx < cap_slots) slots[sidx] = pr;
+    }
+}
+
 __global__ void xs_fill_kernel(const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
                                const int32_t *__restrict__ xs_off, int32_t *__restrict__ xs_cur, int2 *__restrict__ slots, int32_t cap_slots)
 {
@@ -2083,7 +2103,7 @@ void chb_fused_free(chb_ctx *c)
 {
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
-    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
+    cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_xs_slots); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
     cudaFree(c->f_mc); cudaFree(c->f_mc2); cudaFree(c->f_mcnt); cudaFree(c->f_skip); cudaFree(c->f_pair_row); cudaFree(c->f_pair_meta); cudaFree(c->f_ap); cudaFree(c->f_mode); cudaFree(c->f_items); cudaFree(c->f_cta_begin); cudaFree(c->f_row_slot); cudaFree(c->f_row_pt);
     cudaFree(c->f_ub); cudaFree(c->f_ubk2); cudaFree(c->f_row_guess); cudaFree(c->f_rhist); cudaFree(c->f_mcT); cudaFree(c->f_guess_all); cudaFree(c->f_tqs);
     c->f_tqs = nullptr;
@@ -2115,6 +2135,8 @@ void chb_fused_free(chb_ctx *c)
     c->f_col_nrm = c->f_bperm = c->f_cand_key = nullptr;
     c->f_cand_idx = nullptr;
     c->f_fb_pairs = nullptr;
+    c->f_xs_slots = nullptr;
+    c->f_xs_cap = 0;
     c->f_fb_alloc = 0;
 }
 
@@ -2182,6 +2204,12 @@ extern "C" int chb_guess_import(chb_ctx *c, const int32_t *guess_dev)
     return CHB_OK;
 }
 
+int chb_fused_grow_redo_list(chb_ctx *c)
+{
+    c->f_fb_worst = true; // chb_fused_setup sizes the list (and its regrouped copy) from this flag
+    return chb_fused_setup(c);
+}
+
 int chb_fused_setup(chb_ctx *c)
 {
     const int64_t nown = c->u1 - c->u0;
@@ -2243,14 +2271,17 @@ int chb_fused_setup(chb_ctx *c)
         // pairs redone on exact distances: a few per row when they are the exception (k <= 15), every pair that survives
         // the pruning otherwise -- possibly all of them; + XS_G * C: that path pads every bin's range of the list to a
         // multiple of XS_G (exact_group_kernel)
-        const int64_t per_row = (c->k > FUSED_KMAX) ? C : std::min<int64_t>(C, c->k > 15 ? 16 : 8);
-        const int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * per_row, 1024), INT32_MAX - 16 * (int64_t)C - 16);
+        const int64_t per_row = (c->k > FUSED_KMAX || c->f_fb_worst) ? C : std::min<int64_t>(C, c->k > 15 ? 16 : 8);
+        int64_t fbc = std::min<int64_t>(std::max<int64_t>(nown * per_row, 1024), INT32_MAX - 16 * (int64_t)C - 16);
+        if (const char *t = getenv("CHB_TEST_FB_CAP")) // test aid: a tiny list, so that the overflow -> grow -> same window again path runs
+            if (!c->f_fb_worst && c->k <= FUSED_KMAX) fbc = std::max<int64_t>(1, atoll(t));
         if (c->f_fb_alloc < fbc + 8 * (int64_t)C + 8) {
             int64_t z = 0;
             if (reserve(c, &c->f_fb_pairs, &z, fbc + 8 * (int64_t)C + 8)) return CHB_ENOMEM;
             c->f_fb_alloc = z;
         }
         c->f_fb_cap = (int32_t)fbc;
+        if (c->k > 15 && c->k <= FUSED_KMAX && reserve(c, &c->f_xs_slots, &c->f_xs_cap, fbc + 8 * (int64_t)C + 8)) return CHB_ENOMEM;
     }
     c->f_ldt = (nown + 127) & ~int64_t(127);
     if (c->f_cap_thr < c->f_ldt * C || c->f_cap_ldt < c->f_ldt) {
@@ -2432,10 +2463,21 @@ int chb_round_fused(chb_ctx *c)
             exact_pairs_kernel<15><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
                                                                c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot,
                                                                c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
-        else
-            exact_pairs_kernel<FUSED_KMAX><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
-                                                                       c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
-                                                                       c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
+        else {
+            // 16 <= k <= FUSED_KMAX: a few per cent (k = 20) to one in six (k = 24) of the pairs overflow a half-list -- too many
+            // for one CTA per pair; they are regrouped per bin and go through exact_group_kernel, eight pairs of a bin per pass
+            int32_t *gb_cnt = c->f_pair_meta, *gb_off = c->f_pair_meta + (C + 2), *gb_cur = c->f_pair_meta + 2 * (C + 2); // free after the fused kernel
+            const int32_t cap_slots = (int32_t)std::min<int64_t>(((int64_t)c->f_fb_cap + (int64_t)XS_G * C) & ~(int64_t)(XS_G - 1), INT32_MAX & ~(XS_G - 1));
+            CHB_CUDA(c, cudaFuncSetAttribute(exact_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)exact_group_smem(c->d)));
+            CHB_CUDA(c, cudaMemsetAsync(c->f_pair_meta, 0, sizeof(int32_t) * 3 * (size_t)(C + 2), c->stream));
+            CHB_CUDA(c, cudaMemsetAsync(c->f_xs_slots, 0xFF, sizeof(int2) * (size_t)cap_slots, c->stream));
+            fb_hist_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, gb_cnt);
+            xs_plan_kernel<<<1, 32, 0, c->stream>>>(gb_cnt, C, gb_off, &c->counters[13]);
+            fb_scatter_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, gb_off, gb_cur, c->f_xs_slots, cap_slots);
+            exact_group_kernel<<<c->sm_count, XS_THREADS, exact_group_smem(c->d), c->stream>>>(
+                c->f_xs_slots, gb_off, cap_slots, c->f_seg_off, c->f_bin_cnt, c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt,
+                c->f_row_slot, c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
+        }
     }
     CHB_CUDA(c, cudaGetLastError());
     return CHB_OK;

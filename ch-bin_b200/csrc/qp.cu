@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fa
         if (lane == 0) {
             a.dist[pair] = sqrt(ss);
             if (a.status) a.status[pair] = status;
+            if (status == CHB_QP_ITER_CAP && a.cap_count) atomicAdd(a.cap_count, 1); // feasible, possibly not optimal: reported
         }
         if (a.alpha && lane < k) a.alpha[pair * k + lane] = lane < m ? alpha : 0.0;
         __syncwarp();

@@ -70,6 +70,9 @@ typedef struct chb_timers {
     int64_t gram_tiles;     /* 128 x 128 (query, column) tiles contracted, counted by the MMA-issuing warps themselves:
                              * 2*128*128*3*dp8 flop each, dp8 = d rounded up to 8 */
     int64_t gram_tiles_planned; /* the same count as the work-list planner predicted it (must agree) */
+    int64_t qp_iter_cap;    /* QPs of the assignment rounds whose active-set method stopped on its iteration cap (CHB_QP_ITER_CAP):
+                             * their distance comes from a feasible, possibly not optimal alpha (the reference would have fallen
+                             * back to cvxopt, solve_qp.py:126-129); 0 on every workload tested */
 } chb_timers;
 
 /* ---- lifetime ---------------------------------------------------------------------------------------- */
@@ -212,6 +215,10 @@ int chb_get_labels(chb_ctx *ctx, int64_t *labels_out);
 /* In distance mode 2 the permutation is validated on the device: an entry that is out of range, not an un-assigned point
  * or repeated is reported (CHB_EINVAL, same messages) by the first chb_round_commit / chb_iteration_end that follows; the
  * iteration is then abandoned and the labels stay as they were before chb_iteration_begin. */
+/* chb_round_commit / chb_round_commit_end may answer *first_changed = CHB_ROUND_AGAIN (a context that owns every slot
+ * only): more (query, bin) pairs than expected needed the exact redo (many identical contigs), nothing was committed, the
+ * library has enlarged its list -- run the same window [lo, hi) again. */
+#define CHB_ROUND_AGAIN ((int64_t)-2)
 int chb_iteration_begin(chb_ctx *ctx, const int64_t *perm, int64_t U);
 /* The same with the permutation already in DEVICE memory (e.g. rank 0's draw after an NCCL broadcast): distance mode 2 only. */
 int chb_iteration_begin_dev(chb_ctx *ctx, const int64_t *perm_dev, int64_t U);

@@ -670,3 +670,36 @@ def test_candidate_lists_by_compact_pair_id_only(monkeypatch):
     X, bins, _ = synth.make_contig_features(1500, 8, 1, 30, seed=7, concentration=60.0)
     with pytest.raises(MemoryError, match="CHB_DENSE_LIST_GB"):
         chbin_b200.fit_cluster(X, 8, bins, None, 5, 10, reuse_context=False)
+
+
+@pytest.mark.parametrize("k", [5, 20])
+def test_exact_redo_list_overflow_grows_and_reruns_the_window(monkeypatch, k):
+    """More (query, bin) pairs than the exact-redo list holds (forced: CHB_TEST_FB_CAP shrinks the list to 3 entries; many
+    identical contigs make the re-rank send pairs there): nothing is committed, the library grows the list to its worst
+    case and answers CHB_ROUND_AGAIN, the drivers run the window again -- same labels as with the regular list and as the
+    oracle, no error."""
+    X, bins, _ = synth.make_contig_features(1200, 5, 1, 20, seed=17, concentration=300.0)
+    X[300:340] = X[300]
+    X[700:712] = X[700]
+    perms = oracle.draw_permutations(bins, 4, seed=0)
+    ref = oracle.fit_cluster(X, 5, bins, None, k, 4, perms=perms, threads=4)
+    np.random.seed(0)
+    regular, rinfo = chbin_b200.fit_cluster(X, 5, bins, None, k, 4, return_info=True, reuse_context=False)
+    monkeypatch.setenv("CHB_TEST_FB_CAP", "3")
+    np.random.seed(0)
+    got, info = chbin_b200.fit_cluster(X, 5, bins, None, k, 4, return_info=True, reuse_context=False)  # Python round loop
+    assert np.array_equal(got, regular)
+    assert info["iterations"] == rinfo["iterations"] and list(info["changed"]) == list(rinfo["changed"])
+    assert np.array_equal(got, ref)
+    assert info["timers"]["qp_iter_cap"] == 0
+    with capi.Context(0) as ctx:  # chb_fit's own loop
+        ctx.set_features(X); ctx.set_labels(bins, 5); ctx.set_params(k, "convex"); ctx.build_distance_matrix(True)
+        lab, iters, conv, changed = ctx.fit(perms, 4)
+        rounds = ctx.timers()["rounds"]
+    assert np.array_equal(lab, regular)
+    monkeypatch.delenv("CHB_TEST_FB_CAP")
+    with capi.Context(0) as ctx:
+        ctx.set_features(X); ctx.set_labels(bins, 5); ctx.set_params(k, "convex"); ctx.build_distance_matrix(True)
+        ctx.fit(perms, 4)
+        rounds_regular = ctx.timers()["rounds"]
+    assert rounds > rounds_regular, "at least one window must have run twice"
