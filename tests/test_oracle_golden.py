@@ -16,6 +16,16 @@ def G(golden_dir):
     return np.load(os.path.join(golden_dir, "reference_golden.npz"))
 
 
+def test_golden_records_which_solvers_made_it(G, record_property):
+    """quadprog / cvxopt are not in this image: the QP goldens come from the reference's own modules running over the
+    stand-in solvers of oracle/ref_shim.py (scipy SLSQP / trust-constr, same problem, same tolerance class).  The file
+    says which, so a regenerated file made WITH the real packages is recognisable."""
+    flags = G["real_solvers"]
+    assert flags.shape == (2,) and set(flags.tolist()) <= {0, 1}
+    record_property("golden_quadprog_real", int(flags[0]))
+    record_property("golden_cvxopt_real", int(flags[1]))
+
+
 def test_cdist_recipe_bit_exact_vs_scipy():
     from scipy.spatial.distance import cdist
 
