@@ -162,6 +162,8 @@ struct chb_ctx {
 
     int2 *fallback = nullptr; // pairs the small-k QP kernel hands to the general one
     int64_t fallback_cap = 0;
+    double *qp_scratch = nullptr; // qp_lane.cu: the untouched Gram matrix of every resident lane's pair ([entry][lane], L2-resident)
+    int64_t qp_scratch_cap = 0;   // doubles
 
     int64_t window = 0;
     int32_t *tent_win = nullptr; // window-sized tentative buffer for the single-context driver
@@ -301,3 +303,5 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a);
 int chb_launch_qp_small(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count);
 // qp_mid.cu : 6 <= k <= 10
 int chb_launch_qp_mid(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count);
+// qp_lane.cu : 11 <= k <= 24 (FP64 tensor-core Gram, one lane per pair)
+int chb_launch_qp_lane(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count);

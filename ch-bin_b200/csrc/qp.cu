@@ -494,8 +494,10 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
     CHB_CHECK(ctx, a.k >= 1 && a.k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d]", CHB_KMAX);
     CHB_CHECK(ctx, a.metric == CHB_METRIC_CONVEX || a.metric == CHB_METRIC_AFFINE_QP || a.metric == CHB_METRIC_AFFINE,
               CHB_ENOTIMPL, "Metric %d not implemented", a.metric);
-    if (a.k <= 5 && a.metric == CHB_METRIC_CONVEX) {
-        // fast path; pairs whose a'Ga is too small to trust go through the general kernel afterwards
+    const bool lane_path = a.k >= 11 && a.k <= 24 && !getenv("CHB_QP_NO_LANE");
+    if ((a.k <= 10 || lane_path) && a.metric == CHB_METRIC_CONVEX) {
+        // k <= 5: qp_small.cu; 6..10: 8-lane Gram + one lane per pair (qp_mid.cu); 11..24: tensor-core Gram + one lane per pair
+        // (qp_lane.cu).  Pairs whose a'Ga is too small to trust, and pairs that did not end on a verified face, come back here
         if (ctx->fallback_cap < a.n_work) {
             if (ctx->fallback) cudaFree(ctx->fallback);
             ctx->fallback = nullptr;
@@ -508,33 +510,24 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
             ctx->fallback_cap = a.n_work;
         }
         CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[3], 0, sizeof(int32_t), ctx->stream));
-        int rc = chb_launch_qp_small(ctx, a, ctx->fallback, &ctx->counters[3]);
+        int rc = a.k <= 5 ? chb_launch_qp_small(ctx, a, ctx->fallback, &ctx->counters[3])
+                          : (a.k <= 10 ? chb_launch_qp_mid(ctx, a, ctx->fallback, &ctx->counters[3])
+                                       : chb_launch_qp_lane(ctx, a, ctx->fallback, &ctx->counters[3]));
         if (rc != CHB_OK) return rc;
-        chb_qp_args b = a;
-        b.work = ctx->fallback;
-        b.work_count = &ctx->counters[3];
-        return launch<8>(ctx, b, 1);
-    }
-    if (a.k <= 10 && a.metric == CHB_METRIC_CONVEX) {
-        // 6..10 neighbours: 8-lane Gram + one-lane-per-pair active set (qp_mid.cu); ill-conditioned pairs come back here
-        if (ctx->fallback_cap < a.n_work) {
-            if (ctx->fallback) cudaFree(ctx->fallback);
-            ctx->fallback = nullptr;
-            cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&ctx->fallback), sizeof(int2) * (size_t)a.n_work);
-            if (e != cudaSuccess) {
-                (void)cudaGetLastError();
-                ctx->fallback_cap = 0;
-                return chb_fail(ctx, CHB_ENOMEM, "cudaMalloc of the QP fallback list failed: %s", cudaGetErrorString(e));
-            }
-            ctx->fallback_cap = a.n_work;
+        if (getenv("CHB_QP_DEBUG")) { // development aid: how many pairs the first-line kernel handed back
+            int32_t nfb = 0;
+            cudaMemcpyAsync(&nfb, &ctx->counters[3], sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+            fprintf(stderr, "[chbin_b200] qp k=%d: %lld pairs (upper bound), %d handed to the general kernel\n", a.k, (long long)a.n_work, nfb);
         }
-        CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[3], 0, sizeof(int32_t), ctx->stream));
-        int rc = chb_launch_qp_mid(ctx, a, ctx->fallback, &ctx->counters[3]);
-        if (rc != CHB_OK) return rc;
         chb_qp_args b = a;
         b.work = ctx->fallback;
         b.work_count = &ctx->counters[3];
-        return launch<16>(ctx, b, 1);
+        if (a.k <= 5) return launch<8>(ctx, b, 1);
+        if (a.k <= 10) return launch<16>(ctx, b, 1);
+        // low-dimensional inputs put most queries INSIDE the hull (a'Ga = 0): the whole batch may come back
+        const int fb_fast = getenv("CHB_QP_NO_TABLEAU") ? 0 : 1;
+        return a.k <= 16 ? launch<16>(ctx, b, 16, fb_fast) : launch<24>(ctx, b, 16, fb_fast);
     }
     // main kernel for these neighbour counts: the exchanged tableau is kept across the iterations of a pair
     // fast: 0 = Wolfe with a fresh solve per minor cycle (test aid CHB_QP_NO_TABLEAU), 1 = block principal pivoting on the
