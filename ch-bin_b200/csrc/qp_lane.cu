@@ -10,9 +10,9 @@
 //    coincide for a Gram matrix), operands straight from L2 with 16-byte loads (two k-steps per load), the lower triangle
 //    of the 8 x 8 tiles per k-step.  G goes to a scratch laid out [batch of 32 pairs][entry][pair in batch];
 //  * qp_lane_solve_kernel gives every lane ITS OWN pair of a batch: block principal pivoting on the exchanged tableau of
-//    M = G + s 11' kept in shared memory as a symmetric lower triangle, one private copy per lane at pitch 33 doubles per
-//    entry ([entry][lane]: every statically indexed access is conflict-free whatever the lane's pivot is, and
-//    lane-dependent entries cost nothing extra to address).  A sweep reads r_i = sum_{c in S} T_ic off the tableau: for i
+//    M = G + s 11' kept in shared memory as a symmetric lower triangle, one private copy per lane ([entry][lane]: a lane
+//    only ever touches its own bank pair, so lane-dependent entry indices -- the pivot row -- are conflict-free and cost
+//    nothing extra to address).  A sweep reads r_i = sum_{c in S} T_ic off the tableau: for i
 //    in S that is y_i (weights ~ r_i / sum r), for i outside S it is (M y)_i, and the multiplier test g_i < f is r_i < 1.
 //    All vertices with a negative weight leave and all violated ones enter, one principal pivot (rank-1 update of the
 //    triangle) each;
@@ -28,7 +28,7 @@
 
 namespace {
 
-constexpr int LD = 33;        // pitch of one tableau entry across the 32 lanes (doubles)
+constexpr int LD = 32;        // pitch of one tableau entry across the 32 lanes (doubles): lane l only ever touches bank pair l mod 16
 constexpr int SWEEP_CAP = 10;
 constexpr int GRAM_WARPS = 8;
 
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(GRAM_WARPS * 32) gram_dmma_kernel(chb_qp_args 
 //   T_jk <- -/+ T_jk / p (minus for j in S),   T_kk <- 1 / p
 // Returns false (tableau untouched) if the pivot p is not above min_piv.
 template <int KMAX>
-__device__ __forceinline__ bool lane_pivot(double *__restrict__ T, int kv, unsigned &S, int mw, double min_piv)
+__device__ __forceinline__ bool lane_pivot(double *__restrict__ T, int kv, unsigned &S, double min_piv)
 {
     const int bk = kv * (kv + 1) / 2;
     const double p = T[(bk + kv) * LD];
@@ -145,38 +145,32 @@ __device__ __forceinline__ bool lane_pivot(double *__restrict__ T, int kv, unsig
     const double rinv = 1.0 / p;
     const bool entering = !((S >> kv) & 1u);
     const unsigned B = entering ? S : ~S;
+    // straight-line code over all KMAX (KMAX + 1) / 2 entries (rows beyond the pair's m are bystanders that nobody reads): no
+    // per-row branch, so the loads of later rows are in flight behind the arithmetic of earlier ones
     double c[KMAX], h[KMAX];
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
-        c[i] = 0.0;
-        if (i < mw) {
-            const int e = (i >= kv) ? (i * (i + 1) / 2 + kv) : (bk + i); // entry (max, min) of the triangle
-            const double v = T[e * LD];
-            c[i] = (i == kv) ? 0.0 : v;
-        }
+        const int e = (i >= kv) ? (i * (i + 1) / 2 + kv) : (bk + i); // entry (max, min) of the triangle
+        c[i] = T[e * LD]; // c[kv] = p spoils row / column kv in the update below: they are rewritten afterwards
         h[i] = ((B >> i) & 1u) ? c[i] : 0.0;
     }
 #pragma unroll
     for (int i = 0; i < KMAX; ++i) {
-        if (i < mw) {
-            const double fi = c[i] * rinv;
-            const double hi = 2.0 * h[i] * rinv;
+        const double fi = c[i] * rinv;
+        const double hi = 2.0 * h[i] * rinv;
 #pragma unroll
-            for (int j = 0; j <= i; ++j) {
-                double v = T[lidx(i, j) * LD];
-                v = fma(-fi, c[j], v);
-                v = fma(hi, h[j], v);
-                T[lidx(i, j) * LD] = v; // row / column kv: c[kv] = h[kv] = 0, nothing changes; rewritten below
-            }
+        for (int j = 0; j <= i; ++j) {
+            double v = T[lidx(i, j) * LD];
+            v = fma(-fi, c[j], v);
+            v = fma(hi, h[j], v);
+            T[lidx(i, j) * LD] = v;
         }
     }
 #pragma unroll
     for (int j = 0; j < KMAX; ++j) {
-        if (j < mw && j != kv) {
-            const int e = (j >= kv) ? (j * (j + 1) / 2 + kv) : (bk + j);
-            const double v = c[j] * rinv;
-            T[e * LD] = ((S >> j) & 1u) ? -v : v;
-        }
+        const int e = (j >= kv) ? (j * (j + 1) / 2 + kv) : (bk + j);
+        const double v = c[j] * rinv;
+        if (j != kv) T[e * LD] = ((S >> j) & 1u) ? -v : v;
     }
     T[(bk + kv) * LD] = rinv;
     S ^= 1u << kv;
@@ -207,7 +201,6 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) qp_lane_solve_kernel(chb_qp_a
             pair = (int64_t)wk.x * C + wk.y;
             m = a.knn_cnt[pair];
         }
-        const int mw = __reduce_max_sync(CHB_FULL, m);
         const double *scr = gin + ((base - item0) >> 5) * (int64_t)(NE * 32) + lane; // G of this lane's pair: scr[e * 32]
         double best = 0.0, scale = 0.0;
         int status = CHB_QP_OK;
@@ -233,12 +226,11 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) qp_lane_solve_kernel(chb_qp_a
             solved = true;
         }
         // the tableau starts at M = G + scale 11' (G stays untouched in the scratch for the final check)
+        if (__any_sync(CHB_FULL, active)) {
 #pragma unroll
-        for (int i = 0; i < KMAX; ++i) {
-            if (i < mw) {
+            for (int i = 0; i < KMAX; ++i)
 #pragma unroll
                 for (int j = 0; j <= i; ++j) T[lidx(i, j) * LD] = scr[lidx(i, j) * 32] + scale;
-            }
         }
         const double tol = 1e-14 * scale;
         unsigned S = 0u, banned = 0u;
@@ -246,7 +238,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) qp_lane_solve_kernel(chb_qp_a
         double sy = 0.0;
         double r[KMAX];
         if (active) {
-            lane_pivot<KMAX>(T, start, S, mw, 0.0); // G_ss + scale >= scale > 0
+            lane_pivot<KMAX>(T, start, S, 0.0); // G_ss + scale >= scale > 0
         }
 #pragma unroll 1
         for (int sweep = 0; sweep < SWEEP_CAP; ++sweep) {
@@ -257,16 +249,13 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) qp_lane_solve_kernel(chb_qp_a
 #pragma unroll
                 for (int i = 0; i < KMAX; ++i) r[i] = 0.0;
 #pragma unroll
-                for (int i = 0; i < KMAX; ++i) {
-                    if (i < mw) {
+                for (int i = 0; i < KMAX; ++i)
 #pragma unroll
-                        for (int j = 0; j <= i; ++j) {
-                            const double v = T[lidx(i, j) * LD];
-                            if ((S >> j) & 1u) r[i] += v;
-                            if (j != i && ((S >> i) & 1u)) r[j] += v;
-                        }
+                    for (int j = 0; j <= i; ++j) {
+                        const double v = T[lidx(i, j) * LD];
+                        if ((S >> j) & 1u) r[i] += v;
+                        if (j != i && ((S >> i) & 1u)) r[j] += v;
                     }
-                }
                 sy = 0.0;
 #pragma unroll
                 for (int i = 0; i < KMAX; ++i)
@@ -295,7 +284,7 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) qp_lane_solve_kernel(chb_qp_a
                     const int v = __ffs(flip) - 1;
                     flip &= flip - 1;
                     const bool entering = (dual >> v) & 1u;
-                    if (lane_pivot<KMAX>(T, v, S, mw, entering ? 2e-11 * scale : 0.0)) {
+                    if (lane_pivot<KMAX>(T, v, S, entering ? 2e-11 * scale : 0.0)) {
                         if (!entering) banned = 0u; // the face shrank: a vertex that depended on it may be independent now
                     } else if (entering) {
                         banned |= 1u << v; // affinely dependent on the face: same hull without it
@@ -317,16 +306,13 @@ __global__ void __launch_bounds__(LANE_WARPS * 32) qp_lane_solve_kernel(chb_qp_a
 #pragma unroll
                 for (int i = 0; i < KMAX; ++i) g[i] = 0.0;
 #pragma unroll
-                for (int i = 0; i < KMAX; ++i) {
-                    if (i < mw) {
+                for (int i = 0; i < KMAX; ++i)
 #pragma unroll
-                        for (int j = 0; j <= i; ++j) {
-                            const double v = scr[lidx(i, j) * 32];
-                            g[i] = fma(v, beta[j], g[i]);
-                            if (j != i) g[j] = fma(v, beta[i], g[j]);
-                        }
+                    for (int j = 0; j <= i; ++j) {
+                        const double v = scr[lidx(i, j) * 32];
+                        g[i] = fma(v, beta[j], g[i]);
+                        if (j != i) g[j] = fma(v, beta[i], g[j]);
                     }
-                }
                 double f = 0.0;
 #pragma unroll
                 for (int i = 0; i < KMAX; ++i) f = fma(beta[i], g[i], f);
@@ -405,10 +391,15 @@ int launch_lane(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fal
         int64_t blocks = (n + LANE_WARPS * 32 - 1) / (LANE_WARPS * 32);
         const int64_t cap = (int64_t)ctx->sm_count * per_sm;
         if (blocks > cap) blocks = cap;
-        chb_stage_timer t(ctx, CHB_ST_QP);
-        gram_dmma_kernel<KMAX><<<(unsigned)gblocks, GRAM_WARPS * 32, 0, ctx->stream>>>(a, item0, n, ctx->qp_scratch);
-        qp_lane_solve_kernel<KMAX, LANE_WARPS><<<(unsigned)blocks, LANE_WARPS * 32, smem, ctx->stream>>>(a, item0, n, ctx->qp_scratch, fallback,
-                                                                                                  fallback_count);
+        {
+            chb_stage_timer t(ctx, CHB_ST_QP);
+            gram_dmma_kernel<KMAX><<<(unsigned)gblocks, GRAM_WARPS * 32, 0, ctx->stream>>>(a, item0, n, ctx->qp_scratch);
+        }
+        {
+            chb_stage_timer t(ctx, CHB_ST_QP);
+            qp_lane_solve_kernel<KMAX, LANE_WARPS><<<(unsigned)blocks, LANE_WARPS * 32, smem, ctx->stream>>>(a, item0, n, ctx->qp_scratch,
+                                                                                                      fallback, fallback_count);
+        }
     }
     CHB_CUDA(ctx, cudaGetLastError());
     return CHB_OK;
@@ -418,10 +409,10 @@ int launch_lane(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fal
 
 int chb_launch_qp_lane(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fallback_count)
 {
-    // warps per CTA chosen so that the per-lane tableaus (k (k + 1) / 2 entries x 33 x 8 bytes per warp) fill the SM's shared memory
+    // warps per CTA chosen so that the per-lane tableaus (k (k + 1) / 2 entries x 32 x 8 bytes per warp) fill the SM's shared memory
     if (a.k <= 12) return launch_lane<12, 2>(ctx, a, fallback, fallback_count); // 20 KB per warp
     if (a.k <= 14) return launch_lane<14, 2>(ctx, a, fallback, fallback_count); // 27 KB per warp
     if (a.k <= 16) return launch_lane<16, 2>(ctx, a, fallback, fallback_count); // 35 KB per warp: 3 CTAs
     if (a.k <= 20) return launch_lane<20, 1>(ctx, a, fallback, fallback_count); // 54 KB per warp: 4 CTAs
-    return launch_lane<24, 1>(ctx, a, fallback, fallback_count);                // 77 KB per warp: 2 CTAs
+    return launch_lane<24, 1>(ctx, a, fallback, fallback_count);                // 75 KB per warp: 3 CTAs fill the 228 KB exactly
 }
