@@ -162,7 +162,7 @@ struct chb_ctx {
 
     int2 *fallback = nullptr; // pairs the small-k QP kernel hands to the general one
     int64_t fallback_cap = 0;
-    double *qp_scratch = nullptr; // qp_lane.cu: the untouched Gram matrix of every resident lane's pair ([entry][lane], L2-resident)
+    double *qp_scratch = nullptr; // qp_lane.cu: the Gram matrices of one chunk of pairs, [batch of 32][entry][pair in batch]
     int64_t qp_scratch_cap = 0;   // doubles
 
     int64_t window = 0;

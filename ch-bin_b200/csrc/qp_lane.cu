@@ -366,11 +366,21 @@ int launch_lane(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fal
     int per_sm = 0;
     CHB_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qp_lane_solve_kernel<KMAX, LANE_WARPS>, LANE_WARPS * 32, smem));
     if (per_sm < 1) per_sm = 1;
-    // The Gram scratch holds one chunk of pairs (NE doubles each), at most 1 GiB: the kernels run chunk after chunk.  The
-    // count of pairs is only known on the device (a.work_count); chunks beyond it return at once.
+    // The exact number of pairs (the rounds only keep it on the device; the list is a fraction of its bound n_work): the
+    // chunking below follows it, at the price of one 4-byte read-back instead of dozens of empty launches
+    int64_t total = a.n_work;
+    if (a.work_count) {
+        CHB_CUDA(ctx, cudaMemcpyAsync(&ctx->counters_host[15], a.work_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CHB_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        total = ctx->counters_host[15] < a.n_work ? ctx->counters_host[15] : a.n_work;
+    }
+    if (total <= 0) return CHB_OK;
+    // The Gram scratch holds one chunk of pairs (NE doubles each), at most 1 GiB: the two kernels run chunk after chunk.
+    // (Running the Gram kernel of the next chunk on a second stream beside the solve kernel was tried: the two compete for
+    // CTA slots and the pair came out slower than back to back for k <= 16, within 7 % for 20 and 24.)
     int64_t chunk_cap = ((int64_t)1 << 30) / (int64_t)(sizeof(double) * NE);
     chunk_cap &= ~(int64_t)31;
-    const int64_t chunk = a.n_work < chunk_cap ? ((a.n_work + 31) & ~(int64_t)31) : chunk_cap;
+    const int64_t chunk = total < chunk_cap ? ((total + 31) & ~(int64_t)31) : chunk_cap;
     const int64_t need = chunk * NE;
     if (ctx->qp_scratch_cap < need) {
         if (ctx->qp_scratch) cudaFree(ctx->qp_scratch);
@@ -383,8 +393,8 @@ int launch_lane(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_t *fal
         }
         ctx->qp_scratch_cap = need;
     }
-    for (int64_t item0 = 0; item0 < a.n_work; item0 += chunk) {
-        const int64_t n = (a.n_work - item0 < chunk) ? a.n_work - item0 : chunk;
+    for (int64_t item0 = 0; item0 < total; item0 += chunk) {
+        const int64_t n = (total - item0 < chunk) ? total - item0 : chunk;
         int64_t gblocks = (n + GRAM_WARPS - 1) / GRAM_WARPS;
         const int64_t gcap = (int64_t)ctx->sm_count * 8;
         if (gblocks > gcap) gblocks = gcap;
