@@ -612,7 +612,8 @@ def report(args, cfg, X, bins, U, world, elapsed_ms, elapsed_ms_b, total_iters, 
             stages["knn"] = {"kernel": "knn_scan_kernel", "bound": "hbm", "achieved": b / (ms["knn"] * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "ms_total": ms["knn"], "launches": ln["knn"], "bytes_per_launch": b / ln["knn"],
                              "peak_source": hbm_src}
-    qp_name = "qp_small_kernel" if k <= 5 else ("qp_mid_kernel" if k <= 10 else "qp_kernel")
+    qp_name = ("qp_small_kernel" if k <= 5 else "qp_mid_kernel" if k <= 10 else
+               "gram_dmma_kernel + qp_lane_solve_kernel" if k <= 24 else "qp_kernel")
     ceil, bind = qp_ceilings()
     if ln["qp"]:
         f = tm["qps_solved"] * flops_per_qp(k, d)

@@ -302,20 +302,28 @@ __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__r
 
 constexpr int DMAX_F = 160; // fused mode: d <= 160
 
-// |a_u - m_c|^2 for every query slot u and every bin c, once per label set: an FP64 GEMM (U x C x d) in 128 x 64 tiles, 8 x 4
-// outputs per thread (16-byte shared-memory reads: 6 per 32 DFMA), 16 features per shared-memory stage.
+// |a_u - m_c|^2 for every query slot u and every bin c, once per label set: an FP64 GEMM (U x C x d) on the FP64 tensor cores
+// (mma.sync m8n8k4.f64 -> DMMA.8x8x4): 128 x 64 tiles per CTA, 8 warps of 32 x 32 (4 x 4 MMA tiles, 16 DMMA per 8 shared-memory
+// reads), 16 features per shared-memory stage, the next stage's global loads in flight behind the arithmetic.
 // tqs[u][c] = fl32( |a_u|^2 - 2 a_u.m_c + |m_c|^2 ), a_u = the FP32 centred feature row the tensor core contracts.  Both the
 // speculation start (argmin over bins -- every rank must derive the same vector, and the summation order here is fixed) and
 // the query terms of the owned rows come from it.
 constexpr int CT_M = 128, CT_N = 64, CT_K = 16;
-__global__ void __launch_bounds__(256) centroid_terms_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
-                                                             int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
-                                                             const double *__restrict__ mc2, int32_t C, float *__restrict__ tqs)
+constexpr int CT_LDA = CT_M + 4, CT_LDB = CT_N + 4; // pitch = 4 mod 16 doubles: the (k-slot t, row g) fragment reads hit 16 bank pairs
+__device__ __forceinline__ void ct_dmma(double (&c)[2], double a, double b)
 {
-    __shared__ __align__(16) double As[CT_K][CT_M + 2];
-    __shared__ __align__(16) double Bs[CT_K][CT_N + 2];
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__global__ void __launch_bounds__(256, 2) centroid_terms_kernel(const int32_t *__restrict__ qpoint, int64_t U, const float *__restrict__ Xf,
+                                                                int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
+                                                                const double *__restrict__ mc2, int32_t C, float *__restrict__ tqs)
+{
+    __shared__ __align__(16) double As[CT_K][CT_LDA];
+    __shared__ __align__(16) double Bs[CT_K][CT_LDB];
     __shared__ double aa_s[CT_M];
-    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4; // rows 8 ty .. 8 ty + 7, bins 4 tx .. 4 tx + 3
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int gq = lane >> 2, tq = lane & 3;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32; // the warp's 32 x 32 corner of the CTA tile
     const int64_t u0 = (int64_t)blockIdx.x * CT_M;
     const int c0 = blockIdx.y * CT_N;
     // loader roles: A: query lq (two per thread: lq, lq + 64), features 4 lk .. 4 lk + 3 of the stage; B: feature bk, bins 4 bc ..
@@ -327,71 +335,87 @@ __global__ void __launch_bounds__(256) centroid_terms_kernel(const int32_t *__re
         const int64_t uq = u0 + lq + 64 * h;
         xrow[h] = uq < U ? Xf + (int64_t)qpoint[uq] * ldf : nullptr;
     }
-    double acc[8][4];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-    double aa[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    for (int k0 = 0; k0 < d; k0 += CT_K) {
-        {
-            const int t = k0 + 4 * lk;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    double aa[2] = {0.0, 0.0}; // |a|^2 of the loader's two rows over its features (4 of every 16); summed over the 4 loaders below
+    float4 va[2];
+    double vb[4];
+    auto fetch = [&](int k0) {
+        const int t = k0 + 4 * lk;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (xrow[h] && t < ldf) v = *reinterpret_cast<const float4 *>(xrow[h] + t); // pads beyond d are zero (prep_f32_kernel)
-                As[4 * lk + 0][lq + 64 * h] = t + 0 < d ? (double)v.x : 0.0;
-                As[4 * lk + 1][lq + 64 * h] = t + 1 < d ? (double)v.y : 0.0;
-                As[4 * lk + 2][lq + 64 * h] = t + 2 < d ? (double)v.z : 0.0;
-                As[4 * lk + 3][lq + 64 * h] = t + 3 < d ? (double)v.w : 0.0;
-            }
-            const int tb = k0 + bk;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int c = c0 + 4 * bc + j;
-                Bs[bk][4 * bc + j] = (tb < d && c < Cp) ? mcT[(int64_t)tb * Cp + c] : 0.0;
-            }
+        for (int h = 0; h < 2; ++h) {
+            va[h] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (xrow[h] && t < ldf) va[h] = *reinterpret_cast<const float4 *>(xrow[h] + t); // pads beyond d are zero (prep_f32_kernel)
+            if (t + 0 >= d) va[h].x = 0.f;
+            if (t + 1 >= d) va[h].y = 0.f;
+            if (t + 2 >= d) va[h].z = 0.f;
+            if (t + 3 >= d) va[h].w = 0.f;
         }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < CT_K; ++k) {
-            double av[8], bv[4];
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const double2 t2 = *reinterpret_cast<const double2 *>(&As[k][8 * ty + i]);
-                av[i] = t2.x;
-                av[i + 1] = t2.y;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; j += 2) {
-                const double2 t2 = *reinterpret_cast<const double2 *>(&Bs[k][4 * tx + j]);
-                bv[j] = t2.x;
-                bv[j + 1] = t2.y;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if (tx == 0) aa[i] = fma(av[i], av[i], aa[i]);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
-            }
-        }
-        __syncthreads();
-    }
-    if (tx == 0) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) aa_s[8 * ty + i] = aa[i];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t u = u0 + 8 * ty + i;
-        if (u >= U) continue;
-        const double au = aa_s[8 * ty + i];
+        const int tb = k0 + bk;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int c = c0 + 4 * tx + j;
-            if (c < C) tqs[u * Cp + c] = (float)fmax(au - 2.0 * acc[i][j] + mc2[c], 0.0);
+            const int c = c0 + 4 * bc + j;
+            vb[j] = (tb < d && c < Cp) ? mcT[(int64_t)tb * Cp + c] : 0.0;
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < d; k0 += CT_K) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const double x0 = (double)va[h].x, x1 = (double)va[h].y, x2 = (double)va[h].z, x3 = (double)va[h].w;
+            As[4 * lk + 0][lq + 64 * h] = x0;
+            As[4 * lk + 1][lq + 64 * h] = x1;
+            As[4 * lk + 2][lq + 64 * h] = x2;
+            As[4 * lk + 3][lq + 64 * h] = x3;
+            aa[h] = fma(x0, x0, aa[h]);
+            aa[h] = fma(x1, x1, aa[h]);
+            aa[h] = fma(x2, x2, aa[h]);
+            aa[h] = fma(x3, x3, aa[h]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) Bs[bk][4 * bc + j] = vb[j];
+        __syncthreads();
+        if (k0 + CT_K < d) fetch(k0 + CT_K);
+#pragma unroll
+        for (int k = 0; k < CT_K; k += 4) {
+            // A fragment: (row g, k-slot t); B fragment: (k-slot t, column g)
+            double af[4], bf[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = As[k + tq][wr + 8 * i + gq];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = Bs[k + tq][wc + 8 * j + gq];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) ct_dmma(acc[i][j], af[i], bf[j]);
+        }
+        __syncthreads();
+    }
+    // |a_u|^2: the four loaders of a row are neighbouring lanes
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        aa[h] += __shfl_xor_sync(CHB_FULL, aa[h], 1);
+        aa[h] += __shfl_xor_sync(CHB_FULL, aa[h], 2);
+        if (lk == 0) aa_s[lq + 64 * h] = aa[h];
+    }
+    __syncthreads();
+    // C fragment: lane (g, t) holds rows 8 i + g, columns 8 j + 2t, + 1
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int r = wr + 8 * i + gq;
+        const int64_t u = u0 + r;
+        if (u >= U) continue;
+        const double au = aa_s[r];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = c0 + wc + 8 * j + 2 * tq + e;
+                if (c < C) tqs[u * Cp + c] = (float)fmax(au - 2.0 * acc[i][j][e] + mc2[c], 0.0);
+            }
     }
 }
 
