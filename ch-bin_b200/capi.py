@@ -22,7 +22,7 @@ EXPORTED_SYMBOLS = [
     "chb_abi_version", "chb_create", "chb_destroy", "chb_last_error", "chb_set_stream", "chb_synchronize",
     "chb_get_timers", "chb_reset_timers", "chb_enable_timers", "chb_set_features", "chb_set_features_dev", "chb_set_features_dev_async", "chb_features_buffer", "chb_features_commit",
     "chb_set_labels", "chb_set_params", "chb_build_distance_matrix", "chb_get_distance_rows", "chb_knn_per_bin",
-    "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin", "chb_iteration_begin_dev",
+    "chb_hull_distance_batch", "chb_fit_iteration", "chb_fit", "chb_get_labels", "chb_iteration_begin", "chb_iteration_begin_dev", "chb_iteration_prefetch",
     "chb_round_run", "chb_round_commit", "chb_round_commit_end", "chb_iteration_end", "chb_set_window", "chb_get_window",
     "chb_measure_fp64_tflops", "chb_measure_l2_gbs", "chb_guess_export", "chb_guess_import", "chb_set_distance_mode", "chb_set_gram_engine", "chb_get_candidate_rows", "chb_get_pair_cache",
     "chb_get_fused_candidates", "chb_set_features_async", "chb_set_features_colmajor", "chb_set_features_merged", "chb_get_features",
@@ -102,6 +102,7 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     L.chb_get_labels.argtypes = [_vp, _vp]
     L.chb_iteration_begin.argtypes = [_vp, _vp, _i64]
     L.chb_iteration_begin_dev.argtypes = [_vp, _vp, _i64]
+    L.chb_iteration_prefetch.argtypes = [_vp, _vp, _i64]
     L.chb_round_run.argtypes = [_vp, _i64, _i64, _vp]
     L.chb_round_commit.argtypes = [_vp, _i64, _i64, _vp, ctypes.POINTER(_i64)]
     L.chb_iteration_end.argtypes = [_vp, ctypes.POINTER(_i64)]
@@ -365,6 +366,13 @@ class Context:
     def iteration_begin(self, perm: np.ndarray):
         perm = np.ascontiguousarray(perm, dtype=np.int64)
         self._check(self._lib.chb_iteration_begin(self._h, _ptr(perm), len(perm)))
+
+    def iteration_prefetch(self, perm: np.ndarray):
+        """chb_iteration_prefetch: uploads the NEXT iteration's permutation while the current rounds run; `perm` must be the
+        very array (int64, contiguous) later handed to iteration_begin."""
+        if perm.dtype != np.int64 or not perm.flags.c_contiguous:
+            return  # iteration_begin would convert it into a temporary: nothing to match the prefetched copy with
+        self._check(self._lib.chb_iteration_prefetch(self._h, _ptr(perm), len(perm)))
 
     def guess_export(self, guess_dev_ptr: int) -> bool:
         """chb_guess_export: the owned slots' speculation start into a device buffer of U int32; False = nothing to exchange."""

@@ -165,6 +165,9 @@ class _ContextEngine:
     def iteration_begin(self, perm):
         self.ctx.iteration_begin(perm)
 
+    def prefetch(self, perm):
+        self.ctx.iteration_prefetch(perm)
+
     def round_run(self, lo, hi):
         self.ctx.round_run(lo, hi)
         return None
@@ -408,6 +411,8 @@ def fit_cluster(
                     if spec_state is None and i_iter + 1 < max_iterations:
                         spec_state = np.random.get_state()
                         spec_perm = _draw_permutation(points_to_assign, dist_mod, device, keep_on_device=on_device)
+                        if isinstance(spec_perm, np.ndarray) and hasattr(eng, "prefetch"):
+                            eng.prefetch(spec_perm)  # uploaded on a side stream while this round runs on the device
                     first, done, change_count = eng.round_commit_end(lo, hi, tent)
                     rounds += 1
                     if first == ROUND_AGAIN:

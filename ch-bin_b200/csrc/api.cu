@@ -97,6 +97,7 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 // ---------------------------------------------------------------------------------------------------------
 __global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v)
 {
+    chb_pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
 }
@@ -183,6 +184,7 @@ __global__ void argmin_kernel(const int32_t *__restrict__ own_pos, int64_t cnt, 
 __global__ void commit_kernel(const int32_t *__restrict__ tent, int64_t lo, int64_t hi, const int32_t *__restrict__ perm_pt,
                               int32_t *__restrict__ tent_pt, int32_t *__restrict__ counters, int32_t fb_cap)
 {
+    chb_pdl_enter();
     const int64_t p = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= hi) return;
     // more pairs needed the exact redo than its list holds: this round's tentative labels are incomplete and must not be
@@ -227,6 +229,7 @@ __device__ __forceinline__ int block_exclusive_scan_256(int v, int *s_warp, int 
 }
 __global__ void __launch_bounds__(256) slots_count_kernel(const int32_t *__restrict__ lab, int64_t n, int32_t *__restrict__ tile_cnt)
 {
+    chb_pdl_enter();
     __shared__ int s_warp[8];
     const int64_t base = (int64_t)blockIdx.x * SLOT_TILE + threadIdx.x * 4;
     int v = 0;
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256) slots_count_kernel(const int32_t *__restr
 }
 __global__ void __launch_bounds__(256) slots_tile_scan_kernel(int32_t *__restrict__ tile_cnt, int32_t ntiles)
 {
+    chb_pdl_enter();
     __shared__ int s_warp[8];
     int carry = 0;
     for (int32_t t0 = 0; t0 < ntiles; t0 += 256) {
@@ -252,6 +256,7 @@ __global__ void __launch_bounds__(256) slots_tile_scan_kernel(int32_t *__restric
 __global__ void __launch_bounds__(256) slots_fill_kernel(const int32_t *__restrict__ lab, int64_t n, const int32_t *__restrict__ tile_off,
                                                          int32_t *__restrict__ qslot, int32_t *__restrict__ qpoint, int32_t *__restrict__ pos)
 {
+    chb_pdl_enter();
     __shared__ int s_warp[8];
     const int64_t base = (int64_t)blockIdx.x * SLOT_TILE + threadIdx.x * 4;
     bool f[4];
@@ -284,9 +289,12 @@ __global__ void __launch_bounds__(256) slots_fill_kernel(const int32_t *__restri
 // by the next commit.  An offending entry is replaced by a valid query point so that the round stays memory-safe.
 __global__ void begin_perm_kernel(const int64_t *__restrict__ perm64, int64_t U, int64_t n, const int32_t *__restrict__ qslot,
                                   const int32_t *__restrict__ qpoint, int64_t u0, int64_t u1, int32_t *__restrict__ perm_pt,
-                                  int32_t *__restrict__ pos, int32_t *__restrict__ own_pos, int32_t *__restrict__ counters)
+                                  int32_t *__restrict__ pos, int32_t *__restrict__ own_pos, int32_t *__restrict__ counters,
+                                  const int32_t *__restrict__ old_label, int32_t *__restrict__ tent_pt)
 {
+    chb_pdl_enter();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) tent_pt[p] = old_label[p]; // the iteration starts from the labels the last one ended on (grid covers max(U, n))
     if (p >= U) return;
     int64_t pt = perm64[p];
     if (pt < 0 || pt >= n) {
@@ -305,6 +313,7 @@ __global__ void begin_perm_kernel(const int64_t *__restrict__ perm64, int64_t U,
 __global__ void check_perm_kernel(const int32_t *__restrict__ perm_pt, int64_t U, const int32_t *__restrict__ pos,
                                   int32_t *__restrict__ counters)
 {
+    chb_pdl_enter();
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p < U && pos[perm_pt[p]] != (int32_t)p) atomicMin(&counters[11], (int32_t)p);
 }
@@ -312,8 +321,9 @@ __global__ void check_perm_kernel(const int32_t *__restrict__ perm_pt, int64_t U
 // algorithm.py:63-72 on the device, taken only when the round just committed changed nothing (counters[1] still holds the
 // "none" pattern): the iteration is over -- count sum(initial_bins != curr_bins) and make the new labels the old ones.
 __global__ void end_if_done_kernel(int32_t *__restrict__ old_label, const int32_t *__restrict__ tent_pt, int64_t n,
-                                   int32_t *__restrict__ counters)
+                                   int32_t *__restrict__ counters, int64_t *__restrict__ lab64)
 {
+    chb_pdl_enter();
     if (counters[1] != 0x7f7f7f7f) return;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool ch = false;
@@ -321,6 +331,7 @@ __global__ void end_if_done_kernel(int32_t *__restrict__ old_label, const int32_
         const int32_t t = tent_pt[i];
         ch = old_label[i] != t;
         if (ch) old_label[i] = t;
+        if (lab64) lab64[i] = t; // the caller's int64 labels, staged with this commit's read-back (stage_labels)
     }
     const unsigned m = __ballot_sync(CHB_FULL, ch);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counters[2], __popc(m));
@@ -328,6 +339,7 @@ __global__ void end_if_done_kernel(int32_t *__restrict__ old_label, const int32_
 
 __global__ void widen_labels_kernel(const int32_t *__restrict__ lab, int64_t n, int64_t *__restrict__ out)
 {
+    chb_pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = lab[i];
 }
@@ -376,6 +388,16 @@ int ensure_work(chb_ctx *c, int64_t items)
     }
     return CHB_OK;
 }
+
+} // namespace
+
+bool chb_pdl_enabled()
+{
+    static const bool on = getenv("CHB_NO_PDL") == nullptr;
+    return on;
+}
+
+namespace {
 
 int sync_stream(chb_ctx *c)
 {
@@ -428,13 +450,20 @@ int chb_create(chb_ctx **out, int device_id)
         return chb_fail(nullptr, CHB_ECUDA, "cudaStreamCreate failed");
     }
     c->stream = c->own_stream;
+    if (cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_perm, cudaEventDisableTiming) != cudaSuccess) {
+        delete c;
+        return chb_fail(nullptr, CHB_ECUDA, "side stream / event creation failed");
+    }
     if (cudaMalloc(&c->counters, sizeof(int32_t) * 16) != cudaSuccess ||
-        cudaMallocHost(&c->counters_host, sizeof(int32_t) * 16) != cudaSuccess) {
+        cudaMallocHost(&c->counters_host, sizeof(int32_t) * 32) != cudaSuccess) {
         delete c;
         return chb_fail(nullptr, CHB_ENOMEM, "counter allocation failed");
     }
     cudaMemsetAsync(c->counters, 0, sizeof(int32_t) * 16, c->stream);
-    memset(c->counters_host, 0, sizeof(int32_t) * 16);
+    memset(c->counters_host, 0, sizeof(int32_t) * 32);
     *out = c;
     return CHB_OK;
 }
@@ -444,10 +473,11 @@ int chb_destroy(chb_ctx *c)
     if (!c) return CHB_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
     chb_resolve_timers(c);
     for (auto &p : c->ev_free) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     dev_free(&c->X); dev_free(&c->old_label); dev_free(&c->tent_pt); dev_free(&c->pos); dev_free(&c->qslot);
-    dev_free(&c->perm64); dev_free(&c->lab64); dev_free(&c->slot_tiles); dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
+    dev_free(&c->perm64); dev_free(&c->perm64_next); dev_free(&c->lab64); dev_free(&c->slot_tiles); dev_free(&c->qpoint); dev_free(&c->perm_pt); dev_free(&c->own_pos); dev_free(&c->Dq); dev_free(&c->Dscratch);
     dev_free(&c->knn_idx); dev_free(&c->knn_cnt); dev_free(&c->pair_dist); dev_free(&c->pair_status);
     dev_free(&c->work); dev_free(&c->counters); dev_free(&c->tent_win); dev_free(&c->fallback); dev_free(&c->qp_scratch);
     dev_free(&c->Xf); dev_free(&c->nrm); dev_free(&c->packed); dev_free(&c->Asplit); dev_free(&c->Bsplit); dev_free(&c->colsum); dev_free(&c->stage_X); dev_free(&c->colpart); dev_free(&c->seed_off); dev_free(&c->seed_idx);
@@ -456,6 +486,10 @@ int chb_destroy(chb_ctx *c)
     if (c->pin_i32) cudaFreeHost(c->pin_i32);
     if (c->pin_lab64) cudaFreeHost(c->pin_lab64);
     delete[] c->own_pos_host;
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_perm) cudaEventDestroy(c->ev_perm);
+    if (c->side_stream) cudaStreamDestroy(c->side_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return CHB_OK;
@@ -466,6 +500,7 @@ int chb_set_stream(chb_ctx *c, void *cuda_stream)
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CUDA(c, cudaSetDevice(c->device));
     CHB_TRY(sync_stream(c));
+    CHB_CUDA(c, cudaStreamSynchronize(c->side_stream));
     // (void*)-1 = back to the context's own stream; anything else (including NULL, the legacy default stream) is adopted
     c->stream = (cuda_stream == reinterpret_cast<void *>(static_cast<intptr_t>(-1))) ? c->own_stream
                                                                                      : reinterpret_cast<cudaStream_t>(cuda_stream);
@@ -839,6 +874,7 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     CHB_CUDA(c, cudaSetDevice(c->device));
     c->labels_set = false; // the staging block (and with it the host mirror of the slots) is rewritten below
     c->labels_staged = false;
+    c->perm_prefetch_src = nullptr; // a permutation prefetched for the previous label set is void
     // Host staging in ONE page-locked block: lab[n] | qslot[n] | qpoint[n] | seed_idx[n] | seed_off[C + 1].  Copies from
     // page-locked memory neither stage nor wait for earlier work on the stream, so they (and the host loops here) overlap a
     // feature upload still in flight (chb_set_features_async).  The block is rewritten by the next chb_set_labels only.
@@ -921,9 +957,9 @@ int chb_set_labels(chb_ctx *c, const int64_t *bins, int64_t n, int32_t C, int64_
     {
         const int32_t ntiles = (int32_t)((n + SLOT_TILE - 1) / SLOT_TILE);
         CHB_TRY(dev_reserve(c, &c->slot_tiles, &c->cap_slot_tiles, (int64_t)ntiles));
-        slots_count_kernel<<<(unsigned)ntiles, 256, 0, c->stream>>>(c->old_label, n, c->slot_tiles);
-        slots_tile_scan_kernel<<<1, 256, 0, c->stream>>>(c->slot_tiles, ntiles);
-        slots_fill_kernel<<<(unsigned)ntiles, 256, 0, c->stream>>>(c->old_label, n, c->slot_tiles, c->qslot, c->qpoint, c->pos);
+        CHB_PDL_LAUNCH(c, slots_count_kernel, (unsigned)ntiles, 256, 0, c->old_label, n, c->slot_tiles);
+        CHB_PDL_LAUNCH(c, slots_tile_scan_kernel, 1, 256, 0, c->slot_tiles, ntiles);
+        CHB_PDL_LAUNCH(c, slots_fill_kernel, (unsigned)ntiles, 256, 0, c->old_label, n, c->slot_tiles, c->qslot, c->qpoint, c->pos);
         CHB_CUDA(c, cudaGetLastError());
         c->tm.launches_other += 3;
     }
@@ -1152,6 +1188,24 @@ static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bo
 
 int chb_iteration_begin(chb_ctx *c, const int64_t *perm, int64_t U) { return iteration_begin_common(c, perm, U, false); }
 
+// The NEXT iteration's permutation, uploaded on the side stream while the current iteration's rounds run: a stage at 20k
+// contigs spends ~20 us per iteration staging 140 KB of pageable host memory with the device idle (the upload sits right
+// after the commit's synchronisation).  Used by the next chb_iteration_begin iff it is called with the same `perm`.
+int chb_iteration_prefetch(chb_ctx *c, const int64_t *perm, int64_t U)
+{
+    CHB_CHECK(c, c && (perm || U == 0), CHB_EINVAL, "NULL argument");
+    CHB_CHECK(c, c->labels_set && U == c->U, CHB_EINVAL, "permutation length %lld != number of points to assign %lld", (long long)U,
+              (long long)c->U);
+    c->perm_prefetch_src = nullptr;
+    if (U == 0 || !use_fused(c)) return CHB_OK; // the host path of chb_iteration_begin reads the permutation on the host
+    CHB_CUDA(c, cudaSetDevice(c->device));
+    CHB_TRY(dev_reserve(c, &c->perm64_next, &c->cap_perm64_next, U));
+    CHB_CUDA(c, cudaMemcpyAsync(c->perm64_next, perm, sizeof(int64_t) * (size_t)U, cudaMemcpyHostToDevice, c->side_stream));
+    CHB_CUDA(c, cudaEventRecord(c->ev_perm, c->side_stream));
+    c->perm_prefetch_src = perm;
+    return CHB_OK;
+}
+
 int chb_iteration_begin_dev(chb_ctx *c, const int64_t *perm_dev, int64_t U)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
@@ -1172,13 +1226,24 @@ static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bo
     if (use_fused(c) && U > 0) {
         // Device path (distance mode 2): the permutation is uploaded as it is and turned into perm_pt / pos / own_pos by
         // one kernel; its validation travels with the next commit's read-back (no host pass over U, no host mirror).
-        CHB_TRY(dev_reserve(c, &c->perm64, &c->cap_perm64, U));
-        CHB_CUDA(c, cudaMemcpyAsync(c->perm64, perm, sizeof(int64_t) * (size_t)U,
-                                    perm_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        const int64_t *src64 = nullptr;
+        if (!perm_on_device && c->perm_prefetch_src && c->perm_prefetch_src == perm && c->cap_perm64_next >= U) {
+            // uploaded ahead on the side stream while the previous iteration ran (chb_iteration_prefetch): the buffers swap roles
+            std::swap(c->perm64, c->perm64_next);
+            std::swap(c->cap_perm64, c->cap_perm64_next);
+            CHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_perm, 0));
+            src64 = c->perm64;
+        } else {
+            CHB_TRY(dev_reserve(c, &c->perm64, &c->cap_perm64, U));
+            CHB_CUDA(c, cudaMemcpyAsync(c->perm64, perm, sizeof(int64_t) * (size_t)U,
+                                        perm_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+            src64 = c->perm64;
+        }
+        c->perm_prefetch_src = nullptr;
         CHB_CUDA(c, cudaMemsetAsync(&c->counters[9], 0x7f, 3 * sizeof(int32_t), c->stream));
-        begin_perm_kernel<<<nblk(U, 256), 256, 0, c->stream>>>(c->perm64, U, c->n, c->qslot, c->qpoint, c->u0, c->u1, c->perm_pt, c->pos,
-                                                             c->own_pos, c->counters);
-        check_perm_kernel<<<nblk(U, 256), 256, 0, c->stream>>>(c->perm_pt, U, c->pos, c->counters);
+        CHB_PDL_LAUNCH(c, begin_perm_kernel, nblk(std::max<int64_t>(U, c->n), 256), 256, 0, src64, U, c->n, c->qslot, c->qpoint, c->u0, c->u1,
+                       c->perm_pt, c->pos, c->own_pos, c->counters, c->old_label, c->tent_pt);
+        CHB_PDL_LAUNCH(c, check_perm_kernel, nblk(U, 256), 256, 0, c->perm_pt, U, c->pos, c->counters);
         CHB_CUDA(c, cudaGetLastError());
         c->tm.launches_other += 2;
         c->n_own_pos = c->u1 - c->u0;
@@ -1225,7 +1290,8 @@ static int iteration_begin_common(chb_ctx *c, const int64_t *perm, int64_t U, bo
         ++c->tm.launches_other;
     }
     }
-    CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
+    if (!c->own_pos_by_slot) // (the device path's begin_perm_kernel has done this copy)
+        CHB_CUDA(c, cudaMemcpyAsync(c->tent_pt, c->old_label, sizeof(int32_t) * (size_t)c->n, cudaMemcpyDeviceToDevice, c->stream));
     if (c->guess_pending && use_fused(c) && U > 0) {
         // First iteration: every query still carries -1.  Any starting vector T0 leads the speculate/repair rounds to
         // the same fixed point (position p is final once positions < p are, whatever it started from), so start from
@@ -1268,7 +1334,7 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         cnt = (std::lower_bound(ob, oe, hi) - ob) - b;
     }
     if (c->n_own_pos < c->U) { // positions of other ranks' queries stay CHB_UNOWNED; a context that owns them all skips the fill
-        fill_i32_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, hi - lo, CHB_UNOWNED);
+        CHB_PDL_LAUNCH(c, fill_i32_kernel, nblk(hi - lo, 256), 256, 0, tent_dev, hi - lo, CHB_UNOWNED);
         CHB_CUDA(c, cudaGetLastError());
         ++c->tm.launches_other;
     }
@@ -1284,18 +1350,17 @@ int chb_round_run(chb_ctx *c, int64_t lo, int64_t hi, int32_t *tent_dev)
         const int64_t nown = c->u1 - c->u0;
         CHB_TRY(ensure_work(c, nown)); // a pair is listed at most once per round (re-rank or exact redo)
         CHB_TRY(chb_round_fused(c)); // resets the work counter itself (round_reset_kernel)
-        // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the
-        // tile / redo counters travel with the commit's read-back
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[6], &c->counters[6], 7 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        // pairs whose kept lists were incomplete were redone exactly inside chb_round_fused (no host round trip); the work /
+        // tile / redo / cap counters all travel with the commit's ONE 64-byte read-back (commit_common) -- copy nodes between
+        // the kernels would also break the programmatic launch chain
         chb_qp_args q{};
         q.X = c->X; q.ldx = c->ldx; q.d = c->d; q.work = c->work; q.work_count = c->counters; q.n_work = nown * c->C;
         q.row_point = c->qpoint + c->u0; q.knn_idx = c->knn_idx; q.knn_cnt = c->knn_cnt; q.C = c->C; q.k = c->k;
         q.metric = c->metric; q.dist = c->pair_dist; q.status = c->pair_status; q.alpha = nullptr;
         q.cap_count = &c->counters[14];
         CHB_TRY(chb_launch_qp(c, q));
-        cudaMemcpyAsync(&c->counters_host[4], c->counters, sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
-        cudaMemcpyAsync(&c->counters_host[14], &c->counters[14], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
         CHB_TRY(chb_fused_argmin(c, c->own_pos + b, cnt, lo, hi, tent_dev));
+        c->round_snapshot_pending = true;
         return CHB_OK;
     }
     CHB_TRY(ensure_work(c, c->materialise ? cnt : std::min(cnt, c->scratch_rows)));
@@ -1371,7 +1436,7 @@ static int resolve_perm_check(chb_ctx *c)
 
 // Labels widened to the caller's int64 on the device and copied into the page-locked staging block (enqueued only)
 constexpr int64_t LABEL_STAGE_MAX = 1 << 18;
-static int stage_labels(chb_ctx *c, const int32_t *lab_dev)
+static int ensure_label_stage(chb_ctx *c)
 {
     CHB_TRY(dev_reserve(c, &c->lab64, &c->cap_lab64, c->n));
     if (c->pin_lab_cap < c->n) {
@@ -1382,9 +1447,15 @@ static int stage_labels(chb_ctx *c, const int32_t *lab_dev)
         CHB_CUDA(c, cudaMallocHost(reinterpret_cast<void **>(&c->pin_lab64), sizeof(int64_t) * (size_t)c->n));
         c->pin_lab_cap = c->n;
     }
-    widen_labels_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(lab_dev, c->n, c->lab64);
-    CHB_CUDA(c, cudaGetLastError());
-    ++c->tm.launches_other;
+    return CHB_OK;
+}
+static int stage_labels(chb_ctx *c, const int32_t *lab_dev, bool widened = false) // widened: lab64 is already filled
+{
+    CHB_TRY(ensure_label_stage(c));
+    if (!widened) {
+        CHB_PDL_LAUNCH(c, widen_labels_kernel, nblk(c->n, 256), 256, 0, lab_dev, c->n, c->lab64);
+        ++c->tm.launches_other;
+    }
     CHB_CUDA(c, cudaMemcpyAsync(c->pin_lab64, c->lab64, sizeof(int64_t) * (size_t)c->n, cudaMemcpyDeviceToHost, c->stream));
     return CHB_OK;
 }
@@ -1404,29 +1475,48 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
         tent_dev = c->tent_win;
     }
     const bool may_end = n_changed != nullptr && hi == c->U;
-    CHB_CUDA(c, cudaMemsetAsync(&c->counters[1], 0x7f, sizeof(int32_t), c->stream)); // 0x7f7f7f7f: above any position
-    if (may_end) CHB_CUDA(c, cudaMemsetAsync(&c->counters[2], 0, sizeof(int32_t), c->stream));
+    if (c->round_counters_reset) {
+        c->round_counters_reset = false; // this round's round_reset_kernel left counters[1] = "none" and counters[2] = 0
+    } else {
+        CHB_CUDA(c, cudaMemsetAsync(&c->counters[1], 0x7f, sizeof(int32_t), c->stream)); // 0x7f7f7f7f: above any position
+        if (may_end) CHB_CUDA(c, cudaMemsetAsync(&c->counters[2], 0, sizeof(int32_t), c->stream));
+    }
+    // if this commit ends the iteration the caller may well ask for the labels next: they are widened by end_if_done_kernel
+    // itself and travel with the counters (if the iteration goes on the copy is simply not used)
+    const bool stage = may_end && c->n <= LABEL_STAGE_MAX;
+    if (stage) CHB_TRY(ensure_label_stage(c));
     {
         chb_stage_timer t(c, CHB_ST_COMMIT);
-        commit_kernel<<<nblk(hi - lo, 256), 256, 0, c->stream>>>(tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters,
+        CHB_PDL_LAUNCH(c, commit_kernel, nblk(hi - lo, 256), 256, 0, tent_dev, lo, hi, c->perm_pt, c->tent_pt, c->counters,
                                                                   (use_fused(c) && c->u1 - c->u0 == c->U) ? c->f_fb_cap : 0);
     }
     bool staged = false;
     if (may_end) {
-        end_if_done_kernel<<<nblk(c->n, 256), 256, 0, c->stream>>>(c->old_label, c->tent_pt, c->n, c->counters);
+        CHB_PDL_LAUNCH(c, end_if_done_kernel, nblk(c->n, 256), 256, 0, c->old_label, c->tent_pt, c->n, c->counters,
+                       stage ? c->lab64 : nullptr);
         ++c->tm.launches_other;
-        if (c->n <= LABEL_STAGE_MAX) {
-            // if this commit ends the iteration the caller may well ask for the labels next: they travel with the counters
-            // (old_label holds them once end_if_done_kernel has run; if the iteration goes on the copy is simply not used)
-            CHB_TRY(stage_labels(c, c->old_label));
+        if (stage) {
+            CHB_TRY(stage_labels(c, c->old_label, true));
             staged = true;
         }
     }
-    CHB_CUDA(c, cudaGetLastError());
-    CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[1], &c->counters[1], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    if (c->perm_check_pending)
-        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[9], &c->counters[9], 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
-    CHB_TRY(sync_stream(c));
+    if (c->round_snapshot_pending) {
+        // fused path: every counter of the round in one 64-byte read-back (round_run enqueued none)
+        c->round_snapshot_pending = false;
+        int32_t *snap = c->counters_host + 16;
+        CHB_CUDA(c, cudaMemcpyAsync(snap, c->counters, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_TRY(sync_stream(c));
+        int32_t *h = c->counters_host;
+        h[1] = snap[1]; h[2] = snap[2];
+        h[4] = snap[0];   // QPs solved this round (work-list length)
+        for (int i = 6; i <= 12; ++i) h[i] = snap[i]; // exact-redo pairs, planned / issued tiles, permutation checks, refusal flag
+        h[14] = snap[14]; // QPs that stopped on the iteration cap
+    } else {
+        CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[1], &c->counters[1], 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        if (c->perm_check_pending)
+            CHB_CUDA(c, cudaMemcpyAsync(&c->counters_host[9], &c->counters[9], 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+        CHB_TRY(sync_stream(c));
+    }
     c->tm.qps_solved += c->counters_host[4];
     c->counters_host[4] = 0;
     c->tm.qp_iter_cap += c->counters_host[14];
@@ -1514,7 +1604,15 @@ int chb_get_labels(chb_ctx *c, int64_t *labels_out)
     return CHB_OK;
 }
 
+static int fit_iteration_impl(chb_ctx *c, const int64_t *perm, const int64_t *next_perm, int64_t U, int64_t *labels_out, int64_t *n_changed);
+
 int chb_fit_iteration(chb_ctx *c, const int64_t *perm, int64_t U, int64_t *labels_out, int64_t *n_changed)
+{
+    return fit_iteration_impl(c, perm, nullptr, U, labels_out, n_changed);
+}
+
+// next_perm != NULL: the permutation of the iteration after this one, uploaded ahead while this iteration's first round runs
+static int fit_iteration_impl(chb_ctx *c, const int64_t *perm, const int64_t *next_perm, int64_t U, int64_t *labels_out, int64_t *n_changed)
 {
     CHB_CHECK(c, c, CHB_EINVAL, "ctx is NULL");
     CHB_CHECK(c, c->u0 == 0 && c->u1 == c->U, CHB_EINVAL,
@@ -1531,6 +1629,10 @@ int chb_fit_iteration(chb_ctx *c, const int64_t *perm, int64_t U, int64_t *label
         while (lo < U) {
             const int64_t hi = std::min(U, lo + W);
             CHB_TRY(chb_round_run(c, lo, hi, c->tent_win));
+            if (next_perm) { // after the round is enqueued: the staging copy on the host overlaps the round on the device
+                CHB_TRY(chb_iteration_prefetch(c, next_perm, U));
+                next_perm = nullptr;
+            }
             int64_t first = -1;
             CHB_TRY(chb_round_commit_end(c, lo, hi, c->tent_win, &first, &nch, &done));
             if (first == CHB_ROUND_AGAIN) continue; // the exact-redo list was too small and has grown: same window again
@@ -1555,7 +1657,8 @@ int chb_fit(chb_ctx *c, const int64_t *perms, int64_t U, int32_t max_iterations,
     int32_t it = 0, conv = 0;
     for (; it < max_iterations; ++it) {
         int64_t nch = 0;
-        CHB_TRY(chb_fit_iteration(c, perms + (int64_t)it * U, U, nullptr, &nch));
+        CHB_TRY(fit_iteration_impl(c, perms + (int64_t)it * U, it + 1 < max_iterations ? perms + (int64_t)(it + 1) * U : nullptr, U, nullptr,
+                                   &nch));
         if (changed_per_iter) changed_per_iter[it] = nch;
         if (nch == 0) { conv = 1; ++it; break; } // algorithm.py:63-66
     }

@@ -20,6 +20,15 @@ struct chb_ctx {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t own_stream = nullptr;
+    // side stream (non-blocking): work that does not sit on the critical chain of a stage -- the upper-bound pass of the label
+    // set-up (row_ub_kernel: only the first round's threshold_kernel reads its result) and the upload of the NEXT iteration's
+    // permutation -- forked from / joined into `stream` with events
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_perm = nullptr;
+    bool side_join_pending = false; // `stream` has not yet waited for ev_join
+    bool round_counters_reset = false; // round_reset_kernel has put counters[1..3] into their pre-commit state for this round
+    bool round_snapshot_pending = false; // the fused round's counters have not been read back yet (one copy at the commit)
+    bool qp_fb_zeroed = false;         // ... and the QP fallback counter (counters[3]): chb_launch_qp skips its memset once
     std::string err;
 
     // ---- features: n x ldx float64, row pitch padded to 16 bytes, pad columns are zero
@@ -61,6 +70,9 @@ struct chb_ctx {
     int64_t *own_pos_host = nullptr;
     int64_t *perm64 = nullptr;     // U : this iteration's permutation as the caller passed it (device path of chb_iteration_begin)
     int64_t cap_perm64 = 0;
+    int64_t *perm64_next = nullptr; // U : the next iteration's permutation, uploaded ahead on the side stream (chb_iteration_prefetch)
+    int64_t cap_perm64_next = 0;
+    const int64_t *perm_prefetch_src = nullptr; // host array the prefetched copy came from (nullptr: nothing prefetched)
     bool perm_check_pending = false; // the device-side validation of this iteration's permutation has not been read back yet
     bool own_pos_by_slot = false;  // own_pos is indexed by owned slot (device path) instead of ascending by position (host path)
     bool labels_set = false, in_iteration = false;
@@ -108,7 +120,7 @@ struct chb_ctx {
     int64_t work_cap = 0;
     int32_t *counters = nullptr;      // 16 ints: [0] work count, [1] first changed position, [2] n_changed, [3] QP fallback count,
                                       // [5] max |x - mu|^2 bits, [6] exact-redo pairs, [7] planned tiles, [8] tiles issued by the MMA warps
-    int32_t *counters_host = nullptr; // pinned mirror
+    int32_t *counters_host = nullptr; // pinned mirror (16 ints) + the commit's snapshot of all 16 device counters
 
     // capacities (elements) of the re-usable allocations above, so that repeated set-ups do not re-malloc
     int64_t cap_X = 0, cap_Xf = 0, cap_nrm = 0, cap_colsum = 0;
@@ -195,6 +207,47 @@ int chb_fail(chb_ctx *ctx, int code, const char *fmt, ...);
     do {                                                    \
         if (!(cond)) return chb_fail(ctx, code, __VA_ARGS__); \
     } while (0)
+
+// ---- programmatic dependent launch (sm_90+) ---------------------------------------------------------------
+// A clustering stage at 20k contigs is a chain of ~50 kernels of 3-70 us: between two of them the stream otherwise pays
+// drain + launch (~2 us).  Kernels of that chain start with chb_pdl_enter() -- wait for the preceding grid (complete and
+// flushed), then let the NEXT grid be scheduled -- and are launched through chb_launch_pdl, so that the next grid's CTAs
+// are already resident (blocked in griddepcontrol.wait) when this one drains.  Rules: chb_pdl_enter() is the FIRST
+// statement of the kernel, before any early return and before any global-memory access (a grid that exits without
+// waiting would let its own dependents overtake the grid before it).  Both instructions are no-ops in a kernel launched
+// the ordinary way.  CHB_NO_PDL=1 launches everything the ordinary way (A/B measurements).
+#ifdef __CUDACC__
+__device__ __forceinline__ void chb_pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// For kernels whose CTAs are all resident at once and run long (the persistent tensor-core kernel, the QP kernels, the
+// exact redo): no early trigger -- the next grid's CTAs would sit beside them for the whole run (measured at 1M contigs:
+// the stage 3.5 ms slower with the early trigger everywhere); the implicit trigger at CTA exit still lets the next grid
+// move in while the last CTAs drain.
+__device__ __forceinline__ void chb_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool chb_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t chb_launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = chb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define CHB_PDL_LAUNCH(ctx, kern, grid, block, smem, ...) \
+    CHB_CUDA(ctx, chb_launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), (ctx)->stream, __VA_ARGS__))
+#endif
 
 enum chb_stage { CHB_ST_DISTANCE = 0, CHB_ST_KNN = 1, CHB_ST_QP = 2, CHB_ST_COMMIT = 3, CHB_ST_OTHER = 4, CHB_ST_GRAM = 5 };
 

@@ -138,6 +138,7 @@ __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_c
                                    int32_t *__restrict__ pair_row, int64_t cap_pairs, int32_t *__restrict__ counters,
                                    int64_t ncol, int32_t *__restrict__ col_pt, int32_t *__restrict__ col_a, int32_t *__restrict__ col_b)
 {
+    chb_pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ncol) { // padding columns: no point, never visible
         col_pt[i] = -1;
@@ -149,7 +150,12 @@ __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_c
     if (i < nown) row_nb[i] = 0;
     if (i < nmeta) pair_meta[i] = 0;
     if (i < cap_pairs) pair_row[i] = -1;
-    if (i == 0) { counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; counters[12] = 0; counters[14] = 0; }
+    if (i == 0) {
+        counters[0] = 0; counters[6] = 0; counters[7] = 0; counters[8] = 0; counters[12] = 0; counters[14] = 0;
+        // the commit that follows this round (api.cu, commit_common) and the QP launch find their counters ready: first changed
+        // position = "none", changed count, QP fallback count -- three memset nodes less on the round's chain
+        counters[1] = 0x7f7f7f7f; counters[2] = 0; counters[3] = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -158,6 +164,7 @@ __global__ void round_reset_kernel(int32_t *__restrict__ bin_cnt, int32_t nbin_c
 __global__ void entries_count_kernel(const int32_t *__restrict__ tent, const int32_t *__restrict__ old, int64_t n, int32_t C,
                                      int32_t *__restrict__ bin_cnt)
 {
+    chb_pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int t = tent[i], o = old[i];
@@ -169,6 +176,7 @@ __global__ void entries_count_kernel(const int32_t *__restrict__ tent, const int
 __global__ void entries_scan_kernel(const int32_t *__restrict__ bin_cnt, int32_t C, int32_t *__restrict__ seg_off,
                                     int32_t *__restrict__ cursor, int32_t *__restrict__ tile_bin, int32_t *__restrict__ ntiles_out)
 {
+    chb_pdl_enter();
     if (threadIdx.x == 0) {
         int off = 0;
         for (int c = 0; c < C; ++c) {
@@ -190,6 +198,7 @@ __global__ void entries_scatter_kernel(const int32_t *__restrict__ tent, const i
                                        int32_t *__restrict__ cursor, int32_t *__restrict__ col_pt, int32_t *__restrict__ col_a,
                                        int32_t *__restrict__ col_b)
 {
+    chb_pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int t = tent[i], o = old[i], ps = pos[i];
@@ -215,6 +224,7 @@ __global__ void split2_gather_kernel(const int32_t *__restrict__ idx, const int3
                                      const float *__restrict__ Xf, int32_t ldf, int32_t d, int32_t dp8, int32_t Kp2,
                                      const float *__restrict__ nrm, float *__restrict__ out, float *__restrict__ out_nrm)
 {
+    chb_pdl_enter();
     const int64_t nr = count_tiles ? (int64_t)(*count_tiles) * BN : nrows_max;
     const int64_t kq = Kp2 / 4; // float4 per row
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -259,6 +269,7 @@ __global__ void __launch_bounds__(256) centre_sum_kernel(const double *__restric
                                                          const int32_t *__restrict__ seed_off, const int32_t *__restrict__ seed_idx,
                                                          double *__restrict__ sum, int32_t *__restrict__ cnt)
 {
+    chb_pdl_enter();
     const int c = blockIdx.x;
     const int b = seed_off[c], e = seed_off[c + 1];
     for (int t = threadIdx.x; t < d; t += blockDim.x) {
@@ -281,6 +292,7 @@ __global__ void __launch_bounds__(256) centre_sum_kernel(const double *__restric
 __global__ void centre_finish_kernel(double *__restrict__ mc, const int32_t *__restrict__ cnt, const double *__restrict__ colsum,
                                      double inv_n, int32_t d, double *__restrict__ mc2, double *__restrict__ mcT, int32_t Cp)
 {
+    chb_pdl_enter();
     const int c = blockIdx.x;
     __shared__ double red[128];
     const double inv = cnt[c] > 0 ? 1.0 / (double)cnt[c] : 0.0;
@@ -319,6 +331,7 @@ __global__ void __launch_bounds__(256, 2) centroid_terms_kernel(const int32_t *_
                                                                 int32_t ldf, int32_t d, const double *__restrict__ mcT, int32_t Cp,
                                                                 const double *__restrict__ mc2, int32_t C, float *__restrict__ tqs)
 {
+    chb_pdl_wait();
     // two stages: the stores of stage s + 1 overlap the MMAs of stage s (54 KB: dynamic shared memory, CT_SMEM)
     extern __shared__ __align__(16) unsigned char ct_smem[];
     double (*As)[CT_K][CT_LDA] = reinterpret_cast<double (*)[CT_K][CT_LDA]>(ct_smem);
@@ -452,6 +465,7 @@ __global__ void __launch_bounds__(256, 2) centroid_terms_kernel(const int32_t *_
 __global__ void __launch_bounds__(256) guess_from_terms_kernel(const float *__restrict__ tqs, int64_t U, int32_t Cp, int32_t C,
                                                                const int32_t *__restrict__ mcnt, int32_t *__restrict__ guess_all)
 {
+    chb_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t u = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (u >= U) return;
@@ -478,6 +492,7 @@ __global__ void __launch_bounds__(256) query_terms_gather_kernel(const float *__
                                                                  const int32_t *__restrict__ row_slot, int64_t nown, int32_t C,
                                                                  int64_t ldt, float *__restrict__ tq)
 {
+    chb_pdl_enter();
     __shared__ float tile[QT_ROWS][33];
     const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
     const int64_t r0 = (int64_t)blockIdx.x * QT_ROWS;
@@ -504,6 +519,7 @@ __global__ void __launch_bounds__(256) query_terms_gather_kernel(const float *__
 __global__ void guess_scatter_kernel(const int32_t *__restrict__ qpoint, const int32_t *__restrict__ guess_all, int64_t U, int32_t C,
                                      int32_t *__restrict__ tent)
 {
+    chb_pdl_enter();
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u < U && guess_all[u] < C) tent[qpoint[u]] = guess_all[u];
 }
@@ -524,6 +540,7 @@ __global__ void guess_scatter_kernel(const int32_t *__restrict__ qpoint, const i
 __global__ void seed_transpose_kernel(const float *__restrict__ Xf, int32_t ldf, int32_t d, const int32_t *__restrict__ seed_idx,
                                       int64_t ns, float *__restrict__ seedT)
 {
+    chb_pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ns * d) return;
     const int64_t sidx = i / d;
@@ -558,6 +575,7 @@ __global__ void __launch_bounds__(RU_THREADS) row_ub_kernel(const int32_t *__res
                                                             const float *__restrict__ sq_row, const unsigned int *__restrict__ nrm_max_bits,
                                                             float *__restrict__ ub_out, float *__restrict__ ubk2_out)
 {
+    chb_pdl_wait();
     __shared__ float dist[RU_ROWS * RU_DP];                 // 33 KB
     __shared__ __align__(16) float qs[RU_TK * RU_QP];       // feature-major slice of the 64 query rows
     __shared__ __align__(16) float ss[RU_TK * RU_SEEDS];
@@ -690,11 +708,13 @@ __global__ void __launch_bounds__(RU_THREADS) row_ub_kernel(const int32_t *__res
 // rows = owned slots grouped by guessed bin (any order inside a group): histogram, scan, scatter -- no host round trip
 __global__ void row_hist_kernel(const int32_t *__restrict__ guess_own, int64_t nown, int32_t *__restrict__ hist)
 {
+    chb_pdl_enter();
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u < nown) atomicAdd(&hist[guess_own[u]], 1);
 }
 __global__ void row_scan_kernel(const int32_t *__restrict__ hist, int32_t nb, int32_t *__restrict__ cursor)
 {
+    chb_pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int acc = 0;
         for (int b = 0; b < nb; ++b) { cursor[b] = acc; acc += hist[b]; }
@@ -703,6 +723,7 @@ __global__ void row_scan_kernel(const int32_t *__restrict__ hist, int32_t nb, in
 __global__ void row_scatter_kernel(const int32_t *__restrict__ guess_own, int64_t nown, int32_t *__restrict__ cursor,
                                    int32_t *__restrict__ row_slot)
 {
+    chb_pdl_enter();
     const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u < nown) row_slot[atomicAdd(&cursor[guess_own[u]], 1)] = (int32_t)u;
 }
@@ -712,6 +733,7 @@ __global__ void row_gather_kernel(const int32_t *__restrict__ row_slot, const in
                                   int32_t *__restrict__ row_pt, int32_t *__restrict__ row_guess, int32_t *__restrict__ slot_row,
                                   float *__restrict__ sq_row)
 {
+    chb_pdl_enter();
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nown) return;
     const int sl = row_slot[r];
@@ -731,6 +753,7 @@ __global__ void __launch_bounds__(256) column_gather_kernel(const int32_t *__res
                                                             float *__restrict__ out, float *__restrict__ col_term,
                                                             unsigned int *__restrict__ ym2_bits, unsigned int *__restrict__ tcmax_bits)
 {
+    chb_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (e >= (int64_t)(*ntiles) * BN) return;
@@ -794,9 +817,11 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
                                                           int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
                                                           int32_t *__restrict__ mode, int32_t dense_ok)
 {
+    chb_pdl_enter();
     __shared__ int s_mode, s_ti, s_tt;
     constexpr int PLAN_SMEM_BINS = 2048;
     __shared__ int s_nb[PLAN_SMEM_BINS], s_w[PLAN_SMEM_BINS];
+    __shared__ int s_begin[1024 + 1]; // cta_begin while it is built (G <= 1024: the serial suffix-min then stays out of L2)
     int32_t *item_off = scratch, *tile_cum = scratch + C + 1;
     const int tid = threadIdx.x;
     const bool in_smem = C <= PLAN_SMEM_BINS; // the serial prefix below then walks shared memory instead of L2
@@ -842,7 +867,9 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
         return;
     }
     if (!s_mode) return; // items_kernel builds the (row block, bin) list instead
-    for (int b = tid; b <= G; b += 1024) cta_begin[b] = INT32_MAX;
+    const bool beg_smem = G <= 1024;
+    int *beg = beg_smem ? s_begin : cta_begin;
+    for (int b = tid; b <= G; b += 1024) beg[b] = INT32_MAX;
     __syncthreads();
     const int TI = s_ti, TT = s_tt;
     for (int c = tid; c < C; c += 1024) {
@@ -852,15 +879,23 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
         for (int b = 0; b < nb; ++b) {
             const int it = item_off[c] + b;
             items[it] = make_int4(pair_off[c] / BM + b, c, seg_off[c] / BN, w);
-            atomicMin(&cta_begin[(int)(((int64_t)(tile_cum[c] + b * w) * G) / (TT > 0 ? TT : 1))], it);
+            atomicMin(&beg[(int)(((int64_t)(tile_cum[c] + b * w) * G) / (TT > 0 ? TT : 1))], it);
         }
     }
     __syncthreads();
     if (tid == 0) {
-        cta_begin[G] = TI;
-        for (int b = G - 1; b >= 0; --b)
-            if (cta_begin[b] > cta_begin[b + 1]) cta_begin[b] = cta_begin[b + 1];
+        beg[G] = TI;
+        int nxt = TI;
+        for (int b = G - 1; b >= 0; --b) { // CTAs without an item of their own
+            const int v = beg[b];
+            nxt = v > nxt ? nxt : v;
+            beg[b] = nxt;
+        }
         totals[0] = TT;
+    }
+    if (beg_smem) {
+        __syncthreads();
+        for (int b = tid; b <= G; b += 1024) cta_begin[b] = s_begin[b];
     }
 }
 
@@ -873,6 +908,7 @@ __global__ void __launch_bounds__(256) pairs_fill_kernel(const int32_t *__restri
                                                          int32_t *__restrict__ pair_row, int32_t *__restrict__ row_pid,
                                                          const float *__restrict__ a2, int32_t Kp2, float *__restrict__ ap)
 {
+    chb_pdl_enter();
     if (*mode != 1) return;
     const int lane = threadIdx.x & 31;
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -901,6 +937,7 @@ __global__ void __launch_bounds__(1024) items_kernel(const uint8_t *__restrict__
                                                      int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
                                                      const int32_t *__restrict__ mode)
 {
+    chb_pdl_enter();
     if (*mode) return; // pairs_plan_kernel already built the compact (pair block, bin) list
     __shared__ int s_items[1024], s_tiles[1024];
     __shared__ int tot_items, tot_tiles;
@@ -998,6 +1035,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                    const int32_t *__restrict__ cta_begin, float *__restrict__ cand_key, int32_t *__restrict__ cand_idx,
                    int32_t *__restrict__ tiles_issued)
 {
+    chb_pdl_wait();
     // This CTA's work: items [cta_begin[b], cta_begin[b + 1]) of the list built by items_kernel, each one surviving
     // (row block, bin) = {row block, bin, first tile, #tiles}.  Pruned (row block, bin) pairs are not in the list: their
     // tiles are neither loaded, contracted nor screened.  All three warp roles walk the same items.
@@ -1347,6 +1385,7 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
                                  int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv,
                                  uint8_t *__restrict__ skip)
 {
+    chb_pdl_enter();
     // grid: x = chunks of 1024 rows (eight 128-row blocks of the fused kernel; a thread takes 4 consecutive rows, a warp one
     // 128-row block), y = bin.  Besides the per-pair tables the block leaves skip[row block][bin] = "every row of the block
     // pruned the bin": the (row block, bin) work items of the uncompacted path, without a second pass over the thresholds.
@@ -1453,6 +1492,7 @@ __global__ void argmin_rows_kernel(const int32_t *__restrict__ own_pos, int64_t 
                                    const double *__restrict__ pair_dist, int32_t C, const int32_t *__restrict__ old_label,
                                    int64_t lo, int64_t hi, int32_t *__restrict__ tent)
 {
+    chb_pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= cnt) return;
@@ -1529,6 +1569,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
                                                      const int32_t *__restrict__ row_nb, const int32_t *__restrict__ row_bins,
                                                      const int32_t *__restrict__ row_pid, const int32_t *__restrict__ mode_p)
 {
+    chb_pdl_enter();
     const int mode = *mode_p; // 1: the fused kernel worked on compact (row, bin) pairs and filed the lists under their ids
     if (mode == 2) return;    // refused round (pairs_plan_kernel): there are no lists
     constexpr int NG = 32 / G;
@@ -1675,6 +1716,7 @@ __global__ void __launch_bounds__(128) exact_pairs_kernel(const int2 *__restrict
                                                           int32_t *__restrict__ knn_idx, int32_t *__restrict__ knn_cnt,
                                                           int2 *__restrict__ work, int32_t *__restrict__ work_count)
 {
+    chb_pdl_wait();
     extern __shared__ __align__(16) double xq_s[];
     __shared__ double s_best[4];
     __shared__ int s_bidx[4], s_bthr[4];
@@ -2107,7 +2149,7 @@ int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &map, cons
     const int grid = c->sm_count; // persistent: one CTA per SM, work split by items_kernel
     {
         chb_stage_timer t(c, CHB_ST_GRAM);
-        gram_select_kernel<KR, NKT><<<grid, FUSED_THREADS, g.smem, c->stream>>>(
+        CHB_PDL_LAUNCH(c, (gram_select_kernel<KR, NKT>), grid, FUSED_THREADS, g.smem,
             ma, map, mb, c->f_mode, c->f_pair_row, g.nbox, g.nk, g.nstage, c->f_col_pt, c->f_col_a, c->f_col_b, c->f_col_nrm, c->f_tq, c->f_row_pt, c->pos, nrows, c->C,
             c->f_t0, c->f_ldt, c->f_items, c->f_cta_begin, c->f_cand_key, c->f_cand_idx, &c->counters[8]);
     }
@@ -2162,6 +2204,8 @@ bool chb_fused_supported(const chb_ctx *c)
 
 void chb_fused_free(chb_ctx *c)
 {
+    if (c->side_stream) cudaStreamSynchronize(c->side_stream);
+    c->side_join_pending = false;
     cudaFree(c->f_bin_cnt); cudaFree(c->f_seg_off); cudaFree(c->f_cursor); cudaFree(c->f_tile_bin); cudaFree(c->f_ntiles);
     cudaFree(c->f_col_pt); cudaFree(c->f_col_a); cudaFree(c->f_col_b); cudaFree(c->f_col_nrm); cudaFree(c->f_bperm);
     cudaFree(c->f_cand_key); cudaFree(c->f_cand_idx); cudaFree(c->f_fb_pairs); cudaFree(c->f_xs_slots); cudaFree(c->f_thr); cudaFree(c->f_t0); cudaFree(c->f_a2); cudaFree(c->f_tq); cudaFree(c->f_slack); cudaFree(c->f_ym2);
@@ -2209,7 +2253,7 @@ int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_
     if (cnt <= 0) return CHB_OK;
     {
         chb_stage_timer t(c, CHB_ST_COMMIT);
-        argmin_rows_kernel<<<nblk(cnt * 32, 256), 256, 0, c->stream>>>(own_pos_dev, cnt, c->perm_pt, c->qslot, c->u0, c->f_slot_row, c->f_row_nb,
+        CHB_PDL_LAUNCH(c, argmin_rows_kernel, nblk(cnt * 32, 256), 256, 0, own_pos_dev, cnt, c->perm_pt, c->qslot, c->u0, c->f_slot_row, c->f_row_nb,
                                                                        c->f_row_bins, c->pair_dist, c->C, c->old_label, lo, hi, tent_dev);
     }
     CHB_CUDA(c, cudaGetLastError());
@@ -2219,7 +2263,7 @@ int chb_fused_argmin(chb_ctx *c, const int32_t *own_pos_dev, int64_t cnt, int64_
 int chb_fused_guess(chb_ctx *c)
 {
     if (c->U <= 0) return CHB_OK;
-    guess_scatter_kernel<<<nblk(c->U, 256), 256, 0, c->stream>>>(c->qpoint, c->f_guess_all, c->U, c->C, c->tent_pt);
+    CHB_PDL_LAUNCH(c, guess_scatter_kernel, nblk(c->U, 256), 256, 0, c->qpoint, c->f_guess_all, c->U, c->C, c->tent_pt);
     CHB_CUDA(c, cudaGetLastError());
     ++c->tm.launches_other;
     return CHB_OK;
@@ -2374,10 +2418,28 @@ int chb_fused_setup(chb_ctx *c)
     // once per (feature set, label set): bin reference points, row order, query operand and query terms
     if (!c->f_asplit_ready || c->f_cap_a2 < nown * g.Kp2) {
         if (reserve(c, &c->f_a2, &c->f_cap_a2, std::max<int64_t>(nown, 1) * g.Kp2)) return CHB_ENOMEM;
+        // the side stream takes what only the first round's threshold_kernel needs (seed transpose, row_ub_kernel: 56 us at
+        // 20k contigs, 2.5 ms at 1M) beside the chain that leads to the first round's column operand
+        if (c->side_join_pending) { // a set-up that no round consumed
+            CHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+            c->side_join_pending = false;
+        }
+        const int64_t ns_seed = std::max<int64_t>(n - c->U, 1);
+        static const bool no_side = getenv("CHB_NO_SIDE") != nullptr; // A/B aid: everything on the one stream
+        cudaStream_t side = no_side ? c->stream : c->side_stream;
+        if (nown > 0) {
+            if (reserve(c, &c->f_seedT, &c->f_cap_seedT, ns_seed * c->d)) return CHB_ENOMEM;
+            if (!no_side) {
+                CHB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+                CHB_CUDA(c, cudaStreamWaitEvent(side, c->ev_fork, 0));
+            }
+            seed_transpose_kernel<<<nblk(ns_seed * c->d, 256), 256, 0, side>>>(c->Xf, c->ldf, c->d, c->seed_idx, n - c->U, c->f_seedT);
+            ++c->tm.launches_other;
+        }
         // bin reference points from the seed contigs (initial bins, fixed summation order)
-        centre_sum_kernel<<<(unsigned)C, 256, 0, c->stream>>>(c->X, c->ldx, c->d, c->seed_off, c->seed_idx, c->f_mc, c->f_mcnt);
+        CHB_PDL_LAUNCH(c, centre_sum_kernel, (unsigned)C, 256, 0, c->X, c->ldx, c->d, c->seed_off, c->seed_idx, c->f_mc, c->f_mcnt);
         const int32_t Cp = (C + 31) & ~31;
-        centre_finish_kernel<<<(unsigned)C, 128, 0, c->stream>>>(c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2,
+        CHB_PDL_LAUNCH(c, centre_finish_kernel, (unsigned)C, 128, 0, c->f_mc, c->f_mcnt, c->colsum, 1.0 / (double)n, c->d, c->f_mc2,
                                                                  c->f_mcT, Cp);
         c->tm.launches_other += 2;
         // centroid terms |a_u - m_c|^2 and the nearest-centroid guess: for every slot, or -- when the ranks exchange their guesses
@@ -2387,29 +2449,35 @@ int chb_fused_setup(chb_ctx *c)
             if (reserve(c, &c->f_tqs, &c->f_cap_tqs, t_cnt * (int64_t)Cp)) return CHB_ENOMEM;
             dim3 gt((unsigned)((t_cnt + CT_M - 1) / CT_M), 1u);
             CHB_CUDA(c, cudaFuncSetAttribute(centroid_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CT_SMEM));
-            centroid_terms_kernel<<<gt, 256, CT_SMEM, c->stream>>>(c->qpoint + t_first, t_cnt, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2, C, c->f_tqs);
-            guess_from_terms_kernel<<<nblk(t_cnt * 32, 256), 256, 0, c->stream>>>(c->f_tqs, t_cnt, Cp, C, c->f_mcnt, c->f_guess_all + t_first);
+            CHB_PDL_LAUNCH(c, centroid_terms_kernel, gt, 256, CT_SMEM, c->qpoint + t_first, t_cnt, c->Xf, c->ldf, c->d, c->f_mcT, Cp, c->f_mc2, C, c->f_tqs);
+            CHB_PDL_LAUNCH(c, guess_from_terms_kernel, nblk(t_cnt * 32, 256), 256, 0, c->f_tqs, t_cnt, Cp, C, c->f_mcnt, c->f_guess_all + t_first);
             c->tm.launches_other += 2;
         }
         if (nown > 0) {
             // rows = owned slots grouped by guessed bin, so that a 128-row block prunes the same bins
-            const int64_t ns = std::max<int64_t>(n - c->U, 1);
-            if (reserve(c, &c->f_seedT, &c->f_cap_seedT, ns * c->d)) return CHB_ENOMEM;
-            seed_transpose_kernel<<<nblk(ns * c->d, 256), 256, 0, c->stream>>>(c->Xf, c->ldf, c->d, c->seed_idx, n - c->U, c->f_seedT);
             CHB_CUDA(c, cudaMemsetAsync(c->f_rhist, 0, sizeof(int32_t) * (size_t)(C + 2), c->stream));
-            row_hist_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_guess_all + c->u0, nown, c->f_rhist);
-            row_scan_kernel<<<1, 32, 0, c->stream>>>(c->f_rhist, C + 1, c->f_rhist + C + 2);
-            row_scatter_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_guess_all + c->u0, nown, c->f_rhist + C + 2, c->f_row_slot);
-            row_gather_kernel<<<nblk(nown, 256), 256, 0, c->stream>>>(c->f_row_slot, c->qpoint + c->u0, c->f_guess_all + c->u0, c->nrm, nown,
+            CHB_PDL_LAUNCH(c, row_hist_kernel, nblk(nown, 256), 256, 0, c->f_guess_all + c->u0, nown, c->f_rhist);
+            CHB_PDL_LAUNCH(c, row_scan_kernel, 1, 32, 0, c->f_rhist, C + 1, c->f_rhist + C + 2);
+            CHB_PDL_LAUNCH(c, row_scatter_kernel, nblk(nown, 256), 256, 0, c->f_guess_all + c->u0, nown, c->f_rhist + C + 2, c->f_row_slot);
+            CHB_PDL_LAUNCH(c, row_gather_kernel, nblk(nown, 256), 256, 0, c->f_row_slot, c->qpoint + c->u0, c->f_guess_all + c->u0, c->nrm, nown,
                                                                       c->f_row_pt, c->f_row_guess, c->f_slot_row, c->f_sq_row);
-            row_ub_kernel<<<(unsigned)(nown / RU_ROWS + C + 2), RU_THREADS, 0, c->stream>>>(
+            // fork: the row order is known; join: before the first round's threshold_kernel (chb_round_fused)
+            if (!no_side) {
+                CHB_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+                CHB_CUDA(c, cudaStreamWaitEvent(side, c->ev_fork, 0));
+            }
+            row_ub_kernel<<<(unsigned)(nown / RU_ROWS + C + 2), RU_THREADS, 0, side>>>(
                 c->f_row_pt, nown, c->Xf, c->ldf, c->d, C, k, c->seed_off, c->f_seedT, n - c->U, c->f_rhist + C + 2, c->f_sq_row,
                 reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ub, c->f_ubk2);
-            c->tm.launches_other += 2;
-            split2_gather_kernel<<<nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->stream>>>(c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
+            if (!no_side) {
+                CHB_CUDA(c, cudaEventRecord(c->ev_join, side));
+                c->side_join_pending = true;
+            }
+            c->tm.launches_other += 1;
+            CHB_PDL_LAUNCH(c, split2_gather_kernel, nblk(nown * (g.Kp2 / 4), 256), 256, 0, c->f_row_pt, nullptr, nown, c->Xf, c->ldf, c->d,
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
             dim3 gq((unsigned)((nown + QT_ROWS - 1) / QT_ROWS), (unsigned)((C + 31) / 32));
-            query_terms_gather_kernel<<<gq, 256, 0, c->stream>>>(c->f_tqs, Cp, c->u0 - t_first, c->f_row_slot, nown, C, c->f_ldt, c->f_tq);
+            CHB_PDL_LAUNCH(c, query_terms_gather_kernel, gq, 256, 0, c->f_tqs, Cp, c->u0 - t_first, c->f_row_slot, nown, C, c->f_ldt, c->f_tq);
             c->tm.launches_other += 4;
         }
         CHB_CUDA(c, cudaGetLastError());
@@ -2433,18 +2501,23 @@ int chb_round_fused(chb_ctx *c)
     }
 
     // ---- 1. column entries
-    round_reset_kernel<<<nblk(std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(nown, c->f_cap_pairs), ncol_max), 5 * (C + 2)), 256), 256, 0,
-                         c->stream>>>(c->f_bin_cnt, C + 1, c->f_ym2, 2 * (C + 1), c->f_row_nb, nown, c->f_pair_meta, 3 * (C + 2),
+    CHB_PDL_LAUNCH(c, round_reset_kernel, nblk(std::max<int64_t>(std::max<int64_t>(std::max<int64_t>(nown, c->f_cap_pairs), ncol_max), 5 * (C + 2)), 256), 256, 0, c->f_bin_cnt, C + 1, c->f_ym2, 2 * (C + 1), c->f_row_nb, nown, c->f_pair_meta, 3 * (C + 2),
                                       c->f_pair_row, c->f_cap_pairs, c->counters, ncol_max, c->f_col_pt, c->f_col_a, c->f_col_b);
-    entries_count_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, n, C, c->f_bin_cnt);
-    entries_scan_kernel<<<1, 256, 0, c->stream>>>(c->f_bin_cnt, C, c->f_seg_off, c->f_cursor, c->f_tile_bin, c->f_ntiles);
-    entries_scatter_kernel<<<nblk(n, 256), 256, 0, c->stream>>>(c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
+    CHB_PDL_LAUNCH(c, entries_count_kernel, nblk(n, 256), 256, 0, c->tent_pt, c->old_label, n, C, c->f_bin_cnt);
+    CHB_PDL_LAUNCH(c, entries_scan_kernel, 1, 256, 0, c->f_bin_cnt, C, c->f_seg_off, c->f_cursor, c->f_tile_bin, c->f_ntiles);
+    CHB_PDL_LAUNCH(c, entries_scatter_kernel, nblk(n, 256), 256, 0, c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
                                                                  c->f_col_pt, c->f_col_a, c->f_col_b);
-    column_gather_kernel<<<nblk(ncol_max * 32, 256), 256, 0, c->stream>>>(
+    CHB_PDL_LAUNCH(c, column_gather_kernel, nblk(ncol_max * 32, 256), 256, 0, 
         c->f_col_pt, c->f_ntiles, c->f_tile_bin, c->X, c->ldx, c->d, c->colsum, 1.0 / (double)n, c->f_mc, g.dp8, g.Kp2, c->f_bperm,
         c->f_col_nrm, reinterpret_cast<unsigned int *>(c->f_ym2), reinterpret_cast<unsigned int *>(c->f_ym2 + C + 1));
     CHB_CUDA(c, cudaGetLastError());
     c->tm.launches_other += 5;
+
+    c->round_counters_reset = c->qp_fb_zeroed = true; // round_reset_kernel (consumed by chb_launch_qp / commit_common)
+    if (c->side_join_pending) { // row_ub_kernel of the label set-up (side stream)
+        CHB_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        c->side_join_pending = false;
+    }
 
     // ---- 2. error slack and admission thresholds per (query, bin), then the fused Gram + selection
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
@@ -2452,7 +2525,7 @@ int chb_round_fused(chb_ctx *c)
         const bool wide = nown * (int64_t)C >= (int64_t)1 << 24; // 16 M pairs and more: a stream over the pair table
         dim3 tg(nblk(nown, wide ? 1024 : 256), (unsigned)C);
         auto tk = wide ? threshold_kernel<4> : threshold_kernel<1>;
-        tk<<<tg, 256, 0, c->stream>>>(
+        CHB_PDL_LAUNCH(c, tk, tg, 256, 0, 
             c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
             reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
             c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb,
@@ -2484,12 +2557,12 @@ int chb_round_fused(chb_ctx *c)
     // test aid: CHB_FUSED_NO_COMPACT forces the (row block, bin) items that are otherwise only used when the compact buffer
     // would overflow
     const int64_t plan_cap = getenv("CHB_FUSED_NO_COMPACT") ? -1 : c->f_cap_pairs;
-    pairs_plan_kernel<<<1, 1024, 0, c->stream>>>(bin_surv, c->f_seg_off, C, plan_cap, c->sm_count, pair_off,
+    CHB_PDL_LAUNCH(c, pairs_plan_kernel, 1, 1024, 0, bin_surv, c->f_seg_off, C, plan_cap, c->sm_count, pair_off,
                                                  c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode,
                                                  c->f_cand_dense ? 1 : 0);
-    items_kernel<<<1, 1024, 0, c->stream>>>(c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
+    CHB_PDL_LAUNCH(c, items_kernel, 1, 1024, 0, c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
                                             c->f_mode);
-    pairs_fill_kernel<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
+    CHB_PDL_LAUNCH(c, pairs_fill_kernel, nblk(nown * 32, 256), 256, 0, c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
                                                                    c->f_pair_row, c->f_row_pid, c->f_a2, g.Kp2, c->f_ap);
     CHB_CUDA(c, cudaGetLastError());
     c->tm.launches_other += 4;
@@ -2508,7 +2581,7 @@ int chb_round_fused(chb_ctx *c)
     {
         chb_stage_timer t(c, CHB_ST_KNN);
         auto kern = (KR == 8) ? rerank_kernel<16> : rerank_kernel<32>;
-        kern<<<nblk(nown * 32, 256), 256, 0, c->stream>>>(
+        CHB_PDL_LAUNCH(c, kern, nblk(nown * 32, 256), 256, 0, 
             nown, c->f_cand_key, c->f_cand_idx, KR, c->f_bin_cnt, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->f_slack, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters,
             c->f_fb_pairs, c->f_fb_cap, &c->counters[6], c->f_t0, c->f_ldt, c->f_thr, c->f_row_nb, c->f_row_bins, c->f_row_pid, c->f_mode);
         // pairs the re-rank could not settle from the kept lists (rare): exact redo, no host round trip -- the grid is
@@ -2518,11 +2591,11 @@ int chb_round_fused(chb_ctx *c)
         // at 1M -- the grid follows the number of rows, up to eight resident CTAs per SM
         const unsigned xgrid = (unsigned)std::min<int64_t>((int64_t)c->sm_count * 8, std::max<int64_t>(64, nown / 256));
         if (KR == 8)
-            exact_pairs_kernel<5><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt, c->f_col_pt,
+            CHB_PDL_LAUNCH(c, exact_pairs_kernel<5>, xgrid, 128, xs, c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt, c->f_col_pt,
                                                               c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot, c->pos, C,
                                                               k, c->knn_idx, c->knn_cnt, c->work, c->counters);
         else if (k <= 15)
-            exact_pairs_kernel<15><<<xgrid, 128, xs, c->stream>>>(c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
+            CHB_PDL_LAUNCH(c, exact_pairs_kernel<15>, xgrid, 128, xs, c->f_fb_pairs, &c->counters[6], c->f_fb_cap, c->f_seg_off, c->f_bin_cnt,
                                                                c->f_col_pt, c->f_col_a, c->f_col_b, c->X, c->ldx, c->d, c->f_row_pt, c->f_row_slot,
                                                                c->pos, C, k, c->knn_idx, c->knn_cnt, c->work, c->counters);
         else {

@@ -134,6 +134,7 @@ __device__ __forceinline__ bool exchange(double (&A)[KMAX], double *sRow, int kv
 template <int KMAX>
 __global__ void __launch_bounds__(QP_WARPS * 32) qp_kernel(chb_qp_args a, int fast)
 {
+    chb_pdl_wait();
     __shared__ __align__(16) double sWall[QP_WARPS][KMAX * LDW];
     __shared__ __align__(16) double sRowAll[QP_WARPS][KMAX + 2];
     __shared__ __align__(16) double sAlphaAll[QP_WARPS][KMAX];
@@ -480,7 +481,7 @@ int launch(chb_ctx *ctx, const chb_qp_args &a, int blocks_per_sm = 16, int fast 
     if (blocks < 1) blocks = 1;
     {
         chb_stage_timer t(ctx, CHB_ST_QP);
-        qp_kernel<KMAX><<<(unsigned)blocks, QP_WARPS * 32, 0, ctx->stream>>>(a, fast);
+        CHB_PDL_LAUNCH(ctx, qp_kernel<KMAX>, (unsigned)blocks, QP_WARPS * 32, 0, a, fast);
     }
     CHB_CUDA(ctx, cudaGetLastError());
     return CHB_OK;
@@ -490,6 +491,8 @@ int launch(chb_ctx *ctx, const chb_qp_args &a, int blocks_per_sm = 16, int fast 
 
 int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
 {
+    const bool fb_zeroed = ctx->qp_fb_zeroed; // round_reset_kernel zeroed the fallback counter for THIS launch only
+    ctx->qp_fb_zeroed = false;
     if (a.n_work <= 0) return CHB_OK;
     CHB_CHECK(ctx, a.k >= 1 && a.k <= CHB_KMAX, CHB_EINVAL, "num_neighbors must be in [1, %d]", CHB_KMAX);
     CHB_CHECK(ctx, a.metric == CHB_METRIC_CONVEX || a.metric == CHB_METRIC_AFFINE_QP || a.metric == CHB_METRIC_AFFINE,
@@ -509,7 +512,7 @@ int chb_launch_qp(chb_ctx *ctx, const chb_qp_args &a)
             }
             ctx->fallback_cap = a.n_work;
         }
-        CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[3], 0, sizeof(int32_t), ctx->stream));
+        if (!fb_zeroed) CHB_CUDA(ctx, cudaMemsetAsync(&ctx->counters[3], 0, sizeof(int32_t), ctx->stream));
         int rc = a.k <= 5 ? chb_launch_qp_small(ctx, a, ctx->fallback, &ctx->counters[3])
                           : (a.k <= 10 ? chb_launch_qp_mid(ctx, a, ctx->fallback, &ctx->counters[3])
                                        : chb_launch_qp_lane(ctx, a, ctx->fallback, &ctx->counters[3]));

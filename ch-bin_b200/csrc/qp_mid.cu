@@ -78,6 +78,7 @@ __device__ __forceinline__ bool affine_min(const double *__restrict__ sg, unsign
 __global__ void __launch_bounds__(WARPS * 32) qp_mid_kernel(chb_qp_args a, int2 *__restrict__ fallback,
                                                              int32_t *__restrict__ fallback_count)
 {
+    chb_pdl_wait();
     __shared__ __align__(16) double sG[WARPS][NPP * 32]; // [entry][pair-in-warp-batch]
     __shared__ int sI[WARPS][32][12];                     // per pair of the batch: m, query point, up to 10 neighbour points
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -367,7 +368,7 @@ int chb_launch_qp_mid(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int32_
     if (blocks < 1) blocks = 1;
     {
         chb_stage_timer t(ctx, CHB_ST_QP);
-        qp_mid_kernel<<<(unsigned)blocks, WARPS * 32, 0, ctx->stream>>>(a, fallback, fallback_count);
+        CHB_PDL_LAUNCH(ctx, qp_mid_kernel, (unsigned)blocks, WARPS * 32, 0, a, fallback, fallback_count);
     }
     CHB_CUDA(ctx, cudaGetLastError());
     return CHB_OK;

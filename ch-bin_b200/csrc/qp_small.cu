@@ -102,6 +102,7 @@ __device__ __forceinline__ bool eval_face(const double (&G)[15], unsigned mask, 
 __global__ void __launch_bounds__(WARPS * 32, 4) qp_small_kernel(chb_qp_args a, int2 *__restrict__ fallback,
                                                                int32_t *__restrict__ fallback_count)
 {
+    chb_pdl_wait();
     __shared__ __align__(16) double sG[WARPS][16 * 32]; // [entry][pair of the warp batch]
     __shared__ int sI[WARPS][32][8];                     // per pair of the batch: m, query point, 5 neighbour points
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -305,7 +306,7 @@ int chb_launch_qp_small(chb_ctx *ctx, const chb_qp_args &a, int2 *fallback, int3
     if (blocks < 1) blocks = 1;
     {
         chb_stage_timer t(ctx, CHB_ST_QP);
-        qp_small_kernel<<<(unsigned)blocks, WARPS * 32, 0, ctx->stream>>>(a, fallback, fallback_count);
+        CHB_PDL_LAUNCH(ctx, qp_small_kernel, (unsigned)blocks, WARPS * 32, 0, a, fallback, fallback_count);
     }
     CHB_CUDA(ctx, cudaGetLastError());
     return CHB_OK;

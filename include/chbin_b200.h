@@ -222,6 +222,11 @@ int chb_get_labels(chb_ctx *ctx, int64_t *labels_out);
 int chb_iteration_begin(chb_ctx *ctx, const int64_t *perm, int64_t U);
 /* The same with the permutation already in DEVICE memory (e.g. rank 0's draw after an NCCL broadcast): distance mode 2 only. */
 int chb_iteration_begin_dev(chb_ctx *ctx, const int64_t *perm_dev, int64_t U);
+/* Optional: the NEXT iteration's permutation (algorithm.py:45 draws one per iteration), uploaded on a side stream while the
+ * current iteration's rounds run on the device.  The next chb_iteration_begin uses that copy iff it is called with the same
+ * `perm` pointer (the host array must stay unchanged in between); any other pointer simply uploads as usual.  Call it after
+ * chb_round_run has enqueued a round, before the commit that synchronises.  No-op outside distance mode 2. */
+int chb_iteration_prefetch(chb_ctx *ctx, const int64_t *perm, int64_t U);
 int chb_round_run(chb_ctx *ctx, int64_t lo, int64_t hi, int32_t *tent_dev);
 int chb_round_commit(chb_ctx *ctx, int64_t lo, int64_t hi, const int32_t *tent_dev, int64_t *first_changed);
 int chb_iteration_end(chb_ctx *ctx, int64_t *n_changed);
