@@ -64,6 +64,20 @@ def owned_slots(U: int, rank: int, world: int) -> Tuple[int, int]:
     return (U * rank) // world, (U * (rank + 1)) // world
 
 
+# Below this many (query, bin) pairs per stage the ranks do not shard: a stage is then a ~1 ms chain of short kernels, and every
+# collective of the sharded protocol (feature broadcast, guess exchange, one label all-reduce per round, the permutation
+# broadcast) costs 30-100 us of launch latency and host time -- measured at 20k contigs x 50 bins (875k pairs): 0.97 ms on one GPU,
+# 0.92-1.06 ms sharded over 2-8, and end to end 1.65 ms against 2.1-2.9 ms.  Every rank then runs the whole (deterministic, exact)
+# stage on its own GPU with no communication at all and returns the same labels.  Ranks must share the RNG state, as they do under
+# the reference's CLI (np.random.seed(0) in every process, ch_bin/ch_bin.py:22).  100k contigs x 100 bins (9.5 M pairs) shards.
+SHARD_MIN_PAIRS = int(os.environ.get("CHB_SHARD_MIN_PAIRS", 2_000_000))
+
+
+def sharding_pays(num_points_to_assign: int, num_clusters: int, world: int) -> bool:
+    """True when `world` ranks should shard the query slots of a stage (see SHARD_MIN_PAIRS)."""
+    return world > 1 and int(num_points_to_assign) * int(num_clusters) >= SHARD_MIN_PAIRS
+
+
 def run_iteration(engine, perm, comm=None) -> Tuple[int, int]:
     """One iteration of algorithm.py:43-72 as speculate/repair rounds (csrc/api.cu header).
 
@@ -320,6 +334,9 @@ def fit_cluster(
     points_to_assign = np.where(curr == -1)[0]  # algorithm.py:38
     num_points_to_assign = len(points_to_assign)
     logger.debug("Assigning %s points.", num_points_to_assign)
+    job_rank, job_world = rank, world
+    if world > 1 and not sharding_pays(num_points_to_assign, num_clusters, world):
+        dist_mod, rank, world = None, 0, 1  # too small to pay for the collectives: every rank runs the whole stage (SHARD_MIN_PAIRS)
 
     marks = [] if os.environ.get("CHB_PROFILE_FIT") else None  # wall-clock marks of the host driver (tools/e2e_multi.py)
 
@@ -445,8 +462,8 @@ def fit_cluster(
         if tm_end.get("qp_iter_cap", 0):
             logger.warning("%s hull-distance QPs stopped on the iteration cap of the active-set method (feasible, possibly not "
                            "optimal); the reference would have fallen back to cvxopt there.", tm_end["qp_iter_cap"])
-        info = dict(iterations=iterations, converged=converged, changed=changed, timers=tm_end, rank=rank,
-                    world=world, owned_slots=(u0, u1))
+        info = dict(iterations=iterations, converged=converged, changed=changed, timers=tm_end, rank=job_rank,
+                    world=job_world, owned_slots=(u0, u1), replicated=job_world > 1 and world == 1)
         if marks is not None:
             info["marks_ms"] = [(lab, (t - marks[0][1]) * 1e3) for lab, t in marks]
     except BaseException:

@@ -804,6 +804,61 @@ __device__ __forceinline__ float pair_slack(double eps_rel, float nrm_q, float y
     return __double2float_ru(e * (1.0 + 1e-6) + 1e-30);
 }
 
+// Work list of the fused kernel: one item per surviving (row block, bin) = {row block, bin, first tile, #tiles}, in row-block
+// order, and for each of the G CTAs the contiguous range of items whose cumulative tile count falls into its 1/G share.
+// Whole items only (a (query, bin) list is built by one CTA), so CTAs differ by at most one bin's tiles.  One block: the tail of
+// pairs_plan_kernel when the compact buffer would overflow (mode 0); s_items / s_tiles: 1024 ints of shared memory each.
+__device__ void items_body(const uint8_t *__restrict__ skip, int64_t nrb, int32_t C, const int32_t *__restrict__ seg_off, int32_t G,
+                           int4 *__restrict__ items, int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals, int *s_items,
+                           int *s_tiles)
+{
+    __shared__ int tot_items, tot_tiles;
+    const int tid = threadIdx.x;
+    const int64_t ne = nrb * C;
+    const int64_t per = (ne + 1023) / 1024;
+    const int64_t e0 = tid * per < ne ? tid * per : ne, e1 = e0 + per < ne ? e0 + per : ne;
+    int ni = 0, nt = 0;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int c = (int)(e % C);
+        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
+        if (!skip[e] && w > 0) { ++ni; nt += w; }
+    }
+    s_items[tid] = ni;
+    s_tiles[tid] = nt;
+    __syncthreads();
+    // inclusive scan (Hillis-Steele) over the 1024 partial counts
+    for (int o = 1; o < 1024; o <<= 1) {
+        const int a = tid >= o ? s_items[tid - o] : 0, b = tid >= o ? s_tiles[tid - o] : 0;
+        __syncthreads();
+        s_items[tid] += a;
+        s_tiles[tid] += b;
+        __syncthreads();
+    }
+    if (tid == 1023) { tot_items = s_items[1023]; tot_tiles = s_tiles[1023]; }
+    for (int b = tid; b <= G; b += 1024) cta_begin[b] = INT32_MAX;
+    __syncthreads();
+    const int TI = tot_items, TT = tot_tiles;
+    int oi = s_items[tid] - ni, ot = s_tiles[tid] - nt; // exclusive prefixes of this thread's chunk
+    for (int64_t e = e0; e < e1; ++e) {
+        const int c = (int)(e % C);
+        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
+        if (!skip[e] && w > 0) {
+            items[oi] = make_int4((int)(e / C), c, seg_off[c] / BN, w);
+            const int cta = (int)(((int64_t)ot * G) / (TT > 0 ? TT : 1));
+            atomicMin(&cta_begin[cta], oi);
+            ++oi;
+            ot += w;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        cta_begin[G] = TI;
+        for (int b = G - 1; b >= 0; --b)
+            if (cta_begin[b] > cta_begin[b + 1]) cta_begin[b] = cta_begin[b + 1]; // CTAs without an item of their own
+        totals[0] = TT;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // compaction.  After pruning, the rows that still need a bin are few and scattered over the row blocks (in a "side" bin
 // of a row block typically 5-10 of the 128 rows survive), so contracting (row block x bin) tiles wastes most of every
@@ -815,7 +870,8 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
                                                           int32_t C, int64_t cap_pairs, int32_t G, int32_t *__restrict__ pair_off,
                                                           int32_t *__restrict__ scratch /* 2 (C + 1) */, int4 *__restrict__ items,
                                                           int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
-                                                          int32_t *__restrict__ mode, int32_t dense_ok)
+                                                          int32_t *__restrict__ mode, int32_t dense_ok,
+                                                          const uint8_t *__restrict__ skip, int64_t nrb)
 {
     chb_pdl_enter();
     __shared__ int s_mode, s_ti, s_tt;
@@ -866,7 +922,10 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
         if (tid == 0) totals[0] = 0;
         return;
     }
-    if (!s_mode) return; // items_kernel builds the (row block, bin) list instead
+    if (!s_mode) { // little pruning: the (row block, bin) list instead (shared memory of the per-bin counts is free again)
+        items_body(skip, nrb, C, seg_off, G, items, cta_begin, totals, s_nb, s_w);
+        return;
+    }
     const bool beg_smem = G <= 1024;
     int *beg = beg_smem ? s_begin : cta_begin;
     for (int b = tid; b <= G; b += 1024) beg[b] = INT32_MAX;
@@ -900,13 +959,15 @@ __global__ void __launch_bounds__(1024) pairs_plan_kernel(const int32_t *__restr
 }
 
 // compact pair id -> row, per bin (any order inside a bin), and the pair's query operand row copied into the compact
-// buffer; one warp per row.  Padding ids keep pair_row = -1 (round_reset_kernel); their operand rows are never
-// initialised -- accumulator rows are independent and the epilogue ignores rows without a query.
+// buffer; one warp per row.  threshold_kernel left every pair's index inside its bin in row_pid: id = pair_off[bin] + index
+// (lane j resolves the row's j-th surviving bin), the operand row is read once and written once per pair.  Padding ids
+// keep pair_row = -1 (round_reset_kernel); their operand rows are never initialised -- accumulator rows are independent
+// and the epilogue ignores rows without a query.
 __global__ void __launch_bounds__(256) pairs_fill_kernel(const int32_t *__restrict__ mode, const int32_t *__restrict__ row_nb,
                                                          const int32_t *__restrict__ row_bins, int64_t nown, int32_t C,
-                                                         const int32_t *__restrict__ pair_off, int32_t *__restrict__ pair_cur,
-                                                         int32_t *__restrict__ pair_row, int32_t *__restrict__ row_pid,
-                                                         const float *__restrict__ a2, int32_t Kp2, float *__restrict__ ap)
+                                                         const int32_t *__restrict__ pair_off, int32_t *__restrict__ pair_row,
+                                                         int32_t *__restrict__ row_pid, const float *__restrict__ a2, int32_t Kp2,
+                                                         float *__restrict__ ap)
 {
     chb_pdl_enter();
     if (*mode != 1) return;
@@ -914,76 +975,29 @@ __global__ void __launch_bounds__(256) pairs_fill_kernel(const int32_t *__restri
     const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (r >= nown) return;
     const int nb = row_nb[r];
+    if (nb == 0) return;
     const float4 *src = reinterpret_cast<const float4 *>(a2 + r * Kp2);
-    for (int j = 0; j < nb; ++j) {
-        int id = 0;
-        if (lane == 0) {
+    const int nq = Kp2 / 4; // <= 96 float4 per row (d <= 160): three per lane
+    float4 v[3];
+#pragma unroll
+    for (int u = 0; u < 3; ++u) v[u] = (lane + 32 * u < nq) ? __ldg(src + lane + 32 * u) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int jb = 0; jb < nb; jb += 32) {
+        const int j = jb + lane;
+        int id = -1;
+        if (j < nb) {
             const int c = row_bins[r * C + j];
-            id = pair_off[c] + atomicAdd(&pair_cur[c], 1);
+            id = pair_off[c] + row_pid[r * C + j];
             pair_row[id] = (int32_t)r;
             row_pid[r * C + j] = id; // the re-rank finds this pair's candidate lists under its compact id
         }
-        id = __shfl_sync(CHB_FULL, id, 0);
-        float4 *dst = reinterpret_cast<float4 *>(ap + (int64_t)id * Kp2);
-        for (int q = lane; q < Kp2 / 4; q += 32) dst[q] = __ldg(src + q);
-    }
-}
-
-// Work list of the fused kernel: one item per surviving (row block, bin) = {row block, bin, first tile, #tiles}, in row-block
-// order, and for each of the G CTAs the contiguous range of items whose cumulative tile count falls into its 1/G share.
-// Whole items only (a (query, bin) list is built by one CTA), so CTAs differ by at most one bin's tiles.  One block.
-__global__ void __launch_bounds__(1024) items_kernel(const uint8_t *__restrict__ skip, int64_t nrb, int32_t C,
-                                                     const int32_t *__restrict__ seg_off, int32_t G, int4 *__restrict__ items,
-                                                     int32_t *__restrict__ cta_begin, int32_t *__restrict__ totals,
-                                                     const int32_t *__restrict__ mode)
-{
-    chb_pdl_enter();
-    if (*mode) return; // pairs_plan_kernel already built the compact (pair block, bin) list
-    __shared__ int s_items[1024], s_tiles[1024];
-    __shared__ int tot_items, tot_tiles;
-    const int tid = threadIdx.x;
-    const int64_t ne = nrb * C;
-    const int64_t per = (ne + 1023) / 1024;
-    const int64_t e0 = tid * per < ne ? tid * per : ne, e1 = e0 + per < ne ? e0 + per : ne;
-    int ni = 0, nt = 0;
-    for (int64_t e = e0; e < e1; ++e) {
-        const int c = (int)(e % C);
-        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
-        if (!skip[e] && w > 0) { ++ni; nt += w; }
-    }
-    s_items[tid] = ni;
-    s_tiles[tid] = nt;
-    __syncthreads();
-    // inclusive scan (Hillis-Steele) over the 1024 partial counts
-    for (int o = 1; o < 1024; o <<= 1) {
-        const int a = tid >= o ? s_items[tid - o] : 0, b = tid >= o ? s_tiles[tid - o] : 0;
-        __syncthreads();
-        s_items[tid] += a;
-        s_tiles[tid] += b;
-        __syncthreads();
-    }
-    if (tid == 1023) { tot_items = s_items[1023]; tot_tiles = s_tiles[1023]; }
-    for (int b = tid; b <= G; b += 1024) cta_begin[b] = INT32_MAX;
-    __syncthreads();
-    const int TI = tot_items, TT = tot_tiles;
-    int oi = s_items[tid] - ni, ot = s_tiles[tid] - nt; // exclusive prefixes of this thread's chunk
-    for (int64_t e = e0; e < e1; ++e) {
-        const int c = (int)(e % C);
-        const int w = (seg_off[c + 1] - seg_off[c]) / BN;
-        if (!skip[e] && w > 0) {
-            items[oi] = make_int4((int)(e / C), c, seg_off[c] / BN, w);
-            const int cta = (int)(((int64_t)ot * G) / (TT > 0 ? TT : 1));
-            atomicMin(&cta_begin[cta], oi);
-            ++oi;
-            ot += w;
+        const int cnt = nb - jb < 32 ? nb - jb : 32;
+        for (int w = 0; w < cnt; ++w) {
+            const int idw = __shfl_sync(CHB_FULL, id, w);
+            float4 *dst = reinterpret_cast<float4 *>(ap + (int64_t)idw * Kp2);
+#pragma unroll
+            for (int u = 0; u < 3; ++u)
+                if (lane + 32 * u < nq) dst[lane + 32 * u] = v[u];
         }
-    }
-    __syncthreads();
-    if (tid == 0) {
-        cta_begin[G] = TI;
-        for (int b = G - 1; b >= 0; --b)
-            if (cta_begin[b] > cta_begin[b + 1]) cta_begin[b] = cta_begin[b + 1]; // CTAs without an item of their own
-        totals[0] = TT;
     }
 }
 
@@ -1383,7 +1397,7 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
                                  const float *__restrict__ ubk2_row, const int32_t *__restrict__ row_guess, double eps_rel, int64_t nown,
                                  int32_t C, int32_t k, int32_t prune, int64_t ldt, float *__restrict__ t0_tab, float *__restrict__ slack_tab,
                                  int32_t *__restrict__ row_nb, int32_t *__restrict__ row_bins, int32_t *__restrict__ bin_surv,
-                                 uint8_t *__restrict__ skip)
+                                 uint8_t *__restrict__ skip, int32_t *__restrict__ row_pid)
 {
     chb_pdl_enter();
     // grid: x = chunks of 1024 rows (eight 128-row blocks of the fused kernel; a thread takes 4 consecutive rows, a warp one
@@ -1431,8 +1445,11 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
                 if (!alive[u]) continue;
                 const int64_t r = r0 + u;
                 const float tq = tqv[u];
-                row_bins[r * C + atomicAdd(&row_nb[r], 1)] = c; // surviving bins of this row, in any order
-                atomicAdd(&bin_surv[c], 1);
+                const int js = atomicAdd(&row_nb[r], 1); // surviving bins of this row, in any order
+                row_bins[r * C + js] = c;
+                // the pair's index among its bin's survivors: pairs_fill_kernel turns it into the compact pair id without a
+                // second round of atomics on the C per-bin counters
+                row_pid[r * C + js] = atomicAdd(&bin_surv[c], 1);
                 const int64_t pair = (int64_t)row_slot[r] * C + c; // caches are indexed by slot
                 const int jq = row_point[r];
                 const float E = pair_slack(eps_rel, nrm[jq], ym2[c], tcmax[c], tq);
@@ -1443,11 +1460,23 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
                     if (ub < INFINITY) {
                         const int p = pos[jq];
                         bool ok = true;
-                        for (int s = 0; s < k; ++s) {
-                            const int j = knn_idx[pair * k + s];
-                            const int ps = pos[j];
-                            const int lab = ps < p ? tent[j] : (ps > p ? old[j] : -1); // algorithm.py:46-60; the query itself never counts
-                            ok = ok && (lab == c);
+                        // four neighbours at a time, loads of a kind issued together: index -> position -> label is a chain of
+                        // three dependent L2 round trips per neighbour, and this thread is the tail of its CTA
+                        for (int s0 = 0; s0 < k; s0 += 4) {
+                            int jn[4], ps[4], lt[4], lo_[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) jn[u] = s0 + u < k ? knn_idx[pair * k + s0 + u] : -1;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                ps[u] = jn[u] >= 0 ? pos[jn[u]] : 0;
+                                lt[u] = jn[u] >= 0 ? tent[jn[u]] : c;
+                                lo_[u] = jn[u] >= 0 ? old[jn[u]] : c;
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int lab = ps[u] < p ? lt[u] : (ps[u] > p ? lo_[u] : -1); // algorithm.py:46-60; the query itself never counts
+                                ok = ok && (jn[u] < 0 || lab == c);
+                            }
                         }
                         // this round's keys of the cached neighbours are <= ub + E, so is the k-th smallest key a_k, and the
                         // re-rank looks no further than a_k + 2E
@@ -1606,17 +1635,35 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
         const int nc = __popc(vm);
         const int m = nc < k ? nc : k; // |bin| <= k: all members (distance_matrix.py:58-59)
         const bool big = nc > k;
-        // rank of every candidate by (key, index) among the valid ones
+        // rank of every candidate by (key, index) among the valid ones, and the set of group lanes holding a smaller index
+        // (for the canonical order of the chosen set below).  Full lists (no admission thresholds yet: first round): all G
+        // lanes are visited, straight-line -- an empty slot holds (+inf, INT32_MAX) and never counts against a valid one, and
+        // 2 x G independent shuffles pipeline where a walk over the set bits of `vm` is a serial chain of dependent shuffles
         int rnk = 0;
-        {
+        unsigned lt_idx = 0; // bit t: group lane t holds a point index below this lane's
+        const int niter = __reduce_max_sync(CHB_FULL, nc); // longest list among the warp's groups
+        if (2 * niter > G) {
+#pragma unroll
+            for (int t = 0; t < G; ++t) {
+                const float ok = __shfl_sync(CHB_FULL, ka, t, G);
+                const int oi = __shfl_sync(CHB_FULL, ki, t, G);
+                rnk += (ok < ka || (ok == ka && oi < ki)) ? 1 : 0;
+                lt_idx |= (oi < ki ? 1u : 0u) << t;
+            }
+        } else {
+            // short lists (admission thresholds at work: k + 2 candidates or so): visit the occupied slots only -- at 1M
+            // contigs the kernel is bound by the shuffle unit, and 2 x G shuffles per pair cost 60 % more than this walk
             unsigned mm = vm;
-            while (__any_sync(CHB_FULL, mm != 0)) {
+            for (int it = 0; it < niter; ++it) {
                 const bool had = mm != 0;
                 const int t = had ? __ffs(mm) - 1 : 0;
                 mm &= mm - 1;
                 const float ok = __shfl_sync(CHB_FULL, ka, t, G);
                 const int oi = __shfl_sync(CHB_FULL, ki, t, G);
-                if (had && (ok < ka || (ok == ka && oi < ki))) ++rnk;
+                if (had) {
+                    rnk += (ok < ka || (ok == ka && oi < ki)) ? 1 : 0;
+                    lt_idx |= (oi < ki ? 1u : 0u) << t;
+                }
             }
         }
         const unsigned bk = (__ballot_sync(CHB_FULL, valid && rnk == k - 1) >> gsh) & GM;
@@ -1665,17 +1712,7 @@ __global__ void __launch_bounds__(256) rerank_kernel(int64_t nrows, const float 
         for (int o = G / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(CHB_FULL, mx, o));
         // neighbour set, stored in ascending index order (canonical for set comparison)
         const unsigned selm = (__ballot_sync(CHB_FULL, sel) >> gsh) & GM;
-        int srt = 0;
-        {
-            unsigned mm = selm;
-            while (__any_sync(CHB_FULL, mm != 0)) {
-                const bool had = mm != 0;
-                const int t = had ? __ffs(mm) - 1 : 0;
-                mm &= mm - 1;
-                const int oi = __shfl_sync(CHB_FULL, ki, t, G);
-                if (had && oi < ki) ++srt;
-            }
-        }
+        const int srt = __popc(selm & lt_idx); // chosen points with a smaller index
         const bool diff = sel && (mo != m || knn_idx[pair * k + srt] != ki);
         const unsigned dm = (__ballot_sync(CHB_FULL, diff) >> gsh) & GM;
         const bool same = (mo == m) && dm == 0;
@@ -2455,6 +2492,9 @@ int chb_fused_setup(chb_ctx *c)
         }
         if (nown > 0) {
             // rows = owned slots grouped by guessed bin, so that a 128-row block prunes the same bins
+            // (one single-CTA kernel for these four was tried for small inputs: slower -- one SM walking 20k entries with
+            // dependent loads loses to four short launches over all SMs; likewise for the column entries below)
+            c->tm.launches_other += 4;
             CHB_CUDA(c, cudaMemsetAsync(c->f_rhist, 0, sizeof(int32_t) * (size_t)(C + 2), c->stream));
             CHB_PDL_LAUNCH(c, row_hist_kernel, nblk(nown, 256), 256, 0, c->f_guess_all + c->u0, nown, c->f_rhist);
             CHB_PDL_LAUNCH(c, row_scan_kernel, 1, 32, 0, c->f_rhist, C + 1, c->f_rhist + C + 2);
@@ -2478,7 +2518,7 @@ int chb_fused_setup(chb_ctx *c)
                                                                                       g.dp8, g.Kp2, c->nrm, c->f_a2, nullptr);
             dim3 gq((unsigned)((nown + QT_ROWS - 1) / QT_ROWS), (unsigned)((C + 31) / 32));
             CHB_PDL_LAUNCH(c, query_terms_gather_kernel, gq, 256, 0, c->f_tqs, Cp, c->u0 - t_first, c->f_row_slot, nown, C, c->f_ldt, c->f_tq);
-            c->tm.launches_other += 4;
+            c->tm.launches_other += 2;
         }
         CHB_CUDA(c, cudaGetLastError());
         c->f_asplit_ready = true;
@@ -2529,7 +2569,7 @@ int chb_round_fused(chb_ctx *c)
             c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,
             reinterpret_cast<const unsigned int *>(&c->counters[5]), c->f_ym2, c->f_ym2 + C + 1, c->f_tq, c->f_ub, c->f_sq_row, c->f_ubk2,
             c->f_row_guess, eps_rel, nown, C, k, c->metric == CHB_METRIC_CONVEX ? 1 : 0, c->f_ldt, c->f_t0, c->f_slack, c->f_row_nb,
-            c->f_row_bins, c->f_pair_meta, c->f_skip);
+            c->f_row_bins, c->f_pair_meta, c->f_skip, c->f_row_pid);
     }
     // KR = 16 serves k <= FUSED_KMAX: the re-rank needs the k + 1 smallest keys of the pair; they are all among the kept 2 x 16
     // unless one 64-column half holds 16 or more of them, which the re-rank's completeness tests detect (exact redo).  k + 3 <= KR
@@ -2559,13 +2599,11 @@ int chb_round_fused(chb_ctx *c)
     const int64_t plan_cap = getenv("CHB_FUSED_NO_COMPACT") ? -1 : c->f_cap_pairs;
     CHB_PDL_LAUNCH(c, pairs_plan_kernel, 1, 1024, 0, bin_surv, c->f_seg_off, C, plan_cap, c->sm_count, pair_off,
                                                  c->f_pair_meta + 3 * (C + 2), c->f_items, c->f_cta_begin, &c->counters[7], c->f_mode,
-                                                 c->f_cand_dense ? 1 : 0);
-    CHB_PDL_LAUNCH(c, items_kernel, 1, 1024, 0, c->f_skip, nrb, C, c->f_seg_off, c->sm_count, c->f_items, c->f_cta_begin, &c->counters[7],
-                                            c->f_mode);
-    CHB_PDL_LAUNCH(c, pairs_fill_kernel, nblk(nown * 32, 256), 256, 0, c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off, pair_cur,
-                                                                   c->f_pair_row, c->f_row_pid, c->f_a2, g.Kp2, c->f_ap);
+                                                 c->f_cand_dense ? 1 : 0, c->f_skip, nrb);
+    CHB_PDL_LAUNCH(c, pairs_fill_kernel, nblk(nown * 32, 256), 256, 0, c->f_mode, c->f_row_nb, c->f_row_bins, nown, C, pair_off,
+                   c->f_pair_row, c->f_row_pid, c->f_a2, g.Kp2, c->f_ap);
     CHB_CUDA(c, cudaGetLastError());
-    c->tm.launches_other += 4;
+    c->tm.launches_other += 3;
     CUtensorMap ma, mb, map;
     int rc = make_map(c, &ma, c->f_a2, nown, g.Kp2);
     if (rc != CHB_OK) return rc;

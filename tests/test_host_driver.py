@@ -96,3 +96,11 @@ def test_sharded_world2_gloo(hard):
     for rank, labels, qps in res:
         assert np.array_equal(labels, ref), f"rank {rank} diverged from the sequential reference"
     assert all(r[2] > 0 for r in res), "both ranks must have solved QPs (work is sharded)"
+
+
+def test_small_stages_are_not_sharded():
+    """clustering.SHARD_MIN_PAIRS: 20k contigs x 50 bins runs whole on every rank, the BASELINE sizes that are asked to scale shard."""
+    assert not chbin_b200.clustering.sharding_pays(17_500, 50, 8)       # config #2
+    assert chbin_b200.clustering.sharding_pays(95_000, 100, 8)          # config #3
+    assert chbin_b200.clustering.sharding_pays(950_000, 500, 2)         # config #4
+    assert not chbin_b200.clustering.sharding_pays(950_000, 500, 1)     # one rank never shards
