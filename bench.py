@@ -329,11 +329,13 @@ class StageRunner:
         if self.engine is None:
             self.engine = self.clustering.GpuEngine(ctx, self.local_rank, self.stream)
             self.comm = self.clustering.TorchComm()
+        ctx.iteration_prefetch(self.perms[0])  # side stream: the upload runs beside the guess exchange
         self.clustering.exchange_guess(self.engine, self.comm, self.U)  # every rank guesses for its own slots only
         iters = 0
         with self.engine.stream_context():
             for it in range(MAX_ITERATIONS):
-                nch, _ = self.clustering.run_iteration(self.engine, self.perms[it], self.comm)
+                nxt = self.perms[it + 1] if it + 1 < MAX_ITERATIONS else None
+                nch, _ = self.clustering.run_iteration(self.engine, self.perms[it], self.comm, next_perm=nxt)
                 iters += 1
                 if nch == 0:
                     break

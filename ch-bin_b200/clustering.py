@@ -78,8 +78,11 @@ def sharding_pays(num_points_to_assign: int, num_clusters: int, world: int) -> b
     return world > 1 and int(num_points_to_assign) * int(num_clusters) >= SHARD_MIN_PAIRS
 
 
-def run_iteration(engine, perm, comm=None) -> Tuple[int, int]:
+def run_iteration(engine, perm, comm=None, next_perm=None) -> Tuple[int, int]:
     """One iteration of algorithm.py:43-72 as speculate/repair rounds (csrc/api.cu header).
+
+    next_perm: the permutation of the iteration after this one, if the caller already has it (host array): engines with a
+    prefetch() upload it while this iteration's first round runs on the device.
 
     engine: iteration_begin(perm), round_run(lo, hi) -> tent, round_commit(lo, hi, tent) -> first_changed (-1 = none),
             iteration_end() -> n_changed, window() -> int; optionally round_commit_end(lo, hi, tent) ->
@@ -96,6 +99,9 @@ def run_iteration(engine, perm, comm=None) -> Tuple[int, int]:
         tent = engine.round_run(lo, hi)
         if comm is not None:
             tent = comm.all_reduce_max(tent)
+        if next_perm is not None and hasattr(engine, "prefetch"):
+            engine.prefetch(next_perm)
+            next_perm = None
         if merged is not None:
             first, done, n_changed = merged(lo, hi, tent)
             rounds += 1
@@ -143,6 +149,10 @@ class GpuEngine:
 
     def round_commit_end(self, lo, hi, tent):
         return self.ctx.round_commit_end(lo, hi, tent.data_ptr())
+
+    def prefetch(self, perm):
+        if isinstance(perm, np.ndarray):  # a host permutation: uploaded on the library's side stream while a round runs
+            self.ctx.iteration_prefetch(perm)
 
     def guess_export(self, U):
         g = self.torch.empty(max(U, 1), dtype=self.torch.int32, device=self.device)[:U]

@@ -71,6 +71,13 @@ struct SmemTail {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_shared_f32(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -1240,6 +1247,9 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int et = threadIdx.x - 64;        // 0..255 index among the epilogue threads
         TopList<KR> L;
         int64_t tt = 0;
+        // the thread's candidate stack through explicit shared-space accesses (S is reached through a generic pointer: the
+        // compiler emitted 64-bit generic ST.E / LD.E with an IMAD.WIDE each)
+        const uint32_t cand_base = smem_u32(&S.cand_val[0][et]);
         for (int it = item_begin; it < item_end; ++it) {
             const int4 item = items[it];
             const int cur_bin = item.y;
@@ -1310,7 +1320,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         _Pragma("unroll") for (int u = 0; u < 4; ++u) {                                                             \
             const float av = fmaf(-2.f, __uint_as_float(v[4 * G + u]), nr + nn[u]);                                 \
             if (((p > aa[u]) || (p < bb[u])) && (av <= thr)) {                                                      \
-                S.cand_val[ncand][et] = av;                                                                         \
+                st_shared_f32(cand_base + (uint32_t)ncand * (EPI_THREADS * 4), av);                                 \
                 if (G < 8) cm_lo |= 1u << ((4 * G + u) & 31);                                                       \
                 else cm_hi |= 1u << ((4 * G + u) & 31);                                                             \
                 ++ncand;                                                                                            \
@@ -1347,7 +1357,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                             int col;
                             if (cm_hi) { col = 63 - __clz(cm_hi); cm_hi &= ~(1u << (col - 32)); }
                             else { col = 31 - __clz(cm_lo); cm_lo &= ~(1u << col); }
-                            const float av = S.cand_val[ncand][et];
+                            const float av = ld_shared_f32(cand_base + (uint32_t)ncand * (EPI_THREADS * 4));
                             if (av < L.key[KR - 1]) L.insert(av, __ldg(tile_pt + col));
                         }
                     }
