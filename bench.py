@@ -329,8 +329,8 @@ class StageRunner:
         if self.engine is None:
             self.engine = self.clustering.GpuEngine(ctx, self.local_rank, self.stream)
             self.comm = self.clustering.TorchComm()
-        ctx.iteration_prefetch(self.perms[0])  # side stream: the upload runs beside the guess exchange
-        self.clustering.exchange_guess(self.engine, self.comm, self.U)  # every rank guesses for its own slots only
+        self.clustering.exchange_guess(self.engine, self.comm, self.U)  # every rank guesses for its own slots only (enqueued)
+        ctx.iteration_prefetch(self.perms[0])  # side stream; the host-side staging of the upload overlaps the set-up kernels
         iters = 0
         with self.engine.stream_context():
             for it in range(MAX_ITERATIONS):

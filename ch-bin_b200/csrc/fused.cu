@@ -801,6 +801,71 @@ __global__ void __launch_bounds__(256) column_gather_kernel(const int32_t *__res
     }
 }
 
+// ---- wide variant
+__global__ void __launch_bounds__(256) column_gather_wide_kernel(const int32_t *__restrict__ col_pt, const int32_t *__restrict__ ntiles,
+                                                            const int32_t *__restrict__ tile_bin, const double *__restrict__ X,
+                                                            int32_t ldx, int32_t d, const double *__restrict__ colsum, double inv_n,
+                                                            const double *__restrict__ mc, int32_t dp8, int32_t Kp2,
+                                                            float *__restrict__ out, float *__restrict__ col_term,
+                                                            unsigned int *__restrict__ ym2_bits, unsigned int *__restrict__ tcmax_bits)
+{
+    chb_pdl_enter();
+    // The same for large inputs: a CTA takes CG_COLS consecutive column entries -- inside one 128-column tile, hence of one
+    // bin -- CG_COLS / 8 per warp, and folds their maxima in shared memory: one atomic pair per CTA, a quarter of the CTAs.
+    // 1M contigs: 1.30 -> 0.83 ms per launch (2.5 GB moved); at 20k contigs the one-column-per-warp kernel above is faster
+    // (24 against 28 us: too few CTAs to fill the machine), so the host picks by the number of columns.
+    constexpr int CG_COLS = 32;
+    __shared__ unsigned int s_y[8], s_t[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e0 = (int64_t)blockIdx.x * CG_COLS;
+    if (e0 >= (int64_t)(*ntiles) * BN) return; // whole CTA (uniform)
+    const int c = tile_bin[e0 / BN];
+    const double *m = mc + (int64_t)c * d;
+    unsigned int ymax = 0, tmax = 0; // non-negative floats order like their bits
+    for (int w = 0; w < CG_COLS / 8; ++w) {
+        const int64_t e = e0 + warp * (CG_COLS / 8) + w;
+        const int ptx = col_pt[e];
+        float *orow = out + e * Kp2;
+        if (ptx < 0) { // padding column: zero row, never visible
+            for (int t = lane; t < Kp2; t += 32) orow[t] = 0.f;
+            if (lane == 0) col_term[e] = 0.f;
+            continue;
+        }
+        const double *xr = X + (int64_t)ptx * ldx;
+        double yy = 0.0, my = 0.0;
+        for (int t = lane; t < dp8; t += 32) {
+            float hi = 0.f, lo = 0.f;
+            if (t < d) {
+                const float yf = (float)(xr[t] - colsum[t] * inv_n - m[t]);
+                hi = __uint_as_float(__float_as_uint(yf) & 0xffffe000u);
+                lo = __uint_as_float(__float_as_uint(yf - hi) & 0xffffe000u);
+                yy = fma((double)yf, (double)yf, yy);
+                my = fma(m[t], (double)yf, my);
+            }
+            orow[t] = hi;
+            orow[dp8 + t] = lo;
+        }
+        for (int t = 2 * dp8 + lane; t < Kp2; t += 32) orow[t] = 0.f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            yy += __shfl_xor_sync(CHB_FULL, yy, o);
+            my += __shfl_xor_sync(CHB_FULL, my, o);
+        }
+        const double term = yy + 2.0 * my;
+        if (lane == 0) col_term[e] = (float)term;
+        ymax = max(ymax, __float_as_uint(__double2float_ru(yy)));
+        tmax = max(tmax, __float_as_uint(__double2float_ru(fabs(term))));
+    }
+    if (lane == 0) { s_y[warp] = ymax; s_t[warp] = tmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { ymax = max(ymax, s_y[w]); tmax = max(tmax, s_t[w]); }
+        if (ymax) atomicMax(&ym2_bits[c], ymax);
+        if (tmax) atomicMax(&tcmax_bits[c], tmax);
+    }
+}
+
 // slack of (query r, bin c): bound on |key - |x_q - x_i|^2| for every column i of the bin (see the block comment above).
 //   contraction: 2 * eps_rel * |a_q| * max|y|      (eps_rel = (3d + 64) 2^-23 bounds the dot-product error, gram_tc.cu)
 //   FP32 roundings of the three terms and of the operands: 2^-21 * (tq + max|column term| + 2 |a_q| max|y| + D (|a_q| + max|y|) + D^2),  D = |a_q - m_c| + max|y|
@@ -2557,9 +2622,14 @@ int chb_round_fused(chb_ctx *c)
     CHB_PDL_LAUNCH(c, entries_scan_kernel, 1, 256, 0, c->f_bin_cnt, C, c->f_seg_off, c->f_cursor, c->f_tile_bin, c->f_ntiles);
     CHB_PDL_LAUNCH(c, entries_scatter_kernel, nblk(n, 256), 256, 0, c->tent_pt, c->old_label, c->pos, n, C, c->f_seg_off, c->f_cursor,
                                                                  c->f_col_pt, c->f_col_a, c->f_col_b);
-    CHB_PDL_LAUNCH(c, column_gather_kernel, nblk(ncol_max * 32, 256), 256, 0, 
-        c->f_col_pt, c->f_ntiles, c->f_tile_bin, c->X, c->ldx, c->d, c->colsum, 1.0 / (double)n, c->f_mc, g.dp8, g.Kp2, c->f_bperm,
-        c->f_col_nrm, reinterpret_cast<unsigned int *>(c->f_ym2), reinterpret_cast<unsigned int *>(c->f_ym2 + C + 1));
+    if (ncol_max >= (int64_t)1 << 18)
+        CHB_PDL_LAUNCH(c, column_gather_wide_kernel, nblk(ncol_max, 32), 256, 0,
+            c->f_col_pt, c->f_ntiles, c->f_tile_bin, c->X, c->ldx, c->d, c->colsum, 1.0 / (double)n, c->f_mc, g.dp8, g.Kp2, c->f_bperm,
+            c->f_col_nrm, reinterpret_cast<unsigned int *>(c->f_ym2), reinterpret_cast<unsigned int *>(c->f_ym2 + C + 1));
+    else
+        CHB_PDL_LAUNCH(c, column_gather_kernel, nblk(ncol_max * 32, 256), 256, 0,
+            c->f_col_pt, c->f_ntiles, c->f_tile_bin, c->X, c->ldx, c->d, c->colsum, 1.0 / (double)n, c->f_mc, g.dp8, g.Kp2, c->f_bperm,
+            c->f_col_nrm, reinterpret_cast<unsigned int *>(c->f_ym2), reinterpret_cast<unsigned int *>(c->f_ym2 + C + 1));
     CHB_CUDA(c, cudaGetLastError());
     c->tm.launches_other += 5;
 
