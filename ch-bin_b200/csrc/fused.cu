@@ -1462,6 +1462,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 // THR_ROWS rows per thread: 4 (16-byte loads of the per-row tables, 16-byte stores of the pruned thresholds) when the pair
 // table is large and nearly everything is pruned -- the kernel is then a stream over 8 bytes per pair; 1 when it is small and
 // the surviving pairs' work (serial per thread) sets the time
+constexpr int THR_BINS = 4;
 template <int THR_ROWS>
 __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restrict__ knn_idx, const int32_t *__restrict__ knn_cnt, const float *__restrict__ thr,
                                  const int32_t *__restrict__ row_point, const int32_t *__restrict__ row_slot,
@@ -1478,16 +1479,30 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
     // grid: x = chunks of 1024 rows (eight 128-row blocks of the fused kernel; a thread takes 4 consecutive rows, a warp one
     // 128-row block), y = bin.  Besides the per-pair tables the block leaves skip[row block][bin] = "every row of the block
     // pruned the bin": the (row block, bin) work items of the uncompacted path, without a second pass over the thresholds.
-    const int c = blockIdx.y;
+    // THR_ROWS == 4 (large pair tables): a thread also walks THR_BINS consecutive bins -- the per-row bounds are read once for
+    // them and the bins' query terms are all in flight before the first is used (the kernel is a stream over 8 B per pair)
+    constexpr int NBIN = THR_ROWS == 4 ? THR_BINS : 1;
     const int lane = threadIdx.x & 31;
     const int64_t r0 = ((int64_t)blockIdx.x * 256 + threadIdx.x) * THR_ROWS; // first row (rows = owned slots ordered by guessed bin)
+    float4 tq4s[NBIN], ub4 = make_float4(0.f, 0.f, 0.f, 0.f), sq4 = ub4;
+    if (THR_ROWS == 4 && r0 < nown) {
+        ub4 = *reinterpret_cast<const float4 *>(ub_row + r0);
+        sq4 = *reinterpret_cast<const float4 *>(sq_row + r0);
+#pragma unroll
+        for (int cb = 0; cb < NBIN; ++cb) {
+            const int cc = blockIdx.y * NBIN + cb;
+            tq4s[cb] = cc < C ? *reinterpret_cast<const float4 *>(tq_tab + (int64_t)cc * ldt + r0) : ub4;
+        }
+    }
+#pragma unroll
+    for (int cb = 0; cb < NBIN; ++cb) {
+    const int c = blockIdx.y * NBIN + cb;
+    if (c >= C) break; // (uniform over the block)
     bool any_alive = false;
     if (r0 < nown) { // ldt is a multiple of 128 and the tables are allocated up to it: whole float4s may be touched
         float tqv[4], ubv[4], sqv[4];
         if (THR_ROWS == 4) {
-            const float4 tq4 = *reinterpret_cast<const float4 *>(tq_tab + (int64_t)c * ldt + r0);
-            const float4 ub4 = *reinterpret_cast<const float4 *>(ub_row + r0);
-            const float4 sq4 = *reinterpret_cast<const float4 *>(sq_row + r0);
+            const float4 tq4 = tq4s[cb];
             tqv[0] = tq4.x; tqv[1] = tq4.y; tqv[2] = tq4.z; tqv[3] = tq4.w;
             ubv[0] = ub4.x; ubv[1] = ub4.y; ubv[2] = ub4.z; ubv[3] = ub4.w;
             sqv[0] = sq4.x; sqv[1] = sq4.y; sqv[2] = sq4.z; sqv[3] = sq4.w;
@@ -1586,6 +1601,7 @@ __global__ void __launch_bounds__(256) threshold_kernel(const int32_t *__restric
             if (rb * BM < nown) skip[rb * C + c] = s_alive[threadIdx.x >> 7] ? 0 : 1;
         }
     }
+    } // bins of this thread
 }
 
 // algorithm.py:47-48,57-58,60 over the surviving bins of each query: strict '<' so the lowest bin wins ties; a query
@@ -2643,7 +2659,7 @@ int chb_round_fused(chb_ctx *c)
     const double eps_rel = (double)(3 * c->d + 64) * 1.1920928955078125e-07;
     {
         const bool wide = nown * (int64_t)C >= (int64_t)1 << 24; // 16 M pairs and more: a stream over the pair table
-        dim3 tg(nblk(nown, wide ? 1024 : 256), (unsigned)C);
+        dim3 tg(nblk(nown, wide ? 1024 : 256), (unsigned)(wide ? (C + THR_BINS - 1) / THR_BINS : C));
         auto tk = wide ? threshold_kernel<4> : threshold_kernel<1>;
         CHB_PDL_LAUNCH(c, tk, tg, 256, 0, 
             c->knn_idx, c->knn_cnt, c->f_thr, c->f_row_pt, c->f_row_slot, c->pos, c->tent_pt, c->old_label, c->nrm,

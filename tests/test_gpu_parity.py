@@ -703,3 +703,44 @@ def test_exact_redo_list_overflow_grows_and_reruns_the_window(monkeypatch, k):
         ctx.fit(perms, 4)
         rounds_regular = ctx.timers()["rounds"]
     assert rounds > rounds_regular, "at least one window must have run twice"
+
+
+def test_prefetched_permutation_is_used_only_when_it_is_the_one_begun():
+    """chb_iteration_prefetch uploads the next permutation on the library's side stream while a round runs; the next
+    chb_iteration_begin takes that copy only when it is handed the very same host array.  A different array, a prefetch that no
+    iteration follows (new label set) and a prefetch in a matrix-backed distance mode (no-op) must all leave the result the
+    sequential reference's (algorithm.py:43-72)."""
+    X, bins, _ = synth.make_contig_features(3000, 6, 10, 20, seed=21, concentration=80.0)
+    perms = oracle.draw_permutations(bins, 4, seed=3)
+    U = perms.shape[1]
+    ref, info = oracle.fit_cluster(X, 6, bins, None, 5, 4, perms=perms, return_info=True)
+    other = np.ascontiguousarray(perms[::-1])  # a decoy: prefetched but never begun
+
+    def iterate(ctx, prefetch):
+        for it in range(info["iterations"]):
+            ctx.iteration_begin(perms[it])
+            lo = 0
+            while lo < U:
+                ctx.round_run(lo, U)
+                if prefetch == "next" and it + 1 < len(perms):
+                    ctx.iteration_prefetch(perms[it + 1])
+                elif prefetch == "decoy":
+                    ctx.iteration_prefetch(other[it])
+                first, done, nch = ctx.round_commit_end(lo, U)
+                if first == chbin_b200.clustering.ROUND_AGAIN:
+                    continue
+                lo = U if first < 0 else first + 1
+            if not done:
+                ctx.iteration_end()
+        return ctx.get_labels()
+
+    for mode in (2, 1):
+        for prefetch in ("next", "decoy", "none"):
+            with _ctx(X, bins, 6, 5, dist_mode=mode) as ctx:
+                got = iterate(ctx, prefetch)
+                assert np.array_equal(got, ref), (mode, prefetch)
+                # a prefetch left pending by the loop above must not leak into the next label set
+                ctx.iteration_prefetch(other[0])
+                ctx.set_labels(bins, 6, 0, -1)
+                ctx.build_distance_matrix(True)
+                assert np.array_equal(iterate(ctx, "none"), ref), (mode, prefetch, "second label set")
