@@ -698,8 +698,12 @@ def report(args, cfg, X, bins, U, world, elapsed_ms, elapsed_ms_b, total_iters, 
         "roofline": roof, "stages": stages, "qp_isolated": qp_iso,
         "latency": {"ms_per_step": elapsed_ms / args.steps, "ms_per_step_with_stage_timers": elapsed_ms_b / args.steps,
                     "timed_kernels_ms_per_step": kernel_ms / args.steps, "launches_per_step": launches_step,
+                    "launch_chain": "programmatic dependent launch (griddepcontrol) through the stage's kernels, no copy / memset "
+                                    "nodes inside a round, row_ub on a side stream, next permutation prefetched"
+                                    + (" [CHB_NO_PDL set: plain launches]" if os.environ.get("CHB_NO_PDL") else ""),
                     "note": "timed kernels = gram_select, rerank (+exact redo), QP, argmin/commit; the rest of the step is the "
-                            "per-label-set and per-round set-up kernels and host round trips"},
+                            "per-label-set and per-round set-up kernels and host round trips; the pass with stage timers records an "
+                            "event pair around each timed kernel, which also breaks the programmatic launch chain there"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "QP/s", "h2d_bytes_per_step": int(n * d * 8 + n * 8 + e2e_iters / args.steps * U * 8),
                 "d2h_bytes_per_step": int(n * 8), "ms_per_step": e2e_s * 1e3 / args.steps,

@@ -1532,7 +1532,7 @@ static int commit_common(chb_ctx *c, int64_t lo, int64_t hi, const int32_t *tent
     c->counters_host[4] = 0;
     c->tm.qp_iter_cap += c->counters_host[14];
     c->counters_host[14] = 0;
-    c->tm.gram_tiles_planned += c->counters_host[7]; // tiles left after bin pruning (pairs_plan_kernel / items_kernel), this round
+    c->tm.gram_tiles_planned += c->counters_host[7]; // tiles left after bin pruning (pairs_plan_kernel), this round
     c->tm.gram_tiles += c->counters_host[8];         // tiles the MMA warps of gram_select_kernel actually issued
     c->counters_host[7] = c->counters_host[8] = 0;
     CHB_TRY(resolve_perm_check(c));

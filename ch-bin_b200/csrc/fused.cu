@@ -14,7 +14,7 @@
 //     to a multiple of 128; column_gather_kernel writes the per-bin-centred TF32 [hi | lo] operand rows in that order.
 //  2. threshold_kernel: per (row, bin) the pruning test (bin cannot be the argmin: admission threshold -inf, nothing
 //     else happens for the pair), else the key error bound E and the admission threshold T0 from the cached set;
-//     the same kernel flags the (row block, bin) pairs none of whose rows survived; pairs_plan_kernel / items_kernel turn
+//     the same kernel flags the (row block, bin) pairs none of whose rows survived; pairs_plan_kernel (and its tail, items_body) turn
 //     the survivors into a balanced work list.
 //  3. gram_select_kernel: one persistent CTA per SM walking its work items.  TMA: the row block's query operand is
 //     loaded once and stays resident, the column operand streams through a 3-4-stage ring -> tcgen05.mma kind::tf32
@@ -1122,7 +1122,7 @@ gram_select_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                    int32_t *__restrict__ tiles_issued)
 {
     chb_pdl_wait();
-    // This CTA's work: items [cta_begin[b], cta_begin[b + 1]) of the list built by items_kernel, each one surviving
+    // This CTA's work: items [cta_begin[b], cta_begin[b + 1]) of the list built by pairs_plan_kernel, each one surviving
     // (row block, bin) = {row block, bin, first tile, #tiles}.  Pruned (row block, bin) pairs are not in the list: their
     // tiles are neither loaded, contracted nor screened.  All three warp roles walk the same items.
     const int item_begin = cta_begin[blockIdx.x], item_end = cta_begin[blockIdx.x + 1];
@@ -2274,7 +2274,7 @@ template <int KR, int NKT>
 int launch_fused(chb_ctx *c, const CUtensorMap &ma, const CUtensorMap &map, const CUtensorMap &mb, int64_t nrows, const FusedGeom &g)
 {
     CHB_CUDA(c, cudaFuncSetAttribute(gram_select_kernel<KR, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
-    const int grid = c->sm_count; // persistent: one CTA per SM, work split by items_kernel
+    const int grid = c->sm_count; // persistent: one CTA per SM, work split by pairs_plan_kernel
     {
         chb_stage_timer t(c, CHB_ST_GRAM);
         CHB_PDL_LAUNCH(c, (gram_select_kernel<KR, NKT>), grid, FUSED_THREADS, g.smem,
