@@ -721,10 +721,12 @@ def report(args, cfg, X, bins, U, world, elapsed_ms, elapsed_ms_b, total_iters, 
 def _emit(line: dict):
     """The ONE JSON line goes to the real stdout; everything else written to fd 1 meanwhile (NCCL's version banner,
     library chatter) was diverted to stderr by main()."""
+    line["bench_wall_s"] = round(time.perf_counter() - _T_START, 1)  # this process, argument parsing to the line (all legs)
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 _REAL_STDOUT = 1
+_T_START = time.perf_counter()
 
 
 def main():
