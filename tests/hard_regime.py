@@ -4,7 +4,7 @@ genomes made to overlap by lowering the generator's Dirichlet concentration (400
 stage per measurement = label set-up + distance structure + iterations up to the limit, features resident, CUDA events
 on the context's stream, L2 flushed between stages.  The final labels are checked against the position-parallel oracle on
 sampled positions of the LAST executed iteration (test infrastructure; not inside the timed region).
-usage: python tools/hard_regime.py [max_iterations] [steps]"""
+usage: python tests/hard_regime.py [max_iterations] [steps]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
