@@ -237,7 +237,7 @@ def cpu_extras(X, bins, cfg, seconds=3.0):
         try:
             j = json.load(open(p))
             out["b1_reference_verbatim"] = dict(j["b1_reference_verbatim"], where="build container (the reference tree does not "
-                                                "travel to the GPU box), tools/baseline_b1.py", solver=j.get("quadprog"), file="profiles/r2_baseline_b1_b3_container.json")
+                                                "travel to the GPU box), oracle/baseline_b1.py", solver=j.get("quadprog"), file="profiles/r2_baseline_b1_b3_container.json")
         except Exception:
             pass
     return out

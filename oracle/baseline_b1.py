@@ -8,7 +8,7 @@ GPU box cannot run them, so bench.py quotes the file this script writes):
       restated Goldfarb-Idnani solver (oracle/gi_qp.c) -- "reference flow + restated solver".
   B3  scipy cdist: create_in_mem_distance_matrix (distance_matrix.py:33-44), single thread, full n (n^2 * 8 B must fit).
 
-usage: python tools/baseline_b1.py [workload=20k] [steps=2000]   ->  profiles/r2_baseline_b1_b3_container.json
+usage: python oracle/baseline_b1.py [workload=20k] [steps=2000]   ->  profiles/r2_baseline_b1_b3_container.json
 """
 import itertools
 import json
